@@ -1,0 +1,142 @@
+/*
+ * smalltts_b200 -- C ABI of the B200-native engine for the smalltts synthesize hot path.
+ *
+ * This is the drop-in boundary.  The reference reaches this path through three opaque
+ * onnxruntime sessions plus host-side numpy sampling:
+ *
+ *   reference call site                                        replaced by
+ *   ---------------------------------------------------------  -----------------------------------------
+ *   ort.InferenceSession(path, ...)  infer/onnx.py:21-24,60-63  stts_create + stts_load_weight* + stts_finalize_weights
+ *     (Rust: Session::builder()...   server/src/pipeline.rs:16-20,40-48)
+ *   cond_enc.run(None, feed)         infer/onnx.py:91-96        stts_encode_conditions
+ *     (Rust: Pipeline::cond_encode   pipeline.rs:122-143)
+ *   denoiser.run(None, feed)[0]      infer/onnx.py:107-124      stts_denoise_step
+ *     (Rust: Pipeline::denoise       pipeline.rs:145-166)
+ *   the 4-step numpy loop            infer/onnx.py:98-125       stts_sample           (loop stays on device)
+ *     (Rust:                         pipeline.rs:81-93)
+ *   codec_dec.run(None, feed)[0]     infer/onnx.py:127-128      stts_decode
+ *     (Decoder.decode codec/onnx.py:42-53; Rust pipeline.rs:168-174)
+ *   SmallTTS.synthesize              infer/onnx.py:68-129       stts_synthesize       (all of the above, one call)
+ *     (Rust: Pipeline::synthesize_timed pipeline.rs:60-112)
+ *   Timing{...}                      pipeline.rs:29-37          stts_get_timings
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Every function returns 0 on success or a negative stts_status;
+ *     stts_last_error() gives the message (per engine; pass NULL for creation failures).
+ *   - The engine owns its CUDA device memory (weights, workspaces, conditions) and one CUDA stream.  A handle
+ *     is NOT thread-safe: one call in flight per engine (the reference serialises with a mutex, main.rs:25).
+ *   - Data pointers may be host or device memory; the `mem` argument says which (STTS_MEM_HOST / STTS_MEM_DEVICE).
+ *     Host buffers are copied with cudaMemcpyAsync on the engine stream (pinned buffers make that truly async);
+ *     the call returns after the stream has been synchronised, so outputs are ready on return.
+ *   - Control metadata -- every length array (ref_len, ph_len, frames) and every timestep array -- is ALWAYS host
+ *     memory, whatever `mem` says; only tensors (latents, ids, noise, audio) follow `mem`.
+ *   - Ragged batches are padded: utterance b owns rows [0, len[b]) of its [*, max, C] slab.  Masks of the
+ *     reference operators (bool tensors) are prefix masks built from these lengths (infer/onnx.py:88-99).
+ *   - There is no CPU fallback: stts_create fails if the device is not compute capability 10.x.
+ */
+#ifndef SMALLTTS_B200_H_
+#define SMALLTTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STTS_SAMPLE_RATE 24000 /* infer/onnx.py:11 */
+#define STTS_HOP_SIZE 3200     /* infer/onnx.py:12 */
+#define STTS_LATENT_DIM 64
+#define STTS_NUM_STEPS 4 /* infer/onnx.py:13 */
+
+typedef enum stts_status {
+  STTS_OK = 0,
+  STTS_ERR_INVALID = -1,    /* bad argument / shape */
+  STTS_ERR_CUDA = -2,       /* CUDA runtime or kernel failure */
+  STTS_ERR_NO_DEVICE = -3,  /* no sm_100 device: there is no fallback */
+  STTS_ERR_WEIGHTS = -4,    /* missing / mis-shaped weight, or not finalized */
+  STTS_ERR_OOM = -5
+} stts_status;
+
+typedef enum stts_mem { STTS_MEM_HOST = 0, STTS_MEM_DEVICE = 1 } stts_mem;
+
+typedef struct stts_engine stts_engine;
+typedef struct stts_cond stts_cond;
+
+typedef struct stts_config {
+  int device;        /* CUDA ordinal */
+  int reserved[7];   /* zero */
+} stts_config;
+
+/* Stage timings in milliseconds of the last stts_synthesize call, CUDA-event timed; same split as the
+ * reference server's Timing (pipeline.rs:29-37). codec_enc_ms is always 0 (encoder not on this path). */
+typedef struct stts_timing {
+  float codec_enc_ms, cond_enc_ms, denoise_ms, codec_dec_ms, total_ms;
+} stts_timing;
+
+int stts_create(const stts_config* cfg, stts_engine** out);
+void stts_destroy(stts_engine* e);
+const char* stts_last_error(const stts_engine* e);
+
+/* Weights: fp32 tensors under the reference's own state-dict names.
+ * model: 0 = DiTModel (models/backbone/model.py:33-54), 1 = VibeVoice acoustic-tokenizer decoder.
+ * `data` is host fp32, row-major, `ndim` <= 4.  stts_finalize_weights packs them for the kernels (bf16,
+ * K-major, tap-major conv layouts) and validates that every tensor of both models is present. */
+int stts_load_weight(stts_engine* e, int model, const char* name, const float* data, int ndim, const int64_t* shape);
+int stts_finalize_weights(stts_engine* e);
+
+/* == condition_encoder.onnx.  ref [B,R,64] f32, ref_len [B] i64, phonemes [B,P] i64, ph_len [B] i64
+ * (phonemes_mask[b, p] = p < ph_len[b]).  The result lives on the device and may be reused for any number of
+ * stts_denoise_step / stts_sample calls with the same batch (voice cloning: one condition, many prompts). */
+int stts_encode_conditions(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* phonemes,
+                           const int64_t* ph_len, int B, int R, int P, int mem, stts_cond** out);
+void stts_cond_free(stts_engine* e, stts_cond* c);
+/* Test hook: copy block `layer`'s cached cross K/V out as fp32 [B,8,N,120] like the reference's
+ * project_cross_kv (dit.py:88-93); which: 0 k_ref, 1 v_ref, 2 k_text, 3 v_text. Host destination. */
+int stts_cond_read_kv(stts_engine* e, const stts_cond* c, int layer, int which, float* dst);
+
+/* == denoiser.onnx: velocity [B,T,64] for x_t [B,T,64], frames [B] i64 (mask[b,t] = t < frames[b]), t [B] f32 (host). */
+int stts_denoise_step(stts_engine* e, const stts_cond* c, const float* x_t, const int64_t* frames, const float* t,
+                      int B, int T, int mem, float* velocity);
+
+/* DMD re-noising loop, on device.  timesteps: host [steps] (NULL -> linspace(1,0,steps), infer/onnx.py:102).
+ * noise: [steps,B,T,64] (NULL -> on-device Philox normal stream keyed by `seed`).  out_latents: [B,T,64]. */
+int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B, int T, int steps,
+                const float* timesteps, const float* noise, uint64_t seed, int mem, float* out_latents);
+
+/* == codec/decoder.onnx: latents [B,T,64] -> audio [B, T*3200] (the reference's (B,1,T*3200)). */
+int stts_decode(stts_engine* e, const float* latents, int B, int T, int mem, float* audio);
+
+/* == SmallTTS.synthesize for a padded batch; intermediates never leave the device. audio: [B, T*3200]. */
+int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* phonemes,
+                    const int64_t* ph_len, const int64_t* frames, int B, int R, int P, int T, int steps,
+                    const float* timesteps, const float* noise, uint64_t seed, int mem, float* audio);
+
+int stts_get_timings(const stts_engine* e, stts_timing* out);
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
+uint64_t stts_launch_count(void);
+/* Per-call device timing of the dominant vocoder kernels (ms, summed over the last stts_decode/stts_synthesize):
+ * which: 0 = HBM-bound tail (stages with C <= 128 + head), 1 = tensor-bound front (stem .. C >= 256). */
+float stts_last_vocoder_ms(const stts_engine* e, int which);
+
+/* Pinned host memory helpers for callers that want truly asynchronous copies. */
+void* stts_host_alloc(size_t bytes);
+void stts_host_free(void* p);
+
+/* ---- kernel-level test hooks (used by tests/ only; all pointers are DEVICE memory) ---- */
+int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T, int a_cols, int a_ld,
+                   const void* w_bf16, int w_rows, int w_ld, int N, int K, int taps, int tap_shift0, int tap_step,
+                   int groups, int a_group_koff, int w_group_rows, int out_group_cols, const float* bias, int act,
+                   const int32_t* row_len, int rows_per_batch, int mask_bf16_only, const float* colscale, const float* rowgate, int ld_gate,
+                   const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out);
+int stts_test_attention(stts_engine* e, const void* q, int B, int tq, int H, int hd, int hd_pad, const void* k0,
+                        const void* v0, const int32_t* len0, int n0, const void* k1, const void* v1,
+                        const int32_t* len1, int n1, const float* gate, int ld_gate, void* out);
+int stts_test_convnext_mix(stts_engine* e, const float* x, int B, int T, int C, const float* norm_w,
+                           const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
+                           float* y, void* a_bf16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMALLTTS_B200_H_ */

@@ -1,0 +1,86 @@
+"""ctypes binding of include/smalltts_b200.h.  No torch types cross this boundary.
+
+The shared library is built in-tree by ``python -m smalltts_b200.build``.  If it is missing this module
+raises: there is deliberately no Python/CPU fallback for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsmalltts_b200.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+OK = 0
+
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+c_f32p = C.POINTER(C.c_float)
+vp = C.c_void_p
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("reserved", C.c_int * 7)]
+
+
+class Timing(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("codec_enc_ms", "cond_enc_ms", "denoise_ms", "codec_dec_ms", "total_ms")]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check every symbol of the header is exported
+SIGNATURES = {
+    "stts_create": (C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
+    "stts_destroy": (None, [vp]),
+    "stts_last_error": (C.c_char_p, [vp]),
+    "stts_load_weight": (C.c_int, [vp, C.c_int, C.c_char_p, vp, C.c_int, c_i64p]),
+    "stts_finalize_weights": (C.c_int, [vp]),
+    "stts_encode_conditions": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "stts_cond_free": (None, [vp, vp]),
+    "stts_cond_read_kv": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
+    "stts_denoise_step": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "stts_sample": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_uint64, C.c_int, vp]),
+    "stts_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "stts_synthesize": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                  C.c_uint64, C.c_int, vp]),
+    "stts_get_timings": (C.c_int, [vp, C.POINTER(Timing)]),
+    "stts_launch_count": (C.c_uint64, []),
+    "stts_last_vocoder_ms": (C.c_float, [vp, C.c_int]),
+    "stts_host_alloc": (vp, [C.c_size_t]),
+    "stts_host_free": (None, [vp]),
+    "stts_test_gemm": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int,
+                                 vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int]),
+    "stts_test_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp,
+                                      vp, C.c_int, vp, C.c_int, vp]),
+    "stts_test_convnext_mix": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m smalltts_b200.build`. "
+                "smalltts_b200 has no CPU or PyTorch fallback for the synthesize path."
+            )
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, handle=None) -> None:
+    if rc == OK:
+        return
+    msg = lib().stts_last_error(handle)
+    msg = msg.decode() if msg else "unknown error"
+    if rc == -1:
+        raise ValueError(f"smalltts_b200: {msg}")
+    raise RuntimeError(f"smalltts_b200 (status {rc}): {msg}")

@@ -1,0 +1,71 @@
+"""Build libsmalltts_b200.so in-tree with nvcc for sm_100a (no torch, no cmake).
+
+    python -m smalltts_b200.build [--force]
+
+The library is plain CUDA C++ behind the C ABI of include/smalltts_b200.h; it links the CUDA runtime
+statically and resolves cuTensorMapEncodeTiled through cudaGetDriverEntryPoint, so it needs no libcuda at
+link time and cross-compiles on a machine without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsmalltts_b200.so")
+SOURCES = ["gemm.cu", "kernels.cu", "engine.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "smalltts_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src}\n{out}")
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{out}")
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    with open(os.path.join(CSRC, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

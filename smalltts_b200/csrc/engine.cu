@@ -1,0 +1,1002 @@
+// C-ABI implementation: weight registry + packing, condition encoder, DiT denoiser, DMD sampler, vocoder.
+// Host orchestration only; all arithmetic is in gemm.cu (tcgen05) and kernels.cu.
+#include <math.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/smalltts_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace stts;
+
+namespace {
+
+struct Err : std::runtime_error {
+  int code;
+  Err(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(expr)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      throw Err(STTS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +  \
+                                   std::to_string(__LINE__) + ")");                                     \
+    }                                                                                                    \
+  } while (0)
+
+constexpr int D = 960, H = 8, HD = 120, HDP = 128, FF = 2400, NBLK = 12, LAT = 64;
+constexpr int MOD_LD = NBLK * 6 * D + 2 * D;  // per-timestep adaLN table: 12 x [6][960] + final [2][960]
+constexpr int ROPE_MAX = 4096;                // dit.py:139, style.py:140, phonemes.py:196
+const int VOC_R[6] = {8, 5, 5, 4, 2, 2};
+const int VOC_C[7] = {2048, 1024, 512, 256, 128, 64, 32};
+const int VOC_DEPTH[7] = {8, 3, 3, 3, 3, 3, 3};
+
+struct RawTensor {
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  size_t numel = 0;
+};
+
+struct EncBlockW {
+  bf16 *wqkvg, *wo, *w13, *w2;
+  const float *qn, *kn, *an, *mn;
+};
+struct EncW {
+  int d, heads, hd, inter, layers;
+  float eps;
+  std::vector<EncBlockW> blk;
+  const float* final_norm;
+};
+struct DitBlockW {
+  bf16 *wqkvg, *wo, *w13, *w2;
+  float *bqkvg, *b13;
+  const float *b2, *qn, *kn, *ada_w, *ada_b;
+};
+struct VocLayerW {
+  const float *norm_w, *conv_w, *conv_b, *gamma, *ffn_norm_w, *b1, *b2, *ffn_gamma;
+  bf16 *w1, *w2;
+};
+
+template <typename T>
+struct Tmp {  // stream-ordered temporary
+  T* p = nullptr;
+  cudaStream_t st = nullptr;
+  Tmp() {}
+  Tmp(cudaStream_t s, size_t n) { alloc(s, n); }
+  void alloc(cudaStream_t s, size_t n) {
+    release();
+    st = s;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&p), (n ? n : 1) * sizeof(T), s));
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, st);
+    p = nullptr;
+  }
+  ~Tmp() { release(); }
+  Tmp(const Tmp&) = delete;
+  Tmp& operator=(const Tmp&) = delete;
+  operator T*() const { return p; }
+};
+
+}  // namespace
+
+struct stts_cond {
+  int B = 0, R = 0, P = 0;
+  int *ref_len = nullptr, *ph_len = nullptr;  // device int32 [B]
+  std::vector<int> h_ref_len, h_ph_len;
+  bf16* kv_ref = nullptr;   // [12][2][B, R, 8, 128]
+  bf16* kv_text = nullptr;  // [12][2][B, P, 8, 128]
+  size_t ref_stride() const { return static_cast<size_t>(B) * R * H * HDP; }
+  size_t text_stride() const { return static_cast<size_t>(B) * P * H * HDP; }
+};
+
+struct stts_engine {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  std::string err;
+  std::map<std::string, RawTensor> raw[2];
+  std::vector<void*> owned;  // packed buffers
+  bool finalized = false;
+
+  // packed DiT-side weights
+  EncW style, text;
+  bf16 *style_in_w, *style_out_w, *ph_proj_w, *wkv_ref, *wkv_text, *in_proj_w, *conv1_w, *conv2_w, *vel_w;
+  float *style_in_b, *bkv_ref, *bkv_text;
+  const float *style_out_b, *ph_proj_b, *in_proj_b, *conv1_b, *conv2_b, *vel_b, *text_emb;
+  std::vector<DitBlockW> blk;
+  float *cos64, *sin64, *cos128, *sin128;
+  std::map<uint32_t, float*> mod_cache;  // timestep bits -> device adaLN table [MOD_LD]
+
+  // packed vocoder weights
+  bf16* stem_w;
+  const float* stem_b;
+  std::vector<std::vector<VocLayerW>> voc;  // [7 stages][depth]
+  bf16* up_w[6];
+  float* up_b[6];
+  const float *head_w, *head_b;
+
+  stts_timing timing = {0, 0, 0, 0, 0};
+  float voc_ms[2] = {0, 0};
+  cudaEvent_t ev[8];
+
+  const RawTensor& W(int model, const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = raw[model].find(name);
+    if (it == raw[model].end()) throw Err(STTS_ERR_WEIGHTS, "missing weight: " + name);
+    if (it->second.shape != std::vector<int64_t>(shape)) throw Err(STTS_ERR_WEIGHTS, "bad shape for weight: " + name);
+    return it->second;
+  }
+  template <typename T>
+  T* dalloc(size_t n, bool zero = true) {
+    T* p = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T)));
+    if (zero) CK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
+    owned.push_back(p);
+    return p;
+  }
+};
+
+namespace {
+
+// ------------------------------------------------------------------ GEMM convenience wrappers
+// Widest tile that still gives the chip a full wave of CTAs (148 SMs); narrow tiles for small problems.
+int pick_bn(long long m, int n) {
+  int bn = 256;
+  while (bn > 32) {
+    const long long tiles = ((m + 127) / 128) * ((n + bn - 1) / bn);
+    if (bn <= n && tiles >= 148) break;
+    bn /= 2;
+  }
+  return bn;
+}
+
+// Plain linear over flattened rows: out = epi(A[rows, K] * W[N, K]^T)
+void linear(stts_engine* e, const bf16* a, long long rows, int k, int lda, const bf16* w, int n, int ldw, GemmEpi epi,
+            int bn = 0) {
+  GemmShape s;
+  s.B = 1;
+  s.T = static_cast<int>(rows);
+  s.N = n;
+  s.K = k;
+  GemmA ga{a, k, lda};
+  GemmW gw{w, n, ldw};
+  if (bn == 0) bn = pick_bn(rows, n);
+  CK(launch_gemm(e->st, bn, ga, gw, s, epi));
+}
+
+template <typename T>
+const T* to_dev(stts_engine* e, const T* p, size_t n, int mem, Tmp<T>& hold) {
+  if (mem == STTS_MEM_DEVICE) return p;
+  hold.alloc(e->st, n);
+  CK(cudaMemcpyAsync(hold.p, p, n * sizeof(T), cudaMemcpyHostToDevice, e->st));
+  return hold.p;
+}
+
+void lens_to_dev(stts_engine* e, const int64_t* h, int n, int maxv, Tmp<int>& hold, std::vector<int>* keep = nullptr) {
+  std::vector<int> v(n);
+  for (int i = 0; i < n; ++i) {
+    if (h[i] < 0 || h[i] > maxv) throw Err(STTS_ERR_INVALID, "length out of range");
+    v[i] = static_cast<int>(h[i]);
+  }
+  hold.alloc(e->st, n);
+  CK(cudaMemcpyAsync(hold.p, v.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->st));
+  CK(cudaStreamSynchronize(e->st));  // v goes out of scope
+  if (keep) *keep = v;
+}
+
+// ------------------------------------------------------------------ weight packing
+bf16* pack_lin(stts_engine* e, const RawTensor& t, int rows, int cols, bf16* dst = nullptr, int ld = 0, int row_off = 0,
+               int row_mode = ROW_PLAIN, int col_mode = COL_PLAIN, float scale = 1.f) {
+  if (ld == 0) ld = cols;
+  if (dst == nullptr) dst = e->dalloc<bf16>(static_cast<size_t>(rows) * ld);
+  CK(pack_matrix(e->st, t.d, rows, cols, scale, row_mode, row_off, col_mode, 0, dst, ld));
+  return dst;
+}
+
+void build_encoder(stts_engine* e, EncW& w, const std::string& pre, int d, int heads, int inter, int layers, float eps) {
+  w.d = d; w.heads = heads; w.hd = d / heads; w.inter = inter; w.layers = layers; w.eps = eps;
+  for (int i = 0; i < layers; ++i) {
+    const std::string p = pre + "blocks." + std::to_string(i) + ".";
+    EncBlockW b;
+    b.wqkvg = e->dalloc<bf16>(static_cast<size_t>(4) * d * d);
+    const char* names[4] = {"wq", "wk", "wv", "gate"};
+    for (int j = 0; j < 4; ++j) {
+      pack_lin(e, e->W(0, p + "attention." + names[j] + ".weight", {d, d}), d, d, b.wqkvg, d, j * d);
+    }
+    b.wo = pack_lin(e, e->W(0, p + "attention.wo.weight", {d, d}), d, d);
+    b.w13 = e->dalloc<bf16>(static_cast<size_t>(2) * inter * d);
+    pack_lin(e, e->W(0, p + "mlp.w1.weight", {inter, d}), inter, d, b.w13, d, 0, ROW_INTERLEAVE16_LO);
+    pack_lin(e, e->W(0, p + "mlp.w3.weight", {inter, d}), inter, d, b.w13, d, 0, ROW_INTERLEAVE16_HI);
+    b.w2 = pack_lin(e, e->W(0, p + "mlp.w2.weight", {d, inter}), d, inter);
+    b.qn = e->W(0, p + "attention.q_norm.weight", {heads, d / heads}).d;
+    b.kn = e->W(0, p + "attention.k_norm.weight", {heads, d / heads}).d;
+    b.an = e->W(0, p + "attention_norm.weight", {d}).d;
+    b.mn = e->W(0, p + "mlp_norm.weight", {d}).d;
+    w.blk.push_back(b);
+  }
+  w.final_norm = e->W(0, pre + "norm.weight", {d}).d;
+}
+
+void build_rope(stts_engine* e, int rot, float** cos_d, float** sin_d) {
+  // angle[p, i] = p * 10000^(-2i/rot) in fp32 like dit.py:141-143 / style.py:13-16; cos/sin of that fp32 angle
+  const int half = rot / 2;
+  std::vector<float> c(static_cast<size_t>(ROPE_MAX) * half), s(c.size());
+  for (int i = 0; i < half; ++i) {
+    const float inv = 1.0f / powf(10000.0f, static_cast<float>(2 * i) / static_cast<float>(rot));
+    for (int p = 0; p < ROPE_MAX; ++p) {
+      const float ang = static_cast<float>(p) * inv;
+      c[static_cast<size_t>(p) * half + i] = static_cast<float>(cos(static_cast<double>(ang)));
+      s[static_cast<size_t>(p) * half + i] = static_cast<float>(sin(static_cast<double>(ang)));
+    }
+  }
+  *cos_d = e->dalloc<float>(c.size(), false);
+  *sin_d = e->dalloc<float>(s.size(), false);
+  CK(cudaMemcpyAsync(*cos_d, c.data(), c.size() * 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemcpyAsync(*sin_d, s.data(), s.size() * 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaStreamSynchronize(e->st));
+}
+
+void finalize(stts_engine* e) {
+  cudaStream_t st = e->st;
+  // ---- style encoder (style.py:118-174).  exp(log_scale) (style.py:167) is folded into in_proj.
+  float log_scale = 0.f;
+  CK(cudaMemcpy(&log_scale, e->W(0, "style_encoder.log_scale", {}).d, 4, cudaMemcpyDeviceToHost));
+  const float sscale = expf(log_scale);
+  e->style_in_w = pack_lin(e, e->W(0, "style_encoder.in_proj.weight", {512, 64}), 512, 64, nullptr, 0, 0, ROW_PLAIN,
+                           COL_PLAIN, sscale);
+  e->style_in_b = e->dalloc<float>(512);
+  CK(pack_vector(st, e->W(0, "style_encoder.in_proj.bias", {512}).d, 512, sscale, ROW_PLAIN, 0, e->style_in_b));
+  build_encoder(e, e->style, "style_encoder.", 512, 8, 1536, 12, 1e-5f);
+  e->style_out_w = pack_lin(e, e->W(0, "style_encoder.out_proj.weight", {D, 512}), D, 512);
+  e->style_out_b = e->W(0, "style_encoder.out_proj.bias", {D}).d;
+  // ---- text encoder (phonemes.py:170-207)
+  e->text_emb = e->W(0, "phoneme_embedding.text_embedding.weight", {198, 512}).d;
+  build_encoder(e, e->text, "phoneme_embedding.", 512, 4, 1024, 8, 1e-6f);
+  e->ph_proj_w = pack_lin(e, e->W(0, "dit.phoneme_proj.weight", {D, 512}), D, 512);
+  e->ph_proj_b = e->W(0, "dit.phoneme_proj.bias", {D}).d;
+  // ---- DiT input embedding (dit.py:215-253)
+  e->in_proj_w = pack_lin(e, e->W(0, "dit.input_embed.proj.weight", {D, 64}), D, 64);
+  e->in_proj_b = e->W(0, "dit.input_embed.proj.bias", {D}).d;
+  for (int c = 0; c < 2; ++c) {
+    const std::string p = std::string("dit.input_embed.conv_pos_embed.conv") + (c ? "2" : "1");
+    bf16* w = e->dalloc<bf16>(static_cast<size_t>(16) * 64 * 31 * 64);
+    CK(pack_conv_taps(st, e->W(0, p + ".weight", {D, 60, 31}).d, D, 60, 31, 64, 60, 64, w, 31 * 64));
+    (c ? e->conv2_w : e->conv1_w) = w;
+    (c ? e->conv2_b : e->conv1_b) = e->W(0, p + ".bias", {D}).d;
+  }
+  // ---- time / adaLN path stays fp32 (GEMV): only check presence
+  e->W(0, "time_embedding.mlp.0.weight", {D, 256}); e->W(0, "time_embedding.mlp.0.bias", {D});
+  e->W(0, "time_embedding.mlp.2.weight", {D, D});   e->W(0, "time_embedding.mlp.2.bias", {D});
+  e->W(0, "dit.emb_proj.0.weight", {2 * D, D});     e->W(0, "dit.emb_proj.0.bias", {2 * D});
+  e->W(0, "dit.emb_proj.2.weight", {D, 2 * D});     e->W(0, "dit.emb_proj.2.bias", {D});
+  e->W(0, "dit.norm_out.linear.weight", {2 * D, D}); e->W(0, "dit.norm_out.linear.bias", {2 * D});
+  // ---- blocks + fused cross-KV projection for all 12 blocks (dit.py:80-93)
+  e->wkv_ref = e->dalloc<bf16>(static_cast<size_t>(NBLK) * 2 * D * D);
+  e->wkv_text = e->dalloc<bf16>(static_cast<size_t>(NBLK) * 2 * D * D);
+  e->bkv_ref = e->dalloc<float>(NBLK * 2 * D);
+  e->bkv_text = e->dalloc<float>(NBLK * 2 * D);
+  for (int i = 0; i < NBLK; ++i) {
+    const std::string p = "dit.transformer_blocks." + std::to_string(i) + ".";
+    DitBlockW b;
+    b.wqkvg = e->dalloc<bf16>(static_cast<size_t>(4) * D * D);
+    b.bqkvg = e->dalloc<float>(4 * D);
+    const char* names[4] = {"to_q", "to_k_self", "to_v_self", "gate"};
+    for (int j = 0; j < 4; ++j) {
+      pack_lin(e, e->W(0, p + "attn." + names[j] + ".weight", {D, D}), D, D, b.wqkvg, D, j * D);
+      if (j < 3) CK(pack_vector(st, e->W(0, p + "attn." + names[j] + ".bias", {D}).d, D, 1.f, ROW_PLAIN, j * D, b.bqkvg));
+    }
+    // to_out consumes head-padded (120 -> 128) attention output: K = 8 * 128
+    b.wo = e->dalloc<bf16>(static_cast<size_t>(D) * H * HDP);
+    pack_lin(e, e->W(0, p + "attn.to_out.0.weight", {D, D}), D, D, b.wo, H * HDP, 0, ROW_PLAIN, COL_HEADPAD_120_128);
+    b.w13 = e->dalloc<bf16>(static_cast<size_t>(2) * FF * D);
+    b.b13 = e->dalloc<float>(2 * FF);
+    pack_lin(e, e->W(0, p + "ff.w1.weight", {FF, D}), FF, D, b.w13, D, 0, ROW_INTERLEAVE16_LO);
+    pack_lin(e, e->W(0, p + "ff.w3.weight", {FF, D}), FF, D, b.w13, D, 0, ROW_INTERLEAVE16_HI);
+    CK(pack_vector(st, e->W(0, p + "ff.w1.bias", {FF}).d, FF, 1.f, ROW_INTERLEAVE16_LO, 0, b.b13));
+    CK(pack_vector(st, e->W(0, p + "ff.w3.bias", {FF}).d, FF, 1.f, ROW_INTERLEAVE16_HI, 0, b.b13));
+    b.w2 = pack_lin(e, e->W(0, p + "ff.w2.weight", {D, FF}), D, FF);
+    b.b2 = e->W(0, p + "ff.w2.bias", {D}).d;
+    b.qn = e->W(0, p + "attn.q_norm.weight", {H, HD}).d;
+    b.kn = e->W(0, p + "attn.k_norm.weight", {H, HD}).d;
+    e->W(0, p + "attn.k_norm_cross.weight", {H, HD});
+    b.ada_w = e->W(0, p + "attn_norm.linear.weight", {6 * D, D}).d;
+    b.ada_b = e->W(0, p + "attn_norm.linear.bias", {6 * D}).d;
+    e->blk.push_back(b);
+    const char* kv[4] = {"to_k_ref", "to_v_ref", "to_k_text", "to_v_text"};
+    for (int j = 0; j < 4; ++j) {
+      bf16* dw = j < 2 ? e->wkv_ref : e->wkv_text;
+      float* db = j < 2 ? e->bkv_ref : e->bkv_text;
+      const int row_off = i * 2 * D + (j & 1) * D;
+      pack_lin(e, e->W(0, p + "attn." + kv[j] + ".weight", {D, D}), D, D, dw, D, row_off);
+      CK(pack_vector(st, e->W(0, p + "attn." + kv[j] + ".bias", {D}).d, D, 1.f, ROW_PLAIN, row_off, db));
+    }
+  }
+  e->vel_w = pack_lin(e, e->W(0, "velocity.weight", {LAT, D}), LAT, D);
+  e->vel_b = e->W(0, "velocity.bias", {LAT}).d;
+  build_rope(e, 64, &e->cos64, &e->sin64);
+  build_rope(e, 128, &e->cos128, &e->sin128);
+
+  // ---- vocoder (hf:406-500)
+  e->stem_w = e->dalloc<bf16>(static_cast<size_t>(2048) * 7 * 64);
+  CK(pack_conv_taps(st, e->W(1, "stem.conv.conv.weight", {2048, 64, 7}).d, 2048, 64, 7, 64, 2048, 2048, e->stem_w, 7 * 64));
+  e->stem_b = e->W(1, "stem.conv.conv.bias", {2048}).d;
+  e->voc.resize(7);
+  for (int s = 0; s < 7; ++s) {
+    const int c = VOC_C[s];
+    for (int l = 0; l < VOC_DEPTH[s]; ++l) {
+      const std::string p = (s == 0 ? std::string("stem.stage.") : "conv_layers." + std::to_string(s - 1) + ".stage.") +
+                            std::to_string(l) + ".";
+      VocLayerW w;
+      w.gamma = e->W(1, p + "gamma", {c}).d;
+      w.ffn_gamma = e->W(1, p + "ffn_gamma", {c}).d;
+      w.norm_w = e->W(1, p + "norm.weight", {c}).d;
+      w.ffn_norm_w = e->W(1, p + "ffn_norm.weight", {c}).d;
+      w.w1 = pack_lin(e, e->W(1, p + "ffn.linear1.weight", {4 * c, c}), 4 * c, c);
+      w.b1 = e->W(1, p + "ffn.linear1.bias", {4 * c}).d;
+      w.w2 = pack_lin(e, e->W(1, p + "ffn.linear2.weight", {c, 4 * c}), c, 4 * c);
+      w.b2 = e->W(1, p + "ffn.linear2.bias", {c}).d;
+      w.conv_w = e->W(1, p + "mixer.conv.weight", {c, 1, 7}).d;
+      w.conv_b = e->W(1, p + "mixer.conv.bias", {c}).d;
+      e->voc[s].push_back(w);
+    }
+    if (s < 6) {
+      const int cin = VOC_C[s], cout = VOC_C[s + 1], r = VOC_R[s];
+      const std::string p = "conv_layers." + std::to_string(s) + ".convtr.convtr.";
+      e->up_w[s] = e->dalloc<bf16>(static_cast<size_t>(r) * cout * 2 * cin);
+      CK(pack_convtr(st, e->W(1, p + "weight", {cin, cout, 2 * r}).d, cin, cout, r, e->up_w[s]));
+      e->up_b[s] = e->dalloc<float>(r * cout);
+      CK(tile_vector(st, e->W(1, p + "bias", {cout}).d, cout, r, e->up_b[s]));
+    }
+  }
+  e->head_w = e->W(1, "head.conv.weight", {1, 32, 7}).d;
+  e->head_b = e->W(1, "head.conv.bias", {1}).d;
+  CK(cudaStreamSynchronize(st));
+  e->finalized = true;
+}
+
+// ------------------------------------------------------------------ condition encoder
+// One pre-norm transformer block of style.py:74-105 / phonemes.py:136-167 on x [B*N, d] (fp32, in place).
+void encoder_block(stts_engine* e, const EncW& W, const EncBlockW& bw, float* x, int B, int N, const int* len_dev) {
+  cudaStream_t st = e->st;
+  const long long M = static_cast<long long>(B) * N;
+  const int d = W.d;
+  Tmp<bf16> a(st, M * d), qb(st, M * d), kb(st, M * d), vb(st, M * d), ob(st, M * d), hb(st, M * W.inter);
+  Tmp<float> qkvg(st, M * 4 * d);
+  CK(rms_norm_bf16(st, x, M, d, bw.an, W.eps, a));
+  GemmEpi ep;
+  ep.out_f32 = qkvg; ep.ld_out = 4 * d;
+  linear(e, a, M, d, d, bw.wqkvg, 4 * d, d, ep);
+  const float* cs = W.hd == 64 ? e->cos64 : e->cos128;
+  const float* sn = W.hd == 64 ? e->sin64 : e->sin128;
+  CK(head_split_bf16(st, qkvg, 4 * d, 0, M, N, W.heads, W.hd, W.hd, bw.qn, W.eps, W.hd, cs, sn, qb));
+  CK(head_split_bf16(st, qkvg, 4 * d, d, M, N, W.heads, W.hd, W.hd, bw.kn, W.eps, W.hd, cs, sn, kb));
+  CK(head_split_bf16(st, qkvg, 4 * d, 2 * d, M, N, W.heads, W.hd, W.hd, nullptr, 0.f, 0, nullptr, nullptr, vb));
+  AttnSeg seg;
+  seg.k = kb; seg.v = vb; seg.len = len_dev; seg.n_max = N;
+  CK(attention_bf16(st, qb, B, N, W.heads, W.hd, W.hd, &seg, 1, qkvg, 4 * d, 3 * d, ob));
+  GemmEpi eo;
+  eo.residual = x; eo.ld_res = d; eo.out_f32 = x; eo.ld_out = d;
+  linear(e, ob, M, d, d, bw.wo, d, d, eo);
+  CK(rms_norm_bf16(st, x, M, d, bw.mn, W.eps, a));
+  GemmEpi e1;
+  e1.act = ACT_SWIGLU16; e1.out_bf16 = hb; e1.ld_out = W.inter;
+  linear(e, a, M, d, d, bw.w13, 2 * W.inter, d, e1);
+  GemmEpi e2;
+  e2.residual = x; e2.ld_res = d; e2.out_f32 = x; e2.ld_out = d;
+  linear(e, hb, M, W.inter, W.inter, bw.w2, d, W.inter, e2);
+}
+
+stts_cond* encode_conditions(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* ids,
+                             const int64_t* ph_len, int B, int R, int P, int mem) {
+  if (B < 1 || R < 1 || P < 1 || R > ROPE_MAX || P > ROPE_MAX) throw Err(STTS_ERR_INVALID, "bad B/R/P");
+  cudaStream_t st = e->st;
+  stts_cond* c = new stts_cond();
+  try {
+    c->B = B; c->R = R; c->P = P;
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->ref_len), B * sizeof(int)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->ph_len), B * sizeof(int)));
+    {
+      Tmp<int> t1, t2;
+      lens_to_dev(e, ref_len, B, R, t1, &c->h_ref_len);
+      lens_to_dev(e, ph_len, B, P, t2, &c->h_ph_len);
+      CK(cudaMemcpyAsync(c->ref_len, t1.p, B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(c->ph_len, t2.p, B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->kv_ref), NBLK * 2 * c->ref_stride() * sizeof(bf16)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->kv_text), NBLK * 2 * c->text_stride() * sizeof(bf16)));
+
+    Tmp<float> href;
+    Tmp<long long> hids;
+    const float* dref = to_dev(e, ref, static_cast<size_t>(B) * R * LAT, mem, href);
+    const long long* dids = reinterpret_cast<const long long*>(
+        to_dev(e, reinterpret_cast<const long long*>(ids), static_cast<size_t>(B) * P, mem, hids));
+
+    for (int src = 0; src < 2; ++src) {
+      const int N = src == 0 ? R : P;
+      const long long M = static_cast<long long>(B) * N;
+      const int* len_dev = src == 0 ? c->ref_len : c->ph_len;
+      const EncW& W = src == 0 ? e->style : e->text;
+      Tmp<float> x(st, M * 512);
+      Tmp<bf16> a(st, M * 512), seq(st, M * D);
+      if (src == 0) {  // style.py:166-167
+        Tmp<bf16> rb(st, M * LAT);
+        CK(cast_bf16(st, dref, M * LAT, rb));
+        GemmEpi ep;
+        ep.bias = e->style_in_b; ep.out_f32 = x; ep.ld_out = 512;
+        linear(e, rb, M, LAT, LAT, e->style_in_w, 512, LAT, ep);
+      } else {  // phonemes.py:203
+        CK(embed_gather(st, dids, M, e->text_emb, 198, 512, x));
+      }
+      for (int i = 0; i < W.layers; ++i) encoder_block(e, W, W.blk[i], x, B, N, len_dev);
+      CK(rms_norm_bf16(st, x, M, 512, W.final_norm, W.eps, a));
+      // out_proj / phoneme_proj with masked rows zeroed (style.py:172-173 / dit.py:293-298)
+      GemmEpi ep;
+      ep.bias = src == 0 ? e->style_out_b : e->ph_proj_b;
+      ep.row_len = len_dev; ep.rows_per_batch = N;
+      ep.out_bf16 = seq; ep.ld_out = D;
+      linear(e, a, M, 512, 512, src == 0 ? e->style_out_w : e->ph_proj_w, D, 512, ep);
+      // all 12 blocks' cross K/V in one GEMM, then per-head k_norm_cross (dit.py:80-93)
+      const int NKV = NBLK * 2 * D;
+      Tmp<float> kvf(st, M * NKV);
+      GemmEpi ek;
+      ek.bias = src == 0 ? e->bkv_ref : e->bkv_text; ek.out_f32 = kvf; ek.ld_out = NKV;
+      linear(e, seq, M, D, D, src == 0 ? e->wkv_ref : e->wkv_text, NKV, D, ek);
+      bf16* cache = src == 0 ? c->kv_ref : c->kv_text;
+      const size_t stride = src == 0 ? c->ref_stride() : c->text_stride();
+      for (int i = 0; i < NBLK; ++i) {
+        const std::string p = "dit.transformer_blocks." + std::to_string(i) + ".attn.k_norm_cross.weight";
+        const float* knc = e->raw[0][p].d;
+        CK(head_split_bf16(st, kvf, NKV, i * 2 * D, M, N, H, HD, HDP, knc, 1e-6f, 0, nullptr, nullptr,
+                           cache + (2 * i) * stride));
+        CK(head_split_bf16(st, kvf, NKV, i * 2 * D + D, M, N, H, HD, HDP, nullptr, 0.f, 0, nullptr, nullptr,
+                           cache + (2 * i + 1) * stride));
+      }
+    }
+    CK(cudaStreamSynchronize(st));
+  } catch (...) {
+    cudaFree(c->ref_len); cudaFree(c->ph_len); cudaFree(c->kv_ref); cudaFree(c->kv_text);
+    delete c;
+    throw;
+  }
+  return c;
+}
+
+// ------------------------------------------------------------------ adaLN tables (function of t only)
+// model.py:23-30 -> dit.py:270-274 -> per block dit.py:19-23 (gates stored as tanh) -> final dit.py:36-37
+void compute_mod(stts_engine* e, const float* t_dev, int rows, float* table /*[rows][MOD_LD]*/) {
+  cudaStream_t st = e->st;
+  auto& R = e->raw[0];
+  Tmp<float> f(st, rows * 256), h(st, rows * D), te(st, rows * D), h2(st, rows * 2 * D), emb(st, rows * D);
+  CK(time_features(st, t_dev, rows, f));
+  CK(gemv_rows(st, f, rows, 256, R["time_embedding.mlp.0.weight"].d, R["time_embedding.mlp.0.bias"].d, D, 0, 1, 0, 0, h, D));
+  CK(gemv_rows(st, h, rows, D, R["time_embedding.mlp.2.weight"].d, R["time_embedding.mlp.2.bias"].d, D, 0, 0, 0, 0, te, D));
+  CK(gemv_rows(st, te, rows, D, R["dit.emb_proj.0.weight"].d, R["dit.emb_proj.0.bias"].d, 2 * D, 0, 1, 0, 0, h2, 2 * D));
+  CK(gemv_rows(st, h2, rows, 2 * D, R["dit.emb_proj.2.weight"].d, R["dit.emb_proj.2.bias"].d, D, 0, 0, 0, 0, emb, D));
+  for (int i = 0; i < NBLK; ++i) {
+    // chunks: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp -> tanh on chunks 2 and 5
+    CK(gemv_rows(st, emb, rows, D, e->blk[i].ada_w, e->blk[i].ada_b, 6 * D, 1, 0, D, 0x24u, table + i * 6 * D, MOD_LD));
+  }
+  CK(gemv_rows(st, emb, rows, D, R["dit.norm_out.linear.weight"].d, R["dit.norm_out.linear.bias"].d, 2 * D, 1, 0, 0, 0,
+               table + NBLK * 6 * D, MOD_LD));
+}
+
+const float* cached_mod(stts_engine* e, float t) {
+  uint32_t bits;
+  memcpy(&bits, &t, 4);
+  auto it = e->mod_cache.find(bits);
+  if (it != e->mod_cache.end()) return it->second;
+  float* table = nullptr;
+  CK(cudaMalloc(reinterpret_cast<void**>(&table), MOD_LD * sizeof(float)));
+  e->owned.push_back(table);
+  Tmp<float> td(e->st, 1);
+  CK(cudaMemcpyAsync(td.p, &t, 4, cudaMemcpyHostToDevice, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  compute_mod(e, td, 1, table);
+  e->mod_cache[bits] = table;
+  return table;
+}
+
+// ------------------------------------------------------------------ denoiser (dit.py:316-327, model.py:97-100)
+struct DenoiseWs {
+  Tmp<float> h, x, qkvg, v;
+  Tmp<bf16> hm, c1, a, qb, kb, vb, ob, hb;
+  void alloc(cudaStream_t st, long long M) {
+    h.alloc(st, M * D); x.alloc(st, M * D); qkvg.alloc(st, M * 4 * D);
+    hm.alloc(st, M * D); c1.alloc(st, M * D); a.alloc(st, M * D);
+    qb.alloc(st, M * H * HDP); kb.alloc(st, M * H * HDP); vb.alloc(st, M * H * HDP); ob.alloc(st, M * H * HDP);
+    hb.alloc(st, M * FF);
+  }
+};
+
+void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_bf16, const int* frames_dev,
+             const float* mod, int ld_mod, int B, int T, float* v_out) {
+  cudaStream_t st = e->st;
+  const long long M = static_cast<long long>(B) * T;
+  // input embedding: h = proj(x); hm = masked bf16 copy; x = mask(mish(conv2(mask(mish(conv1(hm)))))) + h
+  {
+    GemmEpi ep;
+    ep.bias = e->in_proj_b; ep.row_len = frames_dev; ep.rows_per_batch = T; ep.mask_bf16_only = 1;
+    ep.out_f32 = ws.h; ep.out_bf16 = ws.hm; ep.ld_out = D;
+    linear(e, xt_bf16, M, LAT, LAT, e->in_proj_w, D, LAT, ep);
+    GemmShape s;
+    s.B = B; s.T = T; s.N = 60; s.K = 60; s.taps = 31; s.tap_shift0 = -15; s.tap_step = 1;
+    s.groups = 16; s.a_group_koff = 60; s.w_group_rows = 64; s.out_group_cols = 60;
+    GemmW gw1{e->conv1_w, 16 * 64, 31 * 64}, gw2{e->conv2_w, 16 * 64, 31 * 64};
+    GemmEpi e1;
+    e1.bias = e->conv1_b; e1.act = ACT_MISH; e1.row_len = frames_dev; e1.out_bf16 = ws.c1; e1.ld_out = D;
+    CK(launch_gemm(st, 64, GemmA{ws.hm, D, D}, gw1, s, e1));
+    GemmEpi e2;
+    e2.bias = e->conv2_b; e2.act = ACT_MISH; e2.row_len = frames_dev; e2.residual = ws.h; e2.ld_res = D;
+    e2.out_f32 = ws.x; e2.ld_out = D;
+    CK(launch_gemm(st, 64, GemmA{ws.c1, D, D}, gw2, s, e2));
+  }
+  for (int i = 0; i < NBLK; ++i) {
+    const DitBlockW& w = e->blk[i];
+    const float* m = mod + i * 6 * D;  // [shift_msa, scale_msa, tanh gate_msa, shift_mlp, scale_mlp, tanh gate_mlp]
+    CK(ln_mod_bf16(st, ws.x, M, T, D, m + D, m, ld_mod, 1e-6f, ws.a));
+    GemmEpi eq;
+    eq.bias = w.bqkvg; eq.out_f32 = ws.qkvg; eq.ld_out = 4 * D;
+    linear(e, ws.a, M, D, D, w.wqkvg, 4 * D, D, eq);
+    CK(head_split_bf16(st, ws.qkvg, 4 * D, 0, M, T, H, HD, HDP, w.qn, 1e-6f, 64, e->cos64, e->sin64, ws.qb));
+    CK(head_split_bf16(st, ws.qkvg, 4 * D, D, M, T, H, HD, HDP, w.kn, 1e-6f, 64, e->cos64, e->sin64, ws.kb));
+    CK(head_split_bf16(st, ws.qkvg, 4 * D, 2 * D, M, T, H, HD, HDP, nullptr, 0.f, 0, nullptr, nullptr, ws.vb));
+    AttnSeg segs[3];
+    segs[0].k = ws.kb; segs[0].v = ws.vb; segs[0].len = frames_dev; segs[0].n_max = T;
+    segs[1].k = c->kv_ref + (2 * i) * c->ref_stride(); segs[1].v = c->kv_ref + (2 * i + 1) * c->ref_stride();
+    segs[1].len = c->ref_len; segs[1].n_max = c->R;
+    segs[2].k = c->kv_text + (2 * i) * c->text_stride(); segs[2].v = c->kv_text + (2 * i + 1) * c->text_stride();
+    segs[2].len = c->ph_len; segs[2].n_max = c->P;
+    CK(attention_bf16(st, ws.qb, B, T, H, HD, HDP, segs, 3, ws.qkvg, 4 * D, 3 * D, ws.ob));
+    GemmEpi eo;  // x += tanh(gate_msa) * mask(to_out(o))   (dit.py:115-118,198)
+    eo.row_len = frames_dev; eo.rows_per_batch = T; eo.rowgate = m + 2 * D; eo.ld_gate = ld_mod;
+    eo.residual = ws.x; eo.ld_res = D; eo.out_f32 = ws.x; eo.ld_out = D;
+    linear(e, ws.ob, M, H * HDP, H * HDP, w.wo, D, H * HDP, eo);
+    CK(ln_mod_bf16(st, ws.x, M, T, D, m + 4 * D, m + 3 * D, ld_mod, 1e-6f, ws.a));
+    GemmEpi e1;
+    e1.bias = w.b13; e1.act = ACT_SWIGLU16; e1.out_bf16 = ws.hb; e1.ld_out = FF;
+    linear(e, ws.a, M, D, D, w.w13, 2 * FF, D, e1);
+    GemmEpi e2;  // x += tanh(gate_mlp) * ff   (dit.py:201)
+    e2.bias = w.b2; e2.rows_per_batch = T; e2.rowgate = m + 5 * D; e2.ld_gate = ld_mod;
+    e2.residual = ws.x; e2.ld_res = D; e2.out_f32 = ws.x; e2.ld_out = D;
+    linear(e, ws.hb, M, FF, FF, w.w2, D, FF, e2);
+  }
+  const float* mf = mod + NBLK * 6 * D;  // [scale, shift] (dit.py:37)
+  CK(ln_mod_bf16(st, ws.x, M, T, D, mf, mf + D, ld_mod, 1e-6f, ws.a));
+  GemmEpi ev;
+  ev.bias = e->vel_b; ev.out_f32 = v_out; ev.ld_out = LAT;
+  linear(e, ws.a, M, D, D, e->vel_w, LAT, D, ev, 64);
+}
+
+void alpha_sigma(float t32, float* alpha, float* sigma) {  // infer/onnx.py:31-39 (numpy: fp64 inside, fp32 out)
+  double t = static_cast<double>(t32);
+  const double eps = 1e-5;
+  t = t < eps ? eps : (t > 1 - eps ? 1 - eps : t);
+  const double c = cos(M_PI / 2 * t);
+  const double a2 = c * c;
+  const double log_snr = log(a2 / (1 - a2)) + 2 * log(0.5);
+  const double alpha_sq = 1.0 / (1.0 + exp(-log_snr));
+  *alpha = static_cast<float>(sqrt(alpha_sq));
+  *sigma = static_cast<float>(sqrt(1 - alpha_sq));
+}
+
+// DMD loop of infer/onnx.py:98-125 on device. noise_dev may be null (Philox). out: device [B,T,64].
+void sample(stts_engine* e, const stts_cond* c, const int* frames_dev, int B, int T, int steps, const float* timesteps,
+            const float* noise_dev, uint64_t seed, float* x_pred) {
+  cudaStream_t st = e->st;
+  const long long n = static_cast<long long>(B) * T * LAT;
+  std::vector<float> ts(steps);
+  for (int s = 0; s < steps; ++s) {
+    ts[s] = timesteps ? timesteps[s]
+                      : (steps == 1 ? 1.0f : static_cast<float>(1.0 + (0.0 - 1.0) * static_cast<double>(s) / (steps - 1)));
+  }
+  std::vector<const float*> mods(steps);
+  for (int s = 0; s < steps; ++s) mods[s] = cached_mod(e, ts[s]);
+  DenoiseWs ws;
+  ws.alloc(st, static_cast<long long>(B) * T);
+  Tmp<float> xt(st, n), v(st, n), nz;
+  Tmp<bf16> xtb(st, n);
+  if (noise_dev == nullptr) nz.alloc(st, n);
+  CK(cudaMemsetAsync(x_pred, 0, n * sizeof(float), st));
+  for (int s = 0; s < steps; ++s) {
+    float alpha, sigma;
+    alpha_sigma(ts[s], &alpha, &sigma);
+    const float* nzs = noise_dev ? noise_dev + s * n : nz.p;
+    if (noise_dev == nullptr) CK(philox_normal(st, seed, static_cast<unsigned long long>(s), n, nz));
+    CK(noise_mix(st, x_pred, nzs, alpha, sigma, n, xt, xtb));
+    denoise(e, c, ws, xtb, frames_dev, mods[s], 0, B, T, v);
+    CK(dmd_update(st, xt, v, alpha, sigma, n, x_pred));
+  }
+}
+
+// ------------------------------------------------------------------ vocoder (hf:406-500)
+void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev) {
+  cudaStream_t st = e->st;
+  const long long frames = static_cast<long long>(B) * T;
+  const size_t act = static_cast<size_t>(frames) * 102400;  // max over stages of rows*C per latent frame
+  Tmp<float> xa(st, act), xb(st, act);
+  Tmp<bf16> a(st, act), hbuf(st, act * 4), xh(st, act), latb(st, frames * LAT);
+  CK(cudaEventRecord(e->ev[4], st));
+  CK(cast_bf16(st, lat_dev, frames * LAT, latb));
+  {  // stem: causal Conv1d(64 -> 2048, k=7) as a 7-tap GEMM
+    GemmShape s;
+    s.B = B; s.T = T; s.N = 2048; s.K = 64; s.taps = 7; s.tap_shift0 = -6; s.tap_step = 1;
+    GemmEpi ep;
+    ep.bias = e->stem_b; ep.out_f32 = xa; ep.ld_out = 2048;
+    CK(launch_gemm(st, pick_bn(frames, 2048), GemmA{latb, LAT, LAT}, GemmW{e->stem_w, 2048, 7 * 64}, s, ep));
+  }
+  int Ts = T;
+  for (int s = 0; s < 7; ++s) {
+    const int C = VOC_C[s];
+    const long long M = static_cast<long long>(B) * Ts;
+    if (s == 4) CK(cudaEventRecord(e->ev[5], st));  // C <= 128 from here on: the HBM-bound tail
+    for (size_t l = 0; l < e->voc[s].size(); ++l) {
+      const VocLayerW& w = e->voc[s][l];
+      CK(convnext_mix(st, xa, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, xb, a));
+      GemmEpi e1;
+      e1.bias = w.b1; e1.act = ACT_GELU; e1.out_bf16 = hbuf; e1.ld_out = 4 * C;
+      linear(e, a, M, C, C, w.w1, 4 * C, C, e1);
+      GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
+      e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = xb; e2.ld_res = C; e2.out_f32 = xa; e2.ld_out = C;
+      if (s < 6 && l + 1 == e->voc[s].size()) e2.out_bf16 = xh;  // bf16 copy feeds the next upsampler
+      linear(e, hbuf, M, 4 * C, 4 * C, w.w2, C, 4 * C, e2);
+    }
+    if (s < 6) {  // causal ConvTranspose1d(k=2r, stride=r) as a 2-tap GEMM with N = r*Cout (hf:219-260)
+      const int r = VOC_R[s], cout = VOC_C[s + 1];
+      GemmShape g;
+      g.B = B; g.T = Ts; g.N = r * cout; g.K = C; g.taps = 2; g.tap_shift0 = 0; g.tap_step = -1;
+      GemmEpi ep;
+      ep.bias = e->up_b[s]; ep.out_f32 = xb; ep.ld_out = r * cout;
+      CK(launch_gemm(st, pick_bn(M, r * cout), GemmA{xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
+      std::swap(xa.p, xb.p);
+      Ts *= r;
+    }
+  }
+  CK(head_conv(st, xa, B, Ts, 32, e->head_w, e->head_b, audio_dev));
+  CK(cudaEventRecord(e->ev[6], st));
+}
+
+}  // namespace
+
+// ==================================================================== C ABI
+
+namespace {
+thread_local std::string g_create_err;
+
+int guard_impl(stts_engine* e, const std::function<void()>& fn) {
+  try {
+    if (e) CK(cudaSetDevice(e->device));
+    fn();
+    return STTS_OK;
+  } catch (const Err& ex) {
+    (e ? e->err : g_create_err) = ex.what();
+    cudaGetLastError();
+    return ex.code;
+  } catch (const std::exception& ex) {
+    (e ? e->err : g_create_err) = ex.what();
+    return STTS_ERR_INVALID;
+  }
+}
+void need_ready(stts_engine* e) {
+  if (!e->finalized) throw Err(STTS_ERR_WEIGHTS, "weights not finalized: call stts_finalize_weights first");
+}
+}  // namespace
+
+extern "C" {
+
+int stts_create(const stts_config* cfg, stts_engine** out) {
+  if (!out) return STTS_ERR_INVALID;
+  *out = nullptr;
+  stts_engine* e = new stts_engine();
+  int rc = guard_impl(nullptr, [&] {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      throw Err(STTS_ERR_NO_DEVICE, "no CUDA device: smalltts_b200 has no CPU fallback");
+    }
+    e->device = cfg ? cfg->device : 0;
+    if (e->device < 0 || e->device >= n) throw Err(STTS_ERR_INVALID, "bad device ordinal");
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, e->device));
+    if (p.major != 10) {
+      throw Err(STTS_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(p.major * 10 + p.minor) +
+                                        ", this engine is built for sm_100a (B200) only");
+    }
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, e->device));
+    uint64_t thr = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  });
+  if (rc != STTS_OK) {
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return STTS_OK;
+}
+
+void stts_destroy(stts_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->st);
+  for (auto& m : e->raw) for (auto& kv : m) cudaFree(kv.second.d);
+  for (void* p : e->owned) cudaFree(p);
+  for (auto& ev : e->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(e->st);
+  delete e;
+}
+
+const char* stts_last_error(const stts_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+int stts_load_weight(stts_engine* e, int model, const char* name, const float* data, int ndim, const int64_t* shape) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    if (model < 0 || model > 1 || !name || !data || ndim < 0 || ndim > 4) throw Err(STTS_ERR_INVALID, "bad weight args");
+    RawTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) {
+      t.shape.push_back(shape[i]);
+      t.numel *= static_cast<size_t>(shape[i]);
+    }
+    // 16-byte aligned rows are assumed by the float4 paths; cudaMalloc gives 256-byte alignment
+    CK(cudaMalloc(reinterpret_cast<void**>(&t.d), (t.numel ? t.numel : 1) * sizeof(float)));
+    CK(cudaMemcpyAsync(t.d, data, t.numel * sizeof(float), cudaMemcpyHostToDevice, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    auto it = e->raw[model].find(name);
+    if (it != e->raw[model].end()) cudaFree(it->second.d);
+    e->raw[model][name] = t;
+    e->finalized = false;
+  });
+}
+
+int stts_finalize_weights(stts_engine* e) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    if (e->finalized) return;
+    if (!e->blk.empty()) throw Err(STTS_ERR_WEIGHTS, "weights were already finalized once; create a new engine");
+    finalize(e);
+  });
+}
+
+int stts_encode_conditions(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* phonemes,
+                           const int64_t* ph_len, int B, int R, int P, int mem, stts_cond** out) {
+  if (!e || !out) return STTS_ERR_INVALID;
+  *out = nullptr;
+  return guard_impl(e, [&] {
+    need_ready(e);
+    *out = encode_conditions(e, ref, ref_len, phonemes, ph_len, B, R, P, mem);
+  });
+}
+
+void stts_cond_free(stts_engine* e, stts_cond* c) {
+  if (!c) return;
+  if (e) {
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->st);
+  }
+  cudaFree(c->ref_len); cudaFree(c->ph_len); cudaFree(c->kv_ref); cudaFree(c->kv_text);
+  delete c;
+}
+
+int stts_cond_read_kv(stts_engine* e, const stts_cond* c, int layer, int which, float* dst) {
+  if (!e || !c || !dst || layer < 0 || layer >= NBLK || which < 0 || which > 3) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    const bool is_ref = which < 2;
+    const int N = is_ref ? c->R : c->P;
+    const size_t stride = is_ref ? c->ref_stride() : c->text_stride();
+    const bf16* src = (is_ref ? c->kv_ref : c->kv_text) + (2 * layer + (which & 1)) * stride;
+    std::vector<bf16> h(stride);
+    CK(cudaMemcpy(h.data(), src, stride * sizeof(bf16), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < c->B; ++b)
+      for (int hh = 0; hh < H; ++hh)
+        for (int n = 0; n < N; ++n)
+          for (int d = 0; d < HD; ++d)
+            dst[((static_cast<size_t>(b) * H + hh) * N + n) * HD + d] =
+                __bfloat162float(h[((static_cast<size_t>(b) * N + n) * H + hh) * HDP + d]);
+  });
+}
+
+int stts_denoise_step(stts_engine* e, const stts_cond* c, const float* x_t, const int64_t* frames, const float* t,
+                      int B, int T, int mem, float* velocity) {
+  if (!e || !c || !x_t || !frames || !t || !velocity) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    need_ready(e);
+    if (B != c->B || T < 1 || T > ROPE_MAX) throw Err(STTS_ERR_INVALID, "batch/T mismatch with conditions");
+    cudaStream_t st = e->st;
+    const long long n = static_cast<long long>(B) * T * LAT;
+    Tmp<int> fr;
+    lens_to_dev(e, frames, B, T, fr);
+    Tmp<float> hx, vout;
+    const float* xd = to_dev(e, x_t, n, mem, hx);
+    Tmp<bf16> xb(st, n);
+    CK(cast_bf16(st, xd, n, xb));
+    bool same = true;
+    for (int b = 1; b < B; ++b) same = same && (t[b] == t[0]);
+    Tmp<float> table, td;
+    const float* mod;
+    int ld_mod = 0;
+    if (same) {
+      mod = cached_mod(e, t[0]);
+    } else {
+      td.alloc(st, B);
+      table.alloc(st, static_cast<size_t>(B) * MOD_LD);
+      CK(cudaMemcpyAsync(td.p, t, B * sizeof(float), cudaMemcpyHostToDevice, st));
+      compute_mod(e, td, B, table);
+      mod = table;
+      ld_mod = MOD_LD;
+    }
+    DenoiseWs ws;
+    ws.alloc(st, static_cast<long long>(B) * T);
+    float* vd = velocity;
+    if (mem == STTS_MEM_HOST) {
+      vout.alloc(st, n);
+      vd = vout;
+    }
+    denoise(e, c, ws, xb, fr, mod, ld_mod, B, T, vd);
+    if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(velocity, vd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B, int T, int steps,
+                const float* timesteps, const float* noise, uint64_t seed, int mem, float* out_latents) {
+  if (!e || !c || !frames || !out_latents) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    need_ready(e);
+    if (B != c->B || T < 1 || T > ROPE_MAX || steps < 1) throw Err(STTS_ERR_INVALID, "bad sample arguments");
+    cudaStream_t st = e->st;
+    const long long n = static_cast<long long>(B) * T * LAT;
+    Tmp<int> fr;
+    lens_to_dev(e, frames, B, T, fr);
+    Tmp<float> hn, xo;
+    const float* nd = noise ? to_dev(e, noise, static_cast<size_t>(steps) * n, mem, hn) : nullptr;
+    float* xd = out_latents;
+    if (mem == STTS_MEM_HOST) {
+      xo.alloc(st, n);
+      xd = xo;
+    }
+    sample(e, c, fr, B, T, steps, timesteps, nd, seed, xd);
+    if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(out_latents, xd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int stts_decode(stts_engine* e, const float* latents, int B, int T, int mem, float* audio) {
+  if (!e || !latents || !audio) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    need_ready(e);
+    if (B < 1 || T < 1) throw Err(STTS_ERR_INVALID, "bad decode arguments");
+    cudaStream_t st = e->st;
+    const long long n = static_cast<long long>(B) * T * LAT;
+    const long long na = static_cast<long long>(B) * T * STTS_HOP_SIZE;
+    Tmp<float> hl, ao;
+    const float* ld = to_dev(e, latents, n, mem, hl);
+    float* ad = audio;
+    if (mem == STTS_MEM_HOST) {
+      ao.alloc(st, na);
+      ad = ao;
+    }
+    decode(e, ld, B, T, ad);
+    if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(audio, ad, na * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&e->voc_ms[1], e->ev[4], e->ev[5]));
+    CK(cudaEventElapsedTime(&e->voc_ms[0], e->ev[5], e->ev[6]));
+  });
+}
+
+int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* phonemes,
+                    const int64_t* ph_len, const int64_t* frames, int B, int R, int P, int T, int steps,
+                    const float* timesteps, const float* noise, uint64_t seed, int mem, float* audio) {
+  if (!e || !ref || !ref_len || !phonemes || !ph_len || !frames || !audio) return STTS_ERR_INVALID;
+  stts_cond* c = nullptr;
+  int rc = guard_impl(e, [&] {
+    need_ready(e);
+    if (T < 1 || T > ROPE_MAX || steps < 1) throw Err(STTS_ERR_INVALID, "bad synthesize arguments");
+    cudaStream_t st = e->st;
+    const long long n = static_cast<long long>(B) * T * LAT;
+    const long long na = static_cast<long long>(B) * T * STTS_HOP_SIZE;
+    CK(cudaEventRecord(e->ev[0], st));
+    c = encode_conditions(e, ref, ref_len, phonemes, ph_len, B, R, P, mem);
+    CK(cudaEventRecord(e->ev[1], st));
+    Tmp<int> fr;
+    lens_to_dev(e, frames, B, T, fr);
+    Tmp<float> hn, lat(st, n), ao;
+    const float* nd = noise ? to_dev(e, noise, static_cast<size_t>(steps) * n, mem, hn) : nullptr;
+    sample(e, c, fr, B, T, steps, timesteps, nd, seed, lat);
+    CK(cudaEventRecord(e->ev[2], st));
+    float* ad = audio;
+    if (mem == STTS_MEM_HOST) {
+      ao.alloc(st, na);
+      ad = ao;
+    }
+    decode(e, lat, B, T, ad);
+    if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(audio, ad, na * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(e->ev[3], st));
+    CK(cudaStreamSynchronize(st));
+    e->timing.codec_enc_ms = 0.f;
+    CK(cudaEventElapsedTime(&e->timing.cond_enc_ms, e->ev[0], e->ev[1]));
+    CK(cudaEventElapsedTime(&e->timing.denoise_ms, e->ev[1], e->ev[2]));
+    CK(cudaEventElapsedTime(&e->timing.codec_dec_ms, e->ev[2], e->ev[3]));
+    CK(cudaEventElapsedTime(&e->timing.total_ms, e->ev[0], e->ev[3]));
+    CK(cudaEventElapsedTime(&e->voc_ms[1], e->ev[4], e->ev[5]));
+    CK(cudaEventElapsedTime(&e->voc_ms[0], e->ev[5], e->ev[6]));
+  });
+  if (c) stts_cond_free(e, c);
+  return rc;
+}
+
+int stts_get_timings(const stts_engine* e, stts_timing* out) {
+  if (!e || !out) return STTS_ERR_INVALID;
+  *out = e->timing;
+  return STTS_OK;
+}
+
+uint64_t stts_launch_count(void) { return g_launch_count; }
+
+float stts_last_vocoder_ms(const stts_engine* e, int which) {
+  return (e && which >= 0 && which < 2) ? e->voc_ms[which] : -1.f;
+}
+
+void* stts_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void stts_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------- kernel-level test hooks
+int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T, int a_cols, int a_ld,
+                   const void* w_bf16, int w_rows, int w_ld, int N, int K, int taps, int tap_shift0, int tap_step,
+                   int groups, int a_group_koff, int w_group_rows, int out_group_cols, const float* bias, int act,
+                   const int32_t* row_len, int rows_per_batch, int mask_bf16_only, const float* colscale,
+                   const float* rowgate, int ld_gate, const float* residual, int ld_res, float* out_f32,
+                   void* out_bf16, int ld_out) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    GemmShape s;
+    s.B = B; s.T = T; s.N = N; s.K = K; s.taps = taps; s.tap_shift0 = tap_shift0; s.tap_step = tap_step;
+    s.groups = groups; s.a_group_koff = a_group_koff; s.w_group_rows = w_group_rows; s.out_group_cols = out_group_cols;
+    GemmEpi ep;
+    ep.bias = bias; ep.act = act; ep.row_len = row_len; ep.rows_per_batch = rows_per_batch; ep.mask_bf16_only = mask_bf16_only; ep.colscale = colscale;
+    ep.rowgate = rowgate; ep.ld_gate = ld_gate; ep.residual = residual; ep.ld_res = ld_res; ep.out_f32 = out_f32;
+    ep.out_bf16 = static_cast<bf16*>(out_bf16); ep.ld_out = ld_out;
+    CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), a_cols, a_ld},
+                   GemmW{static_cast<const bf16*>(w_bf16), w_rows, w_ld}, s, ep));
+    CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+int stts_test_attention(stts_engine* e, const void* q, int B, int tq, int Hh, int hd, int hd_pad, const void* k0,
+                        const void* v0, const int32_t* len0, int n0, const void* k1, const void* v1,
+                        const int32_t* len1, int n1, const float* gate, int ld_gate, void* out) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    AttnSeg segs[2];
+    segs[0].k = static_cast<const bf16*>(k0); segs[0].v = static_cast<const bf16*>(v0); segs[0].len = len0; segs[0].n_max = n0;
+    segs[1].k = static_cast<const bf16*>(k1); segs[1].v = static_cast<const bf16*>(v1); segs[1].len = len1; segs[1].n_max = n1;
+    CK(attention_bf16(e->st, static_cast<const bf16*>(q), B, tq, Hh, hd, hd_pad, segs, k1 ? 2 : 1, gate, ld_gate, 0,
+                      static_cast<bf16*>(out)));
+    CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+int stts_test_convnext_mix(stts_engine* e, const float* x, int B, int T, int C, const float* norm_w,
+                           const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
+                           float* y, void* a_bf16) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    CK(convnext_mix(e->st, x, B, T, C, norm_w, conv_w, conv_b, gamma, ffn_norm_w, 1e-5f, y, static_cast<bf16*>(a_bf16)));
+    CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+}  // extern "C"

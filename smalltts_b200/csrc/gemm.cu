@@ -1,0 +1,363 @@
+// tcgen05 + TMA multi-tap GEMM (see gemm.cuh).  One 128 x BN output tile per CTA.
+//   warp 0   : TMA producer (one lane): A box [128 rows x 64 k] and W box [BN rows x 64 k] per stage
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane), fp32 accumulator in TMEM
+//   warps 2-5: epilogue, one TMEM lane quarter each: tcgen05.ld -> bias/activation/mask/gate/residual -> global
+#include "gemm.cuh"
+
+#include <mutex>
+
+#include "ptx.cuh"
+
+namespace stts {
+
+unsigned long long g_launch_count = 0;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kThreads = 192;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kSmem = kStages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_GELU:
+      return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    case ACT_MISH: {
+      float sp = v > 20.0f ? v : log1pf(expf(v));
+      return v * tanhf(sp);
+    }
+    case ACT_SIGMOID:
+      return 1.0f / (1.0f + expf(-v));
+    case ACT_SILU:
+      return v / (1.0f + expf(-v));
+    default:
+      return v;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmShape s,
+            const GemmEpi e) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + C::kStages * C::kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smB + C::kStages * C::kBBytes);
+  uint64_t* empty = full + C::kStages;
+  uint64_t* acc_full = empty + C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_t = (s.T + BM - 1) / BM;
+  const int b = blockIdx.y / tiles_t;
+  const int t0 = (blockIdx.y % tiles_t) * BM;
+  const int n0 = blockIdx.x * BN;
+  const int g = blockIdx.z;
+  const int kchunks = (s.K + BK - 1) / BK;
+  const int iters = s.taps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int i = 0; i < C::kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<BN>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1;
+        const int tap = it / kchunks;
+        const int kc = it - tap * kchunks;
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        ptx::mbar_expect_tx(&full[st], C::kABytes + C::kBBytes);
+        ptx::tma_load_3d(smA + st * C::kABytes, &tmA, &full[st], g * s.a_group_koff + kc * BK,
+                         t0 + s.tap_shift0 + tap * s.tap_step, b);
+        ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], (tap * kchunks + kc) * BK,
+                         g * s.w_group_rows + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1;
+        ptx::mbar_wait(&full[st], ph);
+        ptx::tc_fence_after();
+        const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smA + st * C::kABytes));
+        const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smB + st * C::kBBytes));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+          ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[st]);  // frees this smem stage once the MMAs above have read it
+      }
+      ptx::umma_commit(acc_full);  // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = tile rows
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int t = t0 + row;
+    const bool row_ok = t < s.T;
+    const long long m = static_cast<long long>(b) * s.T + t;
+    // batch index / in-batch row used by masking and gating (flattened inputs carry rows_per_batch)
+    const int eb = e.rows_per_batch > 0 ? static_cast<int>(m / e.rows_per_batch) : b;
+    const int et = e.rows_per_batch > 0 ? static_cast<int>(m % e.rows_per_batch) : t;
+    const bool masked = (e.row_len != nullptr) && row_ok && (et >= e.row_len[eb]);
+    const int gcol_base = g * s.out_group_cols;
+    const bool swiglu = (e.act == ACT_SWIGLU16);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nl0 = n0 + c * 32;  // column inside the group
+      if (nl0 >= s.N) break;        // warp-uniform
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      ptx::tmem_ld_wait();
+      if (!row_ok) continue;
+      const int ncols = min(32, s.N - nl0);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = __uint_as_float(r[i]);
+      }
+      const int gc0 = gcol_base + nl0;
+      if (e.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < ncols) v[i] += __ldg(e.bias + gc0 + i);
+        }
+      }
+      int out_c0 = gc0;
+      int out_n = ncols;
+      if (swiglu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = v[i];
+          v[i] = a / (1.0f + expf(-a)) * v[16 + i];
+        }
+        out_c0 = gc0 >> 1;
+        out_n = ncols >> 1;
+      } else if (e.act != ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = act_apply(v[i], e.act);
+        }
+      }
+      float vb[32];  // value destined for the bf16 output (may be masked differently)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        vb[i] = masked ? 0.0f : v[i];
+        if (masked && !e.mask_bf16_only) v[i] = 0.0f;
+      }
+      if (e.colscale != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < out_n) {
+            const float sc = __ldg(e.colscale + out_c0 + i);
+            v[i] *= sc;
+            vb[i] *= sc;
+          }
+        }
+      }
+      if (e.rowgate != nullptr) {
+        const float* gp = e.rowgate + static_cast<long long>(eb) * e.ld_gate + out_c0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < out_n) {
+            const float sc = __ldg(gp + i);
+            v[i] *= sc;
+            vb[i] *= sc;
+          }
+        }
+      }
+      if (e.residual != nullptr) {
+        const float* rp = e.residual + m * e.ld_res + out_c0;
+        if (out_n == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(rp + 4 * i);
+            v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+            vb[4 * i + 0] += x.x; vb[4 * i + 1] += x.y; vb[4 * i + 2] += x.z; vb[4 * i + 3] += x.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < out_n) {
+              const float x = rp[i];
+              v[i] += x;
+              vb[i] += x;
+            }
+          }
+        }
+      }
+      if (e.out_f32 != nullptr) {
+        float* op = e.out_f32 + m * e.ld_out + out_c0;
+        if (out_n == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < out_n) op[i] = v[i];
+          }
+        }
+      }
+      if (e.out_bf16 != nullptr) {
+        __nv_bfloat16* op = e.out_bf16 + m * e.ld_out + out_c0;
+        if ((out_n == 32 || out_n == 16) && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (8 * i < out_n) {
+              uint4 pk;
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(vb[8 * i + 0], vb[8 * i + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(vb[8 * i + 2], vb[8 * i + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(vb[8 * i + 4], vb[8 * i + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(vb[8 * i + 6], vb[8 * i + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&p0);
+              pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              pk.z = *reinterpret_cast<uint32_t*>(&p2);
+              pk.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(op + 8 * i) = pk;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < out_n) op[i] = __float2bfloat16_rn(vb[i]);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeFn>(p);
+    }
+  });
+  return fn;
+}
+
+bool make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  EncodeFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[3];
+  cuuint64_t gstr[2];
+  cuuint32_t bx[3];
+  cuuint32_t es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN>
+cudaError_t launch_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
+                      const GemmEpi& e) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err =
+        cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  const int tiles_t = (s.T + BM - 1) / BM;
+  dim3 grid((s.N + BN - 1) / BN, s.B * tiles_t, s.groups);
+  gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, stream>>>(tmA, tmW, s, e);
+  ++g_launch_count;
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const GemmW& w, const GemmShape& s,
+                        const GemmEpi& e) {
+  if (s.T <= 0 || s.B <= 0 || s.N <= 0 || s.K <= 0) return cudaErrorInvalidValue;
+  if ((a.ld % 8) != 0 || (w.ld % 8) != 0) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(a.ptr) & 15) || (reinterpret_cast<uintptr_t>(w.ptr) & 15)) {
+    return cudaErrorInvalidValue;
+  }
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(a.cols), static_cast<uint64_t>(s.T), static_cast<uint64_t>(s.B)};
+    uint64_t str[2] = {static_cast<uint64_t>(a.ld) * 2, static_cast<uint64_t>(a.ld) * 2 * static_cast<uint64_t>(s.T)};
+    uint32_t box[3] = {BK, BM, 1};
+    if (!make_tmap(&tmA, a.ptr, 3, dims, str, box)) return cudaErrorInvalidValue;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(w.ld), static_cast<uint64_t>(w.rows)};
+    uint64_t str[1] = {static_cast<uint64_t>(w.ld) * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(block_n)};
+    if (!make_tmap(&tmW, w.ptr, 2, dims, str, box)) return cudaErrorInvalidValue;
+  }
+  switch (block_n) {
+    case 32:
+      return launch_bn<32>(stream, tmA, tmW, s, e);
+    case 64:
+      return launch_bn<64>(stream, tmA, tmW, s, e);
+    case 128:
+      return launch_bn<128>(stream, tmA, tmW, s, e);
+    case 256:
+      return launch_bn<256>(stream, tmA, tmW, s, e);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace stts

@@ -1,0 +1,780 @@
+// Non-GEMM kernels of the engine.  See kernels.cuh for the contracts and reference citations.
+#include "kernels.cuh"
+
+#include <math.h>
+
+#include "ptx.cuh"
+
+namespace stts {
+
+namespace {
+
+#define STTS_LAUNCH_OK()  \
+  do {                    \
+    ++g_launch_count;     \
+    return cudaGetLastError(); \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b);
+  __nv_bfloat162 p1 = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&p0);
+  r.y = *reinterpret_cast<uint32_t*>(&p1);
+  return r;
+}
+
+// ------------------------------------------------------------------ row norms (warp per row, dim <= 1024)
+template <bool kLayerNorm>
+__global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ x, int rows, int rpb, int dim,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       int ld_mod, float eps, bf16* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int nv = dim >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * dim);
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + 32 * i;
+    v[i] = idx < nv ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += kLayerNorm ? (v[i].x + v[i].y + v[i].z + v[i].w) : (v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  s = warp_sum(s);
+  float mean = 0.f, rstd;
+  if (kLayerNorm) {
+    mean = s / dim;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane + 32 * i < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + c * c + d * d;
+      }
+    }
+    q = warp_sum(q);
+    rstd = 1.0f / sqrtf(q / dim + eps);
+  } else {
+    rstd = 1.0f / sqrtf(s / dim + eps);
+  }
+  const int b = row / rpb;
+  const float4* sc = reinterpret_cast<const float4*>(scale + static_cast<long long>(kLayerNorm ? b : 0) * ld_mod);
+  const float4* sh = kLayerNorm ? reinterpret_cast<const float4*>(shift + static_cast<long long>(b) * ld_mod) : nullptr;
+  uint2* o = reinterpret_cast<uint2*>(out + static_cast<long long>(row) * dim);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      const float4 w = sc[idx];
+      float4 r;
+      if (kLayerNorm) {
+        const float4 h = sh[idx];
+        r.x = (v[i].x - mean) * rstd * (1.f + w.x) + h.x;
+        r.y = (v[i].y - mean) * rstd * (1.f + w.y) + h.y;
+        r.z = (v[i].z - mean) * rstd * (1.f + w.z) + h.z;
+        r.w = (v[i].w - mean) * rstd * (1.f + w.w) + h.w;
+      } else {
+        r.x = v[i].x * rstd * w.x;
+        r.y = v[i].y * rstd * w.y;
+        r.z = v[i].z * rstd * w.z;
+        r.w = v[i].w * rstd * w.w;
+      }
+      o[idx] = pack_bf16x4(r.x, r.y, r.z, r.w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ head split + per-head RMSNorm + RoPE
+template <int EPL>  // elements per lane: hd_pad / 32
+__global__ void __launch_bounds__(256) head_split_kernel(const float* __restrict__ in, int ld_in, int src_off, int rows,
+                                                         int rpb, int heads, int hd, const float* __restrict__ norm_w,
+                                                         float eps, int rot, const float* __restrict__ cos_t,
+                                                         const float* __restrict__ sin_t, bf16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long item = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (item >= static_cast<long long>(rows) * heads) return;
+  const int row = static_cast<int>(item / heads);
+  const int h = static_cast<int>(item % heads);
+  const int d0 = lane * EPL;
+  const float* src = in + static_cast<long long>(row) * ld_in + src_off + h * hd;
+  float v[EPL];
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    v[e] = (d0 + e < hd) ? src[d0 + e] : 0.f;
+    s += v[e] * v[e];
+  }
+  if (norm_w != nullptr) {
+    s = warp_sum(s);
+    const float r = 1.0f / sqrtf(s / hd + eps);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      if (d0 + e < hd) v[e] = v[e] * r * norm_w[h * hd + d0 + e];
+    }
+  }
+  if (rot > 0 && d0 < rot) {
+    const int pos = row % rpb;
+#pragma unroll
+    for (int e = 0; e < EPL; e += 2) {
+      const int i = (d0 + e) >> 1;
+      const float c = cos_t[pos * (rot >> 1) + i], sn = sin_t[pos * (rot >> 1) + i];
+      const float x0 = v[e], x1 = v[e + 1];
+      v[e] = x0 * c - x1 * sn;
+      v[e + 1] = x1 * c + x0 * sn;
+    }
+  }
+  bf16* o = out + (static_cast<long long>(row) * heads + h) * (EPL * 32) + d0;
+#pragma unroll
+  for (int e = 0; e < EPL; e += 2) {
+    *reinterpret_cast<__nv_bfloat162*>(o + e) = __floats2bfloat162_rn(v[e], v[e + 1]);
+  }
+}
+
+// ------------------------------------------------------------------ attention (warp MMA, online softmax)
+// CTA = 64 query rows (4 warps x 16) of one (batch, head); keys streamed in chunks of 64 through smem.
+template <int HD>
+__global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ q, int tq, int H, int hd, AttnSeg s0,
+                                                        AttnSeg s1, AttnSeg s2, int nseg, const float* __restrict__ gate,
+                                                        int ld_gate, int gate_off, float scale_log2,
+                                                        bf16* __restrict__ out) {
+  constexpr int PITCH = HD + 8;  // bf16 elements; 16-byte rows offset by one bank group -> conflict-free ldmatrix
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_att);
+  bf16* sK = sQ + 64 * PITCH;
+  bf16* sV = sK + 64 * PITCH;
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = H * HD;
+
+  int len[3] = {0, 0, 0};
+  len[0] = s0.len ? min(s0.len[b], s0.n_max) : s0.n_max;
+  if (nseg > 1) len[1] = s1.len ? min(s1.len[b], s1.n_max) : s1.n_max;
+  if (nseg > 2) len[2] = s2.len ? min(s2.len[b], s2.n_max) : s2.n_max;
+  const int total = len[0] + len[1] + len[2];
+
+  // stage Q tile (zero-fill rows beyond tq)
+  constexpr int VPR = HD / 8;  // 16-byte vectors per row
+  for (int i = threadIdx.x; i < 64 * VPR; i += 128) {
+    const int r = i / VPR, c = i % VPR;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (q0 + r < tq) {
+      val = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(b) * tq + q0 + r) * ld + h * HD + c * 8);
+    }
+    *reinterpret_cast<uint4*>(sQ + r * PITCH + c * 8) = val;
+  }
+  __syncthreads();
+  uint32_t qf[HD / 16][4];
+  {
+    const int r = warp * 16 + (lane & 15);
+    const int cofs = (lane >> 4) * 8;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      ptx::ldmatrix_x4(qf[kk], sQ + r * PITCH + kk * 16 + cofs);
+    }
+  }
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+
+  for (int k0 = 0; k0 < total; k0 += 64) {
+    __syncthreads();  // previous chunk fully consumed
+    for (int i = threadIdx.x; i < 64 * VPR; i += 128) {
+      const int r = i / VPR, c = i % VPR;
+      int j = k0 + r;
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (j < total) {
+        const bf16 *kp, *vp;
+        int nmax;
+        if (j < len[0]) {
+          kp = s0.k; vp = s0.v; nmax = s0.n_max;
+        } else if (j < len[0] + len[1]) {
+          j -= len[0]; kp = s1.k; vp = s1.v; nmax = s1.n_max;
+        } else {
+          j -= len[0] + len[1]; kp = s2.k; vp = s2.v; nmax = s2.n_max;
+        }
+        const long long off = (static_cast<long long>(b) * nmax + j) * ld + h * HD + c * 8;
+        kv = *reinterpret_cast<const uint4*>(kp + off);
+        vv = *reinterpret_cast<const uint4*>(vp + off);
+      }
+      *reinterpret_cast<uint4*>(sK + r * PITCH + c * 8) = kv;
+      *reinterpret_cast<uint4*>(sV + r * PITCH + c * 8) = vv;
+    }
+    __syncthreads();
+
+    // S = Q K^T for 16 rows x 64 keys
+    float sc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key tiles
+        uint32_t bfr[4];
+        const int id = lane >> 3, r = lane & 7;
+        const int key = jp * 16 + (id >> 1) * 8 + r;
+        const int dim = kk * 16 + (id & 1) * 8;
+        ptx::ldmatrix_x4(bfr, sK + key * PITCH + dim);
+        ptx::mma_16816(sc[2 * jp], qf[kk], bfr[0], bfr[1]);
+        ptx::mma_16816(sc[2 * jp + 1], qf[kk], bfr[2], bfr[3]);
+      }
+    }
+    // mask tail keys, online softmax (rows: lane/4 and lane/4 + 8; cols: 8j + (lane%4)*2 + {0,1})
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kc = k0 + j * 8 + (lane & 3) * 2;
+      if (kc >= total) sc[j][0] = sc[j][2] = -INFINITY;
+      if (kc + 1 >= total) sc[j][1] = sc[j][3] = -INFINITY;
+      mx[0] = fmaxf(mx[0], fmaxf(sc[j][0], sc[j][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(sc[j][2], sc[j][3]));
+    }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);  // finite: every chunk holds >= 1 valid key
+      corr[r] = exp2f((m_run[r] - m_new) * scale_log2);
+      m_run[r] = m_new;
+      l_run[r] *= corr[r];
+    }
+    uint32_t pf[4][4];  // P as A fragments for the 4 k-steps of 16 keys
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f((sc[j][0] - m_run[0]) * scale_log2);
+      const float p1 = exp2f((sc[j][1] - m_run[0]) * scale_log2);
+      const float p2 = exp2f((sc[j][2] - m_run[1]) * scale_log2);
+      const float p3 = exp2f((sc[j][3] - m_run[1]) * scale_log2);
+      l_run[0] += p0 + p1;
+      l_run[1] += p2 + p3;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(p2, p3);
+      pf[j >> 1][(j & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo);
+      pf[j >> 1][(j & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < HD / 16; ++np) {  // pairs of 8-dim tiles
+        uint32_t bfr[4];
+        const int id = lane >> 3, r = lane & 7;
+        const int key = kk * 16 + (id & 1) * 8 + r;
+        const int dim = (np * 2 + (id >> 1)) * 8;
+        ptx::ldmatrix_x4_trans(bfr, sV + key * PITCH + dim);
+        ptx::mma_16816(o[2 * np], pf[kk], bfr[0], bfr[1]);
+        ptx::mma_16816(o[2 * np + 1], pf[kk], bfr[2], bfr[3]);
+      }
+    }
+  }
+
+  // finalize: divide by row sums (reduced over the 4 lanes of a row), gate, store
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float l = l_run[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    inv[r] = l > 0.f ? 1.0f / l : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+    if (row >= tq) continue;
+    const long long m = static_cast<long long>(b) * tq + row;
+    bf16* op = out + m * ld + h * HD;
+    const float* gp = gate ? gate + m * ld_gate + gate_off + h * hd : nullptr;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      const int d = i * 8 + (lane & 3) * 2;
+      float a = o[i][2 * r] * inv[r], c = o[i][2 * r + 1] * inv[r];
+      if (gp != nullptr) {
+        a = d < hd ? a / (1.0f + expf(-gp[d])) : 0.f;
+        c = d + 1 < hd ? c / (1.0f + expf(-gp[d + 1])) : 0.f;
+      }
+      *reinterpret_cast<__nv_bfloat162*>(op + d) = __floats2bfloat162_rn(a, c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small dense layers
+template <int MAXR>
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict__ x, int rows, int k,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        int n, int pre, int post, int chunk, unsigned tanh_chunks,
+                                                        float* __restrict__ y, int ld_y) {
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (col >= n) return;
+  float acc[MAXR];
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) acc[r] = 0.f;
+  const float4* wr = reinterpret_cast<const float4*>(w + static_cast<long long>(col) * k);
+  for (int i = lane; i < (k >> 2); i += 32) {
+    const float4 wv = wr[i];
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      if (r < rows) {
+        float4 xv = reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k)[i];
+        if (pre == 1) {
+          xv.x = xv.x / (1.f + expf(-xv.x)); xv.y = xv.y / (1.f + expf(-xv.y));
+          xv.z = xv.z / (1.f + expf(-xv.z)); xv.w = xv.w / (1.f + expf(-xv.w));
+        }
+        acc[r] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    if (r < rows) {
+      float v = warp_sum(acc[r]);
+      if (lane == 0) {
+        if (bias != nullptr) v += bias[col];
+        if (post == 1) v = v / (1.f + expf(-v));
+        if (chunk > 0 && ((tanh_chunks >> (col / chunk)) & 1u)) v = tanhf(v);
+        y[static_cast<long long>(r) * ld_y + col] = v;
+      }
+    }
+  }
+}
+
+__global__ void time_features_kernel(const float* __restrict__ t, int rows, float* __restrict__ out) {
+  const int r = blockIdx.x, j = threadIdx.x;  // 128 threads
+  if (r >= rows) return;
+  const float f = expf(static_cast<float>(j) * -0.07252236513367074f);  // ln(1e4)/127
+  const float a = 1e3f * t[r] * f;
+  out[r * 256 + j] = sinf(a);
+  out[r * 256 + 128 + j] = cosf(a);
+}
+
+__global__ void embed_gather_kernel(const long long* __restrict__ ids, int rows, const float* __restrict__ table,
+                                    int vocab, int dim, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  long long id = ids[r];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4* src = reinterpret_cast<const float4*>(table + id * dim);
+  float4* dst = reinterpret_cast<float4*>(out + static_cast<long long>(r) * dim);
+  for (int i = threadIdx.x; i < (dim >> 2); i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, long long n, bf16* __restrict__ out) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    *reinterpret_cast<uint2*>(out + i) = pack_bf16x4(v.x, v.y, v.z, v.w);
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+
+__global__ void noise_mix_kernel(const float* __restrict__ xp, const float* __restrict__ nz, float alpha, float sigma,
+                                 long long n, float* __restrict__ xt, bf16* __restrict__ xtb) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = alpha * xp[i] + sigma * nz[i];
+    xt[i] = v;
+    xtb[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void dmd_update_kernel(const float* __restrict__ xt, const float* __restrict__ v, float alpha, float sigma,
+                                  long long n, float* __restrict__ xp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) xp[i] = alpha * xt[i] - sigma * v[i];
+}
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__global__ void philox_normal_kernel(unsigned long long seed, unsigned long long stream_id, long long n,
+                                     float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i * 4 >= n) return;
+  uint32_t c[4] = {static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(stream_id),
+                   static_cast<uint32_t>(stream_id >> 32)};
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  float z[4];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float u1 = (static_cast<float>(c[2 * p]) + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+    const float u2 = static_cast<float>(c[2 * p + 1]) * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    z[2 * p] = rad * cs;
+    z[2 * p + 1] = rad * sn;
+  }
+  for (int j = 0; j < 4; ++j) {
+    if (i * 4 + j < n) out[i * 4 + j] = z[j];
+  }
+}
+
+// ------------------------------------------------------------------ vocoder ConvNeXt token mixer
+// One CTA = TT output rows (+6 causal halo rows) x all C channels, staged in shared memory.
+__global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restrict__ x, int T, int C, int TT,
+                                                           const float* __restrict__ norm_w,
+                                                           const float* __restrict__ conv_w,
+                                                           const float* __restrict__ conv_b,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ ffn_norm_w, float eps,
+                                                           float* __restrict__ y, bf16* __restrict__ a) {
+  extern __shared__ __align__(16) float smx[];
+  const int R = TT + 6;
+  float* tile = smx;               // [R][C]
+  float* inv1 = smx + R * C;       // [R]
+  float* inv2 = inv1 + R;          // [TT]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TT;
+  const int nrows = min(TT, T - t0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cv = C >> 2;                  // float4 per row
+  const int lpr = cv < 32 ? cv : 32;      // lanes cooperating on one row (power of two)
+  const int rpi = 32 / lpr;               // rows per warp iteration
+  const int sub = lane / lpr, sl = lane % lpr;
+  const float* xb = x + static_cast<long long>(b) * T * C;
+
+  // phase 1: load rows t0-6 .. t0+nrows-1, per-row 1/rms
+  for (int r0 = warp * rpi; r0 < R; r0 += 8 * rpi) {
+    const int r = r0 + sub;
+    const int t = t0 - 6 + r;
+    const bool live = r < R && t >= 0 && r < nrows + 6;
+    float s = 0.f;
+    if (r < R) {
+      float4* dst = reinterpret_cast<float4*>(tile + r * C);
+      for (int i = sl; i < cv; i += lpr) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) v = reinterpret_cast<const float4*>(xb + static_cast<long long>(t) * C)[i];
+        dst[i] = v;
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (r < R && sl == 0) inv1[r] = live ? 1.0f / sqrtf(s / C + eps) : 0.f;
+  }
+  __syncthreads();
+
+  // phase 2: depthwise causal conv along time, one (channel, time segment) per thread
+  const int nseg = C >= 256 ? 1 : 256 / C;
+  const int seg_len = (nrows + nseg - 1) / nseg;
+  const int seg = C >= 256 ? 0 : threadIdx.x / C;
+  const int rs = 6 + seg * seg_len;                       // first output row (tile coordinates)
+  const int re = min(6 + nrows, rs + seg_len);
+  for (int c = (C >= 256 ? threadIdx.x : threadIdx.x % C); c < C; c += 256) {
+    float w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = conv_w[c * 7 + j];
+    const float cb = conv_b[c], gm = gamma[c], nw = norm_w[c];
+    float win[7];
+    win[0] = 0.f;
+#pragma unroll
+    for (int j = 1; j < 7; ++j) {
+      const int r = rs - 7 + j;  // rows rs-6 .. rs-1
+      win[j] = (r >= 0 && rs < re) ? tile[r * C + c] * inv1[r] * nw : 0.f;
+    }
+    if (nseg > 1) __syncthreads();  // all warm-up reads precede in-place writes of neighbouring segments
+    for (int r = rs; r < re; ++r) {
+      const float xv = tile[r * C + c];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+      win[6] = xv * inv1[r] * nw;
+      float acc = cb;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc += w[j] * win[j];
+      tile[r * C + c] = xv + gm * acc;
+    }
+  }
+  __syncthreads();
+
+  // phase 3: 1/rms of the updated rows
+  for (int r0 = warp * rpi; r0 < nrows; r0 += 8 * rpi) {
+    const int r = r0 + sub;
+    float s = 0.f;
+    if (r < nrows) {
+      const float4* src = reinterpret_cast<const float4*>(tile + (r + 6) * C);
+      for (int i = sl; i < cv; i += lpr) {
+        const float4 v = src[i];
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (r < nrows && sl == 0) inv2[r] = 1.0f / sqrtf(s / C + eps);
+  }
+  __syncthreads();
+
+  // phase 4: coalesced stores of y (fp32) and a = rmsnorm(y) (bf16)
+  const long long obase = (static_cast<long long>(b) * T + t0) * C;
+  for (int i = threadIdx.x; i < nrows * cv; i += 256) {
+    const int r = i / cv, c4 = i % cv;
+    const float4 v = reinterpret_cast<const float4*>(tile + (r + 6) * C)[c4];
+    reinterpret_cast<float4*>(y + obase)[i] = v;
+    const float4 fw = reinterpret_cast<const float4*>(ffn_norm_w)[c4];
+    const float s = inv2[r];
+    reinterpret_cast<uint2*>(a + obase)[i] = pack_bf16x4(v.x * s * fw.x, v.y * s * fw.y, v.z * s * fw.z, v.w * s * fw.w);
+  }
+}
+
+__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int T, int C,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ out) {
+  extern __shared__ float sw[];  // [7][C] tap-major
+  for (int i = threadIdx.x; i < 7 * C; i += 256) {
+    const int j = i / C, c = i % C;
+    sw[i] = w[c * 7 + j];
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= T) return;
+  const float* xb = x + static_cast<long long>(b) * T * C;
+  float acc = bias[0];
+  for (int j = 0; j < 7; ++j) {
+    const int tt = t - 6 + j;
+    if (tt < 0) continue;
+    const float4* row = reinterpret_cast<const float4*>(xb + static_cast<long long>(tt) * C);
+    const float4* wr = reinterpret_cast<const float4*>(sw + j * C);
+    for (int c = 0; c < (C >> 2); ++c) {
+      const float4 xv = row[c], wv = wr[c];
+      acc += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+    }
+  }
+  out[static_cast<long long>(b) * T + t] = acc;
+}
+
+// ------------------------------------------------------------------ packing
+__device__ __forceinline__ int map_row(int r, int mode) {
+  if (mode == ROW_INTERLEAVE16_LO) return (r >> 4) * 32 + (r & 15);
+  if (mode == ROW_INTERLEAVE16_HI) return (r >> 4) * 32 + 16 + (r & 15);
+  return r;
+}
+
+__global__ void pack_matrix_kernel(const float* __restrict__ src, int rows, int cols, float scale, int row_mode,
+                                   int row_off, int col_mode, int col_off, bf16* __restrict__ dst, int ld_dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols) return;
+  const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+  const int dr = map_row(r, row_mode) + row_off;
+  const int dc = (col_mode == COL_HEADPAD_120_128 ? (c / 120) * 128 + c % 120 : c) + col_off;
+  dst[static_cast<long long>(dr) * ld_dst + dc] = __float2bfloat16_rn(scale * src[i]);
+}
+
+__global__ void pack_conv_taps_kernel(const float* __restrict__ src, int O, int cin, int taps, int kp, int opg,
+                                      int group_pitch, bf16* __restrict__ dst, int ld_dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(O) * cin * taps) return;
+  const int tap = static_cast<int>(i % taps);
+  const int c = static_cast<int>((i / taps) % cin);
+  const int o = static_cast<int>(i / (static_cast<long long>(taps) * cin));
+  const int dr = (o / opg) * group_pitch + o % opg;
+  dst[static_cast<long long>(dr) * ld_dst + tap * kp + c] = __float2bfloat16_rn(src[i]);
+}
+
+__global__ void pack_convtr_kernel(const float* __restrict__ src, int cin, int cout, int r, bf16* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int kk = 2 * r;
+  if (i >= static_cast<long long>(cin) * cout * kk) return;
+  const int jj = static_cast<int>(i % kk);
+  const int o = static_cast<int>((i / kk) % cout);
+  const int c = static_cast<int>(i / (static_cast<long long>(kk) * cout));
+  const int tap = jj / r, j = jj % r;
+  dst[(static_cast<long long>(j) * cout + o) * (2 * cin) + tap * cin + c] = __float2bfloat16_rn(src[i]);
+}
+
+__global__ void pack_vector_kernel(const float* __restrict__ src, int n, float scale, int row_mode, int off,
+                                   float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[map_row(i, row_mode) + off] = scale * src[i];
+}
+
+__global__ void tile_vector_kernel(const float* __restrict__ src, int n, int reps, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * reps) dst[i] = src[i % n];
+}
+
+inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
+
+}  // namespace
+
+// ==================================================================== launchers
+cudaError_t ln_mod_bf16(cudaStream_t st, const float* x, int rows, int rpb, int dim, const float* scale,
+                        const float* shift, int ld_mod, float eps, bf16* out) {
+  if (dim % 4 != 0 || dim > 1024) return cudaErrorInvalidValue;
+  row_norm_kernel<true><<<blocks_for(rows, 8), 256, 0, st>>>(x, rows, rpb, dim, scale, shift, ld_mod, eps, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t rms_norm_bf16(cudaStream_t st, const float* x, int rows, int dim, const float* w, float eps, bf16* out) {
+  if (dim % 4 != 0 || dim > 1024) return cudaErrorInvalidValue;
+  row_norm_kernel<false><<<blocks_for(rows, 8), 256, 0, st>>>(x, rows, 1, dim, w, nullptr, 0, eps, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t head_split_bf16(cudaStream_t st, const float* in, int ld_in, int src_off, int rows, int rpb, int heads,
+                            int hd, int hd_pad, const float* norm_w, float eps, int rot, const float* cos_t,
+                            const float* sin_t, bf16* out) {
+  const unsigned nb = blocks_for(static_cast<long long>(rows) * heads, 8);
+  if (hd_pad == 128) {
+    head_split_kernel<4><<<nb, 256, 0, st>>>(in, ld_in, src_off, rows, rpb, heads, hd, norm_w, eps, rot, cos_t, sin_t, out);
+  } else if (hd_pad == 64) {
+    head_split_kernel<2><<<nb, 256, 0, st>>>(in, ld_in, src_off, rows, rpb, heads, hd, norm_w, eps, rot, cos_t, sin_t, out);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t attention_bf16(cudaStream_t st, const bf16* q, int B, int tq, int H, int hd, int hd_pad, const AttnSeg* segs,
+                           int nseg, const float* gate, int ld_gate, int gate_off, bf16* out) {
+  if (nseg < 1 || nseg > 3) return cudaErrorInvalidValue;
+  AttnSeg s[3];
+  for (int i = 0; i < nseg; ++i) s[i] = segs[i];
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
+  dim3 grid((tq + 63) / 64, H, B);
+  if (hd_pad == 128) {
+    constexpr int smem = 3 * 64 * (128 + 8) * 2;
+    static bool once = false;
+    if (!once) {
+      cudaError_t e = cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      once = true;
+    }
+    attention_kernel<128><<<grid, 128, smem, st>>>(q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
+  } else if (hd_pad == 64) {
+    constexpr int smem = 3 * 64 * (64 + 8) * 2;
+    attention_kernel<64><<<grid, 128, smem, st>>>(q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t gemv_rows(cudaStream_t st, const float* x, int rows, int k, const float* w, const float* b, int n, int pre,
+                      int post, int chunk, unsigned tanh_chunks, float* y, int ld_y) {
+  if (k % 4 != 0) return cudaErrorInvalidValue;
+  for (int r0 = 0; r0 < rows; r0 += 8) {
+    const int nr = rows - r0 < 8 ? rows - r0 : 8;
+    gemv_rows_kernel<8><<<blocks_for(n, 8), 256, 0, st>>>(x + static_cast<long long>(r0) * k, nr, k, w, b, n, pre, post,
+                                                         chunk, tanh_chunks, y + static_cast<long long>(r0) * ld_y, ld_y);
+    ++g_launch_count;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t time_features(cudaStream_t st, const float* t, int rows, float* out) {
+  time_features_kernel<<<rows, 128, 0, st>>>(t, rows, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t embed_gather(cudaStream_t st, const long long* ids, int rows, const float* table, int vocab, int dim,
+                         float* out) {
+  embed_gather_kernel<<<rows, 128, 0, st>>>(ids, rows, table, vocab, dim, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t cast_bf16(cudaStream_t st, const float* in, long long n, bf16* out) {
+  cast_bf16_kernel<<<blocks_for(n, 1024), 256, 0, st>>>(in, n, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t noise_mix(cudaStream_t st, const float* x_pred, const float* noise, float alpha, float sigma, long long n,
+                      float* x_t, bf16* x_t_bf16) {
+  noise_mix_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_pred, noise, alpha, sigma, n, x_t, x_t_bf16);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t dmd_update(cudaStream_t st, const float* x_t, const float* v, float alpha, float sigma, long long n,
+                       float* x_pred) {
+  dmd_update_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_t, v, alpha, sigma, n, x_pred);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t philox_normal(cudaStream_t st, unsigned long long seed, unsigned long long stream_id, long long n,
+                          float* out) {
+  philox_normal_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>(seed, stream_id, n, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, const float* norm_w, const float* conv_w,
+                         const float* conv_b, const float* gamma, const float* ffn_norm_w, float eps, float* y,
+                         bf16* a) {
+  if (C < 16 || (C & (C - 1)) != 0 || C > 2048) return cudaErrorInvalidValue;
+  int TT = 16384 / C;
+  if (TT < 8) TT = 8;
+  if (TT > 512) TT = 512;
+  if (TT > T) TT = T;
+  const int smem = ((TT + 6) * C + (TT + 6) + TT) * 4;
+  static bool once = false;
+  if (!once) {
+    cudaError_t e = cudaFuncSetAttribute(convnext_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    if (e != cudaSuccess) return e;
+    once = true;
+  }
+  dim3 grid((T + TT - 1) / TT, B);
+  convnext_mix_kernel<<<grid, 256, smem, st>>>(x, T, C, TT, norm_w, conv_w, conv_b, gamma, ffn_norm_w, eps, y, a);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, const float* w, const float* bias,
+                      float* out) {
+  if (C % 4 != 0) return cudaErrorInvalidValue;
+  dim3 grid((T + 255) / 256, B);
+  head_conv_kernel<<<grid, 256, 7 * C * 4, st>>>(x, T, C, w, bias, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t pack_matrix(cudaStream_t st, const float* src, int rows, int cols, float scale, int row_mode, int row_off,
+                        int col_mode, int col_off, bf16* dst, int ld_dst) {
+  pack_matrix_kernel<<<blocks_for(static_cast<long long>(rows) * cols, 256), 256, 0, st>>>(
+      src, rows, cols, scale, row_mode, row_off, col_mode, col_off, dst, ld_dst);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t pack_conv_taps(cudaStream_t st, const float* src, int O, int cin, int taps, int kp, int opg, int group_pitch,
+                           bf16* dst, int ld_dst) {
+  pack_conv_taps_kernel<<<blocks_for(static_cast<long long>(O) * cin * taps, 256), 256, 0, st>>>(
+      src, O, cin, taps, kp, opg, group_pitch, dst, ld_dst);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t pack_convtr(cudaStream_t st, const float* src, int cin, int cout, int r, bf16* dst) {
+  pack_convtr_kernel<<<blocks_for(static_cast<long long>(cin) * cout * 2 * r, 256), 256, 0, st>>>(src, cin, cout, r, dst);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t pack_vector(cudaStream_t st, const float* src, int n, float scale, int row_mode, int off, float* dst) {
+  pack_vector_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, n, scale, row_mode, off, dst);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t tile_vector(cudaStream_t st, const float* src, int n, int reps, float* dst) {
+  tile_vector_kernel<<<blocks_for(static_cast<long long>(n) * reps, 256), 256, 0, st>>>(src, n, reps, dst);
+  STTS_LAUNCH_OK();
+}
+
+}  // namespace stts

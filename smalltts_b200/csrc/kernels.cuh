@@ -1,0 +1,89 @@
+// Non-GEMM kernels of the engine (declarations).  All launch on the given stream and return the
+// CUDA launch status.  Layouts are channels-last: activations [B, T, C] row-major.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stts {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- normalisation producing the bf16 A operand of the next GEMM
+// LayerNorm(no affine, eps) * (1 + scale[b]) + shift[b]   (dit.py:24,199 / :38).  scale/shift: [B or 1, ld_mod].
+cudaError_t ln_mod_bf16(cudaStream_t st, const float* x, int rows, int rows_per_batch, int dim, const float* scale,
+                        const float* shift, int ld_mod, float eps, bf16* out);
+// x * rsqrt(mean(x^2) + eps) * w   (dit.py:52 1-D weight; style.py:100-105 block norms)
+cudaError_t rms_norm_bf16(cudaStream_t st, const float* x, int rows, int dim, const float* w, float eps, bf16* out);
+
+// ---- head split: fp32 [rows, ld_in] (columns src_off + h*hd + d) -> bf16 [rows, heads, hd_pad], with optional
+// per-head RMSNorm weight [heads, hd] (dit.py:52-53) and optional interleaved-pair RoPE on the first `rot` dims
+// using position (row % rows_per_batch) (dit.py:152-173 / style.py:21-25).  cos/sin tables: [max_pos, rot/2].
+cudaError_t head_split_bf16(cudaStream_t st, const float* in, int ld_in, int src_off, int rows, int rows_per_batch,
+                            int heads, int hd, int hd_pad, const float* norm_w, float eps, int rot, const float* cos_t,
+                            const float* sin_t, bf16* out);
+
+// ---- attention over up to three key segments (self | ref | text), prefix-valid lengths per batch.
+struct AttnSeg {
+  const bf16* k = nullptr;   // [B, n_max, H, hd_pad]
+  const bf16* v = nullptr;
+  const int* len = nullptr;  // [B] valid prefix length (nullptr -> n_max)
+  int n_max = 0;
+};
+// q: [B, tq, H, hd_pad]; out: bf16 [B*tq, H*hd_pad]; gate (optional): fp32 pre-sigmoid [B*tq, ld_gate] at column
+// gate_off + h*hd + d (dit.py:111-115); softmax scale = 1/sqrt(hd).
+cudaError_t attention_bf16(cudaStream_t st, const bf16* q, int B, int tq, int H, int hd, int hd_pad, const AttnSeg* segs,
+                           int nseg, const float* gate, int ld_gate, int gate_off, bf16* out);
+
+// ---- small dense layers on <= 16 rows (time embedding, adaLN tables): fp32 weights, warp per output.
+// y[r, n] = post( sum_k pre(x[r,k]) * W[n,k] + b[n] ); pre/post: 0 none, 1 SiLU; tanh applied to output chunk
+// (n / chunk) when bit set in tanh_chunks.
+cudaError_t gemv_rows(cudaStream_t st, const float* x, int rows, int k, const float* w, const float* b, int n, int pre,
+                      int post, int chunk, unsigned tanh_chunks, float* y, int ld_y);
+// sinusoidal timestep features (model.py:23-29): out [rows, 256]
+cudaError_t time_features(cudaStream_t st, const float* t, int rows, float* out);
+
+// ---- text embedding gather: ids int64 [rows] -> fp32 [rows, dim]
+cudaError_t embed_gather(cudaStream_t st, const long long* ids, int rows, const float* table, int vocab, int dim,
+                         float* out);
+cudaError_t cast_bf16(cudaStream_t st, const float* in, long long n, bf16* out);
+
+// ---- sampler math (infer/onnx.py:105,125): all [n] fp32
+// x_t = alpha*x_pred + sigma*noise ; writes fp32 and bf16 copies
+cudaError_t noise_mix(cudaStream_t st, const float* x_pred, const float* noise, float alpha, float sigma, long long n,
+                      float* x_t, bf16* x_t_bf16);
+// x_pred = alpha*x_t - sigma*v
+cudaError_t dmd_update(cudaStream_t st, const float* x_t, const float* v, float alpha, float sigma, long long n,
+                       float* x_pred);
+// standard normal noise, Philox4x32-10 + Box-Muller, counter = element index
+cudaError_t philox_normal(cudaStream_t st, unsigned long long seed, unsigned long long stream_id, long long n,
+                          float* out);
+
+// ---- vocoder ConvNeXt token mixer (hf:284-292) fused with the FFN pre-norm (hf:295):
+//   y = x + gamma * (dwconv7_causal(rmsnorm(x; norm_w)) + conv_b) ;  a = bf16(rmsnorm(y; ffn_norm_w))
+// x, y: fp32 [B, T, C]; conv_w: [C, 7]
+cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, const float* norm_w, const float* conv_w,
+                         const float* conv_b, const float* gamma, const float* ffn_norm_w, float eps, float* y,
+                         bf16* a);
+// vocoder head: causal Conv1d(C -> 1, k=7) (hf:484-489).  x fp32 [B, T, C], w [C, 7] -> out [B, T]
+cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, const float* w, const float* bias,
+                      float* out);
+
+// ---- weight packing (run once at stts_finalize_weights)
+enum PackRow : int { ROW_PLAIN = 0, ROW_INTERLEAVE16_LO = 1, ROW_INTERLEAVE16_HI = 2 };
+enum PackCol : int { COL_PLAIN = 0, COL_HEADPAD_120_128 = 1 };
+// dst[rowmap(r) + row_off, colmap(c) + col_off] = bf16(scale * src[r, c])
+cudaError_t pack_matrix(cudaStream_t st, const float* src, int rows, int cols, float scale, int row_mode, int row_off,
+                        int col_mode, int col_off, bf16* dst, int ld_dst);
+// Conv1d weight [O, Cin, taps] -> dst[(o / opg) * group_pitch + o % opg, tap * kp + c]
+cudaError_t pack_conv_taps(cudaStream_t st, const float* src, int O, int cin, int taps, int kp, int opg, int group_pitch,
+                           bf16* dst, int ld_dst);
+// ConvTranspose1d weight [Cin, Cout, 2r] -> dst[j*Cout + o, tap*Cin + c] = w[c, o, j + tap*r]
+cudaError_t pack_convtr(cudaStream_t st, const float* src, int cin, int cout, int r, bf16* dst);
+// fp32 vector helpers: dst[map(i) + off] = scale * src[i]
+cudaError_t pack_vector(cudaStream_t st, const float* src, int n, float scale, int row_mode, int off, float* dst);
+cudaError_t tile_vector(cudaStream_t st, const float* src, int n, int reps, float* dst);  // dst[j*n+i] = src[i]
+
+extern unsigned long long g_launch_count;
+
+}  // namespace stts

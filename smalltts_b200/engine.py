@@ -1,0 +1,218 @@
+"""Host-side handle on the C-ABI engine: one engine per GPU, not thread-safe (like the reference's
+``Arc<Mutex<Pipeline>>``, server/src/main.rs:25).  Tensors may be numpy arrays (host memory, copied by the
+library) or torch CUDA tensors (device memory, used in place); control metadata is always host."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+
+HOP_SIZE = 3200
+LATENT_DIM = 64
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _buf(x, dtype, name: str):
+    """-> (pointer, mem, keepalive).  numpy -> host pointer; torch cuda tensor -> device pointer."""
+    if _is_torch(x):
+        import torch
+
+        want = {np.float32: torch.float32, np.int64: torch.int64}[dtype]
+        if x.dtype != want:
+            raise ValueError(f"{name}: expected dtype {want}, got {x.dtype}")
+        x = x.contiguous()
+        if x.is_cuda:
+            return C.c_void_p(x.data_ptr()), _cabi.MEM_DEVICE, x
+        x = x.numpy()
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return C.c_void_p(a.ctypes.data), _cabi.MEM_HOST, a
+
+
+def _i64(v: Sequence[int]) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(list(v), dtype=np.int64))
+
+
+class Conditions:
+    """Device-resident output of the condition encoder (== the five tensors returned by
+    condition_encoder.onnx, infer/onnx.py:94-96).  Reusable across prompts that share a batch of voices."""
+
+    def __init__(self, engine: "Engine", handle, B: int, R: int, P: int):
+        self._engine, self._h, self.B, self.R, self.P = engine, handle, B, R, P
+
+    def read_kv(self, layer: int, which: str) -> np.ndarray:
+        idx = {"k_ref": 0, "v_ref": 1, "k_text": 2, "v_text": 3}[which]
+        n = self.R if idx < 2 else self.P
+        out = np.empty((self.B, 8, n, 120), dtype=np.float32)
+        _cabi.check(_cabi.lib().stts_cond_read_kv(self._engine._h, self._h, layer, idx, C.c_void_p(out.ctypes.data)),
+                    self._engine._h)
+        return out
+
+    def free(self) -> None:
+        if self._h is not None:
+            _cabi.lib().stts_cond_free(self._engine._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _cabi.lib()
+        cfg = _cabi.Config(device=device)
+        h = C.c_void_p()
+        _cabi.check(self._lib.stts_create(C.byref(cfg), C.byref(h)), None)
+        self._h = h
+        self.device = device
+        self._ready = False
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dicts(self, dit_sd: Dict[str, "np.ndarray"], vocoder_sd: Dict[str, "np.ndarray"]) -> None:
+        """fp32 tensors under the reference's own key names (DiTModel.state_dict(), HF decoder state_dict())."""
+        for model, sd in ((0, dit_sd), (1, vocoder_sd)):
+            for name, t in sd.items():
+                a = t.detach().cpu().numpy() if _is_torch(t) else np.asarray(t)
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+                _cabi.check(self._lib.stts_load_weight(self._h, model, name.encode(), C.c_void_p(a.ctypes.data), a.ndim,
+                                                       shape), self._h)
+        _cabi.check(self._lib.stts_finalize_weights(self._h), self._h)
+        self._ready = True
+
+    # ------------------------------------------------------------------ operators
+    def encode_conditions(self, ref, ref_len: Sequence[int], phonemes, ph_len: Sequence[int]) -> Conditions:
+        B, R, _ = ref.shape
+        P = phonemes.shape[1]
+        rp, m1, k1 = _buf(ref, np.float32, "ref")
+        pp, m2, k2 = _buf(phonemes, np.int64, "phonemes")
+        if m1 != m2:
+            raise ValueError("ref and phonemes must live in the same memory space")
+        rl, pl = _i64(ref_len), _i64(ph_len)
+        h = C.c_void_p()
+        _cabi.check(self._lib.stts_encode_conditions(self._h, rp, C.c_void_p(rl.ctypes.data), pp,
+                                                     C.c_void_p(pl.ctypes.data), B, R, P, m1, C.byref(h)), self._h)
+        return Conditions(self, h, B, R, P)
+
+    def denoise_step(self, cond: Conditions, x_t, frames: Sequence[int], t: Sequence[float]):
+        B, T, _ = x_t.shape
+        xp, mem, keep = _buf(x_t, np.float32, "x_t")
+        fr = _i64(frames)
+        tt = np.ascontiguousarray(np.asarray(list(t), dtype=np.float32))
+        out, op = self._out_like(x_t, (B, T, LATENT_DIM), mem)
+        _cabi.check(self._lib.stts_denoise_step(self._h, cond._h, xp, C.c_void_p(fr.ctypes.data),
+                                                C.c_void_p(tt.ctypes.data), B, T, mem, op), self._h)
+        return out
+
+    def sample(self, cond: Conditions, frames: Sequence[int], T: int, noise=None, seed: int = 0, steps: int = 4,
+               timesteps: Optional[Sequence[float]] = None, device_out: bool = False):
+        B = cond.B
+        fr = _i64(frames)
+        ts = None if timesteps is None else np.ascontiguousarray(np.asarray(list(timesteps), dtype=np.float32))
+        if noise is not None:
+            np_, mem, keep = _buf(noise, np.float32, "noise")
+            if tuple(noise.shape) != (steps, B, T, LATENT_DIM):
+                raise ValueError(f"noise must be {(steps, B, T, LATENT_DIM)}, got {tuple(noise.shape)}")
+        else:
+            np_, mem = None, (_cabi.MEM_DEVICE if device_out else _cabi.MEM_HOST)
+        out, op = self._out_like(noise, (B, T, LATENT_DIM), mem)
+        _cabi.check(self._lib.stts_sample(self._h, cond._h, C.c_void_p(fr.ctypes.data), B, T, steps,
+                                          None if ts is None else C.c_void_p(ts.ctypes.data), np_, seed, mem, op),
+                    self._h)
+        return out
+
+    def decode(self, latents):
+        B, T, _ = latents.shape
+        lp, mem, keep = _buf(latents, np.float32, "latents")
+        out, op = self._out_like(latents, (B, T * HOP_SIZE), mem)
+        _cabi.check(self._lib.stts_decode(self._h, lp, B, T, mem, op), self._h)
+        return out
+
+    def synthesize(self, ref, ref_len, phonemes, ph_len, frames, T: int, noise=None, seed: int = 0, steps: int = 4,
+                   timesteps: Optional[Sequence[float]] = None, out=None):
+        """Padded-batch SmallTTS.synthesize: returns audio [B, T*3200] (numpy if inputs are numpy, torch cuda if
+        inputs are cuda tensors).  ``out`` may be a preallocated (pinned) numpy array / cuda tensor."""
+        B, R, _ = ref.shape
+        P = phonemes.shape[1]
+        rp, mem, k1 = _buf(ref, np.float32, "ref")
+        pp, m2, k2 = _buf(phonemes, np.int64, "phonemes")
+        np_ = None
+        if noise is not None:
+            np_, m3, k3 = _buf(noise, np.float32, "noise")
+            if tuple(noise.shape) != (steps, B, T, LATENT_DIM):
+                raise ValueError(f"noise must be {(steps, B, T, LATENT_DIM)}, got {tuple(noise.shape)}")
+            if m3 != mem:
+                raise ValueError("all tensors must live in the same memory space")
+        if m2 != mem:
+            raise ValueError("all tensors must live in the same memory space")
+        rl, pl, fr = _i64(ref_len), _i64(ph_len), _i64(frames)
+        ts = None if timesteps is None else np.ascontiguousarray(np.asarray(list(timesteps), dtype=np.float32))
+        if out is None:
+            out, op = self._out_like(ref, (B, T * HOP_SIZE), mem)
+        else:
+            op, mo, _ = _buf(out, np.float32, "out")
+            if mo != mem:
+                raise ValueError("out must live in the same memory space as the inputs")
+        _cabi.check(self._lib.stts_synthesize(self._h, rp, C.c_void_p(rl.ctypes.data), pp, C.c_void_p(pl.ctypes.data),
+                                              C.c_void_p(fr.ctypes.data), B, R, P, T, steps,
+                                              None if ts is None else C.c_void_p(ts.ctypes.data), np_, seed, mem, op),
+                    self._h)
+        return out
+
+    # ------------------------------------------------------------------ misc
+    def timings(self) -> Dict[str, float]:
+        t = _cabi.Timing()
+        _cabi.check(self._lib.stts_get_timings(self._h, C.byref(t)), self._h)
+        return {n: getattr(t, n) for n, _ in _cabi.Timing._fields_}
+
+    def vocoder_ms(self) -> Dict[str, float]:
+        return {"tail_hbm": self._lib.stts_last_vocoder_ms(self._h, 0),
+                "front_tensor": self._lib.stts_last_vocoder_ms(self._h, 1)}
+
+    @staticmethod
+    def launch_count() -> int:
+        return int(_cabi.lib().stts_launch_count())
+
+    def _out_like(self, like, shape, mem):
+        if mem == _cabi.MEM_DEVICE:
+            import torch
+
+            out = torch.empty(shape, dtype=torch.float32, device=f"cuda:{self.device}")
+            return out, C.c_void_p(out.data_ptr())
+        out = np.empty(shape, dtype=np.float32)
+        return out, C.c_void_p(out.ctypes.data)
+
+    def close(self) -> None:
+        if self._h is not None:
+            self._lib.stts_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pad_batch(ref_list, ids_list: Sequence[Sequence[int]], frames: Sequence[int]):
+    """Ragged python inputs -> padded numpy batch (ref [B,R,64], ref_len, ids [B,P], ph_len)."""
+    B = len(ref_list)
+    refs = [np.asarray(r.detach().cpu().numpy() if _is_torch(r) else r, dtype=np.float32) for r in ref_list]
+    R = max(r.shape[0] for r in refs)
+    P = max(1, max(len(p) for p in ids_list))
+    ref = np.zeros((B, R, LATENT_DIM), dtype=np.float32)
+    ids = np.zeros((B, P), dtype=np.int64)
+    for i in range(B):
+        if refs[i].ndim != 2 or refs[i].shape[1] != LATENT_DIM:
+            raise ValueError(f"ref_latents[{i}] must be (R, 64), got {refs[i].shape}")
+        ref[i, : refs[i].shape[0]] = refs[i]
+        ids[i, : len(ids_list[i])] = np.asarray(list(ids_list[i]), dtype=np.int64)
+    return ref, [r.shape[0] for r in refs], ids, [len(p) for p in ids_list]

@@ -1,0 +1,156 @@
+"""Drop-in for the reference's ``smalltts.infer.onnx`` (infer/onnx.py:1-159): same module constants, same
+``SmallTTS`` constructor / ``synthesize`` / ``forward`` / ``__call__`` signatures, but every operator runs in the
+B200 engine behind the C ABI (no onnxruntime, no PyTorch ops, no CPU fallback).
+
+Differences a caller can see, all additive:
+  * the three path arguments point at weight files instead of ``.onnx`` graphs: ``cond_encoder_path`` /
+    ``denoiser_path`` name the DiT checkpoint (``.pt`` / ``.safetensors`` with ``DiTModel.state_dict()`` keys; both
+    graphs of the reference are exports of that one model, so the two paths normally coincide) and
+    ``codec_decoder_path`` the VibeVoice decoder weights (HF ``state_dict`` keys);
+  * ``synthesize_batch`` runs a ragged batch in ONE engine call (the reference loops, infer/onnx.py:143-156);
+  * ``noise=`` / ``seed=`` make the DMD loop reproducible (the reference draws from the global numpy RNG).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from .engine import Engine, pad_batch
+
+SAMPLE_RATE = 24_000  # infer/onnx.py:11
+HOP_SIZE = 3_200  # infer/onnx.py:12
+NUM_STEPS = 4  # infer/onnx.py:13
+CHARS_PER_SECOND = 11.5  # infer/onnx.py:14
+
+
+def estimate_duration(text: str, min_sec: float = 0.5, max_sec: float = 30.0) -> float:
+    """infer/onnx.py:17-18."""
+    return max(min_sec, min(len(text) / CHARS_PER_SECOND, max_sec))
+
+
+def frames_for(duration_sec: float) -> int:
+    """infer/onnx.py:84."""
+    return max(1, int(duration_sec * SAMPLE_RATE / HOP_SIZE))
+
+
+_PREFIXES = ("ema_model.", "module.", "_orig_mod.", "online_model.")  # scripts/train/dmd2/distill.py:39-57
+
+
+def load_state_dict_file(path: str, container_keys: Sequence[str] = ("student_model", "model", "state_dict")) -> Dict:
+    """Read a ``.pt`` / ``.safetensors`` checkpoint into {name: tensor}; strips the wrapper prefixes the reference's
+    trainers leave behind and drops their ``initted`` / ``step`` extras (distill.py:39-57,468-470)."""
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+
+        sd = load_file(path)
+    else:
+        import torch
+
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        for k in container_keys:
+            if isinstance(sd, dict) and k in sd and isinstance(sd[k], dict):
+                sd = sd[k]
+                break
+    out = {}
+    for k, v in sd.items():
+        changed = True
+        while changed:
+            changed = False
+            for p in _PREFIXES:
+                if k.startswith(p):
+                    k, changed = k[len(p):], True
+        if k in ("initted", "step"):
+            continue
+        out[k] = v
+    return out
+
+
+def _tokens(x) -> List[int]:
+    if isinstance(x, str):
+        try:  # the reference's own text front-end (espeak), when that package is installed
+            from smalltts.data.phonemization.phonemes import get_token_ids
+        except Exception as exc:  # pragma: no cover - depends on the host environment
+            raise RuntimeError(
+                "string inputs need the reference phonemizer (smalltts.data.phonemization); pass token ids instead"
+            ) from exc
+        return get_token_ids(x)
+    return list(map(int, x))
+
+
+class SmallTTS:
+    """DMD 4-step inference on the B200 engine; mirrors infer/onnx.py:50-159."""
+
+    def __init__(
+        self,
+        cond_encoder_path: str = "assets/dmd/model.safetensors",
+        denoiser_path: Optional[str] = None,
+        codec_decoder_path: str = "assets/codec/decoder.safetensors",
+        providers: Optional[Iterable[str]] = None,  # accepted for call compatibility; the engine is CUDA-only
+        *,
+        device: int = 0,
+        state_dicts: Optional[tuple] = None,
+        num_steps: int = NUM_STEPS,
+        seed: Optional[int] = None,
+    ) -> None:
+        self.num_steps = num_steps
+        self._seed = 0 if seed is None else int(seed)
+        self._calls = 0
+        if state_dicts is None:
+            if denoiser_path is not None and os.path.abspath(denoiser_path) != os.path.abspath(cond_encoder_path):
+                dit = load_state_dict_file(cond_encoder_path)
+                dit.update(load_state_dict_file(denoiser_path))
+            else:
+                dit = load_state_dict_file(cond_encoder_path)
+            state_dicts = (dit, load_state_dict_file(codec_decoder_path))
+        self.engine = Engine(device)
+        self.engine.load_state_dicts(*state_dicts)
+
+    @classmethod
+    def synthetic(cls, dit_seed: int = 0, vocoder_seed: int = 1, **kw) -> "SmallTTS":
+        """Engine on seeded random weights of the reference architecture (no checkpoint can be fetched offline)."""
+        from . import synthetic
+
+        return cls(state_dicts=(synthetic.dit_state_dict(dit_seed), synthetic.vocoder_state_dict(vocoder_seed)), **kw)
+
+    # ------------------------------------------------------------------ reference API
+    def synthesize(self, ref_latents: np.ndarray, phoneme_ids: List[int], duration_sec: float,
+                   noise: Optional[np.ndarray] = None) -> np.ndarray:
+        """infer/onnx.py:68-129: (R,64) f32, token ids, seconds -> (1, samples) f32 @ 24 kHz."""
+        if noise is not None:
+            noise = np.asarray(noise, dtype=np.float32)
+            if noise.ndim == 3:  # (steps, T, 64) -> (steps, 1, T, 64)
+                noise = noise[:, None]
+        return self.synthesize_batch([ref_latents], [phoneme_ids], [duration_sec], noise=noise)[0]
+
+    def synthesize_batch(self, ref_latents: Sequence, phoneme_ids: Sequence[Sequence[int]],
+                         durations: Sequence[float], noise=None, seed: Optional[int] = None) -> List[np.ndarray]:
+        """Ragged batch in one engine call.  noise: optional (steps, B, Tmax, 64).  Returns [(1, frames_i*3200)]."""
+        if not (len(ref_latents) == len(phoneme_ids) == len(durations)) or len(durations) == 0:
+            raise ValueError("ref_latents, phoneme_ids and durations must be equally long and non-empty")
+        frames = [frames_for(d) for d in durations]
+        T = max(frames)
+        ref, ref_len, ids, ph_len = pad_batch(ref_latents, phoneme_ids, frames)
+        if seed is None:
+            seed = self._seed + self._calls
+        self._calls += 1
+        audio = self.engine.synthesize(ref, ref_len, ids, ph_len, frames, T, noise=noise, seed=seed,
+                                       steps=self.num_steps)
+        return [audio[i : i + 1, : frames[i] * HOP_SIZE].copy() for i in range(len(frames))]
+
+    def forward(self, conditionings: List, transcriptions: list, texts: list, duration_sec: float = 3.0) -> List:
+        """infer/onnx.py:131-157: tokens = transcription tokens + text tokens, one shared duration; returns a list of
+        torch tensors (1, samples).  Unlike the reference loop this is a single batched engine call."""
+        import torch
+
+        toks = [_tokens(tr) + _tokens(tx) for tr, tx in zip(transcriptions, texts)]
+        conds = list(conditionings)[: len(toks)]
+        if not toks:
+            return []
+        out = self.synthesize_batch(conds, toks, [duration_sec] * len(toks))
+        return [torch.from_numpy(a) for a in out]
+
+    __call__ = forward
