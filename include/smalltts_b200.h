@@ -119,6 +119,11 @@ uint64_t stts_launch_count(void);
  * which: 0 = HBM-bound tail (stages with C <= 128 + head), 1 = tensor-bound front (stem .. C >= 256). */
 float stts_last_vocoder_ms(const stts_engine* e, int which);
 
+/* Device-side stopwatch on the engine's stream (CUDA events): start records, stop records + synchronises and
+ * returns the elapsed milliseconds of everything the engine ran in between. */
+int stts_timer_start(stts_engine* e);
+int stts_timer_stop(stts_engine* e, float* ms);
+
 /* Pinned host memory helpers for callers that want truly asynchronous copies. */
 void* stts_host_alloc(size_t bytes);
 void stts_host_free(void* p);

@@ -46,6 +46,8 @@ SIGNATURES = {
     "stts_get_timings": (C.c_int, [vp, C.POINTER(Timing)]),
     "stts_launch_count": (C.c_uint64, []),
     "stts_last_vocoder_ms": (C.c_float, [vp, C.c_int]),
+    "stts_timer_start": (C.c_int, [vp]),
+    "stts_timer_stop": (C.c_int, [vp, c_f32p]),
     "stts_host_alloc": (vp, [C.c_size_t]),
     "stts_host_free": (None, [vp]),
     "stts_test_gemm": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int,

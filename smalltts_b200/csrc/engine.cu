@@ -32,6 +32,7 @@ struct Err : std::runtime_error {
   } while (0)
 
 constexpr int D = 960, H = 8, HD = 120, HDP = 128, FF = 2400, NBLK = 12, LAT = 64;
+constexpr int DP = 1024;  // 16 conv groups x (60 -> 64) padded channel layout of the conv position embedding
 constexpr int MOD_LD = NBLK * 6 * D + 2 * D;  // per-timestep adaLN table: 12 x [6][960] + final [2][960]
 constexpr int ROPE_MAX = 4096;                // dit.py:139, style.py:140, phonemes.py:196
 const int VOC_R[6] = {8, 5, 5, 4, 2, 2};
@@ -108,8 +109,8 @@ struct stts_engine {
   // packed DiT-side weights
   EncW style, text;
   bf16 *style_in_w, *style_out_w, *ph_proj_w, *wkv_ref, *wkv_text, *in_proj_w, *conv1_w, *conv2_w, *vel_w;
-  float *style_in_b, *bkv_ref, *bkv_text;
-  const float *style_out_b, *ph_proj_b, *in_proj_b, *conv1_b, *conv2_b, *vel_b, *text_emb;
+  float *style_in_b, *bkv_ref, *bkv_text, *in_proj_b, *conv1_b;
+  const float *style_out_b, *ph_proj_b, *conv2_b, *vel_b, *text_emb;
   std::vector<DitBlockW> blk;
   float *cos64, *sin64, *cos128, *sin128;
   std::map<uint32_t, float*> mod_cache;  // timestep bits -> device adaLN table [MOD_LD]
@@ -125,6 +126,7 @@ struct stts_engine {
   stts_timing timing = {0, 0, 0, 0, 0};
   float voc_ms[2] = {0, 0};
   cudaEvent_t ev[8];
+  cudaEvent_t ev_stop = nullptr;
 
   const RawTensor& W(int model, const std::string& name, std::initializer_list<int64_t> shape) {
     auto it = raw[model].find(name);
@@ -246,7 +248,11 @@ void finalize(stts_engine* e) {
   cudaStream_t st = e->st;
   // ---- style encoder (style.py:118-174).  exp(log_scale) (style.py:167) is folded into in_proj.
   float log_scale = 0.f;
-  CK(cudaMemcpy(&log_scale, e->W(0, "style_encoder.log_scale", {}).d, 4, cudaMemcpyDeviceToHost));
+  {
+    auto it = e->raw[0].find("style_encoder.log_scale");
+    if (it == e->raw[0].end() || it->second.numel != 1) throw Err(STTS_ERR_WEIGHTS, "missing/bad weight: style_encoder.log_scale");
+    CK(cudaMemcpy(&log_scale, it->second.d, 4, cudaMemcpyDeviceToHost));
+  }
   const float sscale = expf(log_scale);
   e->style_in_w = pack_lin(e, e->W(0, "style_encoder.in_proj.weight", {512, 64}), 512, 64, nullptr, 0, 0, ROW_PLAIN,
                            COL_PLAIN, sscale);
@@ -261,14 +267,23 @@ void finalize(stts_engine* e) {
   e->ph_proj_w = pack_lin(e, e->W(0, "dit.phoneme_proj.weight", {D, 512}), D, 512);
   e->ph_proj_b = e->W(0, "dit.phoneme_proj.bias", {D}).d;
   // ---- DiT input embedding (dit.py:215-253)
-  e->in_proj_w = pack_lin(e, e->W(0, "dit.input_embed.proj.weight", {D, 64}), D, 64);
-  e->in_proj_b = e->W(0, "dit.input_embed.proj.bias", {D}).d;
+  // The grouped k=31 convs read 16 groups of 60 channels.  TMA box starts must be 16-byte aligned, so the conv
+  // input lives in a padded layout (group g at columns [64g, 64g+60), pads zero): proj emits that layout directly.
+  e->in_proj_w = e->dalloc<bf16>(static_cast<size_t>(DP) * 64);
+  CK(pack_conv_taps(st, e->W(0, "dit.input_embed.proj.weight", {D, 64}).d, D, 64, 1, 64, 60, 64, e->in_proj_w, 64));
+  e->in_proj_b = e->dalloc<float>(DP);
+  CK(pack_vector(st, e->W(0, "dit.input_embed.proj.bias", {D}).d, D, 1.f, ROW_GROUPPAD_60_64, 0, e->in_proj_b));
   for (int c = 0; c < 2; ++c) {
     const std::string p = std::string("dit.input_embed.conv_pos_embed.conv") + (c ? "2" : "1");
     bf16* w = e->dalloc<bf16>(static_cast<size_t>(16) * 64 * 31 * 64);
     CK(pack_conv_taps(st, e->W(0, p + ".weight", {D, 60, 31}).d, D, 60, 31, 64, 60, 64, w, 31 * 64));
     (c ? e->conv2_w : e->conv1_w) = w;
-    (c ? e->conv2_b : e->conv1_b) = e->W(0, p + ".bias", {D}).d;
+    if (c == 0) {  // conv1 writes the padded layout again (pad columns: zero weights + zero bias -> mish(0) = 0)
+      e->conv1_b = e->dalloc<float>(DP);
+      CK(pack_vector(st, e->W(0, p + ".bias", {D}).d, D, 1.f, ROW_GROUPPAD_60_64, 0, e->conv1_b));
+    } else {
+      e->conv2_b = e->W(0, p + ".bias", {D}).d;
+    }
   }
   // ---- time / adaLN path stays fp32 (GEMV): only check presence
   e->W(0, "time_embedding.mlp.0.weight", {D, 256}); e->W(0, "time_embedding.mlp.0.bias", {D});
@@ -507,8 +522,8 @@ struct DenoiseWs {
   Tmp<float> h, x, qkvg, v;
   Tmp<bf16> hm, c1, a, qb, kb, vb, ob, hb;
   void alloc(cudaStream_t st, long long M) {
-    h.alloc(st, M * D); x.alloc(st, M * D); qkvg.alloc(st, M * 4 * D);
-    hm.alloc(st, M * D); c1.alloc(st, M * D); a.alloc(st, M * D);
+    h.alloc(st, M * DP); x.alloc(st, M * D); qkvg.alloc(st, M * 4 * D);
+    hm.alloc(st, M * DP); c1.alloc(st, M * DP); a.alloc(st, M * D);
     qb.alloc(st, M * H * HDP); kb.alloc(st, M * H * HDP); vb.alloc(st, M * H * HDP); ob.alloc(st, M * H * HDP);
     hb.alloc(st, M * FF);
   }
@@ -522,19 +537,20 @@ void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_b
   {
     GemmEpi ep;
     ep.bias = e->in_proj_b; ep.row_len = frames_dev; ep.rows_per_batch = T; ep.mask_bf16_only = 1;
-    ep.out_f32 = ws.h; ep.out_bf16 = ws.hm; ep.ld_out = D;
-    linear(e, xt_bf16, M, LAT, LAT, e->in_proj_w, D, LAT, ep);
+    ep.out_f32 = ws.h; ep.out_bf16 = ws.hm; ep.ld_out = DP;
+    linear(e, xt_bf16, M, LAT, LAT, e->in_proj_w, DP, LAT, ep);
     GemmShape s;
-    s.B = B; s.T = T; s.N = 60; s.K = 60; s.taps = 31; s.tap_shift0 = -15; s.tap_step = 1;
-    s.groups = 16; s.a_group_koff = 60; s.w_group_rows = 64; s.out_group_cols = 60;
+    s.B = B; s.T = T; s.N = 64; s.K = 64; s.taps = 31; s.tap_shift0 = -15; s.tap_step = 1;
+    s.groups = 16; s.a_group_koff = 64; s.w_group_rows = 64; s.out_group_cols = 64; s.res_group_cols = 64;
     GemmW gw1{e->conv1_w, 16 * 64, 31 * 64}, gw2{e->conv2_w, 16 * 64, 31 * 64};
     GemmEpi e1;
-    e1.bias = e->conv1_b; e1.act = ACT_MISH; e1.row_len = frames_dev; e1.out_bf16 = ws.c1; e1.ld_out = D;
-    CK(launch_gemm(st, 64, GemmA{ws.hm, D, D}, gw1, s, e1));
+    e1.bias = e->conv1_b; e1.act = ACT_MISH; e1.row_len = frames_dev; e1.out_bf16 = ws.c1; e1.ld_out = DP;
+    CK(launch_gemm(st, 64, GemmA{ws.hm, DP, DP}, gw1, s, e1));
+    s.N = 60; s.out_group_cols = 60;  // conv2 writes the dense [M, 960] residual stream; residual h is padded
     GemmEpi e2;
-    e2.bias = e->conv2_b; e2.act = ACT_MISH; e2.row_len = frames_dev; e2.residual = ws.h; e2.ld_res = D;
+    e2.bias = e->conv2_b; e2.act = ACT_MISH; e2.row_len = frames_dev; e2.residual = ws.h; e2.ld_res = DP;
     e2.out_f32 = ws.x; e2.ld_out = D;
-    CK(launch_gemm(st, 64, GemmA{ws.c1, D, D}, gw2, s, e2));
+    CK(launch_gemm(st, 64, GemmA{ws.c1, DP, DP}, gw2, s, e2));
   }
   for (int i = 0; i < NBLK; ++i) {
     const DitBlockW& w = e->blk[i];
@@ -709,6 +725,7 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+    CK(cudaEventCreate(&e->ev_stop));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, e->device));
     uint64_t thr = UINT64_MAX;
@@ -942,6 +959,19 @@ uint64_t stts_launch_count(void) { return g_launch_count; }
 
 float stts_last_vocoder_ms(const stts_engine* e, int which) {
   return (e && which >= 0 && which < 2) ? e->voc_ms[which] : -1.f;
+}
+
+int stts_timer_start(stts_engine* e) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] { CK(cudaEventRecord(e->ev[7], e->st)); });
+}
+int stts_timer_stop(stts_engine* e, float* ms) {
+  if (!e || !ms) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    CK(cudaEventRecord(e->ev_stop, e->st));
+    CK(cudaEventSynchronize(e->ev_stop));
+    CK(cudaEventElapsedTime(ms, e->ev[7], e->ev_stop));
+  });
 }
 
 void* stts_host_alloc(size_t bytes) {

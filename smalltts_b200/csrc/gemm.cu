@@ -201,7 +201,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if (e.residual != nullptr) {
-        const float* rp = e.residual + m * e.ld_res + out_c0;
+        const float* rp = e.residual + m * e.ld_res + out_c0 + g * (s.res_group_cols - s.out_group_cols);
         if (out_n == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -329,6 +329,7 @@ cudaError_t launch_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtenso
 cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const GemmW& w, const GemmShape& s,
                         const GemmEpi& e) {
   if (s.T <= 0 || s.B <= 0 || s.N <= 0 || s.K <= 0) return cudaErrorInvalidValue;
+  if (s.groups > 1 && (s.a_group_koff % 8) != 0) return cudaErrorInvalidValue;  // TMA: 16-byte aligned box start
   if ((a.ld % 8) != 0 || (w.ld % 8) != 0) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(a.ptr) & 15) || (reinterpret_cast<uintptr_t>(w.ptr) & 15)) {
     return cudaErrorInvalidValue;

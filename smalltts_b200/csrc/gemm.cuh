@@ -8,7 +8,8 @@
 //   * nn.Linear                       : taps=1, B=1, T=rows (flattened batch)
 //   * causal Conv1d k=7 (vocoder stem): taps=7, shift = tap-6        (hf:181-216)
 //   * causal ConvTranspose1d k=2r,s=r : taps=2, shift = 0,-1, N=r*Cout (hf:219-260; trim is implicit)
-//   * grouped Conv1d k=31,g=16,pad=15 : taps=31, shift = tap-15, groups=16 (dit.py:223-236)
+//   * grouped Conv1d k=31,g=16,pad=15 : taps=31, shift = tap-15, groups=16 (dit.py:223-236), channels of each
+//                                       group padded 60 -> 64 so that group offsets are 16-byte aligned
 // W is bf16 [rows, taps*Kp] K-major (nn.Linear's own [out,in] layout), Kp = K rounded up to 64.
 #pragma once
 #include <cuda.h>
@@ -32,7 +33,9 @@ struct GemmShape {
   int N = 0;         // valid output columns per group
   int K = 0;         // reduction length per tap
   int taps = 1, tap_shift0 = 0, tap_step = 1;
-  int groups = 1, a_group_koff = 0, w_group_rows = 0, out_group_cols = 0;
+  // groups: A columns start at g*a_group_koff (must be a multiple of 8 elements: TMA needs 16-byte aligned box
+  // starts), W rows at g*w_group_rows, output columns at g*out_group_cols, residual columns at g*res_group_cols
+  int groups = 1, a_group_koff = 0, w_group_rows = 0, out_group_cols = 0, res_group_cols = 0;
 };
 
 struct GemmEpi {

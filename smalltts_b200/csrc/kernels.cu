@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
 __device__ __forceinline__ int map_row(int r, int mode) {
   if (mode == ROW_INTERLEAVE16_LO) return (r >> 4) * 32 + (r & 15);
   if (mode == ROW_INTERLEAVE16_HI) return (r >> 4) * 32 + 16 + (r & 15);
+  if (mode == ROW_GROUPPAD_60_64) return (r / 60) * 64 + r % 60;
   return r;
 }
 

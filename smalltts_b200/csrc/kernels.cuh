@@ -70,7 +70,7 @@ cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, cons
                       float* out);
 
 // ---- weight packing (run once at stts_finalize_weights)
-enum PackRow : int { ROW_PLAIN = 0, ROW_INTERLEAVE16_LO = 1, ROW_INTERLEAVE16_HI = 2 };
+enum PackRow : int { ROW_PLAIN = 0, ROW_INTERLEAVE16_LO = 1, ROW_INTERLEAVE16_HI = 2, ROW_GROUPPAD_60_64 = 3 };
 enum PackCol : int { COL_PLAIN = 0, COL_HEADPAD_120_128 = 1 };
 // dst[rowmap(r) + row_off, colmap(c) + col_off] = bf16(scale * src[r, c])
 cudaError_t pack_matrix(cudaStream_t st, const float* src, int rows, int cols, float scale, int row_mode, int row_off,

@@ -81,7 +81,7 @@ class Engine:
         for model, sd in ((0, dit_sd), (1, vocoder_sd)):
             for name, t in sd.items():
                 a = t.detach().cpu().numpy() if _is_torch(t) else np.asarray(t)
-                a = np.ascontiguousarray(a, dtype=np.float32)
+                a = np.require(a, dtype=np.float32, requirements=["C"])  # keeps 0-d tensors 0-d
                 shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
                 _cabi.check(self._lib.stts_load_weight(self._h, model, name.encode(), C.c_void_p(a.ctypes.data), a.ndim,
                                                        shape), self._h)
@@ -176,6 +176,23 @@ class Engine:
     def vocoder_ms(self) -> Dict[str, float]:
         return {"tail_hbm": self._lib.stts_last_vocoder_ms(self._h, 0),
                 "front_tensor": self._lib.stts_last_vocoder_ms(self._h, 1)}
+
+    def timer_start(self) -> None:
+        _cabi.check(self._lib.stts_timer_start(self._h), self._h)
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _cabi.check(self._lib.stts_timer_stop(self._h, C.byref(ms)), self._h)
+        return float(ms.value)
+
+    def pinned(self, shape, dtype=np.float32) -> np.ndarray:
+        """numpy array backed by page-locked host memory (cudaHostAlloc) for truly asynchronous copies."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self._lib.stts_host_alloc(max(n, 1))
+        if not p:
+            raise MemoryError("cudaHostAlloc failed")
+        buf = (C.c_byte * max(n, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     @staticmethod
     def launch_count() -> int:

@@ -149,7 +149,10 @@ def test_grouped_conv_k31(eng):
     w = torch.zeros(16 * 64, 31 * 64, device="cuda", dtype=torch.bfloat16)
     wv = w.view(16, 64, 31, 64)
     wv[:, :60, :, :60] = wc.view(16, 60, 60, 31).permute(0, 1, 3, 2)
-    _, out16 = run_gemm(eng, x, w, B=B, T=T, N=60, K=60, bn=64, taps=31, shift0=-15, step=1, groups=16, a_koff=60,
+    # groups padded 60 -> 64 channels so that every TMA box start is 16-byte aligned
+    xp = torch.zeros(B, T, 1024, device="cuda", dtype=torch.bfloat16)
+    xp.view(B, T, 16, 64)[..., :60] = x.view(B, T, 16, 60)
+    _, out16 = run_gemm(eng, xp, w, B=B, T=T, N=60, K=64, bn=64, taps=31, shift0=-15, step=1, groups=16, a_koff=64,
                         w_grows=64, out_gcols=60, bias=bias, act="mish", row_len=lens, want_bf16=True, ld_out=Cdim,
                         out_cols=Cdim)
     want = torch.nn.functional.mish(
@@ -187,7 +190,8 @@ def test_attention(eng, hd, hd_pad, H):
     want = o.reshape(B * Tq, H * hd) * torch.sigmoid(gate)
     got = out.view(B * Tq, H, hd_pad)[..., :hd].reshape(B * Tq, H * hd)
     _assert_close(got, want, tol=2e-2)
-    assert out.view(B * Tq, H, hd_pad)[..., hd:].abs().max().item() == 0.0
+    if hd_pad > hd:
+        assert out.view(B * Tq, H, hd_pad)[..., hd:].abs().max().item() == 0.0
 
 
 @pytest.mark.parametrize("C_,T", [(32, 1700), (64, 900), (128, 300), (256, 130), (2048, 21)])
