@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the smalltts synthesize hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1],
+batch = 8 x 10 s utterances per GPU (T = 75 latent frames, R = 15 reference frames, P = 120 phonemes), condition
+encoder + 4-step DMD denoiser loop + VibeVoice decoder, random-init weights of the reference architecture (seeded;
+no checkpoints can be fetched offline).  Metric: audio-seconds generated per wall second (= 1/RTF, the reference's
+bench.rs:69-71), aggregated over all GPUs.
+
+  value : device-timed (CUDA events on the engine stream), inputs resident in HBM, output left in HBM
+  e2e   : the same through the public Python API / C ABI with pinned HOST buffers; H2D of inputs and D2H of the
+          waveform are inside the timed region
+  --impl reference : the reference's own CPU path (PyTorch fp32 restatement in oracle/, all host threads), a bounded
+          sample of the same workload per step (1 utterance x 10 s; the reference is sequential per utterance)
+
+N > 1: one process per GPU (torchrun), utterance batches are independent -> weak scaling, no data-path collective;
+NCCL only for the barrier and the max-over-ranks of the timings.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH, T, R, P, STEPS_DMD = 8, 75, 15, 120, 4
+AUDIO_S_PER_UTT = T * 3200 / 24000.0
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+WORKLOAD = "configs[1]: batch=8 x 10 s utterances per GPU (T=75, R=15, P=120), DMD 4-step DiT + vocoder"
+
+
+def tail_algorithmic_bytes(batch: int, frames: int) -> float:
+    """fp32 activations, every conv / ConvNeXt layer reads its input once and writes its output
+    once.  Vocoder HBM-bound tail = stages with C <= 128 (up3, up4, up5) + head."""
+    total = 0.0
+    rows_in, c_in = frames * 200, 256  # output of up2
+    for r, c in ((4, 128), (2, 64), (2, 32)):
+        rows = rows_in * r
+        total += rows_in * c_in * 4 + rows * c * 4  # transposed conv: read input, write output
+        total += 3 * 2 * rows * c * 4  # three ConvNeXt layers
+        rows_in, c_in = rows, c
+    total += rows_in * 32 * 4 + rows_in * 4  # head conv 32 -> 1
+    return total * batch
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference_run(steps: int, warmup: int):
+    """The reference's own CPU implementation of the path, restated in oracle/ (PyTorch fp32, torch threads = all
+    host cores).  Each step = ONE utterance of the workload (10 s, R=15, P=120): the reference processes a batch as a
+    sequential loop over utterances (infer/onnx.py:143-156, bench.rs:29), so its batch throughput equals its
+    single-utterance throughput."""
+    import torch
+
+    from oracle import smalltts_oracle as O
+    from smalltts_b200 import synthetic
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd, vsd = synthetic.dit_state_dict(0), synthetic.vocoder_state_dict(1)
+    refs, ids, frames, noise = synthetic.synthetic_inputs(1, T, R, P)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.synthesize_batch(sd, vsd, refs, ids, frames, noise)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    return AUDIO_S_PER_UTT / per_step, per_step, torch.get_num_threads()
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    value, per_step, cores = cpu_reference_run(steps, warmup)
+    sample = f"{steps} steps x 1 utterance x 10 s (T=75,R=15,P=120), {warmup} warm-up; sequential per utterance like the reference"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_path": "PyTorch fp32 CPU restatement (oracle/); onnxruntime and the "
+                   ".onnx assets are not available offline"},
+        "rtf": 1.0 / value,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------ our arm (B200)
+def main_ours(args, rank, local_rank, world):
+    import torch
+
+    from smalltts_b200 import synthetic
+    from smalltts_b200.engine import Engine, pad_batch
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = f"cuda:{local_rank}"
+    eng = Engine(local_rank)
+    eng.load_state_dicts(synthetic.dit_state_dict(0), synthetic.vocoder_state_dict(1))
+
+    # per-rank batch: same shapes, rank-dependent content
+    refs, ids, frames, _ = synthetic.synthetic_inputs(BATCH, T, R, P, seed=20260217 + rank)
+    ref, ref_len, idt, ph_len = pad_batch(refs, ids, frames)
+    d_ref = torch.from_numpy(ref).to(dev)
+    d_ids = torch.from_numpy(idt).to(dev)
+    d_out = torch.empty(BATCH, T * 3200, dtype=torch.float32, device=dev)
+    h_ref, h_ids = eng.pinned(ref.shape), eng.pinned(idt.shape, np.int64)
+    h_ref[...] = ref
+    h_ids[...] = idt
+    h_out = eng.pinned((BATCH, T * 3200))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        eng.synthesize(d_ref, ref_len, d_ids, ph_len, frames, T, seed=1000 + i, steps=STEPS_DMD, out=d_out)
+
+    def step_host(i):
+        eng.synthesize(h_ref, ref_len, h_ids, ph_len, frames, T, seed=1000 + i, steps=STEPS_DMD, out=h_out)
+
+    def timed(fn, steps, warmup, sample_clocks):
+        for i in range(warmup):
+            fn(i)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        l0 = Engine.launch_count()
+        tail = front = 0.0
+        stage = {"cond_enc_ms": 0.0, "denoise_ms": 0.0, "codec_dec_ms": 0.0}
+        eng.timer_start()
+        w0 = time.perf_counter()
+        for i in range(steps):
+            fn(warmup + i)
+            v = eng.vocoder_ms()
+            tail += v["tail_hbm"]
+            front += v["front_tensor"]
+            tm = eng.timings()
+            for k in stage:
+                stage[k] += tm[k]
+        dev_ms = eng.timer_stop()
+        barrier()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        launches = Engine.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), launches, tail / steps, front / steps, {k: v / steps for k, v in stage.items()}, clocks
+
+    dev_ms, wall_ms, launches, tail_ms, front_ms, stage, clocks = timed(step_device, args.steps, args.warmup, True)
+    e2e_ms, e2e_wall, _, _, _, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2), False)
+
+    # correctness guard inside the bench: finite, non-trivial output
+    a = d_out[:, ::997].float().cpu().numpy()
+    assert np.isfinite(a).all() and a.std() > 0, "engine produced non-finite or constant audio"
+
+    audio_s = BATCH * AUDIO_S_PER_UTT * world * args.steps
+    value = audio_s / (dev_ms / 1e3)
+    e2e_value = audio_s / (e2e_wall / 1e3)
+    peak, peak_src = measured_peaks()
+    tail_bytes = tail_algorithmic_bytes(BATCH, T)
+    achieved = tail_bytes / (tail_ms / 1e3) / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, per_step, cores = cpu_reference_run(3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "3 steps x 1 utterance x 10 s (T=75,R=15,P=120) after 1 warm-up; reference semantics "
+                         "(sequential per utterance), PyTorch fp32 oracle"}
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "dmd_steps": STEPS_DMD, "noise": "on-device Philox",
+                       "l2": "no explicit flush: per-step working set (1.3 GB bf16 weights + >1 GB activations) >> 126 MB L2",
+                       "weights": "seeded random init of the reference architecture (328 M DiT + 344 M vocoder params)"},
+            "rtf": (dev_ms / 1e3) / audio_s,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "stage_ms": stage,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_wall / args.steps,
+                    "h2d_bytes_per_step": int(ref.nbytes + idt.nbytes), "d2h_bytes_per_step": int(BATCH * T * 3200 * 4),
+                    "api": "Engine.synthesize / stts_synthesize with pinned host buffers, wall clock around the call"},
+            "roofline": {"bound": "hbm", "kernel": "vocoder tail (stages up3..up5 with C<=128 + head): token-mixer + "
+                         "tcgen05 FFN GEMMs + transposed-conv GEMMs, CUDA events around the group on the engine stream",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_bytes": tail_bytes, "ms": tail_ms, "traffic": None,
+                         "front_ms": front_ms},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        main_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

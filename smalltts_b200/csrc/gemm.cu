@@ -20,42 +20,59 @@ constexpr int kThreads = 192;
 
 template <int BN>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kMaxStages = (BN == 256) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kSmem = kStages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int smem_bytes(int stages) {
+    return stages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+  }
 };
+
+// Branch-free activations built on ex2/rcp (MUFU), accurate far below the bf16 rounding of their consumers.
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  return __frcp_rn(1.0f + exp2f(-1.4426950408889634f * x));
+}
+// erf-GELU: 0.5 x (1 + tanh(u)) = x * sigmoid(2u) with u = x (a + b x^2 + c x^4), coefficients fitted to
+// 0.5 x (1 + erf(x / sqrt 2)) on [-10, 10]: max abs error 2.6e-5 (the usual 2-term tanh form has 4.7e-4).
+// Input clamped to +-8 where the quintic is still monotone; beyond that GELU(x) = max(x, 0) to fp32 accuracy.
+__device__ __forceinline__ float fast_gelu(float x) {
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+  const float x2 = xc * xc;
+  // -2 * log2(e) * (a, b, c)
+  const float p = fmaf(x2, fmaf(x2, 1.0153833e-3f, -0.10678167f), -2.3011139f);
+  return x * __frcp_rn(1.0f + exp2f(xc * p));
+}
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {
     case ACT_GELU:
-      return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+      return fast_gelu(v);
     case ACT_MISH: {
       float sp = v > 20.0f ? v : log1pf(expf(v));
       return v * tanhf(sp);
     }
     case ACT_SIGMOID:
-      return 1.0f / (1.0f + expf(-v));
+      return fast_sigmoid(v);
     case ACT_SILU:
-      return v / (1.0f + expf(-v));
+      return v * fast_sigmoid(v);
     default:
       return v;
   }
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmShape s,
-            const GemmEpi e) {
+            const GemmEpi e, const int kStages) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* smA = smem;
-  uint8_t* smB = smem + C::kStages * C::kABytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smB + C::kStages * C::kBBytes);
-  uint64_t* empty = full + C::kStages;
-  uint64_t* acc_full = empty + C::kStages;
+  uint8_t* smB = smem + kStages * C::kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smB + kStages * C::kBBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -72,7 +89,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
@@ -90,8 +107,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < iters; ++it) {
-        const int st = it % C::kStages;
-        const uint32_t ph = (it / C::kStages) & 1;
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
         const int tap = it / kchunks;
         const int kc = it - tap * kchunks;
         ptx::mbar_wait(&empty[st], ph ^ 1);
@@ -106,8 +123,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
       for (int it = 0; it < iters; ++it) {
-        const int st = it % C::kStages;
-        const uint32_t ph = (it / C::kStages) & 1;
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
         ptx::mbar_wait(&full[st], ph);
         ptx::tc_fence_after();
         const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smA + st * C::kABytes));
@@ -163,7 +180,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float a = v[i];
-          v[i] = a / (1.0f + expf(-a)) * v[16 + i];
+          v[i] = a * fast_sigmoid(a) * v[16 + i];
         }
         out_c0 = gc0 >> 1;
         out_n = ncols >> 1;
@@ -173,31 +190,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           v[i] = act_apply(v[i], e.act);
         }
       }
-      float vb[32];  // value destined for the bf16 output (may be masked differently)
+      // row masking: the fp32 output keeps the unmasked value when only the bf16 copy is masked
+      const bool mask32 = masked && !e.mask_bf16_only;
+      if (mask32) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        vb[i] = masked ? 0.0f : v[i];
-        if (masked && !e.mask_bf16_only) v[i] = 0.0f;
+        for (int i = 0; i < 32; ++i) v[i] = 0.0f;
       }
       if (e.colscale != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (i < out_n) {
-            const float sc = __ldg(e.colscale + out_c0 + i);
-            v[i] *= sc;
-            vb[i] *= sc;
-          }
+          if (i < out_n) v[i] *= __ldg(e.colscale + out_c0 + i);
         }
       }
       if (e.rowgate != nullptr) {
         const float* gp = e.rowgate + static_cast<long long>(eb) * e.ld_gate + out_c0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (i < out_n) {
-            const float sc = __ldg(gp + i);
-            v[i] *= sc;
-            vb[i] *= sc;
-          }
+          if (i < out_n) v[i] *= __ldg(gp + i);
         }
       }
       if (e.residual != nullptr) {
@@ -207,16 +216,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int i = 0; i < 8; ++i) {
             const float4 x = *reinterpret_cast<const float4*>(rp + 4 * i);
             v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
-            vb[4 * i + 0] += x.x; vb[4 * i + 1] += x.y; vb[4 * i + 2] += x.z; vb[4 * i + 3] += x.w;
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if (i < out_n) {
-              const float x = rp[i];
-              v[i] += x;
-              vb[i] += x;
-            }
+            if (i < out_n) v[i] += rp[i];
           }
         }
       }
@@ -235,16 +239,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if (e.out_bf16 != nullptr) {
+        const float bz = (masked && e.mask_bf16_only) ? 0.0f : 1.0f;  // bf16-only masking (no scale/residual there)
         __nv_bfloat16* op = e.out_bf16 + m * e.ld_out + out_c0;
         if ((out_n == 32 || out_n == 16) && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (8 * i < out_n) {
               uint4 pk;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(vb[8 * i + 0], vb[8 * i + 1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(vb[8 * i + 2], vb[8 * i + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(vb[8 * i + 4], vb[8 * i + 5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(vb[8 * i + 6], vb[8 * i + 7]);
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(bz * v[8 * i + 0], bz * v[8 * i + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(bz * v[8 * i + 2], bz * v[8 * i + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(bz * v[8 * i + 4], bz * v[8 * i + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(bz * v[8 * i + 6], bz * v[8 * i + 7]);
               pk.x = *reinterpret_cast<uint32_t*>(&p0);
               pk.y = *reinterpret_cast<uint32_t*>(&p1);
               pk.z = *reinterpret_cast<uint32_t*>(&p2);
@@ -255,7 +260,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if (i < out_n) op[i] = __float2bfloat16_rn(vb[i]);
+            if (i < out_n) op[i] = __float2bfloat16_rn(bz * v[i]);
           }
         }
       }
@@ -312,14 +317,19 @@ cudaError_t launch_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtenso
                       const GemmEpi& e) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err =
-        cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<BN>::smem_bytes(Cfg<BN>::kMaxStages));
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
   const int tiles_t = (s.T + BM - 1) / BM;
   dim3 grid((s.N + BN - 1) / BN, s.B * tiles_t, s.groups);
-  gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, stream>>>(tmA, tmW, s, e);
+  // Short reductions need few pipeline stages; the smaller footprint lets 2-3 CTAs share an SM so that one CTA's
+  // epilogue overlaps another's loads and MMAs.
+  const int iters = s.taps * ((s.K + BK - 1) / BK);
+  int stages = iters < 2 ? 2 : iters;
+  if (stages > Cfg<BN>::kMaxStages) stages = Cfg<BN>::kMaxStages;
+  gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::smem_bytes(stages), stream>>>(tmA, tmW, s, e, stages);
   ++g_launch_count;
   return cudaGetLastError();
 }

@@ -540,29 +540,40 @@ __global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restri
   }
 }
 
+// 256 outputs per CTA; the 262 input rows are staged in shared memory with coalesced float4 loads (row pitch C+1
+// words so that the per-thread sliding reads below are bank-conflict free).
 __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int T, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         float* __restrict__ out) {
-  extern __shared__ float sw[];  // [7][C] tap-major
+  extern __shared__ float sh[];
+  float* sw = sh;            // [7][C] tap-major
+  float* sx = sh + 7 * C;    // [262][C + 1]
+  const int P = C + 1;
   for (int i = threadIdx.x; i < 7 * C; i += 256) {
     const int j = i / C, c = i % C;
     sw[i] = w[c * 7 + j];
   }
-  __syncthreads();
   const int b = blockIdx.y;
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= T) return;
+  const int t0 = blockIdx.x * 256;
   const float* xb = x + static_cast<long long>(b) * T * C;
+  const int cv = C >> 2;
+  for (int i = threadIdx.x; i < 262 * cv; i += 256) {
+    const int r = i / cv, c4 = i % cv;
+    const int t = t0 - 6 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < T) v = reinterpret_cast<const float4*>(xb + static_cast<long long>(t) * C)[c4];
+    float* d = sx + r * P + 4 * c4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= T) return;
   float acc = bias[0];
   for (int j = 0; j < 7; ++j) {
-    const int tt = t - 6 + j;
-    if (tt < 0) continue;
-    const float4* row = reinterpret_cast<const float4*>(xb + static_cast<long long>(tt) * C);
-    const float4* wr = reinterpret_cast<const float4*>(sw + j * C);
-    for (int c = 0; c < (C >> 2); ++c) {
-      const float4 xv = row[c], wv = wr[c];
-      acc += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
-    }
+    const float* row = sx + (threadIdx.x + j) * P;
+    const float* wr = sw + j * C;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) acc = fmaf(row[c], wr[c], acc);
   }
   out[static_cast<long long>(b) * T + t] = acc;
 }
@@ -745,7 +756,8 @@ cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, cons
                       float* out) {
   if (C % 4 != 0) return cudaErrorInvalidValue;
   dim3 grid((T + 255) / 256, B);
-  head_conv_kernel<<<grid, 256, 7 * C * 4, st>>>(x, T, C, w, bias, out);
+  if (C > 40) return cudaErrorInvalidValue;  // 262 x (C+1) fp32 tile must fit the default 48 KB
+  head_conv_kernel<<<grid, 256, (7 * C + 262 * (C + 1)) * 4, st>>>(x, T, C, w, bias, out);
   STTS_LAUNCH_OK();
 }
 
