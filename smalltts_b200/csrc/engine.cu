@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <functional>
+#include <array>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -88,6 +89,10 @@ struct Tmp {  // stream-ordered temporary
 
 }  // namespace
 
+namespace {
+struct Plan;
+}
+
 struct stts_cond {
   int B = 0, R = 0, P = 0;
   int *ref_len = nullptr, *ph_len = nullptr;  // device int32 [B]
@@ -122,6 +127,13 @@ struct stts_engine {
   bf16* up_w[6];
   float* up_b[6];
   const float *head_w, *head_b;
+
+  // per-shape persistent plans (buffers + CUDA graphs) used by stts_synthesize
+  std::map<std::array<int, 5>, Plan*> plans;
+  uint64_t use_counter = 0;
+  bool use_graphs = true;
+  unsigned long long* seed_dev = nullptr;   // device u64 read by the Philox kernel
+  unsigned long long* seed_host = nullptr;  // pinned staging for seed_dev
 
   stts_timing timing = {0, 0, 0, 0, 0};
   float voc_ms[2] = {0, 0};
@@ -407,6 +419,8 @@ void encoder_block(stts_engine* e, const EncW& W, const EncBlockW& bw, float* x,
   linear(e, hb, M, W.inter, W.inter, bw.w2, d, W.inter, e2);
 }
 
+void encode_conditions_core(stts_engine* e, stts_cond* c, const float* dref, const long long* dids);
+
 stts_cond* encode_conditions(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* ids,
                              const int64_t* ph_len, int B, int R, int P, int mem) {
   if (B < 1 || R < 1 || P < 1 || R > ROPE_MAX || P > ROPE_MAX) throw Err(STTS_ERR_INVALID, "bad B/R/P");
@@ -431,7 +445,22 @@ stts_cond* encode_conditions(stts_engine* e, const float* ref, const int64_t* re
     const float* dref = to_dev(e, ref, static_cast<size_t>(B) * R * LAT, mem, href);
     const long long* dids = reinterpret_cast<const long long*>(
         to_dev(e, reinterpret_cast<const long long*>(ids), static_cast<size_t>(B) * P, mem, hids));
+    encode_conditions_core(e, c, dref, dids);
+    CK(cudaStreamSynchronize(st));
+  } catch (...) {
+    cudaFree(c->ref_len); cudaFree(c->ph_len); cudaFree(c->kv_ref); cudaFree(c->kv_text);
+    delete c;
+    throw;
+  }
+  return c;
+}
 
+// Launch-only part of the condition encoder (no allocation of persistent state, no synchronisation): safe to
+// capture into a CUDA graph.  `c` carries device lengths and the K/V cache buffers to fill.
+void encode_conditions_core(stts_engine* e, stts_cond* c, const float* dref, const long long* dids) {
+  cudaStream_t st = e->st;
+  const int B = c->B, R = c->R, P = c->P;
+  {
     for (int src = 0; src < 2; ++src) {
       const int N = src == 0 ? R : P;
       const long long M = static_cast<long long>(B) * N;
@@ -473,13 +502,7 @@ stts_cond* encode_conditions(stts_engine* e, const float* ref, const int64_t* re
                            cache + (2 * i + 1) * stride));
       }
     }
-    CK(cudaStreamSynchronize(st));
-  } catch (...) {
-    cudaFree(c->ref_len); cudaFree(c->ph_len); cudaFree(c->kv_ref); cudaFree(c->kv_text);
-    delete c;
-    throw;
   }
-  return c;
 }
 
 // ------------------------------------------------------------------ adaLN tables (function of t only)
@@ -602,17 +625,29 @@ void alpha_sigma(float t32, float* alpha, float* sigma) {  // infer/onnx.py:31-3
 }
 
 // DMD loop of infer/onnx.py:98-125 on device. noise_dev may be null (Philox). out: device [B,T,64].
-void sample(stts_engine* e, const stts_cond* c, const int* frames_dev, int B, int T, int steps, const float* timesteps,
-            const float* noise_dev, uint64_t seed, float* x_pred) {
-  cudaStream_t st = e->st;
-  const long long n = static_cast<long long>(B) * T * LAT;
+std::vector<float> resolve_timesteps(int steps, const float* timesteps) {
   std::vector<float> ts(steps);
-  for (int s = 0; s < steps; ++s) {
+  for (int s = 0; s < steps; ++s) {  // default: np.linspace(1, 0, steps, dtype=float32) (infer/onnx.py:102)
     ts[s] = timesteps ? timesteps[s]
                       : (steps == 1 ? 1.0f : static_cast<float>(1.0 + (0.0 - 1.0) * static_cast<double>(s) / (steps - 1)));
   }
-  std::vector<const float*> mods(steps);
-  for (int s = 0; s < steps; ++s) mods[s] = cached_mod(e, ts[s]);
+  return ts;
+}
+
+// Build (or fetch) the adaLN tables of every timestep.  Allocates and synchronises, so it runs BEFORE any capture.
+std::vector<const float*> prepare_mods(stts_engine* e, const std::vector<float>& ts) {
+  std::vector<const float*> mods(ts.size());
+  for (size_t s = 0; s < ts.size(); ++s) mods[s] = cached_mod(e, ts[s]);
+  return mods;
+}
+
+// Launch-only (graph-capturable).  seed_dev: device u64 read by the Philox kernel when noise_dev is null.
+void sample(stts_engine* e, const stts_cond* c, const int* frames_dev, int B, int T, const std::vector<float>& ts,
+            const std::vector<const float*>& mods, const float* noise_dev, const unsigned long long* seed_dev,
+            float* x_pred) {
+  cudaStream_t st = e->st;
+  const int steps = static_cast<int>(ts.size());
+  const long long n = static_cast<long long>(B) * T * LAT;
   DenoiseWs ws;
   ws.alloc(st, static_cast<long long>(B) * T);
   Tmp<float> xt(st, n), v(st, n), nz;
@@ -623,7 +658,7 @@ void sample(stts_engine* e, const stts_cond* c, const int* frames_dev, int B, in
     float alpha, sigma;
     alpha_sigma(ts[s], &alpha, &sigma);
     const float* nzs = noise_dev ? noise_dev + s * n : nz.p;
-    if (noise_dev == nullptr) CK(philox_normal(st, seed, static_cast<unsigned long long>(s), n, nz));
+    if (noise_dev == nullptr) CK(philox_normal(st, seed_dev, static_cast<unsigned long long>(s), n, nz));
     CK(noise_mix(st, x_pred, nzs, alpha, sigma, n, xt, xtb));
     denoise(e, c, ws, xtb, frames_dev, mods[s], 0, B, T, v);
     CK(dmd_update(st, xt, v, alpha, sigma, n, x_pred));
@@ -631,50 +666,178 @@ void sample(stts_engine* e, const stts_cond* c, const int* frames_dev, int B, in
 }
 
 // ------------------------------------------------------------------ vocoder (hf:406-500)
-void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev) {
+struct VocWs {  // activations of one decode; persistent inside a Plan, temporaries otherwise
+  float *xa = nullptr, *xb = nullptr;
+  bf16 *a = nullptr, *hbuf = nullptr, *xh = nullptr, *latb = nullptr;
+  static size_t act_elems(long long frames) { return static_cast<size_t>(frames) * 102400; }  // max rows*C per frame
+};
+enum VocPart : int { VOC_FRONT = 1, VOC_TAIL = 2, VOC_ALL = 3 };
+
+// Launch-only (graph-capturable).  FRONT = stem + stages with C >= 256 (tensor-bound) incl. the upsampler into
+// C = 128; TAIL = stages with C <= 128 + head (HBM-bound).  Stage s works in buffer (s even ? xa : xb).
+void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev, const VocWs& ws, int part) {
   cudaStream_t st = e->st;
   const long long frames = static_cast<long long>(B) * T;
-  const size_t act = static_cast<size_t>(frames) * 102400;  // max over stages of rows*C per latent frame
-  Tmp<float> xa(st, act), xb(st, act);
-  Tmp<bf16> a(st, act), hbuf(st, act * 4), xh(st, act), latb(st, frames * LAT);
-  CK(cudaEventRecord(e->ev[4], st));
-  CK(cast_bf16(st, lat_dev, frames * LAT, latb));
-  {  // stem: causal Conv1d(64 -> 2048, k=7) as a 7-tap GEMM
+  if (part & VOC_FRONT) {
+    CK(cast_bf16(st, lat_dev, frames * LAT, ws.latb));
+    // stem: causal Conv1d(64 -> 2048, k=7) as a 7-tap GEMM
     GemmShape s;
     s.B = B; s.T = T; s.N = 2048; s.K = 64; s.taps = 7; s.tap_shift0 = -6; s.tap_step = 1;
     GemmEpi ep;
-    ep.bias = e->stem_b; ep.out_f32 = xa; ep.ld_out = 2048;
-    CK(launch_gemm(st, pick_bn(frames, 2048), GemmA{latb, LAT, LAT}, GemmW{e->stem_w, 2048, 7 * 64}, s, ep));
+    ep.bias = e->stem_b; ep.out_f32 = ws.xa; ep.ld_out = 2048;
+    CK(launch_gemm(st, pick_bn(frames, 2048), GemmA{ws.latb, LAT, LAT}, GemmW{e->stem_w, 2048, 7 * 64}, s, ep));
   }
   int Ts = T;
   for (int s = 0; s < 7; ++s) {
     const int C = VOC_C[s];
     const long long M = static_cast<long long>(B) * Ts;
-    if (s == 4) CK(cudaEventRecord(e->ev[5], st));  // C <= 128 from here on: the HBM-bound tail
-    for (size_t l = 0; l < e->voc[s].size(); ++l) {
-      const VocLayerW& w = e->voc[s][l];
-      CK(convnext_mix(st, xa, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, xb, a));
-      GemmEpi e1;
-      e1.bias = w.b1; e1.act = ACT_GELU; e1.out_bf16 = hbuf; e1.ld_out = 4 * C;
-      linear(e, a, M, C, C, w.w1, 4 * C, C, e1);
-      GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
-      e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = xb; e2.ld_res = C; e2.out_f32 = xa; e2.ld_out = C;
-      if (s < 6 && l + 1 == e->voc[s].size()) e2.out_bf16 = xh;  // bf16 copy feeds the next upsampler
-      linear(e, hbuf, M, 4 * C, 4 * C, w.w2, C, 4 * C, e2);
+    const bool mine = (s < 4) ? (part & VOC_FRONT) != 0 : (part & VOC_TAIL) != 0;
+    float* cur = (s & 1) ? ws.xb : ws.xa;
+    float* oth = (s & 1) ? ws.xa : ws.xb;
+    if (mine) {
+      for (size_t l = 0; l < e->voc[s].size(); ++l) {
+        const VocLayerW& w = e->voc[s][l];
+        CK(convnext_mix(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, oth, ws.a));
+        GemmEpi e1;
+        e1.bias = w.b1; e1.act = ACT_GELU; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
+        linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1);
+        GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
+        e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = oth; e2.ld_res = C; e2.out_f32 = cur; e2.ld_out = C;
+        if (s < 6 && l + 1 == e->voc[s].size()) e2.out_bf16 = ws.xh;  // bf16 copy feeds the next upsampler
+        linear(e, ws.hbuf, M, 4 * C, 4 * C, w.w2, C, 4 * C, e2);
+      }
+      if (s < 6) {  // causal ConvTranspose1d(k=2r, stride=r) as a 2-tap GEMM with N = r*Cout (hf:219-260)
+        const int r = VOC_R[s], cout = VOC_C[s + 1];
+        GemmShape g;
+        g.B = B; g.T = Ts; g.N = r * cout; g.K = C; g.taps = 2; g.tap_shift0 = 0; g.tap_step = -1;
+        GemmEpi ep;
+        ep.bias = e->up_b[s]; ep.out_f32 = oth; ep.ld_out = r * cout;
+        CK(launch_gemm(st, pick_bn(M, r * cout), GemmA{ws.xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
+      }
     }
-    if (s < 6) {  // causal ConvTranspose1d(k=2r, stride=r) as a 2-tap GEMM with N = r*Cout (hf:219-260)
-      const int r = VOC_R[s], cout = VOC_C[s + 1];
-      GemmShape g;
-      g.B = B; g.T = Ts; g.N = r * cout; g.K = C; g.taps = 2; g.tap_shift0 = 0; g.tap_step = -1;
-      GemmEpi ep;
-      ep.bias = e->up_b[s]; ep.out_f32 = xb; ep.ld_out = r * cout;
-      CK(launch_gemm(st, pick_bn(M, r * cout), GemmA{xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
-      std::swap(xa.p, xb.p);
-      Ts *= r;
-    }
+    if (s < 6) Ts *= VOC_R[s];
   }
-  CK(head_conv(st, xa, B, Ts, 32, e->head_w, e->head_b, audio_dev));
-  CK(cudaEventRecord(e->ev[6], st));
+  if (part & VOC_TAIL) CK(head_conv(st, ws.xa, B, Ts, 32, e->head_w, e->head_b, audio_dev));  // stage 6 is even -> xa
+}
+
+struct VocTmp {  // stream-ordered temporaries for the stand-alone decode entry point
+  Tmp<float> xa, xb;
+  Tmp<bf16> a, hbuf, xh, latb;
+  VocWs ws;
+  VocTmp(cudaStream_t st, long long frames) {
+    const size_t act = VocWs::act_elems(frames);
+    xa.alloc(st, act); xb.alloc(st, act); a.alloc(st, act); hbuf.alloc(st, act * 4); xh.alloc(st, act);
+    latb.alloc(st, frames * LAT);
+    ws.xa = xa; ws.xb = xb; ws.a = a; ws.hbuf = hbuf; ws.xh = xh; ws.latb = latb;
+  }
+};
+
+// ------------------------------------------------------------------ plans: persistent state + CUDA graphs per shape
+// Everything stts_synthesize needs for one (B, R, P, T, steps) shape lives here, so the steady state performs no
+// allocation and no intermediate synchronisation, and the ~850 kernel launches of a step replay as four graphs
+// (condition encoder | DMD loop | vocoder front | vocoder tail) with CUDA events between them for stage timing.
+struct Plan {
+  int B = 0, R = 0, P = 0, T = 0, steps = 0;
+  stts_cond cond;
+  int* frames_dev = nullptr;
+  int* h_lens = nullptr;  // pinned [3][B]: ref_len, ph_len, frames
+  float *ref = nullptr, *noise = nullptr, *lat = nullptr, *audio = nullptr;
+  long long* ids = nullptr;
+  VocWs voc;
+  std::vector<void*> owned;
+  std::vector<float> ts;
+  std::vector<const float*> mods;
+  cudaGraphExec_t g_cond = nullptr, g_sample[2] = {nullptr, nullptr}, g_front = nullptr, g_tail = nullptr;
+  int graph_state = 0;  // 0 = not captured yet, 1 = captured, -1 = capture failed: stay eager
+  uint64_t last_use = 0;
+  template <typename T>
+  T* dalloc(size_t n) {
+    T* p = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&p), (n ? n : 1) * sizeof(T)));
+    owned.push_back(p);
+    return p;
+  }
+  void destroy() {
+    for (cudaGraphExec_t g : {g_cond, g_sample[0], g_sample[1], g_front, g_tail}) if (g) cudaGraphExecDestroy(g);
+    for (void* p : owned) cudaFree(p);
+    if (h_lens) cudaFreeHost(h_lens);
+    owned.clear();
+  }
+};
+
+void set_seed(stts_engine* e, uint64_t seed) {
+  *e->seed_host = seed;
+  CK(cudaMemcpyAsync(e->seed_dev, e->seed_host, sizeof(unsigned long long), cudaMemcpyHostToDevice, e->st));
+}
+
+Plan* get_plan(stts_engine* e, int B, int R, int P, int T, int steps) {
+  const std::array<int, 5> key = {B, R, P, T, steps};
+  auto it = e->plans.find(key);
+  if (it != e->plans.end()) {
+    it->second->last_use = ++e->use_counter;
+    return it->second;
+  }
+  if (e->plans.size() >= 6) {  // bound the memory held by cached shapes: evict the least recently used plan
+    auto victim = e->plans.begin();
+    for (auto j = e->plans.begin(); j != e->plans.end(); ++j) {
+      if (j->second->last_use < victim->second->last_use) victim = j;
+    }
+    CK(cudaStreamSynchronize(e->st));
+    victim->second->destroy();
+    delete victim->second;
+    e->plans.erase(victim);
+  }
+  Plan* p = new Plan();
+  try {
+    p->B = B; p->R = R; p->P = P; p->T = T; p->steps = steps;
+    const long long n = static_cast<long long>(B) * T * LAT, frames = static_cast<long long>(B) * T;
+    p->cond.B = B; p->cond.R = R; p->cond.P = P;
+    p->cond.ref_len = p->dalloc<int>(B);
+    p->cond.ph_len = p->dalloc<int>(B);
+    p->frames_dev = p->dalloc<int>(B);
+    p->cond.kv_ref = p->dalloc<bf16>(NBLK * 2 * p->cond.ref_stride());
+    p->cond.kv_text = p->dalloc<bf16>(NBLK * 2 * p->cond.text_stride());
+    p->ref = p->dalloc<float>(static_cast<size_t>(B) * R * LAT);
+    p->ids = p->dalloc<long long>(static_cast<size_t>(B) * P);
+    p->noise = p->dalloc<float>(static_cast<size_t>(steps) * n);
+    p->lat = p->dalloc<float>(n);
+    p->audio = p->dalloc<float>(static_cast<size_t>(frames) * STTS_HOP_SIZE);
+    const size_t act = VocWs::act_elems(frames);
+    p->voc.xa = p->dalloc<float>(act); p->voc.xb = p->dalloc<float>(act);
+    p->voc.a = p->dalloc<bf16>(act); p->voc.hbuf = p->dalloc<bf16>(act * 4); p->voc.xh = p->dalloc<bf16>(act);
+    p->voc.latb = p->dalloc<bf16>(frames * LAT);
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&p->h_lens), 3 * B * sizeof(int), cudaHostAllocDefault));
+    p->ts = resolve_timesteps(steps, nullptr);
+    p->mods = prepare_mods(e, p->ts);
+  } catch (...) {
+    p->destroy();
+    delete p;
+    throw;
+  }
+  p->last_use = ++e->use_counter;
+  e->plans[key] = p;
+  return p;
+}
+
+// Record `fn`'s launches into an executable graph (nothing runs).  Relaxed mode: the launchers make driver calls
+// (tensor-map encoding) that are not stream operations.
+template <typename F>
+cudaGraphExec_t capture(stts_engine* e, F&& fn) {
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeRelaxed));
+  try {
+    fn();
+  } catch (...) {
+    cudaStreamEndCapture(e->st, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  CK(cudaStreamEndCapture(e->st, &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (err != cudaSuccess) throw Err(STTS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+  return exec;
 }
 
 }  // namespace
@@ -726,6 +889,10 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
     CK(cudaEventCreate(&e->ev_stop));
+    CK(cudaMalloc(reinterpret_cast<void**>(&e->seed_dev), sizeof(unsigned long long)));
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&e->seed_host), sizeof(unsigned long long), cudaHostAllocDefault));
+    const char* ng = getenv("STTS_NO_GRAPH");
+    e->use_graphs = !(ng && ng[0] == '1');
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, e->device));
     uint64_t thr = UINT64_MAX;
@@ -745,7 +912,14 @@ void stts_destroy(stts_engine* e) {
   cudaStreamSynchronize(e->st);
   for (auto& m : e->raw) for (auto& kv : m) cudaFree(kv.second.d);
   for (void* p : e->owned) cudaFree(p);
+  for (auto& kv : e->plans) {
+    kv.second->destroy();
+    delete kv.second;
+  }
+  cudaFree(e->seed_dev);
+  cudaFreeHost(e->seed_host);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
+  cudaEventDestroy(e->ev_stop);
   cudaStreamDestroy(e->st);
   delete e;
 }
@@ -872,6 +1046,9 @@ int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B
     const long long n = static_cast<long long>(B) * T * LAT;
     Tmp<int> fr;
     lens_to_dev(e, frames, B, T, fr);
+    const std::vector<float> ts = resolve_timesteps(steps, timesteps);
+    const std::vector<const float*> mods = prepare_mods(e, ts);
+    set_seed(e, seed);
     Tmp<float> hn, xo;
     const float* nd = noise ? to_dev(e, noise, static_cast<size_t>(steps) * n, mem, hn) : nullptr;
     float* xd = out_latents;
@@ -879,7 +1056,7 @@ int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B
       xo.alloc(st, n);
       xd = xo;
     }
-    sample(e, c, fr, B, T, steps, timesteps, nd, seed, xd);
+    sample(e, c, fr, B, T, ts, mods, nd, e->seed_dev, xd);
     if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(out_latents, xd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   });
@@ -900,7 +1077,12 @@ int stts_decode(stts_engine* e, const float* latents, int B, int T, int mem, flo
       ao.alloc(st, na);
       ad = ao;
     }
-    decode(e, ld, B, T, ad);
+    VocTmp vt(st, static_cast<long long>(B) * T);
+    CK(cudaEventRecord(e->ev[4], st));
+    decode(e, ld, B, T, ad, vt.ws, VOC_FRONT);
+    CK(cudaEventRecord(e->ev[5], st));
+    decode(e, ld, B, T, ad, vt.ws, VOC_TAIL);
+    CK(cudaEventRecord(e->ev[6], st));
     if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(audio, ad, na * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&e->voc_ms[1], e->ev[4], e->ev[5]));
@@ -912,29 +1094,58 @@ int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, co
                     const int64_t* ph_len, const int64_t* frames, int B, int R, int P, int T, int steps,
                     const float* timesteps, const float* noise, uint64_t seed, int mem, float* audio) {
   if (!e || !ref || !ref_len || !phonemes || !ph_len || !frames || !audio) return STTS_ERR_INVALID;
-  stts_cond* c = nullptr;
-  int rc = guard_impl(e, [&] {
+  return guard_impl(e, [&] {
     need_ready(e);
-    if (T < 1 || T > ROPE_MAX || steps < 1) throw Err(STTS_ERR_INVALID, "bad synthesize arguments");
+    if (B < 1 || R < 1 || P < 1 || R > ROPE_MAX || P > ROPE_MAX || T < 1 || T > ROPE_MAX || steps < 1) {
+      throw Err(STTS_ERR_INVALID, "bad synthesize arguments");
+    }
     cudaStream_t st = e->st;
     const long long n = static_cast<long long>(B) * T * LAT;
     const long long na = static_cast<long long>(B) * T * STTS_HOP_SIZE;
-    CK(cudaEventRecord(e->ev[0], st));
-    c = encode_conditions(e, ref, ref_len, phonemes, ph_len, B, R, P, mem);
-    CK(cudaEventRecord(e->ev[1], st));
-    Tmp<int> fr;
-    lens_to_dev(e, frames, B, T, fr);
-    Tmp<float> hn, lat(st, n), ao;
-    const float* nd = noise ? to_dev(e, noise, static_cast<size_t>(steps) * n, mem, hn) : nullptr;
-    sample(e, c, fr, B, T, steps, timesteps, nd, seed, lat);
-    CK(cudaEventRecord(e->ev[2], st));
-    float* ad = audio;
-    if (mem == STTS_MEM_HOST) {
-      ao.alloc(st, na);
-      ad = ao;
+    Plan* p = get_plan(e, B, R, P, T, steps);
+    // ---- stage inputs into the plan's persistent buffers (async; no intermediate synchronisation)
+    for (int b = 0; b < B; ++b) {
+      if (ref_len[b] < 0 || ref_len[b] > R || ph_len[b] < 0 || ph_len[b] > P || frames[b] < 1 || frames[b] > T) {
+        throw Err(STTS_ERR_INVALID, "length out of range");
+      }
+      p->h_lens[b] = static_cast<int>(ref_len[b]);
+      p->h_lens[B + b] = static_cast<int>(ph_len[b]);
+      p->h_lens[2 * B + b] = static_cast<int>(frames[b]);
     }
-    decode(e, lat, B, T, ad);
-    if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(audio, ad, na * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p->cond.ref_len, p->h_lens, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->cond.ph_len, p->h_lens + B, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->frames_dev, p->h_lens + 2 * B, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    const cudaMemcpyKind in_kind = mem == STTS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(p->ref, ref, static_cast<size_t>(B) * R * LAT * sizeof(float), in_kind, st));
+    CK(cudaMemcpyAsync(p->ids, phonemes, static_cast<size_t>(B) * P * sizeof(long long), in_kind, st));
+    if (noise) CK(cudaMemcpyAsync(p->noise, noise, static_cast<size_t>(steps) * n * sizeof(float), in_kind, st));
+    set_seed(e, seed);
+    // custom timestep schedules run eagerly; the default schedule is what the graphs were captured with
+    std::vector<float> ts = resolve_timesteps(steps, timesteps);
+    const bool default_ts = (ts == p->ts);
+    std::vector<const float*> mods = default_ts ? p->mods : prepare_mods(e, ts);
+    const float* nd = noise ? p->noise : nullptr;
+    float* ad = mem == STTS_MEM_DEVICE ? audio : p->audio;
+
+    auto run_cond = [&] { encode_conditions_core(e, &p->cond, p->ref, p->ids); };
+    auto run_sample = [&](const float* nz) { sample(e, &p->cond, p->frames_dev, B, T, ts, mods, nz, e->seed_dev, p->lat); };
+    auto run_front = [&] { decode(e, p->lat, B, T, p->audio, p->voc, VOC_FRONT); };
+    auto run_tail = [&] { decode(e, p->lat, B, T, p->audio, p->voc, VOC_TAIL); };
+
+    const bool graphs = e->use_graphs && default_ts && p->graph_state == 1;
+    CK(cudaEventRecord(e->ev[0], st));
+    if (graphs) CK(cudaGraphLaunch(p->g_cond, st)); else run_cond();
+    CK(cudaEventRecord(e->ev[1], st));
+    if (graphs) CK(cudaGraphLaunch(p->g_sample[noise ? 1 : 0], st)); else run_sample(nd);
+    CK(cudaEventRecord(e->ev[2], st));
+    if (graphs) CK(cudaGraphLaunch(p->g_front, st)); else run_front();
+    CK(cudaEventRecord(e->ev[5], st));
+    if (graphs) CK(cudaGraphLaunch(p->g_tail, st)); else run_tail();
+    CK(cudaEventRecord(e->ev[6], st));
+    // the graphs write the plan's own audio buffer; hand the result to the caller
+    const cudaMemcpyKind out_kind = mem == STTS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(audio, p->audio, na * sizeof(float), out_kind, st));
+    (void)ad;
     CK(cudaEventRecord(e->ev[3], st));
     CK(cudaStreamSynchronize(st));
     e->timing.codec_enc_ms = 0.f;
@@ -942,11 +1153,24 @@ int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, co
     CK(cudaEventElapsedTime(&e->timing.denoise_ms, e->ev[1], e->ev[2]));
     CK(cudaEventElapsedTime(&e->timing.codec_dec_ms, e->ev[2], e->ev[3]));
     CK(cudaEventElapsedTime(&e->timing.total_ms, e->ev[0], e->ev[3]));
-    CK(cudaEventElapsedTime(&e->voc_ms[1], e->ev[4], e->ev[5]));
+    CK(cudaEventElapsedTime(&e->voc_ms[1], e->ev[2], e->ev[5]));
     CK(cudaEventElapsedTime(&e->voc_ms[0], e->ev[5], e->ev[6]));
+
+    // First (eager) run of this shape succeeded: capture the four stage graphs for every later call.
+    if (e->use_graphs && p->graph_state == 0 && default_ts) {
+      try {
+        p->g_cond = capture(e, run_cond);
+        p->g_sample[0] = capture(e, [&] { run_sample(nullptr); });
+        p->g_sample[1] = capture(e, [&] { run_sample(p->noise); });
+        p->g_front = capture(e, run_front);
+        p->g_tail = capture(e, run_tail);
+        p->graph_state = 1;
+      } catch (const Err&) {
+        p->graph_state = -1;  // keep working eagerly
+        cudaGetLastError();
+      }
+    }
   });
-  if (c) stts_cond_free(e, c);
-  return rc;
 }
 
 int stts_get_timings(const stts_engine* e, stts_timing* out) {

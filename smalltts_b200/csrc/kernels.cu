@@ -407,12 +407,13 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
 
-__global__ void philox_normal_kernel(unsigned long long seed, unsigned long long stream_id, long long n,
+__global__ void philox_normal_kernel(const unsigned long long* __restrict__ seed_ptr, unsigned long long stream_id, long long n,
                                      float* __restrict__ out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i * 4 >= n) return;
   uint32_t c[4] = {static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(stream_id),
                    static_cast<uint32_t>(stream_id >> 32)};
+  const unsigned long long seed = *seed_ptr;  // device-resident so that a captured graph can be re-seeded
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -726,7 +727,7 @@ cudaError_t dmd_update(cudaStream_t st, const float* x_t, const float* v, float 
   STTS_LAUNCH_OK();
 }
 
-cudaError_t philox_normal(cudaStream_t st, unsigned long long seed, unsigned long long stream_id, long long n,
+cudaError_t philox_normal(cudaStream_t st, const unsigned long long* seed, unsigned long long stream_id, long long n,
                           float* out) {
   philox_normal_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>(seed, stream_id, n, out);
   STTS_LAUNCH_OK();

@@ -55,8 +55,8 @@ cudaError_t noise_mix(cudaStream_t st, const float* x_pred, const float* noise, 
 // x_pred = alpha*x_t - sigma*v
 cudaError_t dmd_update(cudaStream_t st, const float* x_t, const float* v, float alpha, float sigma, long long n,
                        float* x_pred);
-// standard normal noise, Philox4x32-10 + Box-Muller, counter = element index
-cudaError_t philox_normal(cudaStream_t st, unsigned long long seed, unsigned long long stream_id, long long n,
+// standard normal noise, Philox4x32-10 + Box-Muller, counter = element index; seed read from device memory
+cudaError_t philox_normal(cudaStream_t st, const unsigned long long* seed, unsigned long long stream_id, long long n,
                           float* out);
 
 // ---- vocoder ConvNeXt token mixer (hf:284-292) fused with the FFN pre-norm (hf:295):
