@@ -115,6 +115,8 @@ struct stts_engine {
   EncW style, text;
   bf16 *style_in_w, *style_out_w, *ph_proj_w, *wkv_ref, *wkv_text, *in_proj_w, *conv1_w, *conv2_w, *vel_w;
   float *style_in_b, *bkv_ref, *bkv_text, *in_proj_b, *conv1_b;
+  bf16* in_proj_w_dense;
+  const float* in_proj_b_dense;
   const float *style_out_b, *ph_proj_b, *conv2_b, *vel_b, *text_emb;
   std::vector<DitBlockW> blk;
   float *cos64, *sin64, *cos128, *sin128;
@@ -285,10 +287,19 @@ void finalize(stts_engine* e) {
   CK(pack_conv_taps(st, e->W(0, "dit.input_embed.proj.weight", {D, 64}).d, D, 64, 1, 64, 60, 64, e->in_proj_w, 64));
   e->in_proj_b = e->dalloc<float>(DP);
   CK(pack_vector(st, e->W(0, "dit.input_embed.proj.bias", {D}).d, D, 1.f, ROW_GROUPPAD_60_64, 0, e->in_proj_b));
+  // ... and once more densely for the fp32 residual h (dit.py:252: conv_pos_embed(x) + x)
+  e->in_proj_w_dense = pack_lin(e, e->W(0, "dit.input_embed.proj.weight", {D, 64}), D, 64);
+  e->in_proj_b_dense = e->W(0, "dit.input_embed.proj.bias", {D}).d;
   for (int c = 0; c < 2; ++c) {
     const std::string p = std::string("dit.input_embed.conv_pos_embed.conv") + (c ? "2" : "1");
-    bf16* w = e->dalloc<bf16>(static_cast<size_t>(16) * 64 * 31 * 64);
-    CK(pack_conv_taps(st, e->W(0, p + ".weight", {D, 60, 31}).d, D, 60, 31, 64, 60, 64, w, 31 * 64));
+    bf16* w;
+    if (c == 0) {  // conv1: 16 groups, padded 64-channel input AND output layout
+      w = e->dalloc<bf16>(static_cast<size_t>(16) * 64 * 31 * 64);
+      CK(pack_conv_taps(st, e->W(0, p + ".weight", {D, 60, 31}).d, D, 60, 31, 64, 60, 64, w, 31 * 64));
+    } else {  // conv2: dense [M, 960] output in 15 tiles of 64 columns, each over two adjacent padded input groups
+      w = e->dalloc<bf16>(static_cast<size_t>(D) * 31 * 128);
+      CK(pack_conv_dense_tiles(st, e->W(0, p + ".weight", {D, 60, 31}).d, 31, w));
+    }
     (c ? e->conv2_w : e->conv1_w) = w;
     if (c == 0) {  // conv1 writes the padded layout again (pad columns: zero weights + zero bias -> mish(0) = 0)
       e->conv1_b = e->dalloc<float>(DP);
@@ -545,7 +556,7 @@ struct DenoiseWs {
   Tmp<float> h, x, qkvg, v;
   Tmp<bf16> hm, c1, a, qb, kb, vb, ob, hb;
   void alloc(cudaStream_t st, long long M) {
-    h.alloc(st, M * DP); x.alloc(st, M * D); qkvg.alloc(st, M * 4 * D);
+    h.alloc(st, M * D); x.alloc(st, M * D); qkvg.alloc(st, M * 4 * D);
     hm.alloc(st, M * DP); c1.alloc(st, M * DP); a.alloc(st, M * D);
     qb.alloc(st, M * H * HDP); kb.alloc(st, M * H * HDP); vb.alloc(st, M * H * HDP); ob.alloc(st, M * H * HDP);
     hb.alloc(st, M * FF);
@@ -558,22 +569,25 @@ void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_b
   const long long M = static_cast<long long>(B) * T;
   // input embedding: h = proj(x); hm = masked bf16 copy; x = mask(mish(conv2(mask(mish(conv1(hm)))))) + h
   {
-    GemmEpi ep;
-    ep.bias = e->in_proj_b; ep.row_len = frames_dev; ep.rows_per_batch = T; ep.mask_bf16_only = 1;
-    ep.out_f32 = ws.h; ep.out_bf16 = ws.hm; ep.ld_out = DP;
+    GemmEpi ep;  // masked bf16 copy in the group-padded layout (conv input)
+    ep.bias = e->in_proj_b; ep.row_len = frames_dev; ep.rows_per_batch = T;
+    ep.out_bf16 = ws.hm; ep.ld_out = DP;
     linear(e, xt_bf16, M, LAT, LAT, e->in_proj_w, DP, LAT, ep);
+    GemmEpi eh;  // dense fp32 h (unmasked) for the residual
+    eh.bias = e->in_proj_b_dense; eh.out_f32 = ws.h; eh.ld_out = D;
+    linear(e, xt_bf16, M, LAT, LAT, e->in_proj_w_dense, D, LAT, eh);
     GemmShape s;
     s.B = B; s.T = T; s.N = 64; s.K = 64; s.taps = 31; s.tap_shift0 = -15; s.tap_step = 1;
     s.groups = 16; s.a_group_koff = 64; s.w_group_rows = 64; s.out_group_cols = 64; s.res_group_cols = 64;
-    GemmW gw1{e->conv1_w, 16 * 64, 31 * 64}, gw2{e->conv2_w, 16 * 64, 31 * 64};
     GemmEpi e1;
     e1.bias = e->conv1_b; e1.act = ACT_MISH; e1.row_len = frames_dev; e1.out_bf16 = ws.c1; e1.ld_out = DP;
-    CK(launch_gemm(st, 64, GemmA{ws.hm, DP, DP}, gw1, s, e1));
-    s.N = 60; s.out_group_cols = 60;  // conv2 writes the dense [M, 960] residual stream; residual h is padded
+    CK(launch_gemm(st, 64, GemmA{ws.hm, DP, DP}, GemmW{e->conv1_w, 16 * 64, 31 * 64}, s, e1));
+    // conv2: 15 dense 64-column tiles; tile n reads padded groups n and n+1 (K = 128)
+    s.groups = 15; s.K = 128;
     GemmEpi e2;
-    e2.bias = e->conv2_b; e2.act = ACT_MISH; e2.row_len = frames_dev; e2.residual = ws.h; e2.ld_res = DP;
+    e2.bias = e->conv2_b; e2.act = ACT_MISH; e2.row_len = frames_dev; e2.residual = ws.h; e2.ld_res = D;
     e2.out_f32 = ws.x; e2.ld_out = D;
-    CK(launch_gemm(st, 64, GemmA{ws.c1, DP, DP}, gw2, s, e2));
+    CK(launch_gemm(st, 64, GemmA{ws.c1, DP, DP}, GemmW{e->conv2_w, D, 31 * 128}, s, e2));
   }
   for (int i = 0; i < NBLK; ++i) {
     const DitBlockW& w = e->blk[i];
@@ -748,6 +762,7 @@ struct Plan {
   std::vector<float> ts;
   std::vector<const float*> mods;
   cudaGraphExec_t g_cond = nullptr, g_sample[2] = {nullptr, nullptr}, g_front = nullptr, g_tail = nullptr;
+  unsigned long long n_cond = 0, n_sample[2] = {0, 0}, n_front = 0, n_tail = 0;  // kernels per graph
   int graph_state = 0;  // 0 = not captured yet, 1 = captured, -1 = capture failed: stay eager
   uint64_t last_use = 0;
   template <typename T>
@@ -822,8 +837,9 @@ Plan* get_plan(stts_engine* e, int B, int R, int P, int T, int steps) {
 // Record `fn`'s launches into an executable graph (nothing runs).  Relaxed mode: the launchers make driver calls
 // (tensor-map encoding) that are not stream operations.
 template <typename F>
-cudaGraphExec_t capture(stts_engine* e, F&& fn) {
+cudaGraphExec_t capture(stts_engine* e, F&& fn, unsigned long long* n_kernels) {
   cudaGraph_t graph = nullptr;
+  const unsigned long long before = g_launch_count;
   CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeRelaxed));
   try {
     fn();
@@ -833,6 +849,8 @@ cudaGraphExec_t capture(stts_engine* e, F&& fn) {
     throw;
   }
   CK(cudaStreamEndCapture(e->st, &graph));
+  *n_kernels = g_launch_count - before;  // recorded, not executed: replays add this to the launch counter
+  g_launch_count = before;
   cudaGraphExec_t exec = nullptr;
   cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -1134,6 +1152,7 @@ int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, co
 
     const bool graphs = e->use_graphs && default_ts && p->graph_state == 1;
     CK(cudaEventRecord(e->ev[0], st));
+    if (graphs) g_launch_count += p->n_cond + p->n_sample[noise ? 1 : 0] + p->n_front + p->n_tail;
     if (graphs) CK(cudaGraphLaunch(p->g_cond, st)); else run_cond();
     CK(cudaEventRecord(e->ev[1], st));
     if (graphs) CK(cudaGraphLaunch(p->g_sample[noise ? 1 : 0], st)); else run_sample(nd);
@@ -1159,11 +1178,11 @@ int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, co
     // First (eager) run of this shape succeeded: capture the four stage graphs for every later call.
     if (e->use_graphs && p->graph_state == 0 && default_ts) {
       try {
-        p->g_cond = capture(e, run_cond);
-        p->g_sample[0] = capture(e, [&] { run_sample(nullptr); });
-        p->g_sample[1] = capture(e, [&] { run_sample(p->noise); });
-        p->g_front = capture(e, run_front);
-        p->g_tail = capture(e, run_tail);
+        p->g_cond = capture(e, run_cond, &p->n_cond);
+        p->g_sample[0] = capture(e, [&] { run_sample(nullptr); }, &p->n_sample[0]);
+        p->g_sample[1] = capture(e, [&] { run_sample(p->noise); }, &p->n_sample[1]);
+        p->g_front = capture(e, run_front, &p->n_front);
+        p->g_tail = capture(e, run_tail, &p->n_tail);
         p->graph_state = 1;
       } catch (const Err&) {
         p->graph_state = -1;  // keep working eagerly
@@ -1219,6 +1238,7 @@ int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T
     GemmShape s;
     s.B = B; s.T = T; s.N = N; s.K = K; s.taps = taps; s.tap_shift0 = tap_shift0; s.tap_step = tap_step;
     s.groups = groups; s.a_group_koff = a_group_koff; s.w_group_rows = w_group_rows; s.out_group_cols = out_group_cols;
+    s.res_group_cols = out_group_cols;
     GemmEpi ep;
     ep.bias = bias; ep.act = act; ep.row_len = row_len; ep.rows_per_batch = rows_per_batch; ep.mask_bf16_only = mask_bf16_only; ep.colscale = colscale;
     ep.rowgate = rowgate; ep.ld_gate = ld_gate; ep.residual = residual; ep.ld_res = ld_res; ep.out_f32 = out_f32;

@@ -2,6 +2,9 @@
 //   warp 0   : TMA producer (one lane): A box [128 rows x 64 k] and W box [BN rows x 64 k] per stage
 //   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane), fp32 accumulator in TMEM
 //   warps 2-5: epilogue, one TMEM lane quarter each: tcgen05.ld -> bias/activation/mask/gate/residual -> global
+// The epilogue is compiled per activation and only handles full, 16-byte aligned 32-column chunks (the host
+// checks N % 32 == 0 and the alignments): an earlier all-in-one epilogue was ~100 KB of SASS per kernel and ran
+// instruction-fetch bound (ncu: stall_no_instruction dominant).
 #include "gemm.cuh"
 
 #include <mutex>
@@ -30,7 +33,7 @@ struct Cfg {
 
 // Branch-free activations built on ex2/rcp (MUFU), accurate far below the bf16 rounding of their consumers.
 __device__ __forceinline__ float fast_sigmoid(float x) {
-  return __frcp_rn(1.0f + exp2f(-1.4426950408889634f * x));
+  return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x));
 }
 // erf-GELU: 0.5 x (1 + tanh(u)) = x * sigmoid(2u) with u = x (a + b x^2 + c x^4), coefficients fitted to
 // 0.5 x (1 + erf(x / sqrt 2)) on [-10, 10]: max abs error 2.6e-5 (the usual 2-term tanh form has 4.7e-4).
@@ -40,27 +43,36 @@ __device__ __forceinline__ float fast_gelu(float x) {
   const float x2 = xc * xc;
   // -2 * log2(e) * (a, b, c)
   const float p = fmaf(x2, fmaf(x2, 1.0153833e-3f, -0.10678167f), -2.3011139f);
-  return x * __frcp_rn(1.0f + exp2f(xc * p));
+  return __fdividef(x, 1.0f + exp2f(xc * p));
+}
+// Mish (dit.py:226-229): x * tanh(softplus(x)) = x * (w^2 + 2w) / (w^2 + 2w + 2) with w = e^x; for x > 20 -> x.
+__device__ __forceinline__ float fast_mish(float x) {
+  const float w = exp2f(1.4426950408889634f * fminf(x, 20.0f));
+  const float n = w * (w + 2.0f);
+  return x * __fdividef(n, n + 2.0f);
 }
 
-__device__ __forceinline__ float act_apply(float v, int act) {
-  switch (act) {
-    case ACT_GELU:
-      return fast_gelu(v);
-    case ACT_MISH: {
-      float sp = v > 20.0f ? v : log1pf(expf(v));
-      return v * tanhf(sp);
-    }
-    case ACT_SIGMOID:
-      return fast_sigmoid(v);
-    case ACT_SILU:
-      return v * fast_sigmoid(v);
-    default:
-      return v;
-  }
+template <int ACT>
+__device__ __forceinline__ float act_apply(float v) {
+  if (ACT == ACT_GELU) return fast_gelu(v);
+  if (ACT == ACT_MISH) return fast_mish(v);
+  return v;
 }
 
-template <int BN>
+__device__ __forceinline__ void add4(float* v, const float* __restrict__ p) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w;
+}
+__device__ __forceinline__ void mul4(float* v, const float* __restrict__ p) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] *= x.x; v[1] *= x.y; v[2] *= x.z; v[3] *= x.w;
+}
+__device__ __forceinline__ uint32_t bf2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+template <int BN, int ACT>
 __global__ void __launch_bounds__(kThreads, 2)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmShape s,
             const GemmEpi e, const int kStages) {
@@ -151,8 +163,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int eb = e.rows_per_batch > 0 ? static_cast<int>(m / e.rows_per_batch) : b;
     const int et = e.rows_per_batch > 0 ? static_cast<int>(m % e.rows_per_batch) : t;
     const bool masked = (e.row_len != nullptr) && row_ok && (et >= e.row_len[eb]);
+    const bool mask32 = masked && !e.mask_bf16_only;
+    const float bz = (masked && e.mask_bf16_only) ? 0.0f : 1.0f;  // bf16-only masking
     const int gcol_base = g * s.out_group_cols;
-    const bool swiglu = (e.act == ACT_SWIGLU16);
+    constexpr int kOut = (ACT == ACT_SWIGLU16) ? 16 : 32;  // output columns per 32-column accumulator chunk
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int nl0 = n0 + c * 32;  // column inside the group
@@ -161,107 +175,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
       ptx::tmem_ld_wait();
       if (!row_ok) continue;
-      const int ncols = min(32, s.N - nl0);
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = __uint_as_float(r[i]);
-      }
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
       const int gc0 = gcol_base + nl0;
       if (e.bias != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < ncols) v[i] += __ldg(e.bias + gc0 + i);
-        }
+        for (int i = 0; i < 8; ++i) add4(v + 4 * i, e.bias + gc0 + 4 * i);
       }
       int out_c0 = gc0;
-      int out_n = ncols;
-      if (swiglu) {
+      if (ACT == ACT_SWIGLU16) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float a = v[i];
           v[i] = a * fast_sigmoid(a) * v[16 + i];
         }
         out_c0 = gc0 >> 1;
-        out_n = ncols >> 1;
-      } else if (e.act != ACT_NONE) {
+      } else if (ACT != ACT_NONE) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = act_apply(v[i], e.act);
-        }
+        for (int i = 0; i < 32; ++i) v[i] = act_apply<ACT>(v[i]);
       }
-      // row masking: the fp32 output keeps the unmasked value when only the bf16 copy is masked
-      const bool mask32 = masked && !e.mask_bf16_only;
       if (mask32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+        for (int i = 0; i < kOut; ++i) v[i] = 0.0f;
       }
       if (e.colscale != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < out_n) v[i] *= __ldg(e.colscale + out_c0 + i);
-        }
+        for (int i = 0; i < kOut / 4; ++i) mul4(v + 4 * i, e.colscale + out_c0 + 4 * i);
       }
       if (e.rowgate != nullptr) {
         const float* gp = e.rowgate + static_cast<long long>(eb) * e.ld_gate + out_c0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < out_n) v[i] *= __ldg(gp + i);
-        }
+        for (int i = 0; i < kOut / 4; ++i) mul4(v + 4 * i, gp + 4 * i);
       }
       if (e.residual != nullptr) {
         const float* rp = e.residual + m * e.ld_res + out_c0 + g * (s.res_group_cols - s.out_group_cols);
-        if (out_n == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 x = *reinterpret_cast<const float4*>(rp + 4 * i);
-            v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < out_n) v[i] += rp[i];
-          }
+        for (int i = 0; i < kOut / 4; ++i) {
+          const float4 x = *reinterpret_cast<const float4*>(rp + 4 * i);
+          v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
         }
       }
       if (e.out_f32 != nullptr) {
         float* op = e.out_f32 + m * e.ld_out + out_c0;
-        if (out_n == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < out_n) op[i] = v[i];
-          }
+        for (int i = 0; i < kOut / 4; ++i) {
+          *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
       }
       if (e.out_bf16 != nullptr) {
-        const float bz = (masked && e.mask_bf16_only) ? 0.0f : 1.0f;  // bf16-only masking (no scale/residual there)
         __nv_bfloat16* op = e.out_bf16 + m * e.ld_out + out_c0;
-        if ((out_n == 32 || out_n == 16) && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (8 * i < out_n) {
-              uint4 pk;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(bz * v[8 * i + 0], bz * v[8 * i + 1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(bz * v[8 * i + 2], bz * v[8 * i + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(bz * v[8 * i + 4], bz * v[8 * i + 5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(bz * v[8 * i + 6], bz * v[8 * i + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&p0);
-              pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2);
-              pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(op + 8 * i) = pk;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < out_n) op[i] = __float2bfloat16_rn(bz * v[i]);
-          }
+        for (int i = 0; i < kOut / 8; ++i) {
+          uint4 pk;
+          pk.x = bf2(bz * v[8 * i + 0], bz * v[8 * i + 1]);
+          pk.y = bf2(bz * v[8 * i + 2], bz * v[8 * i + 3]);
+          pk.z = bf2(bz * v[8 * i + 4], bz * v[8 * i + 5]);
+          pk.w = bf2(bz * v[8 * i + 6], bz * v[8 * i + 7]);
+          *reinterpret_cast<uint4*>(op + 8 * i) = pk;
         }
       }
     }
@@ -312,12 +283,12 @@ bool make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims
   return r == CUDA_SUCCESS;
 }
 
-template <int BN>
-cudaError_t launch_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
-                      const GemmEpi& e) {
+template <int BN, int ACT>
+cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
+                        const GemmEpi& e) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<BN>::smem_bytes(Cfg<BN>::kMaxStages));
     if (err != cudaSuccess) return err;
     attr_set = true;
@@ -329,10 +300,30 @@ cudaError_t launch_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtenso
   const int iters = s.taps * ((s.K + BK - 1) / BK);
   int stages = iters < 2 ? 2 : iters;
   if (stages > Cfg<BN>::kMaxStages) stages = Cfg<BN>::kMaxStages;
-  gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::smem_bytes(stages), stream>>>(tmA, tmW, s, e, stages);
+  gemm_kernel<BN, ACT><<<grid, kThreads, Cfg<BN>::smem_bytes(stages), stream>>>(tmA, tmW, s, e, stages);
   ++g_launch_count;
   return cudaGetLastError();
 }
+
+template <int BN>
+cudaError_t launch_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
+                      const GemmEpi& e) {
+  switch (e.act) {
+    case ACT_NONE:
+      return launch_inst<BN, ACT_NONE>(stream, tmA, tmW, s, e);
+    case ACT_GELU:
+      return launch_inst<BN, ACT_GELU>(stream, tmA, tmW, s, e);
+    case ACT_SWIGLU16:
+      return launch_inst<BN, ACT_SWIGLU16>(stream, tmA, tmW, s, e);
+    case ACT_MISH:
+      if (BN == 64) return launch_inst<64, ACT_MISH>(stream, tmA, tmW, s, e);
+      return cudaErrorInvalidValue;
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
@@ -340,8 +331,13 @@ cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const 
                         const GemmEpi& e) {
   if (s.T <= 0 || s.B <= 0 || s.N <= 0 || s.K <= 0) return cudaErrorInvalidValue;
   if (s.groups > 1 && (s.a_group_koff % 8) != 0) return cudaErrorInvalidValue;  // TMA: 16-byte aligned box start
-  if ((a.ld % 8) != 0 || (w.ld % 8) != 0) return cudaErrorInvalidValue;
-  if ((reinterpret_cast<uintptr_t>(a.ptr) & 15) || (reinterpret_cast<uintptr_t>(w.ptr) & 15)) {
+  if ((a.ld % 8) != 0 || (w.ld % 8) != 0 || !aligned16(a.ptr) || !aligned16(w.ptr)) return cudaErrorInvalidValue;
+  // the epilogue works on full, 16-byte aligned 32-column chunks
+  if ((s.N % 32) != 0 || (s.out_group_cols % 32) != 0 || (s.res_group_cols % 4) != 0) return cudaErrorInvalidValue;
+  const int ld_req = e.out_bf16 != nullptr ? 8 : 4;
+  if ((e.ld_out % ld_req) != 0 || !aligned16(e.out_f32) || !aligned16(e.out_bf16)) return cudaErrorInvalidValue;
+  if (e.residual != nullptr && ((e.ld_res % 4) != 0 || !aligned16(e.residual))) return cudaErrorInvalidValue;
+  if (!aligned16(e.bias) || !aligned16(e.colscale) || !aligned16(e.rowgate) || (e.ld_gate % 4) != 0) {
     return cudaErrorInvalidValue;
   }
   CUtensorMap tmA, tmW;

@@ -608,6 +608,16 @@ __global__ void pack_conv_taps_kernel(const float* __restrict__ src, int O, int 
   dst[static_cast<long long>(dr) * ld_dst + tap * kp + c] = __float2bfloat16_rn(src[i]);
 }
 
+__global__ void pack_conv_dense_tiles_kernel(const float* __restrict__ src, int taps, bf16* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(960) * 60 * taps) return;
+  const int tap = static_cast<int>(i % taps);
+  const int c = static_cast<int>((i / taps) % 60);
+  const int o = static_cast<int>(i / (static_cast<long long>(taps) * 60));
+  const int kk = (o / 60 - o / 64) * 64 + c;
+  dst[static_cast<long long>(o) * (taps * 128) + tap * 128 + kk] = __float2bfloat16_rn(src[i]);
+}
+
 __global__ void pack_convtr_kernel(const float* __restrict__ src, int cin, int cout, int r, bf16* __restrict__ dst) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int kk = 2 * r;
@@ -773,6 +783,11 @@ cudaError_t pack_conv_taps(cudaStream_t st, const float* src, int O, int cin, in
                            bf16* dst, int ld_dst) {
   pack_conv_taps_kernel<<<blocks_for(static_cast<long long>(O) * cin * taps, 256), 256, 0, st>>>(
       src, O, cin, taps, kp, opg, group_pitch, dst, ld_dst);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t pack_conv_dense_tiles(cudaStream_t st, const float* src, int taps, bf16* dst) {
+  pack_conv_dense_tiles_kernel<<<blocks_for(static_cast<long long>(960) * 60 * taps, 256), 256, 0, st>>>(src, taps, dst);
   STTS_LAUNCH_OK();
 }
 

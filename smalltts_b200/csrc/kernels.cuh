@@ -78,6 +78,9 @@ cudaError_t pack_matrix(cudaStream_t st, const float* src, int rows, int cols, f
 // Conv1d weight [O, Cin, taps] -> dst[(o / opg) * group_pitch + o % opg, tap * kp + c]
 cudaError_t pack_conv_taps(cudaStream_t st, const float* src, int O, int cin, int taps, int kp, int opg, int group_pitch,
                            bf16* dst, int ld_dst);
+// Grouped Conv1d(960,960,k,groups=16) weight [960, 60, taps] -> 15 dense 64-column output tiles, each reading the two
+// adjacent 64-padded input groups it can touch: dst[o, tap*128 + (o/60 - o/64)*64 + c] = w[o, c, tap]  (dst [960, taps*128])
+cudaError_t pack_conv_dense_tiles(cudaStream_t st, const float* src, int taps, bf16* dst);
 // ConvTranspose1d weight [Cin, Cout, 2r] -> dst[j*Cout + o, tap*Cin + c] = w[c, o, j + tap*r]
 cudaError_t pack_convtr(cudaStream_t st, const float* src, int cin, int cout, int r, bf16* dst);
 // fp32 vector helpers: dst[map(i) + off] = scale * src[i]

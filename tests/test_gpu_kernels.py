@@ -138,27 +138,45 @@ def test_conv_transpose_as_two_taps(eng, r, cin, cout):
 
 
 def test_grouped_conv_k31(eng):
-    """ConvPositionEmbedding conv: Conv1d(960, 960, 31, groups=16, padding=15) + Mish + mask (dit.py:223-236)."""
+    """ConvPositionEmbedding convs: Conv1d(960, 960, 31, groups=16, padding=15) + Mish + mask (dit.py:223-236).
+    Groups are padded 60 -> 64 channels so that every TMA box start is 16-byte aligned.  conv1 keeps the padded
+    layout on its output; conv2 writes the dense [M, 960] stream as 15 tiles of 64 columns, each reading the two
+    adjacent padded groups it can touch (K = 128, block-structured weights)."""
     torch.manual_seed(6)
     B, T, Cdim = 2, 75, 960
     lens = torch.tensor([75, 50], device="cuda", dtype=torch.int32)
-    x = _rand_bf16(B, T, Cdim)
-    x = x * (torch.arange(T, device="cuda")[None, :, None] < lens[:, None, None])
+    keep = (torch.arange(T, device="cuda")[None, :, None] < lens[:, None, None])
+    x = _rand_bf16(B, T, Cdim) * keep
     wc = _rand_bf16(Cdim, 60, 31, scale=(60 * 31) ** -0.5)
     bias = torch.randn(Cdim, device="cuda")
-    w = torch.zeros(16 * 64, 31 * 64, device="cuda", dtype=torch.bfloat16)
-    wv = w.view(16, 64, 31, 64)
-    wv[:, :60, :, :60] = wc.view(16, 60, 60, 31).permute(0, 1, 3, 2)
-    # groups padded 60 -> 64 channels so that every TMA box start is 16-byte aligned
-    xp = torch.zeros(B, T, 1024, device="cuda", dtype=torch.bfloat16)
-    xp.view(B, T, 16, 64)[..., :60] = x.view(B, T, 16, 60)
-    _, out16 = run_gemm(eng, xp, w, B=B, T=T, N=60, K=64, bn=64, taps=31, shift0=-15, step=1, groups=16, a_koff=64,
-                        w_grows=64, out_gcols=60, bias=bias, act="mish", row_len=lens, want_bf16=True, ld_out=Cdim,
-                        out_cols=Cdim)
     want = torch.nn.functional.mish(
         torch.nn.functional.conv1d(x.float().transpose(1, 2), wc.float(), bias, padding=15, groups=16)).transpose(1, 2)
-    want = want * (torch.arange(T, device="cuda")[None, :, None] < lens[:, None, None])
-    _assert_close(out16.view(B, T, Cdim), want, tol=1e-2)
+    want = want * keep
+    xp = torch.zeros(B, T, 1024, device="cuda", dtype=torch.bfloat16)
+    xp.view(B, T, 16, 64)[..., :60] = x.view(B, T, 16, 60)
+    # conv1 style: 16 groups, padded output
+    w1 = torch.zeros(16 * 64, 31 * 64, device="cuda", dtype=torch.bfloat16)
+    w1.view(16, 64, 31, 64)[:, :60, :, :60] = wc.view(16, 60, 60, 31).permute(0, 1, 3, 2)
+    b1 = torch.zeros(1024, device="cuda")
+    b1.view(16, 64)[:, :60] = bias.view(16, 60)
+    _, o1 = run_gemm(eng, xp, w1, B=B, T=T, N=64, K=64, bn=64, taps=31, shift0=-15, step=1, groups=16, a_koff=64,
+                     w_grows=64, out_gcols=64, bias=b1, act="mish", row_len=lens, want_bf16=True, ld_out=1024,
+                     out_cols=1024)
+    got1 = o1.view(B, T, 16, 64)
+    _assert_close(got1[..., :60].reshape(B, T, Cdim), want, tol=1e-2)
+    assert got1[..., 60:].abs().max().item() == 0.0
+    # conv2 style: dense output tiles
+    o = torch.arange(Cdim, device="cuda")
+    w2 = torch.zeros(Cdim, 31, 128, device="cuda", dtype=torch.bfloat16)
+    kk0 = (o // 60 - o // 64) * 64
+    for c in range(60):
+        w2[o, :, kk0 + c] = wc[:, c, :]
+    w2 = w2.reshape(Cdim, 31 * 128).contiguous()
+    res = torch.randn(B * T, Cdim, device="cuda")
+    o2, _ = run_gemm(eng, xp, w2, B=B, T=T, N=64, K=128, bn=64, taps=31, shift0=-15, step=1, groups=15, a_koff=64,
+                     w_grows=64, out_gcols=64, bias=bias, act="mish", row_len=lens, residual=res, ld_out=Cdim,
+                     out_cols=Cdim)
+    _assert_close(o2.view(B, T, Cdim), want + res.view(B, T, Cdim), tol=2e-3)
 
 
 @pytest.mark.parametrize("hd,hd_pad,H", [(120, 128, 8), (64, 64, 8), (128, 128, 4)])
