@@ -134,6 +134,7 @@ struct stts_engine {
   std::map<std::array<int, 5>, Plan*> plans;
   uint64_t use_counter = 0;
   bool use_graphs = true;
+  bool fused_tail = true;  // STTS_NO_FUSED_TAIL=1 falls back to mixer + two GEMMs for C <= 64 (debug / A-B timing)
   unsigned long long* seed_dev = nullptr;   // device u64 read by the Philox kernel
   unsigned long long* seed_host = nullptr;  // pinned staging for seed_dev
 
@@ -702,23 +703,35 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
     CK(launch_gemm(st, pick_bn(frames, 2048), GemmA{ws.latb, LAT, LAT}, GemmW{e->stem_w, 2048, 7 * 64}, s, ep));
   }
   int Ts = T;
+  float* cur = ws.xa;  // activations of the current stage (every stage ends with one swap, see below)
+  float* oth = ws.xb;
   for (int s = 0; s < 7; ++s) {
     const int C = VOC_C[s];
     const long long M = static_cast<long long>(B) * Ts;
     const bool mine = (s < 4) ? (part & VOC_FRONT) != 0 : (part & VOC_TAIL) != 0;
-    float* cur = (s & 1) ? ws.xb : ws.xa;
-    float* oth = (s & 1) ? ws.xa : ws.xb;
     if (mine) {
-      for (size_t l = 0; l < e->voc[s].size(); ++l) {
-        const VocLayerW& w = e->voc[s][l];
-        CK(convnext_mix(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, oth, ws.a));
-        GemmEpi e1;
-        e1.bias = w.b1; e1.act = ACT_GELU; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
-        linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1);
-        GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
-        e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = oth; e2.ld_res = C; e2.out_f32 = cur; e2.ld_out = C;
-        if (s < 6 && l + 1 == e->voc[s].size()) e2.out_bf16 = ws.xh;  // bf16 copy feeds the next upsampler
-        linear(e, ws.hbuf, M, 4 * C, 4 * C, w.w2, C, 4 * C, e2);
+      const size_t nl = e->voc[s].size();
+      if (C <= 64 && e->fused_tail) {
+        // fused layers are out-of-place: ping-pong cur -> oth -> cur -> ...; make `cur` the result afterwards
+        for (size_t l = 0; l < nl; ++l) {
+          const VocLayerW& w = e->voc[s][l];
+          bf16* hb = (s < 6 && l + 1 == nl) ? ws.xh : nullptr;
+          CK(convnext_fused(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, w.w1, w.b1, w.w2,
+                            w.b2, w.ffn_gamma, 1e-5f, oth, hb));
+          std::swap(cur, oth);
+        }
+      } else {
+        for (size_t l = 0; l < nl; ++l) {
+          const VocLayerW& w = e->voc[s][l];
+          CK(convnext_mix(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, oth, ws.a));
+          GemmEpi e1;
+          e1.bias = w.b1; e1.act = ACT_GELU; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
+          linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1);
+          GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
+          e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = oth; e2.ld_res = C; e2.out_f32 = cur; e2.ld_out = C;
+          if (s < 6 && l + 1 == nl) e2.out_bf16 = ws.xh;  // bf16 copy feeds the next upsampler
+          linear(e, ws.hbuf, M, 4 * C, 4 * C, w.w2, C, 4 * C, e2);
+        }
       }
       if (s < 6) {  // causal ConvTranspose1d(k=2r, stride=r) as a 2-tap GEMM with N = r*Cout (hf:219-260)
         const int r = VOC_R[s], cout = VOC_C[s + 1];
@@ -729,9 +742,12 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
         CK(launch_gemm(st, pick_bn(M, r * cout), GemmA{ws.xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
       }
     }
-    if (s < 6) Ts *= VOC_R[s];
+    if (s < 6) {
+      Ts *= VOC_R[s];
+      if (mine || !(C <= 64 && e->fused_tail)) std::swap(cur, oth);
+    }
   }
-  if (part & VOC_TAIL) CK(head_conv(st, ws.xa, B, Ts, 32, e->head_w, e->head_b, audio_dev));  // stage 6 is even -> xa
+  if (part & VOC_TAIL) CK(head_conv(st, cur, B, Ts, 32, e->head_w, e->head_b, audio_dev));
 }
 
 struct VocTmp {  // stream-ordered temporaries for the stand-alone decode entry point
@@ -911,6 +927,8 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     CK(cudaHostAlloc(reinterpret_cast<void**>(&e->seed_host), sizeof(unsigned long long), cudaHostAllocDefault));
     const char* ng = getenv("STTS_NO_GRAPH");
     e->use_graphs = !(ng && ng[0] == '1');
+    const char* nf = getenv("STTS_NO_FUSED_TAIL");
+    e->fused_tail = !(nf && nf[0] == '1');
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, e->device));
     uint64_t thr = UINT64_MAX;
@@ -1269,6 +1287,18 @@ int stts_test_convnext_mix(stts_engine* e, const float* x, int B, int T, int C, 
   if (!e) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
     CK(convnext_mix(e->st, x, B, T, C, norm_w, conv_w, conv_b, gamma, ffn_norm_w, 1e-5f, y, static_cast<bf16*>(a_bf16)));
+    CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+int stts_test_convnext_fused(stts_engine* e, const float* x, int B, int T, int C, const float* norm_w,
+                             const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
+                             const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
+                             const float* ffn_gamma, float* out, void* out_bf16) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    CK(convnext_fused(e->st, x, B, T, C, norm_w, conv_w, conv_b, gamma, ffn_norm_w, static_cast<const bf16*>(w1_bf16), b1,
+                      static_cast<const bf16*>(w2_bf16), b2, ffn_gamma, 1e-5f, out, static_cast<bf16*>(out_bf16)));
     CK(cudaStreamSynchronize(e->st));
   });
 }

@@ -234,3 +234,32 @@ def test_convnext_mix(eng, C_, T):
     want_a = want_y * torch.rsqrt(want_y.pow(2).mean(-1, keepdim=True) + 1e-5) * fw
     _assert_close(y, want_y, tol=1e-5)
     _assert_close(a, want_a, tol=1e-2)
+
+
+@pytest.mark.parametrize("C_,T", [(32, 1000), (64, 700), (64, 128), (32, 57)])
+def test_convnext_fused(eng, C_, T):
+    """Whole ConvNeXt layer (hf:284-297) in one kernel vs torch fp32 on bf16-rounded weights."""
+    from smalltts_b200 import _cabi
+
+    torch.manual_seed(9)
+    B = 3
+    x = torch.randn(B, T, C_, device="cuda")
+    nw, fw = 1 + 0.1 * torch.randn(C_, device="cuda"), 1 + 0.1 * torch.randn(C_, device="cuda")
+    cw, cb = torch.randn(C_, 7, device="cuda") * 0.4, torch.randn(C_, device="cuda")
+    gamma, fgamma = 0.1 + 0.1 * torch.rand(C_, device="cuda"), 0.1 + 0.1 * torch.rand(C_, device="cuda")
+    w1, w2 = _rand_bf16(4 * C_, C_, scale=C_ ** -0.5), _rand_bf16(C_, 4 * C_, scale=(4 * C_) ** -0.5)
+    b1, b2 = torch.randn(4 * C_, device="cuda") * 0.3, torch.randn(C_, device="cuda") * 0.3
+    out = torch.zeros_like(x)
+    out16 = torch.zeros(B, T, C_, device="cuda", dtype=torch.bfloat16)
+    rc = _cabi.lib().stts_test_convnext_fused(eng._h, _p(x), B, T, C_, _p(nw), _p(cw), _p(cb), _p(gamma), _p(fw),
+                                              _p(w1), _p(b1), _p(w2), _p(b2), _p(fgamma), _p(out), _p(out16))
+    _cabi.check(rc, eng._h)
+    torch.cuda.synchronize()
+    xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * nw
+    conv = torch.nn.functional.conv1d(torch.nn.functional.pad(xn.transpose(1, 2), (6, 0)), cw[:, None, :], cb, groups=C_)
+    y = x + gamma * conv.transpose(1, 2)
+    a = (y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + 1e-5) * fw).to(torch.bfloat16).float()
+    h = torch.nn.functional.gelu(a @ w1.float().t() + b1).to(torch.bfloat16).float()
+    want = y + fgamma * (h @ w2.float().t() + b2)
+    _assert_close(out, want, tol=2e-3)
+    _assert_close(out16, want, tol=1e-2)
