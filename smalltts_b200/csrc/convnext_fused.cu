@@ -7,14 +7,15 @@
 // the normalised bf16 operand, the 4C-wide hidden activation and y never leave the SM.  One persistent CTA per SM
 // walks 128-row tiles; five warp roles overlap consecutive tiles through mbarrier pipelines:
 //
-//   warps 0-3   mixer : cp.async prefetch of the next x tile (+6 causal halo rows, zero-filled), RMSNorm, depthwise
+//   warps 0-7   mixer : cp.async prefetch of the next x tile (+6 causal halo rows, zero-filled), RMSNorm, depthwise
 //                       conv in place (fp32 y stays in shared memory), second RMSNorm -> bf16 A operand written in
 //                       the UMMA K-major 128B-swizzled layout
-//   warp  4     MMA   : tcgen05.mma  H[128 x 4C] = A W1^T  and, per 64-wide hidden chunk, O[128 x C] += G W2^T;
+//   warp  8     MMA   : tcgen05.mma  H[128 x 4C] = A W1^T  and, per 64-wide hidden chunk, O[128 x C] += G W2^T;
 //                       accumulators in TMEM (two 256-column buffers; O aliases the first C columns of H, which the
 //                       GELU warps have consumed by then); W1/W2 stay resident in shared memory (TMA-loaded once)
-//   warps 5-12  GELU  : tcgen05.ld H chunk -> +b1 -> GELU -> bf16 -> swizzled shared-memory G chunk (double buffer)
-//   warps 13-16 out   : tcgen05.ld O -> y + ffn_gamma*(O + b2) -> shared -> coalesced fp32 (and optional bf16) store
+//   warps 9-16  GELU  : tcgen05.ld H chunk -> +b1 -> GELU -> bf16 -> swizzled shared-memory G chunk (double buffer)
+//   warps 17-20 out   : y rows -> registers (frees the x buffer early); tcgen05.ld O -> y + ffn_gamma*(O + b2) ->
+//                       fp32 (and optional bf16) store, one full row per thread
 #include <cuda.h>
 
 #include <mutex>
@@ -29,7 +30,9 @@ namespace {
 constexpr int TM = 128;  // rows per tile
 constexpr int HALO = 6;  // causal context of the k=7 depthwise conv
 constexpr int XR = TM + HALO;
-constexpr int kThreadsFused = 17 * 32;
+// warp roles: [0,8) mixer | 8 MMA | [9,17) GELU | [17,21) out.  TMEM lane quarter of a warp = warp % 4.
+constexpr int kMixWarps = 8, kMmaWarp = 8, kGeluWarp0 = 9, kOutWarp0 = 17;
+constexpr int kThreadsFused = 21 * 32;
 
 struct FusedParams {
   const float* x;
@@ -63,11 +66,16 @@ struct FC {
   static constexpr int SMEM = OFF_BAR + 17 * 8 + 16 + 1024;
 };
 
-__device__ __forceinline__ float gelu_fast(float x) {  // same fit as gemm.cu: max abs err 2.6e-5 vs erf GELU
+// erf-GELU as 0.5 x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form (max abs err 2.6e-5 before the
+// MUFU.TANH approximation, whose 2^-11 relative error stays below the bf16 rounding applied right after).
+__device__ __forceinline__ float gelu_fast(float x) {
   const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
   const float x2 = xc * xc;
-  const float p = fmaf(x2, fmaf(x2, 1.0153833e-3f, -0.10678167f), -2.3011139f);
-  return __fdividef(x, 1.0f + exp2f(xc * p));
+  const float u = xc * fmaf(x2, fmaf(x2, -3.5190239e-4f, 3.7008020e-2f), 0.79750528f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
 }
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
@@ -133,26 +141,27 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     for (int i = 0; i < 17; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 4) ptx::tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) ptx::tmem_alloc<512>(tmem_slot);
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ================================================================== mixer
+  if (warp < kMixWarps) {
+    // ================================================================== mixer (8 warps)
+    // Row statistics are computed one row per thread (float4 row reads are bank-conflict free with the C+4 pitch),
+    // so there are no shuffle chains; the conv runs one (channel, time segment) per thread.
     const int tid = threadIdx.x;
-    constexpr int CV = C / 4;      // float4 per row
-    constexpr int LPR = CV;        // lanes per row (16 or 8)
-    constexpr int RPI = 32 / LPR;  // rows per warp iteration
-    constexpr int NSEG = 128 / C;  // time segments per channel
+    constexpr int NT = kMixWarps * 32;
+    constexpr int CV = C / 4;       // float4 per row
+    constexpr int NSEG = NT / C;    // time segments per channel
     constexpr int SEGLEN = TM / NSEG;
     auto issue_load = [&](int tile, int buf) {
       const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * TM;
       const float* src_b = p.x + static_cast<long long>(b) * p.T * C;
       const uint32_t dst0 = ptx::smem_u32(Xbuf(buf));
-      for (int i = tid; i < XR * CV; i += 128) {
+      for (int i = tid; i < XR * CV; i += NT) {
         const int r = i / CV, c4 = i % CV;
         const int t = t0 - HALO + r;
         const bool ok = (t >= 0) && (t < p.T);
@@ -165,28 +174,27 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
       if (it + 1 < n_my) {
-        // the other x buffer was last used by iteration it-1: wait until its out warps released it
+        // the other x buffer was last used by iteration it-1: its out warps release it as soon as they hold y
         if (it >= 1) ptx::mbar_wait(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
         issue_load(first + (it + 1) * stride, buf ^ 1);
         ptx::cp_async_wait<1>();
       } else {
         ptx::cp_async_wait<0>();
       }
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1, NT);
       float* xs = Xbuf(buf);
-      // (1) 1/rms of every staged row
-      for (int r0 = warp * RPI; r0 < XR; r0 += 4 * RPI) {
-        const int r = r0 + lane / LPR, sl = lane % LPR;
-        float s = 0.f;
-        if (r < XR) {
-          const float4 v = *reinterpret_cast<const float4*>(xs + r * F::XP + sl * 4);
-          s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
+      // (1) 1/rms of every staged row: thread t owns row t
+      if (tid < XR) {
+        const float4* row = reinterpret_cast<const float4*>(xs + tid * F::XP);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (r < XR && sl == 0) inv1[r] = 1.0f / sqrtf(s / C + p.eps);
+        for (int j = 0; j < CV; ++j) {
+          const float4 v = row[j];
+          s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+        }
+        inv1[tid] = rsqrtf((s0 + s1 + s2 + s3) * (1.0f / C) + p.eps);
       }
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1, NT);
       // (2) depthwise causal conv along time, one (channel, segment) per thread, y written in place
       {
         const int c = tid % C, seg = tid / C;
@@ -202,41 +210,52 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           const int r = rs - 7 + j;
           win[j] = xs[r * F::XP + c] * inv1[r] * nw;
         }
-        ptx::named_bar_sync(1, 128);  // every warm-up read precedes the in-place writes of the previous segment
-#pragma unroll 4
+        ptx::named_bar_sync(1, NT);  // every warm-up read precedes the in-place writes of the previous segment
+#pragma unroll 8
         for (int r = rs; r < rs + SEGLEN; ++r) {
           const float xv = xs[r * F::XP + c];
 #pragma unroll
           for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
           win[6] = xv * inv1[r] * nw;
-          float acc = cb;
-#pragma unroll
-          for (int j = 0; j < 7; ++j) acc = fmaf(w[j], win[j], acc);
-          xs[r * F::XP + c] = fmaf(gm, acc, xv);
+          // two independent partial sums shorten the dependent FMA chain
+          float a0 = fmaf(w[0], win[0], cb), a1 = w[1] * win[1];
+          a0 = fmaf(w[2], win[2], a0); a1 = fmaf(w[3], win[3], a1);
+          a0 = fmaf(w[4], win[4], a0); a1 = fmaf(w[5], win[5], a1);
+          a0 = fmaf(w[6], win[6], a0);
+          xs[r * F::XP + c] = fmaf(gm, a0 + a1, xv);
         }
       }
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1, NT);
       // (3) second RMSNorm -> bf16 A operand (UMMA K-major, 128B swizzle); A buffer must be free (MMA1 of it-2 done)
       if (it >= 2) ptx::mbar_wait(&a_empty[buf], ((it - 2) >> 1) & 1);
-      uint8_t* As = Abuf(buf);
-      for (int r0 = warp * RPI; r0 < TM; r0 += 4 * RPI) {
-        const int r = r0 + lane / LPR, sl = lane % LPR;
-        const float4 v = *reinterpret_cast<const float4*>(xs + (r + HALO) * F::XP + sl * 4);
-        float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      if (tid < TM) {
+        const float4* row = reinterpret_cast<const float4*>(xs + (tid + HALO) * F::XP);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int o = LPR >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float inv = 1.0f / sqrtf(s / C + p.eps);
-        const float4 fw = *reinterpret_cast<const float4*>(fws + sl * 4);
-        uint2 pk;
-        pk.x = bf2(v.x * inv * fw.x, v.y * inv * fw.y);
-        pk.y = bf2(v.z * inv * fw.z, v.w * inv * fw.w);
-        *reinterpret_cast<uint2*>(As + sw128_off(r, sl * 4)) = pk;
+        for (int j = 0; j < CV; ++j) {
+          const float4 v = row[j];
+          s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+        }
+        const float inv = rsqrtf((s0 + s1 + s2 + s3) * (1.0f / C) + p.eps);
+        uint8_t* As = Abuf(buf);
+#pragma unroll
+        for (int j = 0; j < CV / 2; ++j) {  // 8 columns = one 16-byte swizzle chunk
+          const float4 v0 = row[2 * j], v1 = row[2 * j + 1];
+          const float4 f0 = *reinterpret_cast<const float4*>(fws + 8 * j);
+          const float4 f1 = *reinterpret_cast<const float4*>(fws + 8 * j + 4);
+          uint4 pk;
+          pk.x = bf2(v0.x * inv * f0.x, v0.y * inv * f0.y);
+          pk.y = bf2(v0.z * inv * f0.z, v0.w * inv * f0.w);
+          pk.z = bf2(v1.x * inv * f1.x, v1.y * inv * f1.y);
+          pk.w = bf2(v1.z * inv * f1.z, v1.w * inv * f1.w);
+          *reinterpret_cast<uint4*>(As + sw128_off(tid, 8 * j)) = pk;
+        }
       }
       ptx::fence_proxy_async();
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1, NT);
       if (tid == 0) ptx::mbar_arrive(&a_full[buf]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer
     if (lane == 0 && n_my > 0) {
       ptx::mbar_expect_tx(w_full, F::W1_BYTES + F::W2_BYTES);
@@ -246,6 +265,11 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(TM, F::HID);
       constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(TM, C);
       const uint64_t dW1 = ptx::umma_desc_sw128(ptx::smem_u32(W1s));
+      auto mma1_ready = [&](int it) {  // non-blocking: operand written and TMEM buffer drained?
+        const int buf = it & 1;
+        if (!ptx::mbar_test(&a_full[buf], (it >> 1) & 1)) return false;
+        return it < 2 || ptx::mbar_test(&tm_empty[buf], ((it - 2) >> 1) & 1);
+      };
       auto mma1 = [&](int it) {
         const int buf = it & 1;
         ptx::mbar_wait(&a_full[buf], (it >> 1) & 1);
@@ -260,8 +284,14 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       mma1(0);
       uint32_t gcount = 0;
       for (int it = 0; it < n_my; ++it) {
-        if (it + 1 < n_my) mma1(it + 1);  // run one tile ahead so that the GELU warps always have work
+        // MMA1 of the next tile is issued as early as its operand is ready, but this warp never BLOCKS on it while
+        // MMA2 chunks of the current tile are pending: the mixer's x buffers are only recycled once those finish.
+        bool next_issued = (it + 1 >= n_my);
         for (int c = 0; c < F::NCH; ++c, ++gcount) {
+          if (!next_issued && mma1_ready(it + 1)) {
+            mma1(it + 1);
+            next_issued = true;
+          }
           const int gb = gcount & 1;
           ptx::mbar_wait(&g_full[gb], (gcount >> 1) & 1);
           ptx::tc_fence_after();
@@ -274,11 +304,12 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           ptx::umma_commit(&g_empty[gb]);
         }
         ptx::umma_commit(&o_full[it & 1]);
+        if (!next_issued) mma1(it + 1);
       }
     }
-  } else if (warp < 13) {
+  } else if (warp < kOutWarp0) {
     // ================================================================== GELU: H (TMEM) -> G (smem, bf16)
-    const int gw = warp - 5;
+    const int gw = warp - kGeluWarp0;
     const int q = warp & 3;      // TMEM lane quarter this warp may access
     const int half = gw >> 2;    // which 32 of the chunk's 64 columns
     const int r = q * 32 + lane;
@@ -313,17 +344,25 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     }
   } else {
     // ================================================================== out: O (TMEM) + y -> global
+    // Thread <-> tile row.  y is pulled into registers as soon as the mixer has finished the tile, which frees the
+    // x buffer for the prefetch of tile it+2 long before the FFN of this tile completes.
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const int otid = threadIdx.x - 13 * 32;
-    constexpr int CV = C / 4;
+    const int otid = threadIdx.x - kOutWarp0 * 32;
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
       const int tile = first + it * stride;
+      ptx::mbar_wait(&a_full[buf], (it >> 1) & 1);  // mixer done: y rows are final
+      float4 y[C / 4];
+      {
+        const float* yrow = Xbuf(buf) + (r + HALO) * F::XP;
+#pragma unroll
+        for (int j = 0; j < C / 4; ++j) y[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
+      }
+      ptx::named_bar_sync(3, 128);
+      if (otid == 0) ptx::mbar_arrive(&x_empty[buf]);
       ptx::mbar_wait(&o_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
-      float* xs = Xbuf(buf);
-      float* yrow = xs + (r + HALO) * F::XP;
 #pragma unroll
       for (int cc = 0; cc < C / 32; ++cc) {
         uint32_t rr[32];
@@ -332,44 +371,44 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int col = cc * 32 + 4 * j;
-          float4 y = *reinterpret_cast<const float4*>(yrow + col);
           const float4 b2 = *reinterpret_cast<const float4*>(b2s + col);
           const float4 gf = *reinterpret_cast<const float4*>(gfs + col);
-          y.x = fmaf(gf.x, __uint_as_float(rr[4 * j + 0]) + b2.x, y.x);
-          y.y = fmaf(gf.y, __uint_as_float(rr[4 * j + 1]) + b2.y, y.y);
-          y.z = fmaf(gf.z, __uint_as_float(rr[4 * j + 2]) + b2.z, y.z);
-          y.w = fmaf(gf.w, __uint_as_float(rr[4 * j + 3]) + b2.w, y.w);
-          *reinterpret_cast<float4*>(yrow + col) = y;
+          float4& yy = y[cc * 8 + j];
+          yy.x = fmaf(gf.x, __uint_as_float(rr[4 * j + 0]) + b2.x, yy.x);
+          yy.y = fmaf(gf.y, __uint_as_float(rr[4 * j + 1]) + b2.y, yy.y);
+          yy.z = fmaf(gf.z, __uint_as_float(rr[4 * j + 2]) + b2.z, yy.z);
+          yy.w = fmaf(gf.w, __uint_as_float(rr[4 * j + 3]) + b2.w, yy.w);
         }
       }
       ptx::tc_fence_before();
       ptx::named_bar_sync(3, 128);
       if (otid == 0) ptx::mbar_arrive(&tm_empty[buf]);  // TMEM buffer may be overwritten by MMA1 of tile it+2
-      // coalesced store of the finished rows
+      // each thread owns one full output row: C contiguous floats (whole 128-byte lines)
       const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * TM;
-      const int nrows = min(TM, p.T - t0);
-      const long long obase = (static_cast<long long>(b) * p.T + t0) * C;
-      float4* dst = reinterpret_cast<float4*>(p.out + obase);
-      uint2* dstb = p.out_bf16 ? reinterpret_cast<uint2*>(p.out_bf16 + obase) : nullptr;
-      for (int i = otid; i < nrows * CV; i += 128) {
-        const int rr2 = i / CV, c4 = i % CV;
-        const float4 v = *reinterpret_cast<const float4*>(xs + (rr2 + HALO) * F::XP + c4 * 4);
-        dst[i] = v;
-        if (dstb) {
-          uint2 pk;
-          pk.x = bf2(v.x, v.y);
-          pk.y = bf2(v.z, v.w);
-          dstb[i] = pk;
+      if (t0 + r < p.T) {
+        const long long o = (static_cast<long long>(b) * p.T + t0 + r) * C;
+        float4* dst = reinterpret_cast<float4*>(p.out + o);
+#pragma unroll
+        for (int j = 0; j < C / 4; ++j) dst[j] = y[j];
+        if (p.out_bf16 != nullptr) {
+          uint4* dstb = reinterpret_cast<uint4*>(p.out_bf16 + o);
+#pragma unroll
+          for (int j = 0; j < C / 8; ++j) {
+            uint4 pk;
+            pk.x = bf2(y[2 * j].x, y[2 * j].y);
+            pk.y = bf2(y[2 * j].z, y[2 * j].w);
+            pk.z = bf2(y[2 * j + 1].x, y[2 * j + 1].y);
+            pk.w = bf2(y[2 * j + 1].z, y[2 * j + 1].w);
+            dstb[j] = pk;
+          }
         }
       }
-      ptx::named_bar_sync(3, 128);
-      if (otid == 0) ptx::mbar_arrive(&x_empty[buf]);  // x buffer may be refilled for tile it+2
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc<512>(tmem_base);
+  if (warp == kMmaWarp) ptx::tmem_dealloc<512>(tmem_base);
 }
 
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -236,7 +236,7 @@ def test_convnext_mix(eng, C_, T):
     _assert_close(a, want_a, tol=1e-2)
 
 
-@pytest.mark.parametrize("C_,T", [(32, 1000), (64, 700), (64, 128), (32, 57)])
+@pytest.mark.parametrize("C_,T", [(32, 1000), (64, 700), (64, 128), (32, 57), (64, 19000), (32, 30011)])
 def test_convnext_fused(eng, C_, T):
     """Whole ConvNeXt layer (hf:284-297) in one kernel vs torch fp32 on bf16-rounded weights."""
     from smalltts_b200 import _cabi

@@ -6,5 +6,5 @@ for k in "linear or small_k or swiglu or epilogue or causal or transpose" groupe
   timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "$k" 2>&1 | grep -E "passed|failed|Error|error|assert|FAILED" | head -30
 done
 echo "=== parity"
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu 2>&1 | tail -80 > gpurun_out/parity.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -x 2>&1 | grep -v "^$" | head -150 > gpurun_out/parity.log
 grep -E "passed|failed|Error|assert|FAILED|rel_l2|E  " gpurun_out/parity.log | head -60
