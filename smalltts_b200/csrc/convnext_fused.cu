@@ -66,16 +66,16 @@ struct FC {
   static constexpr int SMEM = OFF_BAR + 17 * 8 + 16 + 1024;
 };
 
-// erf-GELU as 0.5 x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form (max abs err 2.6e-5 before the
-// MUFU.TANH approximation, whose 2^-11 relative error stays below the bf16 rounding applied right after).
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
-  const float x2 = xc * xc;
-  const float u = xc * fmaf(x2, fmaf(x2, -3.5190239e-4f, 3.7008020e-2f), 0.79750528f);
+// TWICE the erf-GELU: x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form (max abs err 2.6e-5 before
+// the MUFU.TANH approximation, whose 2^-11 relative error stays below the bf16 rounding applied right after).  The
+// factor 0.5 is folded into the output scale (0.5 * ffn_gamma).  x^2 is clamped at 64: beyond |x| = 8 the quintic
+// would turn around, with the clamp u = 1.72 x keeps growing and tanh saturates.
+__device__ __forceinline__ float gelu2_fast(float x) {
+  const float x2 = fminf(x * x, 64.0f);
+  const float u = x * fmaf(x2, fmaf(x2, -3.5190239e-4f, 3.7008020e-2f), 0.79750528f);
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  const float h = 0.5f * x;
-  return fmaf(h, t, h);
+  return fmaf(x, t, x);
 }
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
@@ -130,10 +130,12 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   // ---------------- one-time setup
   for (int i = threadIdx.x; i < F::HID; i += kThreadsFused) b1s[i] = p.b1[i];
   for (int i = threadIdx.x; i < C; i += kThreadsFused) {
-    b2s[i] = p.b2[i]; gfs[i] = p.ffn_gamma[i]; nws[i] = p.norm_w[i]; fws[i] = p.ffn_norm_w[i];
+    b2s[i] = p.ffn_gamma[i] * p.b2[i]; gfs[i] = 0.5f * p.ffn_gamma[i]; nws[i] = p.norm_w[i]; fws[i] = p.ffn_norm_w[i];
     gms[i] = p.gamma[i]; cbs[i] = p.conv_b[i];
   }
-  for (int i = threadIdx.x; i < 7 * C; i += kThreadsFused) cws[i] = p.conv_w[(i % C) * 7 + i / C];  // tap-major
+  for (int i = threadIdx.x; i < 7 * C; i += kThreadsFused) {  // tap-major, RMSNorm weight folded in
+    cws[i] = p.conv_w[(i % C) * 7 + i / C] * p.norm_w[i % C];
+  }
   for (int i = threadIdx.x; i < 2 * F::A_BYTES / 16; i += kThreadsFused) {
     reinterpret_cast<uint4*>(smem + F::OFF_A)[i] = make_uint4(0, 0, 0, 0);  // K padding (C = 32) stays zero
   }
@@ -202,13 +204,13 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         float w[7];
 #pragma unroll
         for (int j = 0; j < 7; ++j) w[j] = cws[j * C + c];
-        const float cb = cbs[c], gm = gms[c], nw = nws[c];
+        const float cb = cbs[c], gm = gms[c];
         float win[7];
         win[0] = 0.f;
 #pragma unroll
         for (int j = 1; j < 7; ++j) {
           const int r = rs - 7 + j;
-          win[j] = xs[r * F::XP + c] * inv1[r] * nw;
+          win[j] = xs[r * F::XP + c] * inv1[r];
         }
         ptx::named_bar_sync(1, NT);  // every warm-up read precedes the in-place writes of the previous segment
 #pragma unroll 8
@@ -216,7 +218,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           const float xv = xs[r * F::XP + c];
 #pragma unroll
           for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-          win[6] = xv * inv1[r] * nw;
+          win[6] = xv * inv1[r];
           // two independent partial sums shorten the dependent FMA chain
           float a0 = fmaf(w[0], win[0], cb), a1 = w[1] * win[1];
           a0 = fmaf(w[2], win[2], a0); a1 = fmaf(w[3], win[3], a1);
@@ -330,10 +332,10 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           const float4 ba = *reinterpret_cast<const float4*>(bb + 8 * j);
           const float4 bc = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
           uint4 pk;
-          pk.x = bf2(gelu_fast(__uint_as_float(rr[8 * j + 0]) + ba.x), gelu_fast(__uint_as_float(rr[8 * j + 1]) + ba.y));
-          pk.y = bf2(gelu_fast(__uint_as_float(rr[8 * j + 2]) + ba.z), gelu_fast(__uint_as_float(rr[8 * j + 3]) + ba.w));
-          pk.z = bf2(gelu_fast(__uint_as_float(rr[8 * j + 4]) + bc.x), gelu_fast(__uint_as_float(rr[8 * j + 5]) + bc.y));
-          pk.w = bf2(gelu_fast(__uint_as_float(rr[8 * j + 6]) + bc.z), gelu_fast(__uint_as_float(rr[8 * j + 7]) + bc.w));
+          pk.x = bf2(gelu2_fast(__uint_as_float(rr[8 * j + 0]) + ba.x), gelu2_fast(__uint_as_float(rr[8 * j + 1]) + ba.y));
+          pk.y = bf2(gelu2_fast(__uint_as_float(rr[8 * j + 2]) + ba.z), gelu2_fast(__uint_as_float(rr[8 * j + 3]) + ba.w));
+          pk.z = bf2(gelu2_fast(__uint_as_float(rr[8 * j + 4]) + bc.x), gelu2_fast(__uint_as_float(rr[8 * j + 5]) + bc.y));
+          pk.w = bf2(gelu2_fast(__uint_as_float(rr[8 * j + 6]) + bc.z), gelu2_fast(__uint_as_float(rr[8 * j + 7]) + bc.w));
           *reinterpret_cast<uint4*>(Gs + sw128_off(r, (half * 4 + j) * 8)) = pk;
         }
         ptx::fence_proxy_async();
@@ -374,10 +376,11 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           const float4 b2 = *reinterpret_cast<const float4*>(b2s + col);
           const float4 gf = *reinterpret_cast<const float4*>(gfs + col);
           float4& yy = y[cc * 8 + j];
-          yy.x = fmaf(gf.x, __uint_as_float(rr[4 * j + 0]) + b2.x, yy.x);
-          yy.y = fmaf(gf.y, __uint_as_float(rr[4 * j + 1]) + b2.y, yy.y);
-          yy.z = fmaf(gf.z, __uint_as_float(rr[4 * j + 2]) + b2.z, yy.z);
-          yy.w = fmaf(gf.w, __uint_as_float(rr[4 * j + 3]) + b2.w, yy.w);
+          // O holds W2 (2 gelu): out = y + ffn_gamma*b2 + (0.5 ffn_gamma) * O
+          yy.x = fmaf(gf.x, __uint_as_float(rr[4 * j + 0]), yy.x + b2.x);
+          yy.y = fmaf(gf.y, __uint_as_float(rr[4 * j + 1]), yy.y + b2.y);
+          yy.z = fmaf(gf.z, __uint_as_float(rr[4 * j + 2]), yy.z + b2.z);
+          yy.w = fmaf(gf.w, __uint_as_float(rr[4 * j + 3]), yy.w + b2.w);
         }
       }
       ptx::tc_fence_before();

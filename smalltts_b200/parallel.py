@@ -1,0 +1,100 @@
+"""Data-parallel batch split across the GPUs of one box.
+
+Utterances are independent, so there is no data-path collective: rank r synthesises its own shard on its own
+engine (weights replicated), and only the finished waveforms travel (gathered to rank 0 over the process group:
+NCCL on GPUs, gloo in the CPU tests).  The reference has no multi-GPU inference at all (its "batch" is a loop,
+infer/onnx.py:143-156, scripts/infer/batch.py:31-45); this module is the host-side scheduler that replaces it.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence
+
+import numpy as np
+
+HOP_SIZE = 3200
+
+
+def utterance_cost(frames: int) -> float:
+    """Relative cost model: the vocoder dominates and is linear in frames; a constant covers the condition
+    encoder and launch overheads (measured split in DESIGN.md)."""
+    return 1.0 * frames + 12.0
+
+
+def partition_lpt(costs: Sequence[float], n_ranks: int) -> List[List[int]]:
+    """Greedy longest-processing-time assignment of items to ranks; deterministic; returns indices per rank,
+    each list ordered by decreasing cost (so that consecutive items have similar lengths -> little padding)."""
+    if n_ranks < 1:
+        raise ValueError("n_ranks must be >= 1")
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * n_ranks
+    out: List[List[int]] = [[] for _ in range(n_ranks)]
+    for i in order:
+        r = min(range(n_ranks), key=lambda k: (loads[k], k))
+        out[r].append(i)
+        loads[r] += costs[i]
+    return out
+
+
+def length_buckets(indices: Sequence[int], frames: Sequence[int], max_batch: int = 16,
+                   max_pad_frac: float = 0.25) -> List[List[int]]:
+    """Split a rank's shard (already sorted by decreasing length) into micro-batches whose padding waste stays
+    below ``max_pad_frac`` of the padded size."""
+    out: List[List[int]] = []
+    cur: List[int] = []
+    for i in indices:
+        if cur:
+            tmax = frames[cur[0]]
+            used = sum(frames[j] for j in cur) + frames[i]
+            if len(cur) >= max_batch or 1.0 - used / (tmax * (len(cur) + 1)) > max_pad_frac:
+                out.append(cur)
+                cur = []
+        cur.append(i)
+    if cur:
+        out.append(cur)
+    return out
+
+
+def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], frames: Sequence[int], rank: int,
+                       world: int, group=None, gather_to: int = 0):
+    """Run ``synthesize_fn`` on this rank's shard and gather every waveform to ``gather_to`` in input order.
+
+    synthesize_fn(indices) -> list of (1, frames_i*3200) float32 arrays for those utterances (on a GPU rank this is
+    ``lambda idx: tts.synthesize_batch([refs[i] for i in idx], ...)``).  Returns the full list on ``gather_to``,
+    None elsewhere.  world == 1 needs no process group."""
+    shards = partition_lpt([utterance_cost(f) for f in frames], world)
+    mine = shards[rank]
+    results = {}
+    for mb in length_buckets(mine, frames):
+        for i, a in zip(mb, synthesize_fn(list(mb))):
+            a = np.asarray(a, dtype=np.float32)
+            if a.shape != (1, frames[i] * HOP_SIZE):
+                raise ValueError(f"utterance {i}: expected {(1, frames[i] * HOP_SIZE)}, got {a.shape}")
+            results[i] = a
+    if world == 1:
+        return [results[i] for i in range(len(frames))]
+    import torch
+    import torch.distributed as dist
+
+    # one flat fp32 buffer per rank, sizes are known on every rank from `frames` (no size exchange needed)
+    sizes = [sum(frames[i] for i in s) * HOP_SIZE for s in shards]
+    flat = np.concatenate([results[i].ravel() for i in mine]) if mine else np.zeros(0, np.float32)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    send = torch.from_numpy(flat).to(dev)
+    if rank == gather_to:
+        bufs = [torch.empty(n, dtype=torch.float32, device=dev) for n in sizes]
+        bufs[rank].copy_(send)
+        reqs = [dist.irecv(bufs[r], src=r, group=group) for r in range(world) if r != rank and sizes[r] > 0]
+        for q in reqs:
+            q.wait()
+        out: List[np.ndarray] = [None] * len(frames)  # type: ignore[list-item]
+        for r in range(world):
+            off, host = 0, bufs[r].cpu().numpy()
+            for i in shards[r]:
+                n = frames[i] * HOP_SIZE
+                out[i] = host[off : off + n].reshape(1, n).copy()
+                off += n
+        return out
+    if sizes[rank] > 0:
+        dist.send(send, dst=gather_to, group=group)
+    return None
