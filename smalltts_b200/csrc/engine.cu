@@ -162,15 +162,35 @@ struct stts_engine {
 namespace {
 
 // ------------------------------------------------------------------ GEMM convenience wrappers
-// Widest tile that still gives the chip a full wave of CTAs (148 SMs); narrow tiles for small problems.
-int pick_bn(long long m, int n) {
-  int bn = 256;
-  while (bn > 32) {
+// Tile-width choice by a small cost model (cycles).  Measured on B200: an SM pulls ~64 B/clk from L2, so with a
+// 128 x BN tile every 64-deep k-iteration is load-bound at (16 KB + BN*128 B) / 64 = 256 + 2*BN cycles (the MMA
+// itself needs only 2*BN).  Wider tiles amortise the A panel; narrower ones give more CTAs.  Cost = waves x
+// (iterations x per-iteration cycles + fixed prologue/epilogue), with the CTAs-per-SM the shared memory, TMEM
+// and register budgets allow.
+int pick_bn(long long m, int n, int iters) {
+  int best = 32;
+  double best_cost = 1e30;
+  for (int bn = 32; bn <= 256; bn *= 2) {
+    if (bn > 32 && bn > n) break;
+    const int max_stages = bn == 256 ? 4 : 6;
+    const int stages = iters < 2 ? 2 : (iters > max_stages ? max_stages : iters);
+    const int smem = stages * (16384 + bn * 128) + 1280;
+    int cps = 232448 / smem;
+    if (cps > 512 / bn) cps = 512 / bn;
+    if (cps > 3) cps = 3;
+    if (cps < 1) cps = 1;
     const long long tiles = ((m + 127) / 128) * ((n + bn - 1) / bn);
-    if (bn <= n && tiles >= 148) break;
-    bn /= 2;
+    const long long waves = (tiles + 148LL * cps - 1) / (148LL * cps);
+    // co-resident CTAs share the SM's L2 bandwidth: per-iteration time scales with min(cps, tiles per SM)
+    const long long per_sm = (tiles + 147) / 148;
+    const int share = static_cast<int>(per_sm < cps ? per_sm : cps);
+    const double cost = static_cast<double>(waves) * (iters * (256.0 + 2.0 * bn) * share + 3000.0 + 40.0 * bn);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
   }
-  return bn;
+  return best;
 }
 
 // Plain linear over flattened rows: out = epi(A[rows, K] * W[N, K]^T)
@@ -183,7 +203,7 @@ void linear(stts_engine* e, const bf16* a, long long rows, int k, int lda, const
   s.K = k;
   GemmA ga{a, k, lda};
   GemmW gw{w, n, ldw};
-  if (bn == 0) bn = pick_bn(rows, n);
+  if (bn == 0) bn = pick_bn(rows, n, (k + 63) / 64);
   CK(launch_gemm(e->st, bn, ga, gw, s, epi));
 }
 
@@ -700,7 +720,7 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
     s.B = B; s.T = T; s.N = 2048; s.K = 64; s.taps = 7; s.tap_shift0 = -6; s.tap_step = 1;
     GemmEpi ep;
     ep.bias = e->stem_b; ep.out_f32 = ws.xa; ep.ld_out = 2048;
-    CK(launch_gemm(st, pick_bn(frames, 2048), GemmA{ws.latb, LAT, LAT}, GemmW{e->stem_w, 2048, 7 * 64}, s, ep));
+    CK(launch_gemm(st, pick_bn(frames, 2048, 7), GemmA{ws.latb, LAT, LAT}, GemmW{e->stem_w, 2048, 7 * 64}, s, ep));
   }
   int Ts = T;
   float* cur = ws.xa;  // activations of the current stage (every stage ends with one swap, see below)
@@ -739,7 +759,7 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
         g.B = B; g.T = Ts; g.N = r * cout; g.K = C; g.taps = 2; g.tap_shift0 = 0; g.tap_step = -1;
         GemmEpi ep;
         ep.bias = e->up_b[s]; ep.out_f32 = oth; ep.ld_out = r * cout;
-        CK(launch_gemm(st, pick_bn(M, r * cout), GemmA{ws.xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
+        CK(launch_gemm(st, pick_bn(M, r * cout, 2 * ((C + 63) / 64)), GemmA{ws.xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
       }
     }
     if (s < 6) {

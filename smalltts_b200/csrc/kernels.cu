@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
   constexpr int PITCH = HD + 8;  // bf16 elements; 16-byte rows offset by one bank group -> conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
-  bf16* sK = sQ + 64 * PITCH;
-  bf16* sV = sK + 64 * PITCH;
+  bf16* sKV = sQ + 64 * PITCH;  // [2 buffers][K | V][64][PITCH]
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,57 +160,66 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
   if (nseg > 2) len[2] = s2.len ? min(s2.len[b], s2.n_max) : s2.n_max;
   const int total = len[0] + len[1] + len[2];
 
-  // stage Q tile (zero-fill rows beyond tq)
   constexpr int VPR = HD / 8;  // 16-byte vectors per row
+  // cp.async staging (no register round trip, every 16-byte copy of a chunk in flight at once); rows beyond the
+  // valid range are zero-filled (src-size 0)
   for (int i = threadIdx.x; i < 64 * VPR; i += 128) {
     const int r = i / VPR, c = i % VPR;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (q0 + r < tq) {
-      val = *reinterpret_cast<const uint4*>(q + (static_cast<long long>(b) * tq + q0 + r) * ld + h * HD + c * 8);
-    }
-    *reinterpret_cast<uint4*>(sQ + r * PITCH + c * 8) = val;
+    const bool ok = q0 + r < tq;
+    const bf16* src = q + (static_cast<long long>(b) * tq + (ok ? q0 + r : 0)) * ld + h * HD + c * 8;
+    ptx::cp_async_16(ptx::smem_u32(sQ + r * PITCH + c * 8), src, ok ? 16u : 0u);
   }
-  __syncthreads();
-  uint32_t qf[HD / 16][4];
-  {
-    const int r = warp * 16 + (lane & 15);
-    const int cofs = (lane >> 4) * 8;
-#pragma unroll
-    for (int kk = 0; kk < HD / 16; ++kk) {
-      ptx::ldmatrix_x4(qf[kk], sQ + r * PITCH + kk * 16 + cofs);
+  auto load_chunk = [&](int k0, int bufi) {
+    bf16* dK = sKV + bufi * (2 * 64 * PITCH);
+    bf16* dV = dK + 64 * PITCH;
+    for (int i = threadIdx.x; i < 64 * VPR; i += 128) {
+      const int r = i / VPR, c = i % VPR;
+      int j = k0 + r;
+      const bool ok = j < total;
+      const bf16 *kp = s0.k, *vp = s0.v;
+      int nmax = s0.n_max;
+      if (ok) {
+        if (j >= len[0] + len[1]) {
+          j -= len[0] + len[1]; kp = s2.k; vp = s2.v; nmax = s2.n_max;
+        } else if (j >= len[0]) {
+          j -= len[0]; kp = s1.k; vp = s1.v; nmax = s1.n_max;
+        }
+      } else {
+        j = 0;
+      }
+      const long long off = (static_cast<long long>(b) * nmax + j) * ld + h * HD + c * 8;
+      ptx::cp_async_16(ptx::smem_u32(dK + r * PITCH + c * 8), kp + off, ok ? 16u : 0u);
+      ptx::cp_async_16(ptx::smem_u32(dV + r * PITCH + c * 8), vp + off, ok ? 16u : 0u);
     }
-  }
+    ptx::cp_async_commit();
+  };
+  load_chunk(0, 0);  // commits the Q copies too
 
+  uint32_t qf[HD / 16][4];
   float o[HD / 8][4];
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
 
-  for (int k0 = 0; k0 < total; k0 += 64) {
-    __syncthreads();  // previous chunk fully consumed
-    for (int i = threadIdx.x; i < 64 * VPR; i += 128) {
-      const int r = i / VPR, c = i % VPR;
-      int j = k0 + r;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (j < total) {
-        const bf16 *kp, *vp;
-        int nmax;
-        if (j < len[0]) {
-          kp = s0.k; vp = s0.v; nmax = s0.n_max;
-        } else if (j < len[0] + len[1]) {
-          j -= len[0]; kp = s1.k; vp = s1.v; nmax = s1.n_max;
-        } else {
-          j -= len[0] + len[1]; kp = s2.k; vp = s2.v; nmax = s2.n_max;
-        }
-        const long long off = (static_cast<long long>(b) * nmax + j) * ld + h * HD + c * 8;
-        kv = *reinterpret_cast<const uint4*>(kp + off);
-        vv = *reinterpret_cast<const uint4*>(vp + off);
-      }
-      *reinterpret_cast<uint4*>(sK + r * PITCH + c * 8) = kv;
-      *reinterpret_cast<uint4*>(sV + r * PITCH + c * 8) = vv;
+  int ci = 0;
+  for (int k0 = 0; k0 < total || k0 == 0; k0 += 64, ++ci) {
+    if (k0 + 64 < total) {
+      load_chunk(k0 + 64, (ci + 1) & 1);  // prefetch the next chunk into the other buffer
+      ptx::cp_async_wait<1>();
+    } else {
+      ptx::cp_async_wait<0>();
     }
     __syncthreads();
+    if (k0 == 0) {
+      const int r = warp * 16 + (lane & 15);
+      const int cofs = (lane >> 4) * 8;
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) ptx::ldmatrix_x4(qf[kk], sQ + r * PITCH + kk * 16 + cofs);
+    }
+    if (total == 0) break;
+    const bf16* sK = sKV + (ci & 1) * (2 * 64 * PITCH);
+    const bf16* sV = sK + 64 * PITCH;
 
     // S = Q K^T for 16 rows x 64 keys
     float sc[8][4];
@@ -283,6 +291,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
         ptx::mma_16816(o[2 * np + 1], pf[kk], bfr[2], bfr[3]);
       }
     }
+    __syncthreads();  // every warp is done with this K/V buffer before the prefetch of chunk ci+2 overwrites it
   }
 
   // finalize: divide by row sums (reduced over the 4 lanes of a row), gate, store
@@ -680,7 +689,7 @@ cudaError_t attention_bf16(cudaStream_t st, const bf16* q, int B, int tq, int H,
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
   dim3 grid((tq + 63) / 64, H, B);
   if (hd_pad == 128) {
-    constexpr int smem = 3 * 64 * (128 + 8) * 2;
+    constexpr int smem = 5 * 64 * (128 + 8) * 2;
     static bool once = false;
     if (!once) {
       cudaError_t e = cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -689,7 +698,7 @@ cudaError_t attention_bf16(cudaStream_t st, const bf16* q, int B, int tq, int H,
     }
     attention_kernel<128><<<grid, 128, smem, st>>>(q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
   } else if (hd_pad == 64) {
-    constexpr int smem = 3 * 64 * (64 + 8) * 2;
+    constexpr int smem = 5 * 64 * (64 + 8) * 2;
     attention_kernel<64><<<grid, 128, smem, st>>>(q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
   } else {
     return cudaErrorInvalidValue;
