@@ -164,27 +164,17 @@ namespace {
 // ------------------------------------------------------------------ GEMM convenience wrappers
 // Tile-width choice by a small cost model (cycles).  Measured on B200: an SM pulls ~64 B/clk from L2, so with a
 // 128 x BN tile every 64-deep k-iteration is load-bound at (16 KB + BN*128 B) / 64 = 256 + 2*BN cycles (the MMA
-// itself needs only 2*BN).  Wider tiles amortise the A panel; narrower ones give more CTAs.  Cost = waves x
-// (iterations x per-iteration cycles + fixed prologue/epilogue), with the CTAs-per-SM the shared memory, TMEM
-// and register budgets allow.
+// itself needs only 2*BN).  Wider tiles amortise the A panel; narrower ones give more CTAs.  The GEMM is persistent
+// (one CTA per SM, epilogue overlapped with the next tile): cost = rounds x iterations x per-iteration cycles + a
+// fixed prologue and the last tile's exposed epilogue.
 int pick_bn(long long m, int n, int iters) {
   int best = 32;
   double best_cost = 1e30;
   for (int bn = 32; bn <= 256; bn *= 2) {
     if (bn > 32 && bn > n) break;
-    const int max_stages = bn == 256 ? 4 : 6;
-    const int stages = iters < 2 ? 2 : (iters > max_stages ? max_stages : iters);
-    const int smem = stages * (16384 + bn * 128) + 1280;
-    int cps = 232448 / smem;
-    if (cps > 512 / bn) cps = 512 / bn;
-    if (cps > 3) cps = 3;
-    if (cps < 1) cps = 1;
     const long long tiles = ((m + 127) / 128) * ((n + bn - 1) / bn);
-    const long long waves = (tiles + 148LL * cps - 1) / (148LL * cps);
-    // co-resident CTAs share the SM's L2 bandwidth: per-iteration time scales with min(cps, tiles per SM)
-    const long long per_sm = (tiles + 147) / 148;
-    const int share = static_cast<int>(per_sm < cps ? per_sm : cps);
-    const double cost = static_cast<double>(waves) * (iters * (256.0 + 2.0 * bn) * share + 3000.0 + 40.0 * bn);
+    const long long rounds = (tiles + 147) / 148;
+    const double cost = static_cast<double>(rounds) * iters * (256.0 + 2.0 * bn) + 3000.0 + 30.0 * bn;
     if (cost < best_cost) {
       best_cost = cost;
       best = bn;

@@ -19,15 +19,16 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
 
 template <int BN>
 struct Cfg {
-  static constexpr int kMaxStages = (BN == 256) ? 4 : 6;
+  static constexpr int kMaxStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);  // one persistent CTA per SM
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int smem_bytes(int stages) {
-    return stages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+    return stages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;  // <= 12 barriers + slot
   }
 };
 
@@ -72,10 +73,13 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// Persistent CTA: walks output tiles (tile = blockIdx.x + i * gridDim.x; n fastest, so concurrently running CTAs share
+// A rows in L2).  The smem ring runs ahead across tile boundaries and the accumulator is double-buffered in TMEM
+// (2 x BN columns), so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 template <int BN, int ACT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmShape s,
-            const GemmEpi e, const int kStages) {
+            const GemmEpi e, const int kStages, const int n_tiles, const int m_tiles, const int total_tiles) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -84,19 +88,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smB = smem + kStages * C::kABytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smB + kStages * C::kBBytes);
   uint64_t* empty = full + kStages;
-  uint64_t* acc_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = empty + kStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const int tiles_t = (s.T + BM - 1) / BM;
-  const int b = blockIdx.y / tiles_t;
-  const int t0 = (blockIdx.y % tiles_t) * BM;
-  const int n0 = blockIdx.x * BN;
-  const int g = blockIdx.z;
   const int kchunks = (s.K + BK - 1) / BK;
   const int iters = s.taps * kchunks;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -105,11 +108,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
-    ptx::mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], kEpiWarps);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc<BN>(tmem_slot);
+    ptx::tmem_alloc<2 * BN>(tmem_slot);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -118,130 +124,155 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        const int tap = it / kchunks;
-        const int kc = it - tap * kchunks;
-        ptx::mbar_wait(&empty[st], ph ^ 1);
-        ptx::mbar_expect_tx(&full[st], C::kABytes + C::kBBytes);
-        ptx::tma_load_3d(smA + st * C::kABytes, &tmA, &full[st], g * s.a_group_koff + kc * BK,
-                         t0 + s.tap_shift0 + tap * s.tap_step, b);
-        ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], (tap * kchunks + kc) * BK,
-                         g * s.w_group_rows + n0);
+      uint32_t kidx = 0;  // ring position, continues across tiles
+      for (int li = 0; li < n_my; ++li) {
+        const int tile = first + li * stride;
+        const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
+        const int b = my / tiles_t, t0 = (my % tiles_t) * BM, n0 = nx * BN;
+        for (int it = 0; it < iters; ++it, ++kidx) {
+          const int st = kidx % kStages;
+          const uint32_t ph = (kidx / kStages) & 1;
+          const int tap = it / kchunks;
+          const int kc = it - tap * kchunks;
+          ptx::mbar_wait(&empty[st], ph ^ 1);
+          ptx::mbar_expect_tx(&full[st], C::kABytes + C::kBBytes);
+          ptx::tma_load_3d(smA + st * C::kABytes, &tmA, &full[st], g * s.a_group_koff + kc * BK,
+                           t0 + s.tap_shift0 + tap * s.tap_step, b);
+          ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], (tap * kchunks + kc) * BK,
+                           g * s.w_group_rows + n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
-      for (int it = 0; it < iters; ++it) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        ptx::mbar_wait(&full[st], ph);
+      uint32_t kidx = 0;
+      for (int li = 0; li < n_my; ++li) {
+        const int ab = li & 1;
+        // the epilogue warps must have drained this accumulator buffer (tile li-2)
+        ptx::mbar_wait(&acc_empty[ab], ((li >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smA + st * C::kABytes));
-        const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smB + st * C::kBBytes));
+        for (int it = 0; it < iters; ++it, ++kidx) {
+          const int st = kidx % kStages;
+          const uint32_t ph = (kidx / kStages) & 1;
+          ptx::mbar_wait(&full[st], ph);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smA + st * C::kABytes));
+          const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smB + st * C::kBBytes));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-          ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            ptx::umma_bf16(tmem_base + ab * BN, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[st]);  // frees this smem stage once the MMAs above have read it
         }
-        ptx::umma_commit(&empty[st]);  // frees this smem stage once the MMAs above have read it
+        ptx::umma_commit(&acc_full[ab]);  // accumulator complete
       }
-      ptx::umma_commit(acc_full);  // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = tile rows
-    ptx::mbar_wait(acc_full, 0);
-    ptx::tc_fence_after();
+    // ---------------- epilogue: 8 warps; warp w owns TMEM lanes [32(w%4), +32) = tile rows and every second
+    // 32-column chunk of the accumulator (chunk parity = (w-2)/4)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int t = t0 + row;
-    const bool row_ok = t < s.T;
-    const long long m = static_cast<long long>(b) * s.T + t;
-    // batch index / in-batch row used by masking and gating (flattened inputs carry rows_per_batch)
-    const int eb = e.rows_per_batch > 0 ? static_cast<int>(m / e.rows_per_batch) : b;
-    const int et = e.rows_per_batch > 0 ? static_cast<int>(m % e.rows_per_batch) : t;
-    const bool masked = (e.row_len != nullptr) && row_ok && (et >= e.row_len[eb]);
-    const bool mask32 = masked && !e.mask_bf16_only;
-    const float bz = (masked && e.mask_bf16_only) ? 0.0f : 1.0f;  // bf16-only masking
-    const int gcol_base = g * s.out_group_cols;
     constexpr int kOut = (ACT == ACT_SWIGLU16) ? 16 : 32;  // output columns per 32-column accumulator chunk
+    for (int li = 0; li < n_my; ++li) {
+      const int tile = first + li * stride;
+      const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
+      const int b = my / tiles_t, t0 = (my % tiles_t) * BM, n0 = nx * BN;
+      const int ab = li & 1;
+      ptx::mbar_wait(&acc_full[ab], (li >> 1) & 1);
+      ptx::tc_fence_after();
+      const int t = t0 + row;
+      const bool row_ok = t < s.T;
+      const long long m = static_cast<long long>(b) * s.T + t;
+      // batch index / in-batch row used by masking and gating (flattened inputs carry rows_per_batch)
+      const int eb = e.rows_per_batch > 0 ? static_cast<int>(m / e.rows_per_batch) : b;
+      const int et = e.rows_per_batch > 0 ? static_cast<int>(m % e.rows_per_batch) : t;
+      const bool masked = (e.row_len != nullptr) && row_ok && (et >= e.row_len[eb]);
+      const bool mask32 = masked && !e.mask_bf16_only;
+      const float bz = (masked && e.mask_bf16_only) ? 0.0f : 1.0f;  // bf16-only masking
+      const int gcol_base = g * s.out_group_cols;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int nl0 = n0 + c * 32;  // column inside the group
-      if (nl0 >= s.N) break;        // warp-uniform
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      ptx::tmem_ld_wait();
-      if (!row_ok) continue;
-      float v[32];
+      for (int c = half; c < BN / 32; c += 2) {
+        const int nl0 = n0 + c * 32;  // column inside the group
+        if (nl0 >= s.N) break;        // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-      const int gc0 = gcol_base + nl0;
-      if (e.bias != nullptr) {
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const int gc0 = gcol_base + nl0;
+        if (e.bias != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) add4(v + 4 * i, e.bias + gc0 + 4 * i);
-      }
-      int out_c0 = gc0;
-      if (ACT == ACT_SWIGLU16) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a = v[i];
-          v[i] = a * fast_sigmoid(a) * v[16 + i];
+          for (int i = 0; i < 8; ++i) add4(v + 4 * i, e.bias + gc0 + 4 * i);
         }
-        out_c0 = gc0 >> 1;
-      } else if (ACT != ACT_NONE) {
+        int out_c0 = gc0;
+        if (ACT == ACT_SWIGLU16) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = act_apply<ACT>(v[i]);
-      }
-      if (mask32) {
+          for (int i = 0; i < 16; ++i) {
+            const float a = v[i];
+            v[i] = a * fast_sigmoid(a) * v[16 + i];
+          }
+          out_c0 = gc0 >> 1;
+        } else if (ACT != ACT_NONE) {
 #pragma unroll
-        for (int i = 0; i < kOut; ++i) v[i] = 0.0f;
-      }
-      if (e.colscale != nullptr) {
+          for (int i = 0; i < 32; ++i) v[i] = act_apply<ACT>(v[i]);
+        }
+        if (mask32) {
 #pragma unroll
-        for (int i = 0; i < kOut / 4; ++i) mul4(v + 4 * i, e.colscale + out_c0 + 4 * i);
-      }
-      if (e.rowgate != nullptr) {
-        const float* gp = e.rowgate + static_cast<long long>(eb) * e.ld_gate + out_c0;
+          for (int i = 0; i < kOut; ++i) v[i] = 0.0f;
+        }
+        if (e.colscale != nullptr) {
 #pragma unroll
-        for (int i = 0; i < kOut / 4; ++i) mul4(v + 4 * i, gp + 4 * i);
-      }
-      if (e.residual != nullptr) {
-        const float* rp = e.residual + m * e.ld_res + out_c0 + g * (s.res_group_cols - s.out_group_cols);
+          for (int i = 0; i < kOut / 4; ++i) mul4(v + 4 * i, e.colscale + out_c0 + 4 * i);
+        }
+        if (e.rowgate != nullptr) {
+          const float* gp = e.rowgate + static_cast<long long>(eb) * e.ld_gate + out_c0;
 #pragma unroll
-        for (int i = 0; i < kOut / 4; ++i) {
-          const float4 x = *reinterpret_cast<const float4*>(rp + 4 * i);
-          v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+          for (int i = 0; i < kOut / 4; ++i) mul4(v + 4 * i, gp + 4 * i);
+        }
+        if (e.residual != nullptr) {
+          const float* rp = e.residual + m * e.ld_res + out_c0 + g * (s.res_group_cols - s.out_group_cols);
+#pragma unroll
+          for (int i = 0; i < kOut / 4; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(rp + 4 * i);
+            v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+          }
+        }
+        if (e.out_f32 != nullptr) {
+          float* op = e.out_f32 + m * e.ld_out + out_c0;
+#pragma unroll
+          for (int i = 0; i < kOut / 4; ++i) {
+            *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+        if (e.out_bf16 != nullptr) {
+          __nv_bfloat16* op = e.out_bf16 + m * e.ld_out + out_c0;
+#pragma unroll
+          for (int i = 0; i < kOut / 8; ++i) {
+            uint4 pk;
+            pk.x = bf2(bz * v[8 * i + 0], bz * v[8 * i + 1]);
+            pk.y = bf2(bz * v[8 * i + 2], bz * v[8 * i + 3]);
+            pk.z = bf2(bz * v[8 * i + 4], bz * v[8 * i + 5]);
+            pk.w = bf2(bz * v[8 * i + 6], bz * v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(op + 8 * i) = pk;
+          }
         }
       }
-      if (e.out_f32 != nullptr) {
-        float* op = e.out_f32 + m * e.ld_out + out_c0;
-#pragma unroll
-        for (int i = 0; i < kOut / 4; ++i) {
-          *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-      }
-      if (e.out_bf16 != nullptr) {
-        __nv_bfloat16* op = e.out_bf16 + m * e.ld_out + out_c0;
-#pragma unroll
-        for (int i = 0; i < kOut / 8; ++i) {
-          uint4 pk;
-          pk.x = bf2(bz * v[8 * i + 0], bz * v[8 * i + 1]);
-          pk.y = bf2(bz * v[8 * i + 2], bz * v[8 * i + 3]);
-          pk.z = bf2(bz * v[8 * i + 4], bz * v[8 * i + 5]);
-          pk.w = bf2(bz * v[8 * i + 6], bz * v[8 * i + 7]);
-          *reinterpret_cast<uint4*>(op + 8 * i) = pk;
-        }
-      }
+      // this warp is done reading the accumulator buffer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    ptx::tmem_dealloc<BN>(tmem_base);
+    ptx::tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -294,13 +325,22 @@ cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUten
     attr_set = true;
   }
   const int tiles_t = (s.T + BM - 1) / BM;
-  dim3 grid((s.N + BN - 1) / BN, s.B * tiles_t, s.groups);
-  // Short reductions need few pipeline stages; the smaller footprint lets 2-3 CTAs share an SM so that one CTA's
-  // epilogue overlaps another's loads and MMAs.
+  const int n_tiles = (s.N + BN - 1) / BN, m_tiles = s.B * tiles_t;
+  const long long total = static_cast<long long>(n_tiles) * m_tiles * s.groups;
+  if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = total < num_sms ? static_cast<int>(total) : num_sms;
+  // deep ring (the producer runs ahead into the next tile); short reductions of small problems need fewer stages
   const int iters = s.taps * ((s.K + BK - 1) / BK);
-  int stages = iters < 2 ? 2 : iters;
-  if (stages > Cfg<BN>::kMaxStages) stages = Cfg<BN>::kMaxStages;
-  gemm_kernel<BN, ACT><<<grid, kThreads, Cfg<BN>::smem_bytes(stages), stream>>>(tmA, tmW, s, e, stages);
+  const long long ring = static_cast<long long>(iters) * ((total + grid - 1) / grid);
+  int stages = ring < 2 ? 2 : (ring > Cfg<BN>::kMaxStages ? Cfg<BN>::kMaxStages : static_cast<int>(ring));
+  gemm_kernel<BN, ACT><<<grid, kThreads, Cfg<BN>::smem_bytes(stages), stream>>>(tmA, tmW, s, e, stages, n_tiles,
+                                                                                m_tiles, static_cast<int>(total));
   ++g_launch_count;
   return cudaGetLastError();
 }
