@@ -21,6 +21,7 @@
 #include <mutex>
 
 #include "kernels.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace stts {
@@ -149,6 +150,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();  // PDL: the setup above only read weights; x (written by the predecessor) is read from here on
+  ptx::pdl_trigger();
 
   if (warp < kMixWarps) {
     // ================================================================== mixer (8 warps)
@@ -457,9 +460,9 @@ cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, 
   if (!tmap_2d(&m2, w2, 4 * C, C, C)) return cudaErrorInvalidValue;      // W2 [C, 4C]: one box per 64-wide K chunk
   const int ntiles = p.B * ((p.T + TM - 1) / TM);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  convnext_fused_kernel<C><<<grid, kThreadsFused, FC<C>::SMEM, st>>>(m1, m2, p);
+  const cudaError_t le = launch_k(convnext_fused_kernel<C>, dim3(grid), dim3(kThreadsFused), FC<C>::SMEM, st, m1, m2, p);
   ++g_launch_count;
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace

@@ -162,11 +162,12 @@ struct stts_engine {
 namespace {
 
 // ------------------------------------------------------------------ GEMM convenience wrappers
-// Tile-width choice by a small cost model (cycles).  Measured on B200: an SM pulls ~64 B/clk from L2, so with a
-// 128 x BN tile every 64-deep k-iteration is load-bound at (16 KB + BN*128 B) / 64 = 256 + 2*BN cycles (the MMA
-// itself needs only 2*BN).  Wider tiles amortise the A panel; narrower ones give more CTAs.  The GEMM is persistent
-// (one CTA per SM, epilogue overlapped with the next tile): cost = rounds x iterations x per-iteration cycles + a
-// fixed prologue and the last tile's exposed epilogue.
+// Tile-width choice by a small cost model (cycles), from ncu measurements on B200:
+//   * one SM pulls ~64 B/clk from L2, so a 64-deep k-iteration of a 128 x BN tile costs (16 KB + BN*128 B) / 64 =
+//     256 + 2*BN cycles on its CTA (the MMA itself needs only 2*BN);
+//   * the whole chip pulls ~6 KB/clk from L2, and narrow tiles re-read the A panel once per N tile, so the sum of all
+//     tile loads is a second floor (this is what bounds the DiT GEMMs at M = 600);
+//   * the GEMM is persistent (one CTA per SM, epilogue overlapped with the next tile).
 int pick_bn(long long m, int n, int iters) {
   int best = 32;
   double best_cost = 1e30;
@@ -174,7 +175,9 @@ int pick_bn(long long m, int n, int iters) {
     if (bn > 32 && bn > n) break;
     const long long tiles = ((m + 127) / 128) * ((n + bn - 1) / bn);
     const long long rounds = (tiles + 147) / 148;
-    const double cost = static_cast<double>(rounds) * iters * (256.0 + 2.0 * bn) + 3000.0 + 30.0 * bn;
+    const double per_cta = static_cast<double>(rounds) * iters * (256.0 + 2.0 * bn);
+    const double chip = static_cast<double>(tiles) * iters * (16384.0 + 128.0 * bn) / 6000.0;
+    const double cost = (per_cta > chip ? per_cta : chip) + 3000.0 + 30.0 * bn;
     if (cost < best_cost) {
       best_cost = cost;
       best = bn;

@@ -9,6 +9,7 @@
 
 #include <mutex>
 
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace stts {
@@ -121,6 +122,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail;
+  // from here on global memory written by it is read (A operand, residual) and its inputs may be overwritten.
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -339,10 +344,10 @@ cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUten
   const int iters = s.taps * ((s.K + BK - 1) / BK);
   const long long ring = static_cast<long long>(iters) * ((total + grid - 1) / grid);
   int stages = ring < 2 ? 2 : (ring > Cfg<BN>::kMaxStages ? Cfg<BN>::kMaxStages : static_cast<int>(ring));
-  gemm_kernel<BN, ACT><<<grid, kThreads, Cfg<BN>::smem_bytes(stages), stream>>>(tmA, tmW, s, e, stages, n_tiles,
-                                                                                m_tiles, static_cast<int>(total));
+  const cudaError_t le = launch_k(gemm_kernel<BN, ACT>, dim3(grid), dim3(kThreads), Cfg<BN>::smem_bytes(stages), stream,
+                                  tmA, tmW, s, e, stages, n_tiles, m_tiles, static_cast<int>(total));
   ++g_launch_count;
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 template <int BN>

@@ -3,16 +3,19 @@
 
 #include <math.h>
 
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace stts {
 
 namespace {
 
-#define STTS_LAUNCH_OK()  \
-  do {                    \
-    ++g_launch_count;     \
-    return cudaGetLastError(); \
+thread_local cudaError_t last_launch_status = cudaSuccess;
+#define STTS_LAUNCH_OK()                                                         \
+  do {                                                                           \
+    ++g_launch_count;                                                            \
+    const cudaError_t _e = last_launch_status;                                   \
+    return _e != cudaSuccess ? _e : cudaGetLastError();                          \
   } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -35,6 +38,8 @@ template <bool kLayerNorm>
 __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ x, int rows, int rpb, int dim,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        int ld_mod, float eps, bf16* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -98,6 +103,8 @@ __global__ void __launch_bounds__(256) head_split_kernel(const float* __restrict
                                                          int rpb, int heads, int hd, const float* __restrict__ norm_w,
                                                          float eps, int rot, const float* __restrict__ cos_t,
                                                          const float* __restrict__ sin_t, bf16* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long item = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (item >= static_cast<long long>(rows) * heads) return;
@@ -139,18 +146,24 @@ __global__ void __launch_bounds__(256) head_split_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------ attention (warp MMA, online softmax)
-// CTA = 64 query rows (4 warps x 16) of one (batch, head); keys streamed in chunks of 64 through smem.
+// CTA = 32 query rows (2 warps x 16) of one (batch, head); keys streamed in chunks of 64 through smem with cp.async
+// double buffering.  Small CTAs on purpose: the whole problem is a few hundred warps, so spreading it over all SMs
+// (two CTAs per SM) matters more than re-staging K/V per query tile (L2 hits).
+constexpr int kAttRows = 32, kAttThreads = 64;
+
 template <int HD>
-__global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ q, int tq, int H, int hd, AttnSeg s0,
+__global__ void __launch_bounds__(kAttThreads) attention_kernel(const bf16* __restrict__ q, int tq, int H, int hd, AttnSeg s0,
                                                         AttnSeg s1, AttnSeg s2, int nseg, const float* __restrict__ gate,
                                                         int ld_gate, int gate_off, float scale_log2,
                                                         bf16* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   constexpr int PITCH = HD + 8;  // bf16 elements; 16-byte rows offset by one bank group -> conflict-free ldmatrix
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
-  bf16* sKV = sQ + 64 * PITCH;  // [2 buffers][K | V][64][PITCH]
+  bf16* sKV = sQ + kAttRows * PITCH;  // [2 buffers][K | V][64][PITCH]
 
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = H * HD;
 
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
   constexpr int VPR = HD / 8;  // 16-byte vectors per row
   // cp.async staging (no register round trip, every 16-byte copy of a chunk in flight at once); rows beyond the
   // valid range are zero-filled (src-size 0)
-  for (int i = threadIdx.x; i < 64 * VPR; i += 128) {
+  for (int i = threadIdx.x; i < kAttRows * VPR; i += kAttThreads) {
     const int r = i / VPR, c = i % VPR;
     const bool ok = q0 + r < tq;
     const bf16* src = q + (static_cast<long long>(b) * tq + (ok ? q0 + r : 0)) * ld + h * HD + c * 8;
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
   auto load_chunk = [&](int k0, int bufi) {
     bf16* dK = sKV + bufi * (2 * 64 * PITCH);
     bf16* dV = dK + 64 * PITCH;
-    for (int i = threadIdx.x; i < 64 * VPR; i += 128) {
+    for (int i = threadIdx.x; i < 64 * VPR; i += kAttThreads) {
       const int r = i / VPR, c = i % VPR;
       int j = k0 + r;
       const bool ok = j < total;
@@ -329,6 +342,8 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict_
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         int n, int pre, int post, int chunk, unsigned tanh_chunks,
                                                         float* __restrict__ y, int ld_y) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (col >= n) return;
@@ -365,6 +380,8 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict_
 }
 
 __global__ void time_features_kernel(const float* __restrict__ t, int rows, float* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int r = blockIdx.x, j = threadIdx.x;  // 128 threads
   if (r >= rows) return;
   const float f = expf(static_cast<float>(j) * -0.07252236513367074f);  // ln(1e4)/127
@@ -375,6 +392,8 @@ __global__ void time_features_kernel(const float* __restrict__ t, int rows, floa
 
 __global__ void embed_gather_kernel(const long long* __restrict__ ids, int rows, const float* __restrict__ table,
                                     int vocab, int dim, float* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int r = blockIdx.x;
   long long id = ids[r];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -384,6 +403,8 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, int rows,
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, long long n, bf16* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(in + i);
@@ -395,6 +416,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, long long n, bf16
 
 __global__ void noise_mix_kernel(const float* __restrict__ xp, const float* __restrict__ nz, float alpha, float sigma,
                                  long long n, float* __restrict__ xt, bf16* __restrict__ xtb) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) {
     const float v = alpha * xp[i] + sigma * nz[i];
@@ -405,6 +428,8 @@ __global__ void noise_mix_kernel(const float* __restrict__ xp, const float* __re
 
 __global__ void dmd_update_kernel(const float* __restrict__ xt, const float* __restrict__ v, float alpha, float sigma,
                                   long long n, float* __restrict__ xp) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) xp[i] = alpha * xt[i] - sigma * v[i];
 }
@@ -418,6 +443,8 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
 
 __global__ void philox_normal_kernel(const unsigned long long* __restrict__ seed_ptr, unsigned long long stream_id, long long n,
                                      float* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i * 4 >= n) return;
   uint32_t c[4] = {static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(stream_id),
@@ -455,6 +482,8 @@ __global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ ffn_norm_w, float eps,
                                                            float* __restrict__ y, bf16* __restrict__ a) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   extern __shared__ __align__(16) float smx[];
   const int R = TT + 6;
   float* tile = smx;               // [R][C]
@@ -555,6 +584,8 @@ __global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restri
 __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int T, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         float* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   extern __shared__ float sh[];
   float* sw = sh;            // [7][C] tap-major
   float* sx = sh + 7 * C;    // [262][C + 1]
@@ -598,6 +629,8 @@ __device__ __forceinline__ int map_row(int r, int mode) {
 
 __global__ void pack_matrix_kernel(const float* __restrict__ src, int rows, int cols, float scale, int row_mode,
                                    int row_off, int col_mode, int col_off, bf16* __restrict__ dst, int ld_dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
@@ -608,6 +641,8 @@ __global__ void pack_matrix_kernel(const float* __restrict__ src, int rows, int 
 
 __global__ void pack_conv_taps_kernel(const float* __restrict__ src, int O, int cin, int taps, int kp, int opg,
                                       int group_pitch, bf16* __restrict__ dst, int ld_dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(O) * cin * taps) return;
   const int tap = static_cast<int>(i % taps);
@@ -618,6 +653,8 @@ __global__ void pack_conv_taps_kernel(const float* __restrict__ src, int O, int 
 }
 
 __global__ void pack_conv_dense_tiles_kernel(const float* __restrict__ src, int taps, bf16* __restrict__ dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(960) * 60 * taps) return;
   const int tap = static_cast<int>(i % taps);
@@ -628,6 +665,8 @@ __global__ void pack_conv_dense_tiles_kernel(const float* __restrict__ src, int 
 }
 
 __global__ void pack_convtr_kernel(const float* __restrict__ src, int cin, int cout, int r, bf16* __restrict__ dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int kk = 2 * r;
   if (i >= static_cast<long long>(cin) * cout * kk) return;
@@ -640,11 +679,15 @@ __global__ void pack_convtr_kernel(const float* __restrict__ src, int cin, int c
 
 __global__ void pack_vector_kernel(const float* __restrict__ src, int n, float scale, int row_mode, int off,
                                    float* __restrict__ dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[map_row(i, row_mode) + off] = scale * src[i];
 }
 
 __global__ void tile_vector_kernel(const float* __restrict__ src, int n, int reps, float* __restrict__ dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n * reps) dst[i] = src[i % n];
 }
@@ -657,13 +700,13 @@ inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>(
 cudaError_t ln_mod_bf16(cudaStream_t st, const float* x, int rows, int rpb, int dim, const float* scale,
                         const float* shift, int ld_mod, float eps, bf16* out) {
   if (dim % 4 != 0 || dim > 1024) return cudaErrorInvalidValue;
-  row_norm_kernel<true><<<blocks_for(rows, 8), 256, 0, st>>>(x, rows, rpb, dim, scale, shift, ld_mod, eps, out);
+  last_launch_status = launch_k(row_norm_kernel<true>, dim3(blocks_for(rows, 8)), dim3(256), 0, st, x, rows, rpb, dim, scale, shift, ld_mod, eps, out);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t rms_norm_bf16(cudaStream_t st, const float* x, int rows, int dim, const float* w, float eps, bf16* out) {
   if (dim % 4 != 0 || dim > 1024) return cudaErrorInvalidValue;
-  row_norm_kernel<false><<<blocks_for(rows, 8), 256, 0, st>>>(x, rows, 1, dim, w, nullptr, 0, eps, out);
+  last_launch_status = launch_k(row_norm_kernel<false>, dim3(blocks_for(rows, 8)), dim3(256), 0, st, x, rows, 1, dim, w, nullptr, 0, eps, out);
   STTS_LAUNCH_OK();
 }
 
@@ -672,9 +715,9 @@ cudaError_t head_split_bf16(cudaStream_t st, const float* in, int ld_in, int src
                             const float* sin_t, bf16* out) {
   const unsigned nb = blocks_for(static_cast<long long>(rows) * heads, 8);
   if (hd_pad == 128) {
-    head_split_kernel<4><<<nb, 256, 0, st>>>(in, ld_in, src_off, rows, rpb, heads, hd, norm_w, eps, rot, cos_t, sin_t, out);
+    last_launch_status = launch_k(head_split_kernel<4>, dim3(nb), dim3(256), 0, st, in, ld_in, src_off, rows, rpb, heads, hd, norm_w, eps, rot, cos_t, sin_t, out);
   } else if (hd_pad == 64) {
-    head_split_kernel<2><<<nb, 256, 0, st>>>(in, ld_in, src_off, rows, rpb, heads, hd, norm_w, eps, rot, cos_t, sin_t, out);
+    last_launch_status = launch_k(head_split_kernel<2>, dim3(nb), dim3(256), 0, st, in, ld_in, src_off, rows, rpb, heads, hd, norm_w, eps, rot, cos_t, sin_t, out);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -687,19 +730,19 @@ cudaError_t attention_bf16(cudaStream_t st, const bf16* q, int B, int tq, int H,
   AttnSeg s[3];
   for (int i = 0; i < nseg; ++i) s[i] = segs[i];
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
-  dim3 grid((tq + 63) / 64, H, B);
+  dim3 grid((tq + kAttRows - 1) / kAttRows, H, B);
   if (hd_pad == 128) {
-    constexpr int smem = 5 * 64 * (128 + 8) * 2;
+    constexpr int smem = (kAttRows + 4 * 64) * (128 + 8) * 2;
     static bool once = false;
     if (!once) {
       cudaError_t e = cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
       once = true;
     }
-    attention_kernel<128><<<grid, 128, smem, st>>>(q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
+    last_launch_status = launch_k(attention_kernel<128>, dim3(grid), dim3(kAttThreads), smem, st, q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
   } else if (hd_pad == 64) {
-    constexpr int smem = 5 * 64 * (64 + 8) * 2;
-    attention_kernel<64><<<grid, 128, smem, st>>>(q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
+    constexpr int smem = (kAttRows + 4 * 64) * (64 + 8) * 2;
+    last_launch_status = launch_k(attention_kernel<64>, dim3(grid), dim3(kAttThreads), smem, st, q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -711,7 +754,7 @@ cudaError_t gemv_rows(cudaStream_t st, const float* x, int rows, int k, const fl
   if (k % 4 != 0) return cudaErrorInvalidValue;
   for (int r0 = 0; r0 < rows; r0 += 8) {
     const int nr = rows - r0 < 8 ? rows - r0 : 8;
-    gemv_rows_kernel<8><<<blocks_for(n, 8), 256, 0, st>>>(x + static_cast<long long>(r0) * k, nr, k, w, b, n, pre, post,
+    last_launch_status = launch_k(gemv_rows_kernel<8>, dim3(blocks_for(n, 8)), dim3(256), 0, st, x + static_cast<long long>(r0) * k, nr, k, w, b, n, pre, post,
                                                          chunk, tanh_chunks, y + static_cast<long long>(r0) * ld_y, ld_y);
     ++g_launch_count;
   }
@@ -719,36 +762,36 @@ cudaError_t gemv_rows(cudaStream_t st, const float* x, int rows, int k, const fl
 }
 
 cudaError_t time_features(cudaStream_t st, const float* t, int rows, float* out) {
-  time_features_kernel<<<rows, 128, 0, st>>>(t, rows, out);
+  last_launch_status = launch_k(time_features_kernel, dim3(rows), dim3(128), 0, st, t, rows, out);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t embed_gather(cudaStream_t st, const long long* ids, int rows, const float* table, int vocab, int dim,
                          float* out) {
-  embed_gather_kernel<<<rows, 128, 0, st>>>(ids, rows, table, vocab, dim, out);
+  last_launch_status = launch_k(embed_gather_kernel, dim3(rows), dim3(128), 0, st, ids, rows, table, vocab, dim, out);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t cast_bf16(cudaStream_t st, const float* in, long long n, bf16* out) {
-  cast_bf16_kernel<<<blocks_for(n, 1024), 256, 0, st>>>(in, n, out);
+  last_launch_status = launch_k(cast_bf16_kernel, dim3(blocks_for(n, 1024)), dim3(256), 0, st, in, n, out);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t noise_mix(cudaStream_t st, const float* x_pred, const float* noise, float alpha, float sigma, long long n,
                       float* x_t, bf16* x_t_bf16) {
-  noise_mix_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_pred, noise, alpha, sigma, n, x_t, x_t_bf16);
+  last_launch_status = launch_k(noise_mix_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, x_pred, noise, alpha, sigma, n, x_t, x_t_bf16);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t dmd_update(cudaStream_t st, const float* x_t, const float* v, float alpha, float sigma, long long n,
                        float* x_pred) {
-  dmd_update_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x_t, v, alpha, sigma, n, x_pred);
+  last_launch_status = launch_k(dmd_update_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, x_t, v, alpha, sigma, n, x_pred);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t philox_normal(cudaStream_t st, const unsigned long long* seed, unsigned long long stream_id, long long n,
                           float* out) {
-  philox_normal_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>(seed, stream_id, n, out);
+  last_launch_status = launch_k(philox_normal_kernel, dim3(blocks_for((n + 3) / 4, 256)), dim3(256), 0, st, seed, stream_id, n, out);
   STTS_LAUNCH_OK();
 }
 
@@ -768,7 +811,7 @@ cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, c
     once = true;
   }
   dim3 grid((T + TT - 1) / TT, B);
-  convnext_mix_kernel<<<grid, 256, smem, st>>>(x, T, C, TT, norm_w, conv_w, conv_b, gamma, ffn_norm_w, eps, y, a);
+  last_launch_status = launch_k(convnext_mix_kernel, dim3(grid), dim3(256), smem, st, x, T, C, TT, norm_w, conv_w, conv_b, gamma, ffn_norm_w, eps, y, a);
   STTS_LAUNCH_OK();
 }
 
@@ -777,41 +820,41 @@ cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, cons
   if (C % 4 != 0) return cudaErrorInvalidValue;
   dim3 grid((T + 255) / 256, B);
   if (C > 40) return cudaErrorInvalidValue;  // 262 x (C+1) fp32 tile must fit the default 48 KB
-  head_conv_kernel<<<grid, 256, (7 * C + 262 * (C + 1)) * 4, st>>>(x, T, C, w, bias, out);
+  last_launch_status = launch_k(head_conv_kernel, dim3(grid), dim3(256), (7 * C + 262 * (C + 1)) * 4, st, x, T, C, w, bias, out);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t pack_matrix(cudaStream_t st, const float* src, int rows, int cols, float scale, int row_mode, int row_off,
                         int col_mode, int col_off, bf16* dst, int ld_dst) {
-  pack_matrix_kernel<<<blocks_for(static_cast<long long>(rows) * cols, 256), 256, 0, st>>>(
+  last_launch_status = launch_k(pack_matrix_kernel, dim3(blocks_for(static_cast<long long>(rows) * cols, 256)), dim3(256), 0, st, 
       src, rows, cols, scale, row_mode, row_off, col_mode, col_off, dst, ld_dst);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t pack_conv_taps(cudaStream_t st, const float* src, int O, int cin, int taps, int kp, int opg, int group_pitch,
                            bf16* dst, int ld_dst) {
-  pack_conv_taps_kernel<<<blocks_for(static_cast<long long>(O) * cin * taps, 256), 256, 0, st>>>(
+  last_launch_status = launch_k(pack_conv_taps_kernel, dim3(blocks_for(static_cast<long long>(O) * cin * taps, 256)), dim3(256), 0, st, 
       src, O, cin, taps, kp, opg, group_pitch, dst, ld_dst);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t pack_conv_dense_tiles(cudaStream_t st, const float* src, int taps, bf16* dst) {
-  pack_conv_dense_tiles_kernel<<<blocks_for(static_cast<long long>(960) * 60 * taps, 256), 256, 0, st>>>(src, taps, dst);
+  last_launch_status = launch_k(pack_conv_dense_tiles_kernel, dim3(blocks_for(static_cast<long long>(960) * 60 * taps, 256)), dim3(256), 0, st, src, taps, dst);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t pack_convtr(cudaStream_t st, const float* src, int cin, int cout, int r, bf16* dst) {
-  pack_convtr_kernel<<<blocks_for(static_cast<long long>(cin) * cout * 2 * r, 256), 256, 0, st>>>(src, cin, cout, r, dst);
+  last_launch_status = launch_k(pack_convtr_kernel, dim3(blocks_for(static_cast<long long>(cin) * cout * 2 * r, 256)), dim3(256), 0, st, src, cin, cout, r, dst);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t pack_vector(cudaStream_t st, const float* src, int n, float scale, int row_mode, int off, float* dst) {
-  pack_vector_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, n, scale, row_mode, off, dst);
+  last_launch_status = launch_k(pack_vector_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, src, n, scale, row_mode, off, dst);
   STTS_LAUNCH_OK();
 }
 
 cudaError_t tile_vector(cudaStream_t st, const float* src, int n, int reps, float* dst) {
-  tile_vector_kernel<<<blocks_for(static_cast<long long>(n) * reps, 256), 256, 0, st>>>(src, n, reps, dst);
+  last_launch_status = launch_k(tile_vector_kernel, dim3(blocks_for(static_cast<long long>(n) * reps, 256)), dim3(256), 0, st, src, n, reps, dst);
   STTS_LAUNCH_OK();
 }
 

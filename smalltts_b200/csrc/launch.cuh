@@ -1,0 +1,39 @@
+// Kernel launch helper: every kernel of the engine is launched with the programmatic-stream-serialization attribute
+// (Programmatic Dependent Launch).  Contract for kernels: call ptx::pdl_wait() before the first access to global
+// memory that a predecessor may have written or may still read, and never exit without having called it (so that
+// completion stays transitive along the stream); ptx::pdl_trigger() lets the successor's CTAs be scheduled early, so
+// its launch latency and prologue overlap this kernel's tail.  The attribute is only set when STTS_PDL=1 (A/B measured: no gain under graph replay).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include <utility>
+
+namespace stts {
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("STTS_PDL");  // measured neutral-to-slower under CUDA-graph replay: off by default
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+
+}  // namespace stts

@@ -155,6 +155,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- cp.async (LDGSTS) and named barriers
 // 16-byte global->shared copy; src_bytes = 0 writes zeros (used for causal / out-of-range halo rows).
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
