@@ -13,10 +13,11 @@
 //   warp  8     MMA   : tcgen05.mma  H[128 x 4C] = A W1^T  and, per 64-wide hidden chunk, O[128 x C] += G W2^T;
 //                       accumulators in TMEM (two 256-column buffers; O aliases the first C columns of H, which the
 //                       GELU warps have consumed by then); W1/W2 stay resident in shared memory (TMA-loaded once)
-//   warps 9-16  GELU  : tcgen05.ld H chunk -> +b1 -> GELU -> bf16 -> swizzled shared-memory G chunk (double buffer)
+//   warps 9-16  GELU  : tcgen05.ld H chunk -> +b1 -> GELU in packed fp16 -> swizzled shared-memory G chunk (fp16, double buffer)
 //   warps 17-20 out   : y rows -> registers (frees the x buffer early); tcgen05.ld O -> y + ffn_gamma*(O + b2) ->
 //                       fp32 (and optional bf16) store, one full row per thread
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <mutex>
 
@@ -67,16 +68,31 @@ struct FC {
   static constexpr int SMEM = OFF_BAR + 17 * 8 + 16 + 1024;
 };
 
-// TWICE the erf-GELU: x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form (max abs err 2.6e-5 before
+// (fp32 reference form, kept for documentation) TWICE the erf-GELU: x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form (max abs err 2.6e-5 before
 // the MUFU.TANH approximation, whose 2^-11 relative error stays below the bf16 rounding applied right after).  The
 // factor 0.5 is folded into the output scale (0.5 * ffn_gamma).  x^2 is clamped at 64: beyond |x| = 8 the quintic
 // would turn around, with the clamp u = 1.72 x keeps growing and tanh saturates.
-__device__ __forceinline__ float gelu2_fast(float x) {
+__device__ __forceinline__ float gelu2_fast_f32(float x) {
   const float x2 = fminf(x * x, 64.0f);
   const float u = x * fmaf(x2, fmaf(x2, -3.5190239e-4f, 3.7008020e-2f), 0.79750528f);
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   return fmaf(x, t, x);
+}
+// The same function on two values at once in packed fp16 (HFMA2 pipe, one MUFU.TANH.F16x2 per pair).  The result
+// feeds tcgen05 as an fp16 operand, so fp16's 11-bit significand is the precision floor anyway; inputs are fp32
+// accumulators plus bias rounded once to fp16.
+__device__ __forceinline__ uint32_t gelu2_half2(float a, float b, __half2 bias) {
+  const __half2 x = __hadd2(__floats2half2_rn(a, b), bias);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(64.0f));
+  const __half2 p = __hfma2(x2, __hfma2(x2, __float2half2_rn(-3.5190239e-4f), __float2half2_rn(3.7008020e-2f)),
+                            __float2half2_rn(0.79750528f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 g = __hfma2(x, t, x);
+  return *reinterpret_cast<const uint32_t*>(&g);
 }
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
@@ -129,7 +145,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   const int n_my = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
 
   // ---------------- one-time setup
-  for (int i = threadIdx.x; i < F::HID; i += kThreadsFused) b1s[i] = p.b1[i];
+  __half* b1h = reinterpret_cast<__half*>(b1s);  // b1 kept as fp16 (HID halfs in the fp32-sized slot)
+  for (int i = threadIdx.x; i < F::HID; i += kThreadsFused) b1h[i] = __float2half_rn(p.b1[i]);
   for (int i = threadIdx.x; i < C; i += kThreadsFused) {
     b2s[i] = p.ffn_gamma[i] * p.b2[i]; gfs[i] = 0.5f * p.ffn_gamma[i]; nws[i] = p.norm_w[i]; fws[i] = p.ffn_norm_w[i];
     gms[i] = p.gamma[i]; cbs[i] = p.conv_b[i];
@@ -268,7 +285,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       for (int c = 0; c < F::NCH; ++c) ptx::tma_load_2d(W2s + c * C * 128, &tmW2, w_full, c * 64, 0);
       ptx::mbar_wait(w_full, 0);
       constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(TM, F::HID);
-      constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(TM, C);
+      // MMA2 operands (G and W2) are fp16: clear the two bf16 format fields of the descriptor
+      constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(TM, C) & ~((1u << 7) | (1u << 10));
       const uint64_t dW1 = ptx::umma_desc_sw128(ptx::smem_u32(W1s));
       auto mma1_ready = [&](int it) {  // non-blocking: operand written and TMEM buffer drained?
         const int buf = it & 1;
@@ -328,17 +346,17 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         uint32_t rr[32];
         ptx::tmem_ld_32x32(tmem_base + (it & 1) * 256 + (static_cast<uint32_t>(q * 32) << 16) + c * 64 + half * 32, rr);
         ptx::tmem_ld_wait();
-        const float* bb = b1s + c * 64 + half * 32;
+        const __half2* bb = reinterpret_cast<const __half2*>(b1h + c * 64 + half * 32);
         uint8_t* Gs = Gbuf(gb);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 ba = *reinterpret_cast<const float4*>(bb + 8 * j);
-          const float4 bc = *reinterpret_cast<const float4*>(bb + 8 * j + 4);
+          const uint4 bq = *reinterpret_cast<const uint4*>(bb + 4 * j);  // 8 fp16 biases
+          const __half2* bh = reinterpret_cast<const __half2*>(&bq);
           uint4 pk;
-          pk.x = bf2(gelu2_fast(__uint_as_float(rr[8 * j + 0]) + ba.x), gelu2_fast(__uint_as_float(rr[8 * j + 1]) + ba.y));
-          pk.y = bf2(gelu2_fast(__uint_as_float(rr[8 * j + 2]) + ba.z), gelu2_fast(__uint_as_float(rr[8 * j + 3]) + ba.w));
-          pk.z = bf2(gelu2_fast(__uint_as_float(rr[8 * j + 4]) + bc.x), gelu2_fast(__uint_as_float(rr[8 * j + 5]) + bc.y));
-          pk.w = bf2(gelu2_fast(__uint_as_float(rr[8 * j + 6]) + bc.z), gelu2_fast(__uint_as_float(rr[8 * j + 7]) + bc.w));
+          pk.x = gelu2_half2(__uint_as_float(rr[8 * j + 0]), __uint_as_float(rr[8 * j + 1]), bh[0]);
+          pk.y = gelu2_half2(__uint_as_float(rr[8 * j + 2]), __uint_as_float(rr[8 * j + 3]), bh[1]);
+          pk.z = gelu2_half2(__uint_as_float(rr[8 * j + 4]), __uint_as_float(rr[8 * j + 5]), bh[2]);
+          pk.w = gelu2_half2(__uint_as_float(rr[8 * j + 6]), __uint_as_float(rr[8 * j + 7]), bh[3]);
           *reinterpret_cast<uint4*>(Gs + sw128_off(r, (half * 4 + j) * 8)) = pk;
         }
         ptx::fence_proxy_async();
@@ -448,7 +466,7 @@ bool tmap_2d(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, ui
 }
 
 template <int C>
-cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, const bf16* w2, int num_sms) {
+cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, const void* w2, int num_sms) {
   static bool once = false;
   if (!once) {
     cudaError_t e = cudaFuncSetAttribute(convnext_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC<C>::SMEM);
@@ -469,7 +487,7 @@ cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, 
 
 cudaError_t convnext_fused(cudaStream_t st, const float* x, int B, int T, int C, const float* norm_w,
                            const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
-                           const bf16* w1, const float* b1, const bf16* w2, const float* b2, const float* ffn_gamma,
+                           const bf16* w1, const float* b1, const void* w2_f16, const float* b2, const float* ffn_gamma,
                            float eps, float* out, bf16* out_bf16) {
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -481,8 +499,8 @@ cudaError_t convnext_fused(cudaStream_t st, const float* x, int B, int T, int C,
   p.x = x; p.out = out; p.out_bf16 = out_bf16; p.B = B; p.T = T;
   p.norm_w = norm_w; p.conv_w = conv_w; p.conv_b = conv_b; p.gamma = gamma; p.ffn_norm_w = ffn_norm_w;
   p.b1 = b1; p.b2 = b2; p.ffn_gamma = ffn_gamma; p.eps = eps;
-  if (C == 64) return launch_fused<64>(st, p, w1, w2, num_sms);
-  if (C == 32) return launch_fused<32>(st, p, w1, w2, num_sms);
+  if (C == 64) return launch_fused<64>(st, p, w1, w2_f16, num_sms);
+  if (C == 32) return launch_fused<32>(st, p, w1, w2_f16, num_sms);
   return cudaErrorInvalidValue;
 }
 

@@ -64,6 +64,7 @@ struct DitBlockW {
 struct VocLayerW {
   const float *norm_w, *conv_w, *conv_b, *gamma, *ffn_norm_w, *b1, *b2, *ffn_gamma;
   bf16 *w1, *w2;
+  void* w2h = nullptr;  // fp16 copy of linear2 for the fused tail kernel (C <= 64)
 };
 
 template <typename T>
@@ -392,6 +393,10 @@ void finalize(stts_engine* e) {
       w.w1 = pack_lin(e, e->W(1, p + "ffn.linear1.weight", {4 * c, c}), 4 * c, c);
       w.b1 = e->W(1, p + "ffn.linear1.bias", {4 * c}).d;
       w.w2 = pack_lin(e, e->W(1, p + "ffn.linear2.weight", {c, 4 * c}), c, 4 * c);
+      if (c <= 64) {
+        w.w2h = e->dalloc<uint16_t>(static_cast<size_t>(4) * c * c);
+        CK(cast_f16(st, e->W(1, p + "ffn.linear2.weight", {c, 4 * c}).d, static_cast<long long>(4) * c * c, w.w2h));
+      }
       w.b2 = e->W(1, p + "ffn.linear2.bias", {c}).d;
       w.conv_w = e->W(1, p + "mixer.conv.weight", {c, 1, 7}).d;
       w.conv_b = e->W(1, p + "mixer.conv.bias", {c}).d;
@@ -729,7 +734,7 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
         for (size_t l = 0; l < nl; ++l) {
           const VocLayerW& w = e->voc[s][l];
           bf16* hb = (s < 6 && l + 1 == nl) ? ws.xh : nullptr;
-          CK(convnext_fused(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, w.w1, w.b1, w.w2,
+          CK(convnext_fused(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, w.w1, w.b1, w.w2h,
                             w.b2, w.ffn_gamma, 1e-5f, oth, hb));
           std::swap(cur, oth);
         }
@@ -1306,12 +1311,12 @@ int stts_test_convnext_mix(stts_engine* e, const float* x, int B, int T, int C, 
 
 int stts_test_convnext_fused(stts_engine* e, const float* x, int B, int T, int C, const float* norm_w,
                              const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
-                             const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
+                             const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2,
                              const float* ffn_gamma, float* out, void* out_bf16) {
   if (!e) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
     CK(convnext_fused(e->st, x, B, T, C, norm_w, conv_w, conv_b, gamma, ffn_norm_w, static_cast<const bf16*>(w1_bf16), b1,
-                      static_cast<const bf16*>(w2_bf16), b2, ffn_gamma, 1e-5f, out, static_cast<bf16*>(out_bf16)));
+                      w2_f16, b2, ffn_gamma, 1e-5f, out, static_cast<bf16*>(out_bf16)));
     CK(cudaStreamSynchronize(e->st));
   });
 }

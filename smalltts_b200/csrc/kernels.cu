@@ -1,6 +1,7 @@
 // Non-GEMM kernels of the engine.  See kernels.cuh for the contracts and reference citations.
 #include "kernels.cuh"
 
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "launch.cuh"
@@ -685,6 +686,13 @@ __global__ void pack_vector_kernel(const float* __restrict__ src, int n, float s
   if (i < n) dst[map_row(i, row_mode) + off] = scale * src[i];
 }
 
+__global__ void cast_f16_kernel(const float* __restrict__ src, long long n, __half* __restrict__ dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
 __global__ void tile_vector_kernel(const float* __restrict__ src, int n, int reps, float* __restrict__ dst) {
   ptx::pdl_wait();
   ptx::pdl_trigger();
@@ -850,6 +858,11 @@ cudaError_t pack_convtr(cudaStream_t st, const float* src, int cin, int cout, in
 
 cudaError_t pack_vector(cudaStream_t st, const float* src, int n, float scale, int row_mode, int off, float* dst) {
   last_launch_status = launch_k(pack_vector_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, src, n, scale, row_mode, off, dst);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t cast_f16(cudaStream_t st, const float* src, long long n, void* dst_f16) {
+  last_launch_status = launch_k(cast_f16_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, src, n, static_cast<__half*>(dst_f16));
   STTS_LAUNCH_OK();
 }
 

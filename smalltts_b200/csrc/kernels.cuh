@@ -66,10 +66,11 @@ cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, c
                          const float* conv_b, const float* gamma, const float* ffn_norm_w, float eps, float* y,
                          bf16* a);
 // Whole ConvNeXt layer (token mixer + FFN, hf:284-297) in one persistent tcgen05 kernel for C = 32 / 64: reads x once,
-// writes out once (fp32), optional bf16 copy of out.  w1: bf16 [4C, C], w2: bf16 [C, 4C].  x and out must not alias.
+// writes out once (fp32), optional bf16 copy of out.  w1: bf16 [4C, C], w2: FP16 [C, 4C] (the hidden activation is
+// produced in fp16).  x and out must not alias.
 cudaError_t convnext_fused(cudaStream_t st, const float* x, int B, int T, int C, const float* norm_w,
                            const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
-                           const bf16* w1, const float* b1, const bf16* w2, const float* b2, const float* ffn_gamma,
+                           const bf16* w1, const float* b1, const void* w2_f16, const float* b2, const float* ffn_gamma,
                            float eps, float* out, bf16* out_bf16);
 // vocoder head: causal Conv1d(C -> 1, k=7) (hf:484-489).  x fp32 [B, T, C], w [C, 7] -> out [B, T]
 cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, const float* w, const float* bias,
@@ -92,6 +93,7 @@ cudaError_t pack_convtr(cudaStream_t st, const float* src, int cin, int cout, in
 // fp32 vector helpers: dst[map(i) + off] = scale * src[i]
 cudaError_t pack_vector(cudaStream_t st, const float* src, int n, float scale, int row_mode, int off, float* dst);
 cudaError_t tile_vector(cudaStream_t st, const float* src, int n, int reps, float* dst);  // dst[j*n+i] = src[i]
+cudaError_t cast_f16(cudaStream_t st, const float* src, long long n, void* dst_f16);
 
 extern unsigned long long g_launch_count;
 

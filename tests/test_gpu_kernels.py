@@ -247,7 +247,8 @@ def test_convnext_fused(eng, C_, T):
     nw, fw = 1 + 0.1 * torch.randn(C_, device="cuda"), 1 + 0.1 * torch.randn(C_, device="cuda")
     cw, cb = torch.randn(C_, 7, device="cuda") * 0.4, torch.randn(C_, device="cuda")
     gamma, fgamma = 0.1 + 0.1 * torch.rand(C_, device="cuda"), 0.1 + 0.1 * torch.rand(C_, device="cuda")
-    w1, w2 = _rand_bf16(4 * C_, C_, scale=C_ ** -0.5), _rand_bf16(C_, 4 * C_, scale=(4 * C_) ** -0.5)
+    w1 = _rand_bf16(4 * C_, C_, scale=C_ ** -0.5)
+    w2 = (torch.randn(C_, 4 * C_, device="cuda") * (4 * C_) ** -0.5).to(torch.float16)  # fused kernel: fp16 W2
     b1, b2 = torch.randn(4 * C_, device="cuda") * 0.3, torch.randn(C_, device="cuda") * 0.3
     out = torch.zeros_like(x)
     out16 = torch.zeros(B, T, C_, device="cuda", dtype=torch.bfloat16)
@@ -259,7 +260,7 @@ def test_convnext_fused(eng, C_, T):
     conv = torch.nn.functional.conv1d(torch.nn.functional.pad(xn.transpose(1, 2), (6, 0)), cw[:, None, :], cb, groups=C_)
     y = x + gamma * conv.transpose(1, 2)
     a = (y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + 1e-5) * fw).to(torch.bfloat16).float()
-    h = torch.nn.functional.gelu(a @ w1.float().t() + b1).to(torch.bfloat16).float()
+    h = torch.nn.functional.gelu(a @ w1.float().t() + b1).to(torch.float16).float()
     want = y + fgamma * (h @ w2.float().t() + b2)
     _assert_close(out, want, tol=2e-3)
     _assert_close(out16, want, tol=1e-2)
