@@ -148,7 +148,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   __half* b1h = reinterpret_cast<__half*>(b1s);  // b1 kept as fp16 (HID halfs in the fp32-sized slot)
   for (int i = threadIdx.x; i < F::HID; i += kThreadsFused) b1h[i] = __float2half_rn(p.b1[i]);
   for (int i = threadIdx.x; i < C; i += kThreadsFused) {
-    b2s[i] = p.ffn_gamma[i] * p.b2[i]; gfs[i] = 0.5f * p.ffn_gamma[i]; nws[i] = p.norm_w[i]; fws[i] = p.ffn_norm_w[i];
+    b2s[i] = p.ffn_gamma[i] * p.b2[i]; gfs[i] = p.ffn_gamma[i]; nws[i] = p.norm_w[i]; fws[i] = p.ffn_norm_w[i];
     gms[i] = p.gamma[i]; cbs[i] = p.conv_b[i];
   }
   for (int i = threadIdx.x; i < 7 * C; i += kThreadsFused) {  // tap-major, RMSNorm weight folded in
@@ -397,7 +397,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           const float4 b2 = *reinterpret_cast<const float4*>(b2s + col);
           const float4 gf = *reinterpret_cast<const float4*>(gfs + col);
           float4& yy = y[cc * 8 + j];
-          // O holds W2 (2 gelu): out = y + ffn_gamma*b2 + (0.5 ffn_gamma) * O
+          // O = (0.5 W2)(2 gelu) = W2 gelu (W2 is stored pre-scaled by 0.5): out = y + ffn_gamma*b2 + ffn_gamma * O
           yy.x = fmaf(gf.x, __uint_as_float(rr[4 * j + 0]), yy.x + b2.x);
           yy.y = fmaf(gf.y, __uint_as_float(rr[4 * j + 1]), yy.y + b2.y);
           yy.z = fmaf(gf.z, __uint_as_float(rr[4 * j + 2]), yy.z + b2.z);

@@ -64,7 +64,7 @@ struct DitBlockW {
 struct VocLayerW {
   const float *norm_w, *conv_w, *conv_b, *gamma, *ffn_norm_w, *b1, *b2, *ffn_gamma;
   bf16 *w1, *w2;
-  void* w2h = nullptr;  // fp16 copy of linear2 for the fused tail kernel (C <= 64)
+  void* w2h = nullptr;  // fp16 copy of 0.5 * linear2: the hidden activation is produced as 2*gelu in fp16
 };
 
 template <typename T>
@@ -189,8 +189,9 @@ int pick_bn(long long m, int n, int iters) {
 
 // Plain linear over flattened rows: out = epi(A[rows, K] * W[N, K]^T)
 void linear(stts_engine* e, const bf16* a, long long rows, int k, int lda, const bf16* w, int n, int ldw, GemmEpi epi,
-            int bn = 0) {
+            int bn = 0, bool f16 = false) {
   GemmShape s;
+  s.ab_f16 = f16 ? 1 : 0;
   s.B = 1;
   s.T = static_cast<int>(rows);
   s.N = n;
@@ -392,11 +393,9 @@ void finalize(stts_engine* e) {
       w.ffn_norm_w = e->W(1, p + "ffn_norm.weight", {c}).d;
       w.w1 = pack_lin(e, e->W(1, p + "ffn.linear1.weight", {4 * c, c}), 4 * c, c);
       w.b1 = e->W(1, p + "ffn.linear1.bias", {4 * c}).d;
-      w.w2 = pack_lin(e, e->W(1, p + "ffn.linear2.weight", {c, 4 * c}), c, 4 * c);
-      if (c <= 64) {
-        w.w2h = e->dalloc<uint16_t>(static_cast<size_t>(4) * c * c);
-        CK(cast_f16(st, e->W(1, p + "ffn.linear2.weight", {c, 4 * c}).d, static_cast<long long>(4) * c * c, w.w2h));
-      }
+      w.w2 = nullptr;
+      w.w2h = e->dalloc<uint16_t>(static_cast<size_t>(4) * c * c);
+      CK(cast_f16(st, e->W(1, p + "ffn.linear2.weight", {c, 4 * c}).d, static_cast<long long>(4) * c * c, 0.5f, w.w2h));
       w.b2 = e->W(1, p + "ffn.linear2.bias", {c}).d;
       w.conv_w = e->W(1, p + "mixer.conv.weight", {c, 1, 7}).d;
       w.conv_b = e->W(1, p + "mixer.conv.bias", {c}).d;
@@ -431,9 +430,7 @@ void encoder_block(stts_engine* e, const EncW& W, const EncBlockW& bw, float* x,
   linear(e, a, M, d, d, bw.wqkvg, 4 * d, d, ep);
   const float* cs = W.hd == 64 ? e->cos64 : e->cos128;
   const float* sn = W.hd == 64 ? e->sin64 : e->sin128;
-  CK(head_split_bf16(st, qkvg, 4 * d, 0, M, N, W.heads, W.hd, W.hd, bw.qn, W.eps, W.hd, cs, sn, qb));
-  CK(head_split_bf16(st, qkvg, 4 * d, d, M, N, W.heads, W.hd, W.hd, bw.kn, W.eps, W.hd, cs, sn, kb));
-  CK(head_split_bf16(st, qkvg, 4 * d, 2 * d, M, N, W.heads, W.hd, W.hd, nullptr, 0.f, 0, nullptr, nullptr, vb));
+  CK(head_split_qkv_bf16(st, qkvg, 4 * d, d, M, N, W.heads, W.hd, W.hd, bw.qn, bw.kn, W.eps, W.hd, cs, sn, qb, kb, vb));
   AttnSeg seg;
   seg.k = kb; seg.v = vb; seg.len = len_dev; seg.n_max = N;
   CK(attention_bf16(st, qb, B, N, W.heads, W.hd, W.hd, &seg, 1, qkvg, 4 * d, 3 * d, ob));
@@ -615,9 +612,8 @@ void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_b
     GemmEpi eq;
     eq.bias = w.bqkvg; eq.out_f32 = ws.qkvg; eq.ld_out = 4 * D;
     linear(e, ws.a, M, D, D, w.wqkvg, 4 * D, D, eq);
-    CK(head_split_bf16(st, ws.qkvg, 4 * D, 0, M, T, H, HD, HDP, w.qn, 1e-6f, 64, e->cos64, e->sin64, ws.qb));
-    CK(head_split_bf16(st, ws.qkvg, 4 * D, D, M, T, H, HD, HDP, w.kn, 1e-6f, 64, e->cos64, e->sin64, ws.kb));
-    CK(head_split_bf16(st, ws.qkvg, 4 * D, 2 * D, M, T, H, HD, HDP, nullptr, 0.f, 0, nullptr, nullptr, ws.vb));
+    CK(head_split_qkv_bf16(st, ws.qkvg, 4 * D, D, M, T, H, HD, HDP, w.qn, w.kn, 1e-6f, 64, e->cos64, e->sin64, ws.qb, ws.kb,
+                           ws.vb));
     AttnSeg segs[3];
     segs[0].k = ws.kb; segs[0].v = ws.vb; segs[0].len = frames_dev; segs[0].n_max = T;
     segs[1].k = c->kv_ref + (2 * i) * c->ref_stride(); segs[1].v = c->kv_ref + (2 * i + 1) * c->ref_stride();
@@ -743,12 +739,12 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
           const VocLayerW& w = e->voc[s][l];
           CK(convnext_mix(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, oth, ws.a));
           GemmEpi e1;
-          e1.bias = w.b1; e1.act = ACT_GELU; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
+          e1.bias = w.b1; e1.act = ACT_GELU; e1.gelu2_f16 = 1; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
           linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1);
           GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
           e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = oth; e2.ld_res = C; e2.out_f32 = cur; e2.ld_out = C;
           if (s < 6 && l + 1 == nl) e2.out_bf16 = ws.xh;  // bf16 copy feeds the next upsampler
-          linear(e, ws.hbuf, M, 4 * C, 4 * C, w.w2, C, 4 * C, e2);
+          linear(e, ws.hbuf, M, 4 * C, 4 * C, static_cast<const bf16*>(w.w2h), C, 4 * C, e2, 0, /*f16=*/true);
         }
       }
       if (s < 6) {  // causal ConvTranspose1d(k=2r, stride=r) as a 2-tap GEMM with N = r*Cout (hf:219-260)

@@ -7,6 +7,8 @@
 // instruction-fetch bound (ncu: stall_no_instruction dominant).
 #include "gemm.cuh"
 
+#include <cuda_fp16.h>
+
 #include <mutex>
 
 #include "launch.cuh"
@@ -52,6 +54,20 @@ __device__ __forceinline__ float fast_mish(float x) {
   const float w = exp2f(1.4426950408889634f * fminf(x, 20.0f));
   const float n = w * (w + 2.0f);
   return x * __fdividef(n, n + 2.0f);
+}
+
+// 2*gelu on two values in packed fp16 (same fit; HFMA2 pipe + one MUFU.TANH.F16x2 per pair), result as fp16x2 bits.
+__device__ __forceinline__ uint32_t gelu2_half2(float a, float b) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(64.0f));
+  const __half2 p = __hfma2(x2, __hfma2(x2, __float2half2_rn(-3.5190239e-4f), __float2half2_rn(3.7008020e-2f)),
+                            __float2half2_rn(0.79750528f));
+  const __half2 u = __hmul2(x, p);
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 g = __hfma2(x, t, x);
+  return *reinterpret_cast<const uint32_t*>(&g);
 }
 
 template <int ACT>
@@ -150,7 +166,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      // fp16 operands: clear the bf16 format bits of A and B
+      const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN) & (s.ab_f16 ? ~((1u << 7) | (1u << 10)) : ~0u);
       uint32_t kidx = 0;
       for (int li = 0; li < n_my; ++li) {
         const int ab = li & 1;
@@ -215,6 +232,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int i = 0; i < 8; ++i) add4(v + 4 * i, e.bias + gc0 + 4 * i);
         }
         int out_c0 = gc0;
+        if (ACT == ACT_GELU && e.gelu2_f16) {
+          // FFN hidden activation of the vocoder: 2*gelu in packed fp16, stored as fp16 (no mask/scale/residual here)
+          __nv_bfloat16* op = e.out_bf16 + m * e.ld_out + gc0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 pk;
+            pk.x = gelu2_half2(v[8 * i + 0], v[8 * i + 1]);
+            pk.y = gelu2_half2(v[8 * i + 2], v[8 * i + 3]);
+            pk.z = gelu2_half2(v[8 * i + 4], v[8 * i + 5]);
+            pk.w = gelu2_half2(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(op + 8 * i) = pk;
+          }
+          continue;
+        }
         if (ACT == ACT_SWIGLU16) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {

@@ -36,6 +36,7 @@ struct GemmShape {
   // groups: A columns start at g*a_group_koff (must be a multiple of 8 elements: TMA needs 16-byte aligned box
   // starts), W rows at g*w_group_rows, output columns at g*out_group_cols, residual columns at g*res_group_cols
   int groups = 1, a_group_koff = 0, w_group_rows = 0, out_group_cols = 0, res_group_cols = 0;
+  int ab_f16 = 0;  // A and W hold fp16 (not bf16) values: selects the fp16 input format of tcgen05.mma kind::f16
 };
 
 struct GemmEpi {
@@ -44,6 +45,8 @@ struct GemmEpi {
   int rows_per_batch = 0;           // >0: batch index for row_len/rowgate = row / rows_per_batch (flattened A)
   const int* row_len = nullptr;     // [B]; rows t >= row_len[b] are written as 0 (after activation)
   int mask_bf16_only = 0;           // apply row_len masking to the bf16 output only
+  int gelu2_f16 = 0;                // ACT_GELU only: write 2*gelu(x) as FP16 into out_bf16 (packed half2 math); the
+                                    // consumer GEMM runs with ab_f16 = 1 and weights pre-scaled by 0.5
   const float* colscale = nullptr;  // [cols]
   const float* rowgate = nullptr;   // [B, ld_gate]
   int ld_gate = 0;

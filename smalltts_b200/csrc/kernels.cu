@@ -99,13 +99,24 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------ head split + per-head RMSNorm + RoPE
+struct HeadJobs {  // up to three head-split jobs in one launch (q, k, v of one projection): blockIdx.y selects
+  int src_off[3];
+  const float* norm_w[3];
+  int rot[3];
+  bf16* out[3];
+};
+
 template <int EPL>  // elements per lane: hd_pad / 32
-__global__ void __launch_bounds__(256) head_split_kernel(const float* __restrict__ in, int ld_in, int src_off, int rows,
-                                                         int rpb, int heads, int hd, const float* __restrict__ norm_w,
-                                                         float eps, int rot, const float* __restrict__ cos_t,
-                                                         const float* __restrict__ sin_t, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(256) head_split_kernel(const float* __restrict__ in, int ld_in, int rows, int rpb,
+                                                         int heads, int hd, float eps, const float* __restrict__ cos_t,
+                                                         const float* __restrict__ sin_t, const HeadJobs jobs) {
   ptx::pdl_wait();
   ptx::pdl_trigger();
+  const int job = blockIdx.y;
+  const int src_off = job == 0 ? jobs.src_off[0] : (job == 1 ? jobs.src_off[1] : jobs.src_off[2]);
+  const int rot = job == 0 ? jobs.rot[0] : (job == 1 ? jobs.rot[1] : jobs.rot[2]);
+  const float* __restrict__ norm_w = job == 0 ? jobs.norm_w[0] : (job == 1 ? jobs.norm_w[1] : jobs.norm_w[2]);
+  bf16* __restrict__ out = job == 0 ? jobs.out[0] : (job == 1 ? jobs.out[1] : jobs.out[2]);
   const int lane = threadIdx.x & 31;
   const long long item = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (item >= static_cast<long long>(rows) * heads) return;
@@ -580,6 +591,102 @@ __global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restri
   }
 }
 
+// Token mixer for C = 128 / 256 with per-thread row statistics (no shuffle chains; C+4 pitch keeps float4 row reads
+// bank-conflict free) and cp.async staging.  Same contract as convnext_mix_kernel.
+template <int C>
+__global__ void __launch_bounds__(256) convnext_mix_rows_kernel(const float* __restrict__ x, int T,
+                                                                const float* __restrict__ norm_w,
+                                                                const float* __restrict__ conv_w,
+                                                                const float* __restrict__ conv_b,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ ffn_norm_w, float eps,
+                                                                float* __restrict__ y, bf16* __restrict__ a) {
+  constexpr int TT = 16384 / C;  // 128 or 64 output rows per CTA
+  constexpr int R = TT + 6, P = C + 4, CV = C / 4;
+  constexpr int NSEG = 256 / C > 0 ? 256 / C : 1;  // time segments per channel (2 or 1)
+  constexpr int CPT = C > 256 ? C / 256 : 1;       // channels per thread
+  constexpr int SEGLEN = TT / NSEG;
+  extern __shared__ __align__(16) float smr[];
+  float* tile = smr;          // [R][P]
+  float* inv1 = smr + R * P;  // [R]
+  float* inv2 = inv1 + R;     // [TT]
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const int b = blockIdx.y, t0 = blockIdx.x * TT, tid = threadIdx.x;
+  const int nrows = min(TT, T - t0);
+  const float* xb = x + static_cast<long long>(b) * T * C;
+  {
+    const uint32_t dst0 = ptx::smem_u32(tile);
+    for (int i = tid; i < R * CV; i += 256) {
+      const int r = i / CV, c4 = i % CV;
+      const int t = t0 - 6 + r;
+      const bool ok = t >= 0 && r < nrows + 6;
+      ptx::cp_async_16(dst0 + (r * P + c4 * 4) * 4, xb + static_cast<long long>(ok ? t : 0) * C + c4 * 4, ok ? 16u : 0u);
+    }
+    ptx::cp_async_commit();
+    ptx::cp_async_wait<0>();
+  }
+  __syncthreads();
+  if (tid < R) {
+    const float4* row = reinterpret_cast<const float4*>(tile + tid * P);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < CV; ++j) {
+      const float4 v = row[j];
+      s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+    }
+    inv1[tid] = rsqrtf((s0 + s1 + s2 + s3) * (1.0f / C) + eps);
+  }
+  __syncthreads();
+  {
+    const int c = tid % C, seg = tid / C;
+    const int rs = 6 + seg * SEGLEN;
+    float w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = conv_w[c * 7 + j] * norm_w[c];
+    const float cb = conv_b[c], gm = gamma[c];
+    float win[7];
+    win[0] = 0.f;
+#pragma unroll
+    for (int j = 1; j < 7; ++j) win[j] = tile[(rs - 7 + j) * P + c] * inv1[rs - 7 + j];
+    if (NSEG > 1) __syncthreads();
+#pragma unroll 8
+    for (int r = rs; r < rs + SEGLEN; ++r) {
+      const float xv = tile[r * P + c];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+      win[6] = xv * inv1[r];
+      float a0 = fmaf(w[0], win[0], cb), a1 = w[1] * win[1];
+      a0 = fmaf(w[2], win[2], a0); a1 = fmaf(w[3], win[3], a1);
+      a0 = fmaf(w[4], win[4], a0); a1 = fmaf(w[5], win[5], a1);
+      a0 = fmaf(w[6], win[6], a0);
+      tile[r * P + c] = fmaf(gm, a0 + a1, xv);
+    }
+    (void)CPT;
+  }
+  __syncthreads();
+  if (tid < TT) {
+    const float4* row = reinterpret_cast<const float4*>(tile + (tid + 6) * P);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < CV; ++j) {
+      const float4 v = row[j];
+      s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+    }
+    inv2[tid] = rsqrtf((s0 + s1 + s2 + s3) * (1.0f / C) + eps);
+  }
+  __syncthreads();
+  const long long obase = (static_cast<long long>(b) * T + t0) * C;
+  for (int i = tid; i < nrows * CV; i += 256) {
+    const int r = i / CV, c4 = i % CV;
+    const float4 v = *reinterpret_cast<const float4*>(tile + (r + 6) * P + c4 * 4);
+    reinterpret_cast<float4*>(y + obase)[i] = v;
+    const float4 fw = reinterpret_cast<const float4*>(ffn_norm_w)[c4];
+    const float s = inv2[r];
+    reinterpret_cast<uint2*>(a + obase)[i] = pack_bf16x4(v.x * s * fw.x, v.y * s * fw.y, v.z * s * fw.z, v.w * s * fw.w);
+  }
+}
+
 // 256 outputs per CTA; the 262 input rows are staged in shared memory with coalesced float4 loads (row pitch C+1
 // words so that the per-thread sliding reads below are bank-conflict free).
 __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int T, int C,
@@ -686,11 +793,11 @@ __global__ void pack_vector_kernel(const float* __restrict__ src, int n, float s
   if (i < n) dst[map_row(i, row_mode) + off] = scale * src[i];
 }
 
-__global__ void cast_f16_kernel(const float* __restrict__ src, long long n, __half* __restrict__ dst) {
+__global__ void cast_f16_kernel(const float* __restrict__ src, long long n, float scale, __half* __restrict__ dst) {
   ptx::pdl_wait();
   ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __float2half_rn(src[i]);
+  if (i < n) dst[i] = __float2half_rn(scale * src[i]);
 }
 
 __global__ void tile_vector_kernel(const float* __restrict__ src, int n, int reps, float* __restrict__ dst) {
@@ -718,18 +825,38 @@ cudaError_t rms_norm_bf16(cudaStream_t st, const float* x, int rows, int dim, co
   STTS_LAUNCH_OK();
 }
 
-cudaError_t head_split_bf16(cudaStream_t st, const float* in, int ld_in, int src_off, int rows, int rpb, int heads,
-                            int hd, int hd_pad, const float* norm_w, float eps, int rot, const float* cos_t,
-                            const float* sin_t, bf16* out) {
-  const unsigned nb = blocks_for(static_cast<long long>(rows) * heads, 8);
+namespace {
+cudaError_t head_split_launch(cudaStream_t st, const float* in, int ld_in, int rows, int rpb, int heads, int hd,
+                              int hd_pad, float eps, const float* cos_t, const float* sin_t, const HeadJobs& jobs,
+                              int njobs) {
+  dim3 grid(blocks_for(static_cast<long long>(rows) * heads, 8), njobs);
   if (hd_pad == 128) {
-    last_launch_status = launch_k(head_split_kernel<4>, dim3(nb), dim3(256), 0, st, in, ld_in, src_off, rows, rpb, heads, hd, norm_w, eps, rot, cos_t, sin_t, out);
+    last_launch_status = launch_k(head_split_kernel<4>, grid, dim3(256), 0, st, in, ld_in, rows, rpb, heads, hd, eps, cos_t, sin_t, jobs);
   } else if (hd_pad == 64) {
-    last_launch_status = launch_k(head_split_kernel<2>, dim3(nb), dim3(256), 0, st, in, ld_in, src_off, rows, rpb, heads, hd, norm_w, eps, rot, cos_t, sin_t, out);
+    last_launch_status = launch_k(head_split_kernel<2>, grid, dim3(256), 0, st, in, ld_in, rows, rpb, heads, hd, eps, cos_t, sin_t, jobs);
   } else {
     return cudaErrorInvalidValue;
   }
   STTS_LAUNCH_OK();
+}
+}  // namespace
+
+cudaError_t head_split_bf16(cudaStream_t st, const float* in, int ld_in, int src_off, int rows, int rpb, int heads,
+                            int hd, int hd_pad, const float* norm_w, float eps, int rot, const float* cos_t,
+                            const float* sin_t, bf16* out) {
+  HeadJobs j = {};
+  j.src_off[0] = src_off; j.norm_w[0] = norm_w; j.rot[0] = rot; j.out[0] = out;
+  return head_split_launch(st, in, ld_in, rows, rpb, heads, hd, hd_pad, eps, cos_t, sin_t, j, 1);
+}
+
+cudaError_t head_split_qkv_bf16(cudaStream_t st, const float* in, int ld_in, int stride_off, int rows, int rpb,
+                                int heads, int hd, int hd_pad, const float* q_norm, const float* k_norm, float eps,
+                                int rot, const float* cos_t, const float* sin_t, bf16* q, bf16* k, bf16* v) {
+  HeadJobs j = {};
+  j.src_off[0] = 0;              j.norm_w[0] = q_norm;  j.rot[0] = rot; j.out[0] = q;
+  j.src_off[1] = stride_off;     j.norm_w[1] = k_norm;  j.rot[1] = rot; j.out[1] = k;
+  j.src_off[2] = 2 * stride_off; j.norm_w[2] = nullptr; j.rot[2] = 0;   j.out[2] = v;
+  return head_split_launch(st, in, ld_in, rows, rpb, heads, hd, hd_pad, eps, cos_t, sin_t, j, 3);
 }
 
 cudaError_t attention_bf16(cudaStream_t st, const bf16* q, int B, int tq, int H, int hd, int hd_pad, const AttnSeg* segs,
@@ -807,6 +934,24 @@ cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, c
                          const float* conv_b, const float* gamma, const float* ffn_norm_w, float eps, float* y,
                          bf16* a) {
   if (C < 16 || (C & (C - 1)) != 0 || C > 2048) return cudaErrorInvalidValue;
+  if (C == 128 || C == 256) {
+    const int TTr = 16384 / C;
+    const int smem_r = ((TTr + 6) * (C + 4) + (TTr + 6) + TTr) * 4;
+    static bool once_r = false;
+    if (!once_r) {
+      cudaError_t e1 = cudaFuncSetAttribute(convnext_mix_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+      cudaError_t e2 = cudaFuncSetAttribute(convnext_mix_rows_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) return e1 != cudaSuccess ? e1 : e2;
+      once_r = true;
+    }
+    dim3 gr((T + TTr - 1) / TTr, B);
+    if (C == 128) {
+      last_launch_status = launch_k(convnext_mix_rows_kernel<128>, gr, dim3(256), smem_r, st, x, T, norm_w, conv_w, conv_b, gamma, ffn_norm_w, eps, y, a);
+    } else {
+      last_launch_status = launch_k(convnext_mix_rows_kernel<256>, gr, dim3(256), smem_r, st, x, T, norm_w, conv_w, conv_b, gamma, ffn_norm_w, eps, y, a);
+    }
+    STTS_LAUNCH_OK();
+  }
   int TT = 16384 / C;
   if (TT < 8) TT = 8;
   if (TT > 512) TT = 512;
@@ -861,8 +1006,8 @@ cudaError_t pack_vector(cudaStream_t st, const float* src, int n, float scale, i
   STTS_LAUNCH_OK();
 }
 
-cudaError_t cast_f16(cudaStream_t st, const float* src, long long n, void* dst_f16) {
-  last_launch_status = launch_k(cast_f16_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, src, n, static_cast<__half*>(dst_f16));
+cudaError_t cast_f16(cudaStream_t st, const float* src, long long n, float scale, void* dst_f16) {
+  last_launch_status = launch_k(cast_f16_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, src, n, scale, static_cast<__half*>(dst_f16));
   STTS_LAUNCH_OK();
 }
 

@@ -23,6 +23,12 @@ cudaError_t head_split_bf16(cudaStream_t st, const float* in, int ld_in, int src
                             int heads, int hd, int hd_pad, const float* norm_w, float eps, int rot, const float* cos_t,
                             const float* sin_t, bf16* out);
 
+// q, k, v of one fused projection in ONE launch: sources at column offsets 0, stride_off, 2*stride_off; q and k get
+// per-head RMSNorm + RoPE, v is copied (head-padded).
+cudaError_t head_split_qkv_bf16(cudaStream_t st, const float* in, int ld_in, int stride_off, int rows, int rows_per_batch,
+                                int heads, int hd, int hd_pad, const float* q_norm, const float* k_norm, float eps,
+                                int rot, const float* cos_t, const float* sin_t, bf16* q, bf16* k, bf16* v);
+
 // ---- attention over up to three key segments (self | ref | text), prefix-valid lengths per batch.
 struct AttnSeg {
   const bf16* k = nullptr;   // [B, n_max, H, hd_pad]
@@ -93,7 +99,7 @@ cudaError_t pack_convtr(cudaStream_t st, const float* src, int cin, int cout, in
 // fp32 vector helpers: dst[map(i) + off] = scale * src[i]
 cudaError_t pack_vector(cudaStream_t st, const float* src, int n, float scale, int row_mode, int off, float* dst);
 cudaError_t tile_vector(cudaStream_t st, const float* src, int n, int reps, float* dst);  // dst[j*n+i] = src[i]
-cudaError_t cast_f16(cudaStream_t st, const float* src, long long n, void* dst_f16);
+cudaError_t cast_f16(cudaStream_t st, const float* src, long long n, float scale, void* dst_f16);  // dst = fp16(scale*src)
 
 extern unsigned long long g_launch_count;
 

@@ -253,7 +253,7 @@ def test_convnext_fused(eng, C_, T):
     out = torch.zeros_like(x)
     out16 = torch.zeros(B, T, C_, device="cuda", dtype=torch.bfloat16)
     rc = _cabi.lib().stts_test_convnext_fused(eng._h, _p(x), B, T, C_, _p(nw), _p(cw), _p(cb), _p(gamma), _p(fw),
-                                              _p(w1), _p(b1), _p(w2), _p(b2), _p(fgamma), _p(out), _p(out16))
+                                              _p(w1), _p(b1), _p((w2 * 0.5).contiguous()), _p(b2), _p(fgamma), _p(out), _p(out16))  # kernel takes 0.5*W2
     _cabi.check(rc, eng._h)
     torch.cuda.synchronize()
     xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * nw
