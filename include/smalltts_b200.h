@@ -129,6 +129,10 @@ void* stts_host_alloc(size_t bytes);
 void stts_host_free(void* p);
 
 /* ---- kernel-level test hooks (used by tests/ only; all pointers are DEVICE memory) ---- */
+/* on != 0: the stts_test_* hooks below return without synchronising the engine stream (micro-benchmarks bracket many
+ * launches with stts_timer_start/stop). */
+int stts_test_set_async(stts_engine* e, int on);
+
 int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T, int a_cols, int a_ld,
                    const void* w_bf16, int w_rows, int w_ld, int N, int K, int taps, int tap_shift0, int tap_step,
                    int groups, int a_group_koff, int w_group_rows, int out_group_cols, const float* bias, int act,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "stts_timer_stop": (C.c_int, [vp, c_f32p]),
     "stts_host_alloc": (vp, [C.c_size_t]),
     "stts_host_free": (None, [vp]),
+    "stts_test_set_async": (C.c_int, [vp, C.c_int]),
     "stts_test_gemm": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int,
                                  vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int]),

@@ -135,6 +135,7 @@ struct stts_engine {
   std::map<std::array<int, 5>, Plan*> plans;
   uint64_t use_counter = 0;
   bool use_graphs = true;
+  bool test_async = false;  // test hooks return without synchronising (micro-benchmarks time many launches)
   bool fused_tail = true;  // STTS_NO_FUSED_TAIL=1 falls back to mixer + two GEMMs for C <= 64 (debug / A-B timing)
   unsigned long long* seed_dev = nullptr;   // device u64 read by the Philox kernel
   unsigned long long* seed_host = nullptr;  // pinned staging for seed_dev
@@ -1259,6 +1260,12 @@ void stts_host_free(void* p) {
 }
 
 // ---------------------------------------------------------------- kernel-level test hooks
+int stts_test_set_async(stts_engine* e, int on) {
+  if (!e) return STTS_ERR_INVALID;
+  e->test_async = on != 0;
+  return STTS_OK;
+}
+
 int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T, int a_cols, int a_ld,
                    const void* w_bf16, int w_rows, int w_ld, int N, int K, int taps, int tap_shift0, int tap_step,
                    int groups, int a_group_koff, int w_group_rows, int out_group_cols, const float* bias, int act,
@@ -1277,7 +1284,7 @@ int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T
     ep.out_bf16 = static_cast<bf16*>(out_bf16); ep.ld_out = ld_out;
     CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), a_cols, a_ld},
                    GemmW{static_cast<const bf16*>(w_bf16), w_rows, w_ld}, s, ep));
-    CK(cudaStreamSynchronize(e->st));
+    if (!e->test_async) CK(cudaStreamSynchronize(e->st));
   });
 }
 
@@ -1291,7 +1298,7 @@ int stts_test_attention(stts_engine* e, const void* q, int B, int tq, int Hh, in
     segs[1].k = static_cast<const bf16*>(k1); segs[1].v = static_cast<const bf16*>(v1); segs[1].len = len1; segs[1].n_max = n1;
     CK(attention_bf16(e->st, static_cast<const bf16*>(q), B, tq, Hh, hd, hd_pad, segs, k1 ? 2 : 1, gate, ld_gate, 0,
                       static_cast<bf16*>(out)));
-    CK(cudaStreamSynchronize(e->st));
+    if (!e->test_async) CK(cudaStreamSynchronize(e->st));
   });
 }
 
@@ -1301,7 +1308,7 @@ int stts_test_convnext_mix(stts_engine* e, const float* x, int B, int T, int C, 
   if (!e) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
     CK(convnext_mix(e->st, x, B, T, C, norm_w, conv_w, conv_b, gamma, ffn_norm_w, 1e-5f, y, static_cast<bf16*>(a_bf16)));
-    CK(cudaStreamSynchronize(e->st));
+    if (!e->test_async) CK(cudaStreamSynchronize(e->st));
   });
 }
 
@@ -1313,7 +1320,7 @@ int stts_test_convnext_fused(stts_engine* e, const float* x, int B, int T, int C
   return guard_impl(e, [&] {
     CK(convnext_fused(e->st, x, B, T, C, norm_w, conv_w, conv_b, gamma, ffn_norm_w, static_cast<const bf16*>(w1_bf16), b1,
                       w2_f16, b2, ffn_gamma, 1e-5f, out, static_cast<bf16*>(out_bf16)));
-    CK(cudaStreamSynchronize(e->st));
+    if (!e->test_async) CK(cudaStreamSynchronize(e->st));
   });
 }
 
