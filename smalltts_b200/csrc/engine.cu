@@ -107,6 +107,8 @@ struct stts_cond {
 struct stts_engine {
   int device = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;  // side stream: the style encoder runs beside the text encoder (fork/join on events)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   std::map<std::string, RawTensor> raw[2];
   std::vector<void*> owned;  // packed buffers
@@ -115,7 +117,7 @@ struct stts_engine {
   // packed DiT-side weights
   EncW style, text;
   bf16 *style_in_w, *style_out_w, *ph_proj_w, *wkv_ref, *wkv_text, *in_proj_w, *conv1_w, *conv2_w, *vel_w;
-  float *style_in_b, *bkv_ref, *bkv_text, *in_proj_b, *conv1_b;
+  float *style_in_b, *bkv_ref, *bkv_text, *in_proj_b, *conv1_b, *knorm_cross;
   bf16* in_proj_w_dense;
   const float* in_proj_b_dense;
   const float *style_out_b, *ph_proj_b, *conv2_b, *vel_b, *text_emb;
@@ -336,6 +338,7 @@ void finalize(stts_engine* e) {
   e->wkv_text = e->dalloc<bf16>(static_cast<size_t>(NBLK) * 2 * D * D);
   e->bkv_ref = e->dalloc<float>(NBLK * 2 * D);
   e->bkv_text = e->dalloc<float>(NBLK * 2 * D);
+  e->knorm_cross = e->dalloc<float>(NBLK * H * HD);
   for (int i = 0; i < NBLK; ++i) {
     const std::string p = "dit.transformer_blocks." + std::to_string(i) + ".";
     DitBlockW b;
@@ -359,7 +362,8 @@ void finalize(stts_engine* e) {
     b.b2 = e->W(0, p + "ff.w2.bias", {D}).d;
     b.qn = e->W(0, p + "attn.q_norm.weight", {H, HD}).d;
     b.kn = e->W(0, p + "attn.k_norm.weight", {H, HD}).d;
-    e->W(0, p + "attn.k_norm_cross.weight", {H, HD});
+    CK(cudaMemcpyAsync(e->knorm_cross + static_cast<size_t>(i) * H * HD, e->W(0, p + "attn.k_norm_cross.weight", {H, HD}).d,
+                       H * HD * sizeof(float), cudaMemcpyDeviceToDevice, st));
     b.ada_w = e->W(0, p + "attn_norm.linear.weight", {6 * D, D}).d;
     b.ada_b = e->W(0, p + "attn_norm.linear.bias", {6 * D}).d;
     e->blk.push_back(b);
@@ -486,10 +490,21 @@ stts_cond* encode_conditions(stts_engine* e, const float* ref, const int64_t* re
 // Launch-only part of the condition encoder (no allocation of persistent state, no synchronisation): safe to
 // capture into a CUDA graph.  `c` carries device lengths and the K/V cache buffers to fill.
 void encode_conditions_core(stts_engine* e, stts_cond* c, const float* dref, const long long* dids) {
-  cudaStream_t st = e->st;
+  cudaStream_t main_st = e->st;
   const int B = c->B, R = c->R, P = c->P;
+  // The style path (src 0, B*R rows) and the text path (src 1, B*P rows) are independent chains of small kernels:
+  // fork the style path onto the side stream and join before returning (works eagerly and under stream capture).
+  struct Restore {
+    stts_engine* e;
+    cudaStream_t s;
+    ~Restore() { e->st = s; }
+  } restore{e, main_st};
+  CK(cudaEventRecord(e->ev_fork, main_st));
+  CK(cudaStreamWaitEvent(e->st2, e->ev_fork, 0));
   {
     for (int src = 0; src < 2; ++src) {
+      e->st = src == 0 ? e->st2 : main_st;
+      cudaStream_t st = e->st;
       const int N = src == 0 ? R : P;
       const long long M = static_cast<long long>(B) * N;
       const int* len_dev = src == 0 ? c->ref_len : c->ph_len;
@@ -521,16 +536,12 @@ void encode_conditions_core(stts_engine* e, stts_cond* c, const float* dref, con
       linear(e, seq, M, D, D, src == 0 ? e->wkv_ref : e->wkv_text, NKV, D, ek);
       bf16* cache = src == 0 ? c->kv_ref : c->kv_text;
       const size_t stride = src == 0 ? c->ref_stride() : c->text_stride();
-      for (int i = 0; i < NBLK; ++i) {
-        const std::string p = "dit.transformer_blocks." + std::to_string(i) + ".attn.k_norm_cross.weight";
-        const float* knc = e->raw[0][p].d;
-        CK(head_split_bf16(st, kvf, NKV, i * 2 * D, M, N, H, HD, HDP, knc, 1e-6f, 0, nullptr, nullptr,
-                           cache + (2 * i) * stride));
-        CK(head_split_bf16(st, kvf, NKV, i * 2 * D + D, M, N, H, HD, HDP, nullptr, 0.f, 0, nullptr, nullptr,
-                           cache + (2 * i + 1) * stride));
-      }
+      CK(kv_split_bf16(st, kvf, NKV, M, NBLK, H, HD, HDP, 1e-6f, e->knorm_cross, cache, static_cast<long long>(stride)));
     }
   }
+  e->st = main_st;
+  CK(cudaEventRecord(e->ev_join, e->st2));
+  CK(cudaStreamWaitEvent(main_st, e->ev_join, 0));
 }
 
 // ------------------------------------------------------------------ adaLN tables (function of t only)
@@ -936,6 +947,9 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     }
     CK(cudaSetDevice(e->device));
     CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
     CK(cudaEventCreate(&e->ev_stop));
     CK(cudaMalloc(reinterpret_cast<void**>(&e->seed_dev), sizeof(unsigned long long)));
@@ -971,6 +985,9 @@ void stts_destroy(stts_engine* e) {
   cudaFreeHost(e->seed_host);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
   cudaEventDestroy(e->ev_stop);
+  cudaEventDestroy(e->ev_fork);
+  cudaEventDestroy(e->ev_join);
+  cudaStreamDestroy(e->st2);
   cudaStreamDestroy(e->st);
   delete e;
 }
@@ -1279,7 +1296,8 @@ int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T
     s.groups = groups; s.a_group_koff = a_group_koff; s.w_group_rows = w_group_rows; s.out_group_cols = out_group_cols;
     s.res_group_cols = out_group_cols;
     GemmEpi ep;
-    ep.bias = bias; ep.act = act; ep.row_len = row_len; ep.rows_per_batch = rows_per_batch; ep.mask_bf16_only = mask_bf16_only; ep.colscale = colscale;
+    // act: GemmAct in the low 4 bits; +16 = GELU written as 2*gelu in fp16 (gelu2_f16); +32 = operands are fp16
+    ep.bias = bias; ep.act = act & 15; ep.gelu2_f16 = (act >> 4) & 1; s.ab_f16 = (act >> 5) & 1; ep.row_len = row_len; ep.rows_per_batch = rows_per_batch; ep.mask_bf16_only = mask_bf16_only; ep.colscale = colscale;
     ep.rowgate = rowgate; ep.ld_gate = ld_gate; ep.residual = residual; ep.ld_res = ld_res; ep.out_f32 = out_f32;
     ep.out_bf16 = static_cast<bf16*>(out_bf16); ep.ld_out = ld_out;
     CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), a_cols, a_ld},

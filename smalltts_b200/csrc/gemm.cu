@@ -24,6 +24,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kActGelu2 = 100;  // kernel-internal: ACT_GELU with GemmEpi::gelu2_f16 (own instantiation, no general path)
+constexpr int kStageBytes = 4096;  // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled (no padding)
 
 template <int BN>
 struct Cfg {
@@ -31,7 +33,8 @@ struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int smem_bytes(int stages) {
-    return stages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/;  // <= 12 barriers + slot
+    // <= 12 barriers + slot, then 4 KB of transposition staging per epilogue warp
+    return stages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kStageBytes;
   }
 };
 
@@ -108,6 +111,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* acc_full = empty + kStages;   // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full) + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -193,48 +197,107 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ---------------- epilogue: 8 warps; warp w owns TMEM lanes [32(w%4), +32) = tile rows and every second
-    // 32-column chunk of the accumulator (chunk parity = (w-2)/4)
+    // 32-column chunk of the accumulator (chunk parity = (w-2)/4).
+    // tcgen05.ld hands every lane one ROW of the chunk; storing that directly would make each store instruction
+    // touch 32 different lines.  The chunk is therefore transposed through a warp-private shared-memory buffer so
+    // that in the second half 8 (or 4) consecutive lanes own one row segment: bias / activation / mask / scale /
+    // gate / residual and the stores then run on whole 128-byte (64-byte) row segments.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    constexpr int kOut = (ACT == ACT_SWIGLU16) ? 16 : 32;  // output columns per 32-column accumulator chunk
+    float* stg = reinterpret_cast<float*>(stage_base + (warp - 2) * kStageBytes);
+    const int l8r = lane >> 3, l8c = lane & 7;  // 32-column chunks: rows 4j + l8r (j < 8), float4 column l8c
+    const int l4r = lane >> 2, l4c = lane & 3;  // 64-byte row segments: rows 8j + l4r (j < 4), 16-byte column l4c
     for (int li = 0; li < n_my; ++li) {
       const int tile = first + li * stride;
       const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
       const int b = my / tiles_t, t0 = (my % tiles_t) * BM, n0 = nx * BN;
       const int ab = li & 1;
-      ptx::mbar_wait(&acc_full[ab], (li >> 1) & 1);
-      ptx::tc_fence_after();
       const int t = t0 + row;
       const bool row_ok = t < s.T;
-      const long long m = static_cast<long long>(b) * s.T + t;
+      const int m0 = b * s.T + t0 + q * 32;  // flattened row of this warp's first TMEM lane
       // batch index / in-batch row used by masking and gating (flattened inputs carry rows_per_batch)
-      const int eb = e.rows_per_batch > 0 ? static_cast<int>(m / e.rows_per_batch) : b;
-      const int et = e.rows_per_batch > 0 ? static_cast<int>(m % e.rows_per_batch) : t;
-      const bool masked = (e.row_len != nullptr) && row_ok && (et >= e.row_len[eb]);
-      const bool mask32 = masked && !e.mask_bf16_only;
-      const float bz = (masked && e.mask_bf16_only) ? 0.0f : 1.0f;  // bf16-only masking
+      const int mrow = m0 + lane;
+      const int eb_own = e.rows_per_batch > 0 ? mrow / e.rows_per_batch : b;
+      const int et_own = e.rows_per_batch > 0 ? mrow % e.rows_per_batch : t;
+      const bool masked = (e.row_len != nullptr) && row_ok && (et_own >= e.row_len[eb_own]);
+      const uint32_t okbits = __ballot_sync(0xffffffffu, row_ok);
+      const uint32_t mkbits = __ballot_sync(0xffffffffu, masked);
       const int gcol_base = g * s.out_group_cols;
+      const int res_goff = g * (s.res_group_cols - s.out_group_cols);
+
+      // post-activation part on a float4 of row rr (warp-relative), absolute output column col
+      auto post_store = [&](float4 v, int rr, int col) {
+        const bool mk = (mkbits >> rr) & 1u;
+        if (mk && !e.mask_bf16_only) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.colscale != nullptr) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(e.colscale + col));
+          v.x *= x.x; v.y *= x.y; v.z *= x.z; v.w *= x.w;
+        }
+        const long long mj = m0 + rr;
+        if (e.rowgate != nullptr) {
+          const int ebj = e.rows_per_batch > 0 ? (m0 + rr) / e.rows_per_batch : b;
+          const float4 x = __ldg(reinterpret_cast<const float4*>(e.rowgate + static_cast<long long>(ebj) * e.ld_gate + col));
+          v.x *= x.x; v.y *= x.y; v.z *= x.z; v.w *= x.w;
+        }
+        if (e.residual != nullptr) {
+          const float4 x = *reinterpret_cast<const float4*>(e.residual + mj * e.ld_res + col + res_goff);
+          v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+        }
+        if (e.out_f32 != nullptr) *reinterpret_cast<float4*>(e.out_f32 + mj * e.ld_out + col) = v;
+        if (e.out_bf16 != nullptr) {
+          const float bz = (mk && e.mask_bf16_only) ? 0.0f : 1.0f;  // bf16-only masking
+          uint2 pk;
+          pk.x = bf2(bz * v.x, bz * v.y);
+          pk.y = bf2(bz * v.z, bz * v.w);
+          *reinterpret_cast<uint2*>(e.out_bf16 + mj * e.ld_out + col) = pk;
+        }
+      };
+
+      // Residual rows of the general path are fetched one chunk ahead (the first chunk of a tile before the wait
+      // for its accumulator): they do not depend on the MMAs and their latency would otherwise sit between the
+      // accumulator read and the store of every chunk.
+      constexpr bool kGeneral = (ACT != ACT_SWIGLU16);
+      const bool pre_res = kGeneral && e.residual != nullptr && !(ACT == kActGelu2);
+      float4 rq[8];
+      auto load_res = [&](int c, float4 (&dst)[8]) {
+        const float* base = e.residual + static_cast<long long>(m0 + l8r) * e.ld_res + gcol_base + n0 + c * 32 + 4 * l8c + res_goff;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((okbits >> (4 * j + l8r)) & 1u) dst[j] = *reinterpret_cast<const float4*>(base + static_cast<long long>(j) * 4 * e.ld_res);
+        }
+      };
+      if (pre_res && n0 + half * 32 < s.N) load_res(half, rq);
+      ptx::mbar_wait(&acc_full[ab], (li >> 1) & 1);
+      ptx::tc_fence_after();
+
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int nl0 = n0 + c * 32;  // column inside the group
         if (nl0 >= s.N) break;        // warp-uniform
+        const int gc0 = gcol_base + nl0;
+        float4 bv[8];  // bias of the row-form paths, requested before the accumulator read
+        if ((ACT == ACT_SWIGLU16 || (ACT == kActGelu2)) && e.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(e.bias + gc0 + 4 * i));
+        }
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
         ptx::tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        const int gc0 = gcol_base + nl0;
-        if (e.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) add4(v + 4 * i, e.bias + gc0 + 4 * i);
-        }
-        int out_c0 = gc0;
-        if (ACT == ACT_GELU && e.gelu2_f16) {
+        if (okbits == 0u) continue;  // warp-uniform: no live row in this quarter
+        if (ACT == kActGelu2) {
           // FFN hidden activation of the vocoder: 2*gelu in packed fp16, stored as fp16 (no mask/scale/residual here)
-          __nv_bfloat16* op = e.out_bf16 + m * e.ld_out + gc0;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (e.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
+            }
+          }
+          uint4* srow = reinterpret_cast<uint4*>(stg) + lane * 4;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 pk;
@@ -242,61 +305,113 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             pk.y = gelu2_half2(v[8 * i + 2], v[8 * i + 3]);
             pk.z = gelu2_half2(v[8 * i + 4], v[8 * i + 5]);
             pk.w = gelu2_half2(v[8 * i + 6], v[8 * i + 7]);
-            *reinterpret_cast<uint4*>(op + 8 * i) = pk;
+            srow[i ^ ((lane >> 1) & 3)] = pk;
           }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + l4r;
+            const uint4 pk = reinterpret_cast<const uint4*>(stg)[rr * 4 + (l4c ^ ((rr >> 1) & 3))];
+            if ((okbits >> rr) & 1u) {
+              *reinterpret_cast<uint4*>(e.out_bf16 + static_cast<long long>(m0 + rr) * e.ld_out + gc0 + 8 * l4c) = pk;
+            }
+          }
+          __syncwarp();
           continue;
         }
         if (ACT == ACT_SWIGLU16) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (e.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float a = v[i];
             v[i] = a * fast_sigmoid(a) * v[16 + i];
           }
-          out_c0 = gc0 >> 1;
-        } else if (ACT != ACT_NONE) {
+          float4* srow = reinterpret_cast<float4*>(stg) + lane * 4;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_apply<ACT>(v[i]);
+          for (int i = 0; i < 4; ++i) {
+            srow[i ^ ((lane >> 1) & 3)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          __syncwarp();
+          const int col = (gc0 >> 1) + 4 * l4c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + l4r;
+            const float4 x = reinterpret_cast<const float4*>(stg)[rr * 4 + (l4c ^ ((rr >> 1) & 3))];
+            if ((okbits >> rr) & 1u) post_store(x, rr, col);
+          }
+          __syncwarp();
+          continue;
         }
-        if (mask32) {
+        // general path: stage the raw accumulators, everything else happens on row segments
+        {
+          uint4* srow = reinterpret_cast<uint4*>(stg) + lane * 8;
 #pragma unroll
-          for (int i = 0; i < kOut; ++i) v[i] = 0.0f;
-        }
-        if (e.colscale != nullptr) {
-#pragma unroll
-          for (int i = 0; i < kOut / 4; ++i) mul4(v + 4 * i, e.colscale + out_c0 + 4 * i);
-        }
-        if (e.rowgate != nullptr) {
-          const float* gp = e.rowgate + static_cast<long long>(eb) * e.ld_gate + out_c0;
-#pragma unroll
-          for (int i = 0; i < kOut / 4; ++i) mul4(v + 4 * i, gp + 4 * i);
-        }
-        if (e.residual != nullptr) {
-          const float* rp = e.residual + m * e.ld_res + out_c0 + g * (s.res_group_cols - s.out_group_cols);
-#pragma unroll
-          for (int i = 0; i < kOut / 4; ++i) {
-            const float4 x = *reinterpret_cast<const float4*>(rp + 4 * i);
-            v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+          for (int i = 0; i < 8; ++i) {
+            srow[i ^ (lane & 7)] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
           }
         }
-        if (e.out_f32 != nullptr) {
-          float* op = e.out_f32 + m * e.ld_out + out_c0;
+        __syncwarp();
+        {
+          const int col = gc0 + 4 * l8c;
+          // phase 1: every load of the chunk is in flight before the first store
+          float4 x[8];
 #pragma unroll
-          for (int i = 0; i < kOut / 4; ++i) {
-            *reinterpret_cast<float4*>(op + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + l8r;
+            x[j] = reinterpret_cast<const float4*>(stg)[rr * 8 + (l8c ^ (rr & 7))];
+          }
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (e.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+          if (e.colscale != nullptr) cs4 = __ldg(reinterpret_cast<const float4*>(e.colscale + col));
+          float4 rn[8];
+          const bool more = pre_res && (n0 + (c + 2) * 32 < s.N) && (c + 2 < BN / 32);
+          if (more) load_res(c + 2, rn);
+          // phase 2: arithmetic + stores on 128-byte row segments
+          const long long obase = static_cast<long long>(m0 + l8r) * e.ld_out + col;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + l8r;
+            if (!((okbits >> rr) & 1u)) continue;
+            float4 v = x[j];
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (ACT != ACT_NONE) {
+              v.x = act_apply<ACT>(v.x); v.y = act_apply<ACT>(v.y); v.z = act_apply<ACT>(v.z); v.w = act_apply<ACT>(v.w);
+            }
+            const bool mk = (mkbits >> rr) & 1u;
+            if (mk && !e.mask_bf16_only) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            v.x *= cs4.x; v.y *= cs4.y; v.z *= cs4.z; v.w *= cs4.w;
+            if (e.rowgate != nullptr) {  // read-only path: free to be scheduled above the stores
+              const int ebj = e.rows_per_batch > 0 ? (m0 + rr) / e.rows_per_batch : b;
+              const float4 gt = __ldg(reinterpret_cast<const float4*>(e.rowgate + static_cast<long long>(ebj) * e.ld_gate + col));
+              v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
+            }
+            if (e.residual != nullptr) {
+              v.x += rq[j].x; v.y += rq[j].y; v.z += rq[j].z; v.w += rq[j].w;
+            }
+            const long long off = obase + static_cast<long long>(j) * 4 * e.ld_out;
+            if (e.out_f32 != nullptr) *reinterpret_cast<float4*>(e.out_f32 + off) = v;
+            if (e.out_bf16 != nullptr) {
+              const float bz = (mk && e.mask_bf16_only) ? 0.0f : 1.0f;  // bf16-only masking
+              uint2 pk;
+              pk.x = bf2(bz * v.x, bz * v.y);
+              pk.y = bf2(bz * v.z, bz * v.w);
+              *reinterpret_cast<uint2*>(e.out_bf16 + off) = pk;
+            }
+          }
+          if (more) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rq[j] = rn[j];
           }
         }
-        if (e.out_bf16 != nullptr) {
-          __nv_bfloat16* op = e.out_bf16 + m * e.ld_out + out_c0;
-#pragma unroll
-          for (int i = 0; i < kOut / 8; ++i) {
-            uint4 pk;
-            pk.x = bf2(bz * v[8 * i + 0], bz * v[8 * i + 1]);
-            pk.y = bf2(bz * v[8 * i + 2], bz * v[8 * i + 3]);
-            pk.z = bf2(bz * v[8 * i + 4], bz * v[8 * i + 5]);
-            pk.w = bf2(bz * v[8 * i + 6], bz * v[8 * i + 7]);
-            *reinterpret_cast<uint4*>(op + 8 * i) = pk;
-          }
-        }
+        __syncwarp();
       }
       // this warp is done reading the accumulator buffer
       ptx::tc_fence_before();
@@ -388,6 +503,7 @@ cudaError_t launch_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtenso
     case ACT_NONE:
       return launch_inst<BN, ACT_NONE>(stream, tmA, tmW, s, e);
     case ACT_GELU:
+      if (e.gelu2_f16) return launch_inst<BN, kActGelu2>(stream, tmA, tmW, s, e);
       return launch_inst<BN, ACT_GELU>(stream, tmA, tmW, s, e);
     case ACT_SWIGLU16:
       return launch_inst<BN, ACT_SWIGLU16>(stream, tmA, tmW, s, e);

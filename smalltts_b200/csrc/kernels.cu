@@ -6,6 +6,7 @@
 
 #include "launch.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace stts {
 
@@ -106,17 +107,11 @@ struct HeadJobs {  // up to three head-split jobs in one launch (q, k, v of one 
   bf16* out[3];
 };
 
-template <int EPL>  // elements per lane: hd_pad / 32
-__global__ void __launch_bounds__(256) head_split_kernel(const float* __restrict__ in, int ld_in, int rows, int rpb,
-                                                         int heads, int hd, float eps, const float* __restrict__ cos_t,
-                                                         const float* __restrict__ sin_t, const HeadJobs jobs) {
-  ptx::pdl_wait();
-  ptx::pdl_trigger();
-  const int job = blockIdx.y;
-  const int src_off = job == 0 ? jobs.src_off[0] : (job == 1 ? jobs.src_off[1] : jobs.src_off[2]);
-  const int rot = job == 0 ? jobs.rot[0] : (job == 1 ? jobs.rot[1] : jobs.rot[2]);
-  const float* __restrict__ norm_w = job == 0 ? jobs.norm_w[0] : (job == 1 ? jobs.norm_w[1] : jobs.norm_w[2]);
-  bf16* __restrict__ out = job == 0 ? jobs.out[0] : (job == 1 ? jobs.out[1] : jobs.out[2]);
+template <int EPL>  // elements per lane: hd_pad / 32; one warp per (row, head)
+__device__ __forceinline__ void head_split_body(const float* __restrict__ in, int ld_in, int rows, int rpb, int heads,
+                                                int hd, float eps, const float* __restrict__ cos_t,
+                                                const float* __restrict__ sin_t, int src_off, int rot,
+                                                const float* __restrict__ norm_w, bf16* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const long long item = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (item >= static_cast<long long>(rows) * heads) return;
@@ -157,193 +152,285 @@ __global__ void __launch_bounds__(256) head_split_kernel(const float* __restrict
   }
 }
 
-// ------------------------------------------------------------------ attention (warp MMA, online softmax)
-// CTA = 32 query rows (2 warps x 16) of one (batch, head); keys streamed in chunks of 64 through smem with cp.async
-// double buffering.  Small CTAs on purpose: the whole problem is a few hundred warps, so spreading it over all SMs
-// (two CTAs per SM) matters more than re-staging K/V per query tile (L2 hits).
-constexpr int kAttRows = 32, kAttThreads = 64;
-
-template <int HD>
-__global__ void __launch_bounds__(kAttThreads) attention_kernel(const bf16* __restrict__ q, int tq, int H, int hd, AttnSeg s0,
-                                                        AttnSeg s1, AttnSeg s2, int nseg, const float* __restrict__ gate,
-                                                        int ld_gate, int gate_off, float scale_log2,
-                                                        bf16* __restrict__ out) {
+template <int EPL>
+__global__ void __launch_bounds__(256) head_split_kernel(const float* __restrict__ in, int ld_in, int rows, int rpb,
+                                                         int heads, int hd, float eps, const float* __restrict__ cos_t,
+                                                         const float* __restrict__ sin_t, const HeadJobs jobs) {
   ptx::pdl_wait();
   ptx::pdl_trigger();
-  constexpr int PITCH = HD + 8;  // bf16 elements; 16-byte rows offset by one bank group -> conflict-free ldmatrix
-  extern __shared__ __align__(16) uint8_t smem_att[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem_att);
-  bf16* sKV = sQ + kAttRows * PITCH;  // [2 buffers][K | V][64][PITCH]
+  const int job = blockIdx.y;
+  const int src_off = job == 0 ? jobs.src_off[0] : (job == 1 ? jobs.src_off[1] : jobs.src_off[2]);
+  const int rot = job == 0 ? jobs.rot[0] : (job == 1 ? jobs.rot[1] : jobs.rot[2]);
+  const float* __restrict__ norm_w = job == 0 ? jobs.norm_w[0] : (job == 1 ? jobs.norm_w[1] : jobs.norm_w[2]);
+  bf16* __restrict__ out = job == 0 ? jobs.out[0] : (job == 1 ? jobs.out[1] : jobs.out[2]);
+  head_split_body<EPL>(in, ld_in, rows, rpb, heads, hd, eps, cos_t, sin_t, src_off, rot, norm_w, out);
+}
+
+// Cross K/V caches of all layers in one launch (dit.py:80-93): blockIdx.y = 2*layer + {0: k (k_norm_cross), 1: v};
+// source columns y*width of the fused projection, destination cache + y*out_stride.
+template <int EPL>
+__global__ void __launch_bounds__(256) kv_split_kernel(const float* __restrict__ in, int ld_in, int rows, int heads,
+                                                       int hd, int width, float eps, const float* __restrict__ knorm_all,
+                                                       bf16* __restrict__ cache, long long out_stride) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const int y = blockIdx.y;
+  const float* norm_w = (y & 1) ? nullptr : knorm_all + static_cast<long long>(y >> 1) * heads * hd;
+  head_split_body<EPL>(in, ld_in, rows, 1, heads, hd, eps, nullptr, nullptr, y * width, 0, norm_w, cache + y * out_stride);
+}
+
+// ------------------------------------------------------------------ attention (warp MMA, keys split over warps)
+// CTA = 48 query rows of one (batch, head): 3 row groups x 4 key splits = 12 warps.  The joint key sequence
+// [self | ref | text] is laid out virtually with every segment padded to a multiple of 16 keys; a chunk is 64 virtual
+// keys = four TMA boxes of 16 rows per operand half, so no thread ever computes a K/V address.  Warp (rg, split)
+// scores its 16 rows against chunks split, split+4, ... with an online softmax and the four partial results of a row
+// group are merged through shared memory.  At the DiT's 210 keys every warp sees exactly one chunk: the kernel is one
+// TMA round trip + 128 warp MMAs + the merge deep, instead of a serial walk over all keys by two warps.
+constexpr int kAttRG = 3, kAttSplits = 4;
+constexpr int kAttRows = kAttRG * 16;
+constexpr int kAttThreads = kAttRG * kAttSplits * 32;
+constexpr int kAttChunk = 64;
+
+struct AttnMaps {
+  CUtensorMap q;     // [hd_pad, H, B*tq]      box [64, 1, 48]
+  CUtensorMap k[3];  // [hd_pad, H, B*n_max]   box [64, 1, 16]
+  CUtensorMap v[3];
+};
+struct AttnLens {
+  const int* len[3];
+  int n_max[3];
+};
+
+// byte offset of (row, dim) in a [HD/64 halves][ROWS rows][64] bf16 tile written by TMA with 128-byte swizzle
+template <int ROWS>
+__device__ __forceinline__ uint32_t att_sw(int row, int dim) {
+  return static_cast<uint32_t>((dim >> 6) * (ROWS * 128) + row * 128 + ((((dim & 63) >> 3) ^ (row & 7)) << 4));
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attention_kernel(const __grid_constant__ AttnMaps maps, const AttnLens lens, int tq, int H, int hd, int nseg,
+                 const float* __restrict__ gate, int ld_gate, int gate_off, float scale_log2, bf16* __restrict__ out) {
+  constexpr int NH = HD / 64;                         // 128-byte halves per row
+  constexpr int Q_BYTES = NH * kAttRows * 128;        // 12 KB / 6 KB
+  constexpr int OP_BYTES = NH * kAttChunk * 128;      // one K or V chunk: 16 KB / 8 KB
+  constexpr int SPLIT_BYTES = 2 * OP_BYTES;           // K + V of one split (later: 3 x [16][HD] fp32 partial outputs)
+  constexpr int O_BYTES = 16 * HD * 4;
+  static_assert(kAttRG * O_BYTES <= SPLIT_BYTES, "merge buffers must fit in the K/V buffer of a split");
+  extern __shared__ uint8_t smem_att_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_att_raw);
+  uint8_t* smem = smem_att_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + ((Q_BYTES + 1023) & ~1023);
+  float* ml = reinterpret_cast<float*>(sKV + kAttSplits * SPLIT_BYTES);  // [12 warps][16 rows][m, l]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ml + kAttRG * kAttSplits * 32);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;  // [4]
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ld = H * HD;
+  const int split = warp / kAttRG, rg = warp % kAttRG;
 
-  int len[3] = {0, 0, 0};
-  len[0] = s0.len ? min(s0.len[b], s0.n_max) : s0.n_max;
-  if (nseg > 1) len[1] = s1.len ? min(s1.len[b], s1.n_max) : s1.n_max;
-  if (nseg > 2) len[2] = s2.len ? min(s2.len[b], s2.n_max) : s2.n_max;
-  const int total = len[0] + len[1] + len[2];
-
-  constexpr int VPR = HD / 8;  // 16-byte vectors per row
-  // cp.async staging (no register round trip, every 16-byte copy of a chunk in flight at once); rows beyond the
-  // valid range are zero-filled (src-size 0)
-  for (int i = threadIdx.x; i < kAttRows * VPR; i += kAttThreads) {
-    const int r = i / VPR, c = i % VPR;
-    const bool ok = q0 + r < tq;
-    const bf16* src = q + (static_cast<long long>(b) * tq + (ok ? q0 + r : 0)) * ld + h * HD + c * 8;
-    ptx::cp_async_16(ptx::smem_u32(sQ + r * PITCH + c * 8), src, ok ? 16u : 0u);
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < kAttSplits; ++i) ptx::mbar_init(&kv_full[i], 1);
+    ptx::fence_barrier_init();
   }
-  auto load_chunk = [&](int k0, int bufi) {
-    bf16* dK = sKV + bufi * (2 * 64 * PITCH);
-    bf16* dV = dK + 64 * PITCH;
-    for (int i = threadIdx.x; i < 64 * VPR; i += kAttThreads) {
-      const int r = i / VPR, c = i % VPR;
-      int j = k0 + r;
-      const bool ok = j < total;
-      const bf16 *kp = s0.k, *vp = s0.v;
-      int nmax = s0.n_max;
-      if (ok) {
-        if (j >= len[0] + len[1]) {
-          j -= len[0] + len[1]; kp = s2.k; vp = s2.v; nmax = s2.n_max;
-        } else if (j >= len[0]) {
-          j -= len[0]; kp = s1.k; vp = s1.v; nmax = s1.n_max;
-        }
-      } else {
-        j = 0;
-      }
-      const long long off = (static_cast<long long>(b) * nmax + j) * ld + h * HD + c * 8;
-      ptx::cp_async_16(ptx::smem_u32(dK + r * PITCH + c * 8), kp + off, ok ? 16u : 0u);
-      ptx::cp_async_16(ptx::smem_u32(dV + r * PITCH + c * 8), vp + off, ok ? 16u : 0u);
-    }
-    ptx::cp_async_commit();
-  };
-  load_chunk(0, 0);  // commits the Q copies too
+  __syncthreads();
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
 
-  uint32_t qf[HD / 16][4];
+  // virtual key layout: segment s occupies [es[s-1], es[s-1] + pad16(len_s))
+  int len0 = lens.len[0] ? min(lens.len[0][b], lens.n_max[0]) : lens.n_max[0];
+  int len1 = 0, len2 = 0;
+  if (nseg > 1) len1 = lens.len[1] ? min(lens.len[1][b], lens.n_max[1]) : lens.n_max[1];
+  if (nseg > 2) len2 = lens.len[2] ? min(lens.len[2][b], lens.n_max[2]) : lens.n_max[2];
+  const int e0 = (len0 + 15) & ~15, e1 = e0 + ((len1 + 15) & ~15), e2 = e1 + ((len2 + 15) & ~15);
+  const int n_chunks = (e2 + kAttChunk - 1) / kAttChunk;
+
+  auto issue_chunk = [&](int chunk) {  // one thread: 4 groups x {K, V} x NH boxes of [64 dims x 16 rows]
+    uint64_t* bar = &kv_full[split];
+    ptx::mbar_expect_tx(bar, SPLIT_BYTES);
+    uint8_t* dK = sKV + split * SPLIT_BYTES;
+    uint8_t* dV = dK + OP_BYTES;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int vk = chunk * kAttChunk + g * 16;
+      int s = 0, j = vk;
+      if (vk >= e1) { s = 2; j = vk - e1; } else if (vk >= e0) { s = 1; j = vk - e0; }
+      // groups past the end of the sequence are fetched from beyond the tensor: TMA fills them with zeros
+      const int rowc = vk < e2 ? b * lens.n_max[s] + j : 0x40000000;
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf) {
+        ptx::tma_load_3d(dK + hf * (kAttChunk * 128) + g * 2048, &maps.k[s], bar, hf * 64, h, rowc);
+        ptx::tma_load_3d(dV + hf * (kAttChunk * 128) + g * 2048, &maps.v[s], bar, hf * 64, h, rowc);
+      }
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    ptx::mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+    for (int hf = 0; hf < NH; ++hf) ptx::tma_load_3d(sQ + hf * (kAttRows * 128), &maps.q, q_full, hf * 64, h, b * tq + q0);
+  }
+  if (rg == 0 && lane == 0 && split < n_chunks) issue_chunk(split);
+
+  const bool active = q0 + rg * 16 < tq;  // row groups past the end of the sequence only keep the barriers company
   float o[HD / 8][4];
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
+  const uint32_t qa = ptx::smem_u32(sQ);
+  const uint32_t ka = ptx::smem_u32(sKV + split * SPLIT_BYTES);
+  const uint32_t va = ka + OP_BYTES;
 
-  int ci = 0;
-  for (int k0 = 0; k0 < total || k0 == 0; k0 += 64, ++ci) {
-    if (k0 + 64 < total) {
-      load_chunk(k0 + 64, (ci + 1) & 1);  // prefetch the next chunk into the other buffer
-      ptx::cp_async_wait<1>();
-    } else {
-      ptx::cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (k0 == 0) {
-      const int r = warp * 16 + (lane & 15);
-      const int cofs = (lane >> 4) * 8;
+  ptx::mbar_wait(q_full, 0);  // every thread: the CTA never exits with the Q copy in flight
+  int it = 0;
+  for (int chunk = split; chunk < n_chunks; chunk += kAttSplits, ++it) {
+    if (it > 0 && rg == 0 && lane == 0) issue_chunk(chunk);  // buffer released by the barrier that ended it-1
+    ptx::mbar_wait(&kv_full[split], it & 1);
+    if (active) {
+      // S = Q K^T for 16 rows x 64 keys
+      float sc[8][4];
 #pragma unroll
-      for (int kk = 0; kk < HD / 16; ++kk) ptx::ldmatrix_x4(qf[kk], sQ + r * PITCH + kk * 16 + cofs);
-    }
-    if (total == 0) break;
-    const bf16* sK = sKV + (ci & 1) * (2 * 64 * PITCH);
-    const bf16* sV = sK + 64 * PITCH;
-
-    // S = Q K^T for 16 rows x 64 keys
-    float sc[8][4];
+      for (int j = 0; j < 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      const int id = lane >> 3, r8 = lane & 7;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        uint32_t qf[4];
+        ptx::ldmatrix_x4_addr(qf, qa + att_sw<kAttRows>(rg * 16 + (lane & 15), kk * 16 + (lane >> 4) * 8));
 #pragma unroll
-    for (int kk = 0; kk < HD / 16; ++kk) {
+        for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key tiles
+          uint32_t bfr[4];
+          ptx::ldmatrix_x4_addr(bfr, ka + att_sw<kAttChunk>(jp * 16 + (id >> 1) * 8 + r8, kk * 16 + (id & 1) * 8));
+          ptx::mma_16816(sc[2 * jp], qf, bfr[0], bfr[1]);
+          ptx::mma_16816(sc[2 * jp + 1], qf, bfr[2], bfr[3]);
+        }
+      }
+      // mask padding keys, online softmax (rows: lane/4 and lane/4 + 8; cols: 8j + (lane%4)*2 + {0,1})
+      const int kbase = chunk * kAttChunk;
+      auto valid = [&](int kv) { return kv < e0 ? kv < len0 : (kv < e1 ? kv - e0 < len1 : kv - e1 < len2); };
+      float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {  // pairs of 8-key tiles
-        uint32_t bfr[4];
-        const int id = lane >> 3, r = lane & 7;
-        const int key = jp * 16 + (id >> 1) * 8 + r;
-        const int dim = kk * 16 + (id & 1) * 8;
-        ptx::ldmatrix_x4(bfr, sK + key * PITCH + dim);
-        ptx::mma_16816(sc[2 * jp], qf[kk], bfr[0], bfr[1]);
-        ptx::mma_16816(sc[2 * jp + 1], qf[kk], bfr[2], bfr[3]);
+      for (int j = 0; j < 8; ++j) {
+        const int kc = kbase + j * 8 + (lane & 3) * 2;
+        if (!valid(kc)) sc[j][0] = sc[j][2] = -INFINITY;
+        if (!valid(kc + 1)) sc[j][1] = sc[j][3] = -INFINITY;
+        mx[0] = fmaxf(mx[0], fmaxf(sc[j][0], sc[j][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(sc[j][2], sc[j][3]));
+      }
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[r], mx[r]);  // finite: every chunk holds >= 1 valid key
+        corr[r] = exp2f((m_run[r] - m_new) * scale_log2);
+        m_run[r] = m_new;
+        l_run[r] *= corr[r];
+      }
+      uint32_t pf[4][4];  // P as A fragments for the 4 k-steps of 16 keys
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = exp2f((sc[j][0] - m_run[0]) * scale_log2);
+        const float p1 = exp2f((sc[j][1] - m_run[0]) * scale_log2);
+        const float p2 = exp2f((sc[j][2] - m_run[1]) * scale_log2);
+        const float p3 = exp2f((sc[j][3] - m_run[1]) * scale_log2);
+        l_run[0] += p0 + p1;
+        l_run[1] += p2 + p3;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(p2, p3);
+        pf[j >> 1][(j & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo);
+        pf[j >> 1][(j & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+      if (it > 0) {
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          o[i][0] *= corr[0]; o[i][1] *= corr[0];
+          o[i][2] *= corr[1]; o[i][3] *= corr[1];
+        }
+      }
+      // O += P V
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int np = 0; np < HD / 16; ++np) {  // pairs of 8-dim tiles
+          uint32_t bfr[4];
+          ptx::ldmatrix_x4_trans_addr(bfr, va + att_sw<kAttChunk>(kk * 16 + (id & 1) * 8 + r8, (np * 2 + (id >> 1)) * 8));
+          ptx::mma_16816(o[2 * np], pf[kk], bfr[0], bfr[1]);
+          ptx::mma_16816(o[2 * np + 1], pf[kk], bfr[2], bfr[3]);
+        }
       }
     }
-    // mask tail keys, online softmax (rows: lane/4 and lane/4 + 8; cols: 8j + (lane%4)*2 + {0,1})
-    float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kc = k0 + j * 8 + (lane & 3) * 2;
-      if (kc >= total) sc[j][0] = sc[j][2] = -INFINITY;
-      if (kc + 1 >= total) sc[j][1] = sc[j][3] = -INFINITY;
-      mx[0] = fmaxf(mx[0], fmaxf(sc[j][0], sc[j][1]));
-      mx[1] = fmaxf(mx[1], fmaxf(sc[j][2], sc[j][3]));
-    }
-    float corr[2];
+    // the three warps of this split are done with the K/V buffer (next chunk / merge buffers may overwrite it)
+    ptx::named_bar_sync(1 + split, kAttRG * 32);
+  }
+
+  // ---- merge the four key splits of every row group through shared memory
+  if (active) {
+    float* ob = reinterpret_cast<float*>(sKV + split * SPLIT_BYTES + rg * O_BYTES);  // [16][HD], 8-float XOR swizzle
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float m_new = fmaxf(m_run[r], mx[r]);  // finite: every chunk holds >= 1 valid key
-      corr[r] = exp2f((m_run[r] - m_new) * scale_log2);
-      m_run[r] = m_new;
-      l_run[r] *= corr[r];
-    }
-    uint32_t pf[4][4];  // P as A fragments for the 4 k-steps of 16 keys
+      const int rl = (lane >> 2) + r * 8;
+      float l = l_run[r];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      if ((lane & 3) == 0) {
+        ml[(warp * 16 + rl) * 2 + 0] = m_run[r];
+        ml[(warp * 16 + rl) * 2 + 1] = l;
+      }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float p0 = exp2f((sc[j][0] - m_run[0]) * scale_log2);
-      const float p1 = exp2f((sc[j][1] - m_run[0]) * scale_log2);
-      const float p2 = exp2f((sc[j][2] - m_run[1]) * scale_log2);
-      const float p3 = exp2f((sc[j][3] - m_run[1]) * scale_log2);
-      l_run[0] += p0 + p1;
-      l_run[1] += p2 + p3;
-      __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(p2, p3);
-      pf[j >> 1][(j & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo);
-      pf[j >> 1][(j & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
-    }
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      o[i][0] *= corr[0]; o[i][1] *= corr[0];
-      o[i][2] *= corr[1]; o[i][3] *= corr[1];
-    }
-    // O += P V
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int np = 0; np < HD / 16; ++np) {  // pairs of 8-dim tiles
-        uint32_t bfr[4];
-        const int id = lane >> 3, r = lane & 7;
-        const int key = kk * 16 + (id & 1) * 8 + r;
-        const int dim = (np * 2 + (id >> 1)) * 8;
-        ptx::ldmatrix_x4_trans(bfr, sV + key * PITCH + dim);
-        ptx::mma_16816(o[2 * np], pf[kk], bfr[0], bfr[1]);
-        ptx::mma_16816(o[2 * np + 1], pf[kk], bfr[2], bfr[3]);
+      for (int i = 0; i < HD / 8; ++i) {
+        const int d = i * 8 + (lane & 3) * 2;
+        *reinterpret_cast<float2*>(ob + rl * HD + (d ^ ((rl & 7) << 3))) = make_float2(o[i][2 * r], o[i][2 * r + 1]);
       }
     }
-    __syncthreads();  // every warp is done with this K/V buffer before the prefetch of chunk ci+2 overwrites it
   }
-
-  // finalize: divide by row sums (reduced over the 4 lanes of a row), gate, store
-  float inv[2];
+  __syncthreads();
+  for (int item = threadIdx.x; item < kAttRows * 8; item += kAttThreads) {
+    const int row = item >> 3, c8 = item & 7;
+    if (q0 + row >= tq) continue;
+    const int g = row >> 4, rl = row & 15;
+    float ms[kAttSplits], w[kAttSplits];
+    float m_max = -INFINITY;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    float l = l_run[r];
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    inv[r] = l > 0.f ? 1.0f / l : 0.f;
-  }
+    for (int s = 0; s < kAttSplits; ++s) {
+      ms[s] = ml[((s * kAttRG + g) * 16 + rl) * 2];
+      m_max = fmaxf(m_max, ms[s]);
+    }
+    float L = 0.f;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
-    if (row >= tq) continue;
-    const long long m = static_cast<long long>(b) * tq + row;
-    bf16* op = out + m * ld + h * HD;
+    for (int s = 0; s < kAttSplits; ++s) {
+      w[s] = m_max == -INFINITY ? 0.f : exp2f((ms[s] - m_max) * scale_log2);
+      L += w[s] * ml[((s * kAttRG + g) * 16 + rl) * 2 + 1];
+    }
+    const float inv = L > 0.f ? 1.0f / L : 0.f;
+    const long long m = static_cast<long long>(b) * tq + q0 + row;
+    bf16* op = out + m * (H * HD) + h * HD;
     const float* gp = gate ? gate + m * ld_gate + gate_off + h * hd : nullptr;
 #pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      const int d = i * 8 + (lane & 3) * 2;
-      float a = o[i][2 * r] * inv[r], c = o[i][2 * r + 1] * inv[r];
-      if (gp != nullptr) {
-        a = d < hd ? a / (1.0f + expf(-gp[d])) : 0.f;
-        c = d + 1 < hd ? c / (1.0f + expf(-gp[d + 1])) : 0.f;
+    for (int k = 0; k < HD / 32; ++k) {
+      const int d = 4 * c8 + 32 * k;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < kAttSplits; ++s) {
+        const float* ob = reinterpret_cast<const float*>(sKV + s * SPLIT_BYTES + g * O_BYTES);
+        const float4 x = *reinterpret_cast<const float4*>(ob + rl * HD + (d ^ ((rl & 7) << 3)));
+        acc.x = fmaf(w[s], x.x, acc.x); acc.y = fmaf(w[s], x.y, acc.y);
+        acc.z = fmaf(w[s], x.z, acc.z); acc.w = fmaf(w[s], x.w, acc.w);
       }
-      *reinterpret_cast<__nv_bfloat162*>(op + d) = __floats2bfloat162_rn(a, c);
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      if (gp != nullptr) {
+        if (d < hd) {  // hd is a multiple of 4
+          const float4 gv = *reinterpret_cast<const float4*>(gp + d);
+          acc.x = __fdividef(acc.x, 1.0f + __expf(-gv.x)); acc.y = __fdividef(acc.y, 1.0f + __expf(-gv.y));
+          acc.z = __fdividef(acc.z, 1.0f + __expf(-gv.z)); acc.w = __fdividef(acc.w, 1.0f + __expf(-gv.w));
+        } else {
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      *reinterpret_cast<uint2*>(op + d) = pack_bf16x4(acc.x, acc.y, acc.z, acc.w);
     }
   }
 }
@@ -849,6 +936,14 @@ cudaError_t head_split_bf16(cudaStream_t st, const float* in, int ld_in, int src
   return head_split_launch(st, in, ld_in, rows, rpb, heads, hd, hd_pad, eps, cos_t, sin_t, j, 1);
 }
 
+cudaError_t kv_split_bf16(cudaStream_t st, const float* in, int ld_in, int rows, int layers, int heads, int hd,
+                          int hd_pad, float eps, const float* knorm_all, bf16* cache, long long out_stride) {
+  if (hd_pad != 128) return cudaErrorInvalidValue;
+  dim3 grid(blocks_for(static_cast<long long>(rows) * heads, 8), 2 * layers);
+  last_launch_status = launch_k(kv_split_kernel<4>, grid, dim3(256), 0, st, in, ld_in, rows, heads, hd, heads * hd, eps, knorm_all, cache, out_stride);
+  STTS_LAUNCH_OK();
+}
+
 cudaError_t head_split_qkv_bf16(cudaStream_t st, const float* in, int ld_in, int stride_off, int rows, int rpb,
                                 int heads, int hd, int hd_pad, const float* q_norm, const float* k_norm, float eps,
                                 int rot, const float* cos_t, const float* sin_t, bf16* q, bf16* k, bf16* v) {
@@ -861,25 +956,53 @@ cudaError_t head_split_qkv_bf16(cudaStream_t st, const float* in, int ld_in, int
 
 cudaError_t attention_bf16(cudaStream_t st, const bf16* q, int B, int tq, int H, int hd, int hd_pad, const AttnSeg* segs,
                            int nseg, const float* gate, int ld_gate, int gate_off, bf16* out) {
-  if (nseg < 1 || nseg > 3) return cudaErrorInvalidValue;
-  AttnSeg s[3];
-  for (int i = 0; i < nseg; ++i) s[i] = segs[i];
+  if (nseg < 1 || nseg > 3 || (hd & 3) != 0 || (hd_pad != 64 && hd_pad != 128)) return cudaErrorInvalidValue;
+  if (gate != nullptr && (((ld_gate | gate_off) & 3) != 0 || (reinterpret_cast<uintptr_t>(gate) & 15) != 0)) {
+    return cudaErrorInvalidValue;
+  }
+  AttnMaps maps;
+  AttnLens lens = {};
+  const uint64_t row_bytes = static_cast<uint64_t>(H) * hd_pad * 2;
+  auto make = [&](CUtensorMap* m, const bf16* p, long long rows, uint32_t box_rows) {
+    const uint64_t dims[3] = {static_cast<uint64_t>(hd_pad), static_cast<uint64_t>(H), static_cast<uint64_t>(rows)};
+    const uint64_t str[2] = {static_cast<uint64_t>(hd_pad) * 2, row_bytes};
+    const uint32_t box[3] = {64, 1, box_rows};
+    return tmap_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  if (!make(&maps.q, q, static_cast<long long>(B) * tq, kAttRows)) return cudaErrorInvalidValue;
+  for (int i = 0; i < 3; ++i) {
+    const AttnSeg& sg = segs[i < nseg ? i : 0];
+    if (sg.k == nullptr || sg.v == nullptr || sg.n_max < 1) return cudaErrorInvalidValue;
+    if (!make(&maps.k[i], sg.k, static_cast<long long>(B) * sg.n_max, 16)) return cudaErrorInvalidValue;
+    if (!make(&maps.v[i], sg.v, static_cast<long long>(B) * sg.n_max, 16)) return cudaErrorInvalidValue;
+    lens.len[i] = i < nseg ? sg.len : nullptr;
+    lens.n_max[i] = i < nseg ? sg.n_max : 0;
+  }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
   dim3 grid((tq + kAttRows - 1) / kAttRows, H, B);
+  auto smem_for = [](int hdp) {
+    const int nh = hdp / 64;
+    const int qb = (nh * kAttRows * 128 + 1023) & ~1023;
+    return 1024 + qb + kAttSplits * 2 * nh * kAttChunk * 128 + kAttRG * kAttSplits * 32 * 4 + 64;
+  };
   if (hd_pad == 128) {
-    constexpr int smem = (kAttRows + 4 * 64) * (128 + 8) * 2;
+    const int smem = smem_for(128);
     static bool once = false;
     if (!once) {
       cudaError_t e = cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
       once = true;
     }
-    last_launch_status = launch_k(attention_kernel<128>, dim3(grid), dim3(kAttThreads), smem, st, q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
-  } else if (hd_pad == 64) {
-    constexpr int smem = (kAttRows + 4 * 64) * (64 + 8) * 2;
-    last_launch_status = launch_k(attention_kernel<64>, dim3(grid), dim3(kAttThreads), smem, st, q, tq, H, hd, s[0], s[1], s[2], nseg, gate, ld_gate, gate_off, scale_log2, out);
+    last_launch_status = launch_k(attention_kernel<128>, dim3(grid), dim3(kAttThreads), smem, st, maps, lens, tq, H, hd, nseg, gate, ld_gate, gate_off, scale_log2, out);
   } else {
-    return cudaErrorInvalidValue;
+    const int smem = smem_for(64);
+    static bool once = false;
+    if (!once) {
+      cudaError_t e = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      once = true;
+    }
+    last_launch_status = launch_k(attention_kernel<64>, dim3(grid), dim3(kAttThreads), smem, st, maps, lens, tq, H, hd, nseg, gate, ld_gate, gate_off, scale_log2, out);
   }
   STTS_LAUNCH_OK();
 }

@@ -29,6 +29,12 @@ cudaError_t head_split_qkv_bf16(cudaStream_t st, const float* in, int ld_in, int
                                 int heads, int hd, int hd_pad, const float* q_norm, const float* k_norm, float eps,
                                 int rot, const float* cos_t, const float* sin_t, bf16* q, bf16* k, bf16* v);
 
+// Cross K/V caches of all `layers` DiT blocks from one fused projection (dit.py:80-93): in fp32 [rows, ld_in] with
+// layer l's k at columns 2*l*heads*hd and v right after; k gets per-head RMSNorm with knorm_all[l] ([layers, heads, hd]),
+// v is copied; output y = 2*l + {0,1} goes to cache + y*out_stride as bf16 [rows, heads, hd_pad].
+cudaError_t kv_split_bf16(cudaStream_t st, const float* in, int ld_in, int rows, int layers, int heads, int hd,
+                          int hd_pad, float eps, const float* knorm_all, bf16* cache, long long out_stride);
+
 // ---- attention over up to three key segments (self | ref | text), prefix-valid lengths per batch.
 struct AttnSeg {
   const bf16* k = nullptr;   // [B, n_max, H, hd_pad]

@@ -14,7 +14,7 @@ import torch
 from smalltts_b200 import _cabi
 from smalltts_b200.engine import Engine
 
-ACT = dict(none=0, gelu=1, mish=2, swiglu=4)
+ACT = dict(none=0, gelu=1, mish=2, swiglu=4, gelu2=1 + 16, none_f16=0 + 32)
 
 
 def p(t):
@@ -33,16 +33,16 @@ def main():
         ("dit_wo", 600, 960, 1024, "none", True, "f32"),
         ("dit_w13", 600, 4800, 960, "swiglu", False, "bf16"),
         ("dit_w2", 600, 960, 2400, "none", True, "f32"),
-        ("stem_1", 600, 8192, 2048, "gelu", False, "bf16"),
-        ("stem_2", 600, 2048, 8192, "none", True, "f32"),
-        ("up0_1", 4800, 4096, 1024, "gelu", False, "bf16"),
-        ("up0_2", 4800, 1024, 4096, "none", True, "f32"),
-        ("up1_1", 24000, 2048, 512, "gelu", False, "bf16"),
-        ("up1_2", 24000, 512, 2048, "none", True, "f32"),
-        ("up2_1", 120000, 1024, 256, "gelu", False, "bf16"),
-        ("up2_2", 120000, 256, 1024, "none", True, "f32"),
-        ("up3_1", 480000, 512, 128, "gelu", False, "bf16"),
-        ("up3_2", 480000, 128, 512, "none", True, "f32"),
+        ("stem_1", 600, 8192, 2048, "gelu2", False, "bf16"),
+        ("stem_2", 600, 2048, 8192, "none_f16", True, "f32"),
+        ("up0_1", 4800, 4096, 1024, "gelu2", False, "bf16"),
+        ("up0_2", 4800, 1024, 4096, "none_f16", True, "f32"),
+        ("up1_1", 24000, 2048, 512, "gelu2", False, "bf16"),
+        ("up1_2", 24000, 512, 2048, "none_f16", True, "f32"),
+        ("up2_1", 120000, 1024, 256, "gelu2", False, "bf16"),
+        ("up2_2", 120000, 256, 1024, "none_f16", True, "f32"),
+        ("up3_1", 480000, 512, 128, "gelu2", False, "bf16"),
+        ("up3_2", 480000, 128, 512, "none_f16", True, "f32"),
     ]
     print(f"{'shape':10s} {'M':>7s} {'N':>5s} {'K':>5s} {'bn':>4s} {'warm us':>9s} {'TF/s':>7s} {'coldW us':>9s} {'TF/s':>7s}")
     for name, M, N, K, act, res, out in shapes:
