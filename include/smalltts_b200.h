@@ -104,6 +104,18 @@ int stts_denoise_step(stts_engine* e, const stts_cond* c, const float* x_t, cons
 int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B, int T, int steps,
                 const float* timesteps, const float* noise, uint64_t seed, int mem, float* out_latents);
 
+/* Teacher sampler for the latency/quality sweep (BASELINE config 5).  The reference ships no teacher inference
+ * script; this is the sampler its distillation code implies: 3-way classifier-free guidance as built by get_x_pred
+ * (scripts/train/dmd2/distill.py:60-134: batch rows [cond | text dropped | speaker dropped], velocity =
+ * v_c + s_text (v_c - v_no_text) + s_spk (v_c - v_no_spk)) and a deterministic DDIM walk over
+ * t = linspace(1, 0, steps + 1) with the v-prediction identities of train/utils.py:54-67.
+ * cond3: stts_encode_conditions of the 3*B-row batch [ref,len,ids,plen | ref,len,0,0 | ref,0,ids,plen] (a dropped
+ * condition is a zero length).  noise: [B,T,64] (the start x_1) or NULL for on-device Philox(seed).
+ * out_latents: [B,T,64]. */
+int stts_sample_teacher(stts_engine* e, const stts_cond* cond3, const int64_t* frames, int B, int T, int steps,
+                        float cfg_scale_text, float cfg_scale_speaker, const float* noise, uint64_t seed, int mem,
+                        float* out_latents);
+
 /* == codec/decoder.onnx: latents [B,T,64] -> audio [B, T*3200] (the reference's (B,1,T*3200)). */
 int stts_decode(stts_engine* e, const float* latents, int B, int T, int mem, float* audio);
 

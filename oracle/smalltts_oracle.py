@@ -324,6 +324,46 @@ def sample(sd: SD, cond: dict, mask: Tensor, noise: Tensor, timesteps: Optional[
     return x_pred
 
 
+def cfg_conditions(sd: SD, ref: Tensor, ref_len: Tensor, phonemes: Tensor, phonemes_mask: Tensor) -> dict:
+    """Conditions of the teacher's 3-way CFG batch, rows [cond | text dropped | speaker dropped]
+    (scripts/train/dmd2/distill.py:74-96: dropped text = zero ids + all-False mask, dropped speaker = zero latents
+    + zero length)."""
+    ref3 = torch.cat([ref, ref, torch.zeros_like(ref)], dim=0)
+    len3 = torch.cat([ref_len, ref_len, torch.zeros_like(ref_len)], dim=0)
+    ph3 = torch.cat([phonemes, torch.zeros_like(phonemes), phonemes], dim=0)
+    pm3 = torch.cat([phonemes_mask, torch.zeros_like(phonemes_mask), phonemes_mask], dim=0)
+    return encode_conditions(sd, ref3, len3, ph3, pm3)
+
+
+def cfg_velocity(sd: SD, x_t: Tensor, mask: Tensor, t: Tensor, cond3: dict, cfg_scale_text: float = 2.0,
+                 cfg_scale_speaker: float = 1.5) -> Tensor:
+    """distill.py:75,92-103: one 3B-row evaluation, velocity = v_c + s_t (v_c - v_ut) + s_s (v_c - v_us).
+    (model(...) there is the uncached forward, which equals encode_conditions + denoise_step bit for bit.)"""
+    v3 = denoise_step(sd, x_t.repeat(3, 1, 1), mask.repeat(3, 1), t.repeat(3), cond3)
+    v_c, v_ut, v_us = v3.chunk(3, dim=0)
+    return v_c + cfg_scale_text * (v_c - v_ut) + cfg_scale_speaker * (v_c - v_us)
+
+
+def sample_teacher(sd: SD, cond3: dict, mask: Tensor, noise: Tensor, steps: int = 128, cfg_scale_text: float = 2.0,
+                   cfg_scale_speaker: float = 1.5) -> Tensor:
+    """Teacher sampler for BASELINE config 5.  The reference has no teacher inference script; this is the sampler
+    its training code implies: t = linspace(1, 0, steps + 1), CFG velocity as above, and the
+    v-prediction identities of train/utils.py:54-67 / distill.py:127-130:
+        x0 = alpha x_t - sigma v,  eps = sigma x_t + alpha v,  x_{t'} = alpha' x0 + sigma' eps.
+    noise: (B,T,64) = x_1.  Returns x at t = 0."""
+    ts = np.linspace(1.0, 0.0, steps + 1).astype(np.float32)
+    b = mask.shape[0]
+    x = noise.clone()
+    for s in range(steps):
+        a, sg = alpha_sigma(float(ts[s]))
+        an, sn = alpha_sigma(float(ts[s + 1]))
+        v = cfg_velocity(sd, x, mask, torch.full((b,), float(ts[s])), cond3, cfg_scale_text, cfg_scale_speaker)
+        x0 = float(a) * x - float(sg) * v
+        eps = float(sg) * x + float(a) * v
+        x = float(an) * x0 + float(sn) * eps
+    return x
+
+
 # --------------------------------------------------------------------------
 # vocoder = VibeVoice acoustic-tokenizer decoder (hf:181-297,406-500)
 # --------------------------------------------------------------------------

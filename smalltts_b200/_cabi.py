@@ -40,6 +40,8 @@ SIGNATURES = {
     "stts_cond_read_kv": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
     "stts_denoise_step": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "stts_sample": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_uint64, C.c_int, vp]),
+    "stts_sample_teacher": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, C.c_uint64,
+                                      C.c_int, vp]),
     "stts_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "stts_synthesize": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                   C.c_uint64, C.c_int, vp]),

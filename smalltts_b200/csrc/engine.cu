@@ -706,6 +706,38 @@ void sample(stts_engine* e, const stts_cond* c, const int* frames_dev, int B, in
   }
 }
 
+// Teacher sampler (BASELINE config 5).  The reference has no inference script for its teacher; this is
+// the sampler its distillation code implies: 3-way classifier-free guidance exactly as get_x_pred builds it
+// (scripts/train/dmd2/distill.py:74-103: rows [cond | text dropped | speaker dropped], scales 2.0 / 1.5) and a
+// deterministic DDIM walk over t = linspace(1, 0, steps + 1) in the v-parameterisation of train/utils.py:54-67:
+//   x0 = a x - s v,  eps = s x + a v,  x' = a' x0 + s' eps = (a' a + s' s) x + (s' a - a' s) v.
+// c3 holds the conditions of the 3B-row batch; frames3_dev its frame counts (frames repeated three times).
+void sample_teacher(stts_engine* e, const stts_cond* c3, const int* frames3_dev, int B, int T, int steps, float cfg_text,
+                    float cfg_spk, const float* noise_dev, const unsigned long long* seed_dev, float* x) {
+  cudaStream_t st = e->st;
+  const long long n = static_cast<long long>(B) * T * LAT;
+  std::vector<float> ts(steps + 1);
+  for (int s = 0; s <= steps; ++s) ts[s] = static_cast<float>(1.0 - static_cast<double>(s) / steps);
+  const std::vector<const float*> mods = prepare_mods(e, std::vector<float>(ts.begin(), ts.end() - 1));
+  DenoiseWs ws;
+  ws.alloc(st, static_cast<long long>(3) * B * T);
+  Tmp<float> v3(st, 3 * n);
+  Tmp<bf16> xb(st, 3 * n);
+  if (noise_dev != nullptr) {
+    CK(cudaMemcpyAsync(x, noise_dev, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    CK(philox_normal(st, seed_dev, 0ull, n, x));
+  }
+  for (int s = 0; s < steps; ++s) {
+    float a, sg, an, sn;
+    alpha_sigma(ts[s], &a, &sg);
+    alpha_sigma(ts[s + 1], &an, &sn);
+    CK(repeat_cast_bf16(st, x, n, 3, xb));
+    denoise(e, c3, ws, xb, frames3_dev, mods[s], 0, 3 * B, T, v3);
+    CK(cfg_ddim_update(st, x, v3, n, cfg_text, cfg_spk, an * a + sn * sg, sn * a - an * sg));
+  }
+}
+
 // ------------------------------------------------------------------ vocoder (hf:406-500)
 struct VocWs {  // activations of one decode; persistent inside a Plan, temporaries otherwise
   float *xa = nullptr, *xb = nullptr;
@@ -1125,6 +1157,35 @@ int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B
       xd = xo;
     }
     sample(e, c, fr, B, T, ts, mods, nd, e->seed_dev, xd);
+    if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(out_latents, xd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int stts_sample_teacher(stts_engine* e, const stts_cond* cond3, const int64_t* frames, int B, int T, int steps,
+                        float cfg_scale_text, float cfg_scale_speaker, const float* noise, uint64_t seed, int mem,
+                        float* out_latents) {
+  if (!e || !cond3 || !frames || !out_latents) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    need_ready(e);
+    if (B < 1 || cond3->B != 3 * B || T < 1 || T > ROPE_MAX || steps < 1 || steps > 4096) {
+      throw Err(STTS_ERR_INVALID, "bad teacher-sampler arguments (conditions must hold 3*B rows: cond | no text | no speaker)");
+    }
+    cudaStream_t st = e->st;
+    const long long n = static_cast<long long>(B) * T * LAT;
+    std::vector<int64_t> f3(3 * B);
+    for (int i = 0; i < 3 * B; ++i) f3[i] = frames[i % B];
+    Tmp<int> fr;
+    lens_to_dev(e, f3.data(), 3 * B, T, fr);
+    set_seed(e, seed);
+    Tmp<float> hn, xo;
+    const float* nd = noise ? to_dev(e, noise, static_cast<size_t>(n), mem, hn) : nullptr;
+    float* xd = out_latents;
+    if (mem == STTS_MEM_HOST) {
+      xo.alloc(st, n);
+      xd = xo;
+    }
+    sample_teacher(e, cond3, fr, B, T, steps, cfg_scale_text, cfg_scale_speaker, nd, e->seed_dev, xd);
     if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(out_latents, xd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   });

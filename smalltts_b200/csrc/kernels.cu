@@ -513,6 +513,29 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, long long n, bf16
   }
 }
 
+// x [n] fp32 -> bf16 [reps*n]: the CFG branches of the teacher share x_t (distill.py:75)
+__global__ void repeat_cast_bf16_kernel(const float* __restrict__ in, long long n, int reps, bf16* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bf16 v = __float2bfloat16(in[i]);
+  for (int r = 0; r < reps; ++r) out[r * n + i] = v;
+}
+
+// 3-way CFG combine (distill.py:97-103) + one deterministic DDIM step in v-parameterisation (train/utils.py:54-67):
+//   v = v_c + s_text (v_c - v_no_text) + s_spk (v_c - v_no_spk);  x <- ca * x + cb * v
+__global__ void cfg_ddim_update_kernel(float* __restrict__ x, const float* __restrict__ v3, long long n, float s_text,
+                                       float s_spk, float ca, float cb) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float vc = v3[i], vt = v3[n + i], vs = v3[2 * n + i];
+  const float v = vc + s_text * (vc - vt) + s_spk * (vc - vs);
+  x[i] = ca * x[i] + cb * v;
+}
+
 __global__ void noise_mix_kernel(const float* __restrict__ xp, const float* __restrict__ nz, float alpha, float sigma,
                                  long long n, float* __restrict__ xt, bf16* __restrict__ xtb) {
   ptx::pdl_wait();
@@ -1032,6 +1055,17 @@ cudaError_t embed_gather(cudaStream_t st, const long long* ids, int rows, const 
 
 cudaError_t cast_bf16(cudaStream_t st, const float* in, long long n, bf16* out) {
   last_launch_status = launch_k(cast_bf16_kernel, dim3(blocks_for(n, 1024)), dim3(256), 0, st, in, n, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t repeat_cast_bf16(cudaStream_t st, const float* in, long long n, int reps, bf16* out) {
+  last_launch_status = launch_k(repeat_cast_bf16_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, in, n, reps, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t cfg_ddim_update(cudaStream_t st, float* x, const float* v3, long long n, float s_text, float s_spk, float ca,
+                            float cb) {
+  last_launch_status = launch_k(cfg_ddim_update_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, st, x, v3, n, s_text, s_spk, ca, cb);
   STTS_LAUNCH_OK();
 }
 

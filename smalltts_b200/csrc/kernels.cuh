@@ -67,6 +67,12 @@ cudaError_t noise_mix(cudaStream_t st, const float* x_pred, const float* noise, 
 // x_pred = alpha*x_t - sigma*v
 cudaError_t dmd_update(cudaStream_t st, const float* x_t, const float* v, float alpha, float sigma, long long n,
                        float* x_pred);
+// ---- teacher sampler (config 5): x_t shared by the three CFG branches, CFG combine + DDIM step
+cudaError_t repeat_cast_bf16(cudaStream_t st, const float* in, long long n, int reps, bf16* out);
+// v = v_c + s_text (v_c - v_no_text) + s_spk (v_c - v_no_spk) with v3 = [v_c | v_no_text | v_no_spk] (distill.py:97-103);
+// x <- ca * x + cb * v
+cudaError_t cfg_ddim_update(cudaStream_t st, float* x, const float* v3, long long n, float s_text, float s_spk, float ca,
+                            float cb);
 // standard normal noise, Philox4x32-10 + Box-Muller, counter = element index; seed read from device memory
 cudaError_t philox_normal(cudaStream_t st, const unsigned long long* seed, unsigned long long stream_id, long long n,
                           float* out);

@@ -129,6 +129,35 @@ class Engine:
                     self._h)
         return out
 
+    def encode_conditions_cfg(self, ref, ref_len: Sequence[int], phonemes, ph_len: Sequence[int]) -> Conditions:
+        """Conditions of the 3-way classifier-free-guidance batch of the teacher (distill.py:74-96): rows
+        [cond | text dropped | speaker dropped]; a dropped condition is a zero length (and zeroed ids)."""
+        ref = np.asarray(ref.detach().cpu().numpy() if _is_torch(ref) else ref, dtype=np.float32)
+        ids = np.asarray(phonemes.detach().cpu().numpy() if _is_torch(phonemes) else phonemes, dtype=np.int64)
+        B = ref.shape[0]
+        ref3 = np.concatenate([ref, ref, np.zeros_like(ref)], axis=0)
+        ids3 = np.concatenate([ids, np.zeros_like(ids), ids], axis=0)
+        rl, pl = list(map(int, ref_len)), list(map(int, ph_len))
+        return self.encode_conditions(ref3, rl + rl + [0] * B, ids3, pl + [0] * B + pl)
+
+    def sample_teacher(self, cond3: Conditions, frames: Sequence[int], T: int, steps: int = 128, cfg_text: float = 2.0,
+                       cfg_speaker: float = 1.5, noise=None, seed: int = 0, device_out: bool = False):
+        """DDIM + 3-way CFG teacher sampler (stts_sample_teacher).  noise: optional start x_1 of shape (B,T,64)."""
+        if cond3.B % 3 != 0:
+            raise ValueError("cond3 must come from encode_conditions_cfg (3*B rows)")
+        B = cond3.B // 3
+        fr = _i64(frames)
+        if noise is not None:
+            np_, mem, keep = _buf(noise, np.float32, "noise")
+            if tuple(noise.shape) != (B, T, LATENT_DIM):
+                raise ValueError(f"noise must be {(B, T, LATENT_DIM)}, got {tuple(noise.shape)}")
+        else:
+            np_, mem = None, (_cabi.MEM_DEVICE if device_out else _cabi.MEM_HOST)
+        out, op = self._out_like(noise, (B, T, LATENT_DIM), mem)
+        _cabi.check(self._lib.stts_sample_teacher(self._h, cond3._h, C.c_void_p(fr.ctypes.data), B, T, steps,
+                                                  cfg_text, cfg_speaker, np_, seed, mem, op), self._h)
+        return out
+
     def decode(self, latents):
         B, T, _ = latents.shape
         lp, mem, keep = _buf(latents, np.float32, "latents")

@@ -141,6 +141,28 @@ class SmallTTS:
                                        steps=self.num_steps)
         return [audio[i : i + 1, : frames[i] * HOP_SIZE].copy() for i in range(len(frames))]
 
+    def synthesize_teacher(self, ref_latents: Sequence, phoneme_ids: Sequence[Sequence[int]], durations: Sequence[float],
+                           steps: int = 128, cfg_scale_text: float = 2.0, cfg_scale_speaker: float = 1.5, noise=None,
+                           seed: Optional[int] = None) -> List[np.ndarray]:
+        """Teacher path of the latency/quality sweep (BASELINE config 5): `steps` DDIM steps with the 3-way CFG of
+        scripts/train/dmd2/distill.py:60-134, then the same vocoder.  noise: optional start x_1 (B, Tmax, 64)."""
+        if not (len(ref_latents) == len(phoneme_ids) == len(durations)) or len(durations) == 0:
+            raise ValueError("ref_latents, phoneme_ids and durations must be equally long and non-empty")
+        frames = [frames_for(d) for d in durations]
+        T = max(frames)
+        ref, ref_len, ids, ph_len = pad_batch(ref_latents, phoneme_ids, frames)
+        if seed is None:
+            seed = self._seed + self._calls
+        self._calls += 1
+        cond3 = self.engine.encode_conditions_cfg(ref, ref_len, ids, ph_len)
+        try:
+            lat = self.engine.sample_teacher(cond3, frames, T, steps=steps, cfg_text=cfg_scale_text,
+                                             cfg_speaker=cfg_scale_speaker, noise=noise, seed=seed)
+        finally:
+            cond3.free()
+        audio = self.engine.decode(lat)
+        return [audio[i : i + 1, : frames[i] * HOP_SIZE].copy() for i in range(len(frames))]
+
     def forward(self, conditionings: List, transcriptions: list, texts: list, duration_sec: float = 3.0) -> List:
         """infer/onnx.py:131-157: tokens = transcription tokens + text tokens, one shared duration; returns a list of
         torch tensors (1, samples).  Unlike the reference loop this is a single batched engine call."""

@@ -159,3 +159,43 @@ def test_reference_api_surface(tts):
     assert len(out) == 2 and all(isinstance(o, torch.Tensor) and o.shape == (1, 7 * 3200) for o in out)
     with pytest.raises(ValueError):
         tts.synthesize_batch([np.zeros((4, 63), np.float32)], [[1]], [1.0])
+
+
+def test_teacher_sampler_vs_reference_fixture(tts):
+    """BASELINE config 5: 3-way CFG + DDIM through stts_sample_teacher vs the fixture produced by
+    the reference's DiTModel.forward (oracle/make_golden_teacher.py)."""
+    g = _load("teacher_small.npz")
+    B, T = g["noise"].shape[:2]
+    frames = g["mask"].sum(1).tolist()
+    cond3 = tts.engine.encode_conditions_cfg(g["ref"], g["ref_len"], g["ids"], g["pmask"].sum(1))
+    assert cond3.B == 3 * B
+    s_text, s_spk = map(float, g["cfg"])
+    x = tts.engine.sample_teacher(cond3, frames, T, steps=int(g["steps"]), cfg_text=s_text, cfg_speaker=s_spk,
+                                  noise=g["noise"])
+    cond3.free()
+    valid = np.broadcast_to(g["mask"][..., None], x.shape)
+    err = rel_l2(x[valid], g["latents"][valid])
+    print("teacher latents rel_l2", err)
+    assert np.isfinite(x).all() and err <= TOL_FP32
+
+
+def test_teacher_sampler_guidance_identity(tts):
+    """With both guidance scales at 0 the CFG velocity is the conditional one, so a 1-step teacher walk from
+    x_1 = noise must equal the first DMD step (x_pred = alpha x_t - sigma v at t = 1 up to sigma'(0) = 3e-5)."""
+    from smalltts_b200 import synthetic
+
+    refs, ids, frames, noise = synthetic.synthetic_inputs(2, [9, 7], [6, 4], [11, 8], seed=11)
+    from smalltts_b200.engine import pad_batch
+
+    ref, ref_len, idt, ph_len = pad_batch(refs, ids, frames)
+    T = max(frames)
+    cond3 = tts.engine.encode_conditions_cfg(ref, ref_len, idt, ph_len)
+    x = tts.engine.sample_teacher(cond3, frames, T, steps=1, cfg_text=0.0, cfg_speaker=0.0, noise=noise[0].numpy())
+    cond3.free()
+    cond = tts.engine.encode_conditions(ref, ref_len, idt, ph_len)
+    n4 = np.zeros((1,) + tuple(noise[0].shape), dtype=np.float32)
+    n4[0] = noise[0].numpy()
+    y = tts.engine.sample(cond, frames, T, noise=n4, steps=1, timesteps=[1.0])
+    cond.free()
+    for b in range(2):
+        assert rel_l2(x[b, : frames[b]], y[b, : frames[b]]) <= 2e-3

@@ -88,3 +88,19 @@ def test_ragged_row_equals_solo_run(dit_sd, voc_sd):
     both = O.synthesize_batch(dit_sd, voc_sd, refs, ids, frames, noise)
     solo = O.synthesize_batch(dit_sd, voc_sd, refs[1:], ids[1:], frames[1:], noise[:, 1:, :3])
     _close(both[1], solo[0], atol=1e-4)
+
+
+@torch.inference_mode()
+def test_teacher_sampler_matches_reference(dit_sd):
+    """BASELINE config 5 / SURVEY 8(a18): 3-way CFG (distill.py:74-103) + DDIM walk, fixture built from the
+    reference's DiTModel.forward and get_alpha_sigma by oracle/make_golden_teacher.py."""
+    g = _load("teacher_small.npz")
+    cond3 = O.cfg_conditions(dit_sd, torch.tensor(g["ref"]), torch.tensor(g["ref_len"]), torch.tensor(g["ids"]),
+                             torch.tensor(g["pmask"]))
+    s_text, s_spk = map(float, g["cfg"])
+    mask, noise = torch.tensor(g["mask"]), torch.tensor(g["noise"])
+    v = O.cfg_velocity(dit_sd, noise, mask, torch.ones(noise.shape[0]), cond3, s_text, s_spk)
+    _close(v, g["first_velocity"], atol=2e-4)
+    x = O.sample_teacher(dit_sd, cond3, mask, noise, int(g["steps"]), s_text, s_spk)
+    valid = mask[..., None].expand_as(x).numpy()  # padded frames are never attended to nor decoded
+    _close(x.numpy()[valid], g["latents"][valid], atol=1e-3)
