@@ -79,7 +79,8 @@ void stts_destroy(stts_engine* e);
 const char* stts_last_error(const stts_engine* e);
 
 /* Weights: fp32 tensors under the reference's own state-dict names.
- * model: 0 = DiTModel (models/backbone/model.py:33-54), 1 = VibeVoice acoustic-tokenizer decoder.
+ * model: 0 = DiTModel (models/backbone/model.py:33-54), 1 = VibeVoice acoustic-tokenizer decoder,
+ *        2 = VibeVoice acoustic-tokenizer encoder (optional; only stts_encode_audio needs it).
  * `data` is host fp32, row-major, `ndim` <= 4.  stts_finalize_weights packs them for the kernels (bf16,
  * K-major, tap-major conv layouts) and validates that every tensor of both models is present. */
 int stts_load_weight(stts_engine* e, int model, const char* name, const float* data, int ndim, const int64_t* shape);
@@ -118,6 +119,14 @@ int stts_sample_teacher(stts_engine* e, const stts_cond* cond3, const int64_t* f
 
 /* == codec/decoder.onnx: latents [B,T,64] -> audio [B, T*3200] (the reference's (B,1,T*3200)). */
 int stts_decode(stts_engine* e, const float* latents, int B, int T, int mem, float* audio);
+
+/* Codec encoder: replaces `Encoder.encode` (codec/onnx.py:56-75 == assets/codec/encoder.onnx, the clone path of
+ * scripts/infer/clone.py:36; Rust twin pipeline.rs codec_enc stage).  audio: fp32 [B, N] mono 24 kHz, N a positive
+ * multiple of 3200 (the encoder is causal and floors, so trimming a tail shorter than one hop does not change any
+ * latent); latents: fp32 [B, N/3200, 64] (the VAE mean).  Needs the encoder tensors (model index 2 of
+ * stts_load_weight, HF VibeVoiceAcousticTokenizerEncoderModel.state_dict() names) loaded before stts_finalize_weights.
+ * Sets stts_timing.codec_enc_ms. */
+int stts_encode_audio(stts_engine* e, const float* audio, int B, int N, int mem, float* latents);
 
 /* == SmallTTS.synthesize for a padded batch; intermediates never leave the device. audio: [B, T*3200]. */
 int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* phonemes,

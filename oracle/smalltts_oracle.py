@@ -413,6 +413,32 @@ def vocoder_decode(vsd: SD, latents: Tensor, taps: Optional[Callable[[str, Tenso
 # --------------------------------------------------------------------------
 # whole path (infer/onnx.py:68-129), batched with ragged lengths
 # --------------------------------------------------------------------------
+ENC_RATIOS = (2, 2, 4, 5, 5, 8)  # hf encoder config
+ENC_DEPTHS = (3, 3, 3, 3, 3, 3, 8)
+
+
+def _causal_conv_strided(x: Tensor, w: Tensor, b: Tensor, stride: int) -> Tensor:
+    """hf:181-216 with stride r and k = 2r: left-pad (k-1) - (r-1) = r zeros, then Conv1d(stride=r); T -> T // r."""
+    k = w.shape[-1]
+    return F.conv1d(F.pad(_r(x), (k - 1 - (stride - 1), 0)), _r(w), b, stride=stride)
+
+
+def codec_encode(esd: SD, audio: Tensor) -> Tensor:
+    """codec/onnx.py:56-75 == encoder.onnx; arithmetic per hf:300-403 (VibeVoiceAcousticTokenizerEncoderModel):
+    stem CausalConv1d(1->32,k7) + 3 ConvNeXt layers; six [strided CausalConv1d(C->2C, k=2r, stride r) + ConvNeXt
+    layers] with r = 2,2,4,5,5,8; head CausalConv1d(2048->64,k7).  audio (B,1,N) -> latents (B, N // 3200, 64)
+    (the VAE mean; whether the ONNX export adds sampling noise is unknown)."""
+    x = _causal_conv(audio, esd["stem.conv.conv.weight"], esd["stem.conv.conv.bias"])
+    for l in range(ENC_DEPTHS[0]):
+        x = _convnext(esd, f"stem.stage.{l}.", x)
+    for i, r in enumerate(ENC_RATIOS):
+        x = _causal_conv_strided(x, esd[f"conv_layers.{i}.conv.conv.weight"], esd[f"conv_layers.{i}.conv.conv.bias"], r)
+        for l in range(ENC_DEPTHS[i + 1]):
+            x = _convnext(esd, f"conv_layers.{i}.stage.{l}.", x)
+    x = _causal_conv(x, esd["head.conv.weight"], esd["head.conv.bias"])
+    return x.permute(0, 2, 1)
+
+
 def frames_for(duration_sec: float) -> int:
     """infer/onnx.py:84."""
     return max(1, int(duration_sec * SAMPLE_RATE / HOP_SIZE))

@@ -43,6 +43,7 @@ SIGNATURES = {
     "stts_sample_teacher": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, C.c_uint64,
                                       C.c_int, vp]),
     "stts_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "stts_encode_audio": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "stts_synthesize": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                   C.c_uint64, C.c_int, vp]),
     "stts_get_timings": (C.c_int, [vp, C.POINTER(Timing)]),

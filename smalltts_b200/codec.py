@@ -30,7 +30,21 @@ class Decoder:
 
 
 class Encoder:
-    """codec/onnx.py:56-75.  The codec encoder is not on the synthesize hot path."""
+    """VibeVoice acoustic-tokenizer encoder: audio (B,1,N) @ 24 kHz -> latents (B, N // 3200, 64)
+    (codec/onnx.py:56-75; the clone path, scripts/infer/clone.py:36).  The engine must have been given the encoder
+    weights (``SmallTTS(..., codec_encoder_path=...)`` or ``state_dicts=(dit, decoder, encoder)``)."""
 
-    def __init__(self, *a, **k) -> None:
-        raise NotImplementedError("codec encoder is outside the B200 hot path in this version (SURVEY.md 8f)")
+    def __init__(self, path: str = "assets/codec/encoder.safetensors", providers: Optional[Iterable[str]] = None, *,
+                 engine: Optional[Engine] = None) -> None:
+        if engine is None:
+            raise NotImplementedError(
+                "a standalone Encoder needs an engine in this version; pass engine=SmallTTS(...).engine")
+        self.engine = engine
+
+    def encode(self, audio):
+        import torch
+
+        is_t = isinstance(audio, torch.Tensor)
+        x = audio.detach().cpu().numpy() if is_t and not audio.is_cuda else audio
+        y = self.engine.encode_audio(x if is_t and audio.is_cuda else np.asarray(x, dtype=np.float32))
+        return y if isinstance(y, torch.Tensor) else torch.from_numpy(y)

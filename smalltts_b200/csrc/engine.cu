@@ -39,6 +39,9 @@ constexpr int ROPE_MAX = 4096;                // dit.py:139, style.py:140, phone
 const int VOC_R[6] = {8, 5, 5, 4, 2, 2};
 const int VOC_C[7] = {2048, 1024, 512, 256, 128, 64, 32};
 const int VOC_DEPTH[7] = {8, 3, 3, 3, 3, 3, 3};
+const int ENC_R[6] = {2, 2, 4, 5, 5, 8};  // hf encoder config: downsampling_ratios
+const int ENC_C[7] = {32, 64, 128, 256, 512, 1024, 2048};
+const int ENC_DEPTH[7] = {3, 3, 3, 3, 3, 3, 8};
 
 struct RawTensor {
   float* d = nullptr;
@@ -110,7 +113,7 @@ struct stts_engine {
   cudaStream_t st2 = nullptr;  // side stream: the style encoder runs beside the text encoder (fork/join on events)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
-  std::map<std::string, RawTensor> raw[2];
+  std::map<std::string, RawTensor> raw[3];  // 0 = DiT, 1 = codec decoder (vocoder), 2 = codec encoder (optional)
   std::vector<void*> owned;  // packed buffers
   bool finalized = false;
 
@@ -132,6 +135,14 @@ struct stts_engine {
   bf16* up_w[6];
   float* up_b[6];
   const float *head_w, *head_b;
+
+  // packed codec-encoder weights (model 2; only when its tensors were loaded)
+  bool has_encoder = false;
+  std::vector<std::vector<VocLayerW>> enc;  // [7 stages][depth]
+  bf16* enc_down_w[6];
+  const float* enc_down_b[6];
+  bf16* enc_head_w = nullptr;
+  const float *enc_head_b = nullptr, *enc_stem_w = nullptr, *enc_stem_b = nullptr;
 
   // per-shape persistent plans (buffers + CUDA graphs) used by stts_synthesize
   std::map<std::array<int, 5>, Plan*> plans;
@@ -256,6 +267,52 @@ void build_encoder(stts_engine* e, EncW& w, const std::string& pre, int d, int h
     w.blk.push_back(b);
   }
   w.final_norm = e->W(0, pre + "norm.weight", {d}).d;
+}
+
+// One ConvNeXt-1D layer's weights (hf:263-297) of codec model `model` (1 = decoder, 2 = encoder).
+VocLayerW pack_convnext_layer(stts_engine* e, int model, const std::string& p, int c) {
+  cudaStream_t st = e->st;
+  VocLayerW w;
+  w.gamma = e->W(model, p + "gamma", {c}).d;
+  w.ffn_gamma = e->W(model, p + "ffn_gamma", {c}).d;
+  w.norm_w = e->W(model, p + "norm.weight", {c}).d;
+  w.ffn_norm_w = e->W(model, p + "ffn_norm.weight", {c}).d;
+  w.w1 = pack_lin(e, e->W(model, p + "ffn.linear1.weight", {4 * c, c}), 4 * c, c);
+  w.b1 = e->W(model, p + "ffn.linear1.bias", {4 * c}).d;
+  w.w2 = nullptr;
+  w.w2h = e->dalloc<uint16_t>(static_cast<size_t>(4) * c * c);
+  CK(cast_f16(st, e->W(model, p + "ffn.linear2.weight", {c, 4 * c}).d, static_cast<long long>(4) * c * c, 0.5f, w.w2h));
+  w.b2 = e->W(model, p + "ffn.linear2.bias", {c}).d;
+  w.conv_w = e->W(model, p + "mixer.conv.weight", {c, 1, 7}).d;
+  w.conv_b = e->W(model, p + "mixer.conv.bias", {c}).d;
+  return w;
+}
+
+// Codec encoder (hf:300-403): mirror of the decoder with strided causal convolutions.
+void finalize_encoder(stts_engine* e) {
+  cudaStream_t st = e->st;
+  e->enc_stem_w = e->W(2, "stem.conv.conv.weight", {32, 1, 7}).d;
+  e->enc_stem_b = e->W(2, "stem.conv.conv.bias", {32}).d;
+  e->enc.assign(7, {});
+  for (int s = 0; s < 7; ++s) {
+    const int c = ENC_C[s];
+    for (int l = 0; l < ENC_DEPTH[s]; ++l) {
+      const std::string p = (s == 0 ? std::string("stem.stage.") : "conv_layers." + std::to_string(s - 1) + ".stage.") +
+                            std::to_string(l) + ".";
+      e->enc[s].push_back(pack_convnext_layer(e, 2, p, c));
+    }
+    if (s < 6) {
+      const int cout = ENC_C[s + 1], r = ENC_R[s];
+      const std::string p = "conv_layers." + std::to_string(s) + ".conv.conv.";
+      e->enc_down_w[s] = e->dalloc<bf16>(static_cast<size_t>(cout) * 2 * r * c);
+      CK(pack_conv_strided(st, e->W(2, p + "weight", {cout, c, 2 * r}).d, cout, c, r, e->enc_down_w[s]));
+      e->enc_down_b[s] = e->W(2, p + "bias", {cout}).d;
+    }
+  }
+  e->enc_head_w = e->dalloc<bf16>(static_cast<size_t>(LAT) * 7 * 2048);
+  CK(pack_conv_taps(st, e->W(2, "head.conv.weight", {LAT, 2048, 7}).d, LAT, 2048, 7, 2048, LAT, LAT, e->enc_head_w, 7 * 2048));
+  e->enc_head_b = e->W(2, "head.conv.bias", {LAT}).d;
+  e->has_encoder = true;
 }
 
 void build_rope(stts_engine* e, int rot, float** cos_d, float** sin_d) {
@@ -391,19 +448,7 @@ void finalize(stts_engine* e) {
     for (int l = 0; l < VOC_DEPTH[s]; ++l) {
       const std::string p = (s == 0 ? std::string("stem.stage.") : "conv_layers." + std::to_string(s - 1) + ".stage.") +
                             std::to_string(l) + ".";
-      VocLayerW w;
-      w.gamma = e->W(1, p + "gamma", {c}).d;
-      w.ffn_gamma = e->W(1, p + "ffn_gamma", {c}).d;
-      w.norm_w = e->W(1, p + "norm.weight", {c}).d;
-      w.ffn_norm_w = e->W(1, p + "ffn_norm.weight", {c}).d;
-      w.w1 = pack_lin(e, e->W(1, p + "ffn.linear1.weight", {4 * c, c}), 4 * c, c);
-      w.b1 = e->W(1, p + "ffn.linear1.bias", {4 * c}).d;
-      w.w2 = nullptr;
-      w.w2h = e->dalloc<uint16_t>(static_cast<size_t>(4) * c * c);
-      CK(cast_f16(st, e->W(1, p + "ffn.linear2.weight", {c, 4 * c}).d, static_cast<long long>(4) * c * c, 0.5f, w.w2h));
-      w.b2 = e->W(1, p + "ffn.linear2.bias", {c}).d;
-      w.conv_w = e->W(1, p + "mixer.conv.weight", {c, 1, 7}).d;
-      w.conv_b = e->W(1, p + "mixer.conv.bias", {c}).d;
+      VocLayerW w = pack_convnext_layer(e, 1, p, c);
       e->voc[s].push_back(w);
     }
     if (s < 6) {
@@ -417,6 +462,7 @@ void finalize(stts_engine* e) {
   }
   e->head_w = e->W(1, "head.conv.weight", {1, 32, 7}).d;
   e->head_b = e->W(1, "head.conv.bias", {1}).d;
+  if (!e->raw[2].empty()) finalize_encoder(e);
   CK(cudaStreamSynchronize(st));
   e->finalized = true;
 }
@@ -746,6 +792,37 @@ struct VocWs {  // activations of one decode; persistent inside a Plan, temporar
 };
 enum VocPart : int { VOC_FRONT = 1, VOC_TAIL = 2, VOC_ALL = 3 };
 
+// The ConvNeXt layers of one stage, in place on `cur` (hf:284-297); `oth` is scratch of the same size.  The last layer
+// also writes a bf16 copy to ws.xh when the next operator is a GEMM over the activations.
+void convnext_layers(stts_engine* e, const std::vector<VocLayerW>& layers, float*& cur, float*& oth, const VocWs& ws, int B,
+                     int Ts, int C, bool bf16_copy) {
+  cudaStream_t st = e->st;
+  const long long M = static_cast<long long>(B) * Ts;
+  const size_t nl = layers.size();
+  if (C <= 64 && e->fused_tail) {
+    // fused layers are out-of-place: ping-pong cur -> oth -> cur -> ...; `cur` is the result afterwards
+    for (size_t l = 0; l < nl; ++l) {
+      const VocLayerW& w = layers[l];
+      bf16* hb = (bf16_copy && l + 1 == nl) ? ws.xh : nullptr;
+      CK(convnext_fused(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, w.w1, w.b1, w.w2h,
+                        w.b2, w.ffn_gamma, 1e-5f, oth, hb));
+      std::swap(cur, oth);
+    }
+    return;
+  }
+  for (size_t l = 0; l < nl; ++l) {
+    const VocLayerW& w = layers[l];
+    CK(convnext_mix(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, oth, ws.a));
+    GemmEpi e1;
+    e1.bias = w.b1; e1.act = ACT_GELU; e1.gelu2_f16 = 1; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
+    linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1);
+    GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
+    e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = oth; e2.ld_res = C; e2.out_f32 = cur; e2.ld_out = C;
+    if (bf16_copy && l + 1 == nl) e2.out_bf16 = ws.xh;  // bf16 copy feeds the next (transposed / strided) conv GEMM
+    linear(e, ws.hbuf, M, 4 * C, 4 * C, static_cast<const bf16*>(w.w2h), C, 4 * C, e2, 0, /*f16=*/true);
+  }
+}
+
 // Launch-only (graph-capturable).  FRONT = stem + stages with C >= 256 (tensor-bound) incl. the upsampler into
 // C = 128; TAIL = stages with C <= 128 + head (HBM-bound).  Stage s works in buffer (s even ? xa : xb).
 void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev, const VocWs& ws, int part) {
@@ -768,29 +845,7 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
     const long long M = static_cast<long long>(B) * Ts;
     const bool mine = (s < 4) ? (part & VOC_FRONT) != 0 : (part & VOC_TAIL) != 0;
     if (mine) {
-      const size_t nl = e->voc[s].size();
-      if (C <= 64 && e->fused_tail) {
-        // fused layers are out-of-place: ping-pong cur -> oth -> cur -> ...; make `cur` the result afterwards
-        for (size_t l = 0; l < nl; ++l) {
-          const VocLayerW& w = e->voc[s][l];
-          bf16* hb = (s < 6 && l + 1 == nl) ? ws.xh : nullptr;
-          CK(convnext_fused(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, w.w1, w.b1, w.w2h,
-                            w.b2, w.ffn_gamma, 1e-5f, oth, hb));
-          std::swap(cur, oth);
-        }
-      } else {
-        for (size_t l = 0; l < nl; ++l) {
-          const VocLayerW& w = e->voc[s][l];
-          CK(convnext_mix(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, oth, ws.a));
-          GemmEpi e1;
-          e1.bias = w.b1; e1.act = ACT_GELU; e1.gelu2_f16 = 1; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
-          linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1);
-          GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
-          e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = oth; e2.ld_res = C; e2.out_f32 = cur; e2.ld_out = C;
-          if (s < 6 && l + 1 == nl) e2.out_bf16 = ws.xh;  // bf16 copy feeds the next upsampler
-          linear(e, ws.hbuf, M, 4 * C, 4 * C, static_cast<const bf16*>(w.w2h), C, 4 * C, e2, 0, /*f16=*/true);
-        }
-      }
+      convnext_layers(e, e->voc[s], cur, oth, ws, B, Ts, C, /*bf16_copy=*/s < 6);
       if (s < 6) {  // causal ConvTranspose1d(k=2r, stride=r) as a 2-tap GEMM with N = r*Cout (hf:219-260)
         const int r = VOC_R[s], cout = VOC_C[s + 1];
         GemmShape g;
@@ -806,6 +861,39 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
     }
   }
   if (part & VOC_TAIL) CK(head_conv(st, cur, B, Ts, 32, e->head_w, e->head_b, audio_dev));
+}
+
+// Codec encoder (codec/onnx.py:56-75 == encoder.onnx; arithmetic per hf:300-403).  audio fp32 [B, N] with N a multiple
+// of the hop (3200) -> latents fp32 [B, N/3200, 64] (the VAE mean).  Launch-only.
+//   stem Conv1d(1->32,k7) | 3 ConvNeXt @32 | 6 x [strided causal Conv1d(C->2C, k=2r, stride r) + ConvNeXt layers] | head
+// A strided conv with k = 2r is a two-tap GEMM over the activations regrouped r rows at a time ([T, C] read as
+// [T/r, r*C]): out[t'] = W_a X'[t'-1] + W_b X'[t'] -- the mirror image of the decoder's transposed convolutions.
+void encode_audio(stts_engine* e, const float* audio_dev, int B, int N, float* lat_dev, const VocWs& ws) {
+  cudaStream_t st = e->st;
+  float* cur = ws.xa;
+  float* oth = ws.xb;
+  CK(audio_stem_conv(st, audio_dev, B, N, 32, e->enc_stem_w, e->enc_stem_b, cur));
+  int Ts = N;
+  for (int s = 0; s < 7; ++s) {
+    const int C = ENC_C[s];
+    convnext_layers(e, e->enc[s], cur, oth, ws, B, Ts, C, /*bf16_copy=*/true);
+    if (s < 6) {
+      const int r = ENC_R[s], cout = ENC_C[s + 1];
+      GemmShape g;
+      g.B = B; g.T = Ts / r; g.N = cout; g.K = r * C; g.taps = 2; g.tap_shift0 = -1; g.tap_step = 1;
+      GemmEpi ep;
+      ep.bias = e->enc_down_b[s]; ep.out_f32 = oth; ep.ld_out = cout;
+      CK(launch_gemm(st, pick_bn(static_cast<long long>(B) * (Ts / r), cout, 2 * ((r * C + 63) / 64)),
+                     GemmA{ws.xh, r * C, r * C}, GemmW{e->enc_down_w[s], cout, 2 * r * C}, g, ep));
+      std::swap(cur, oth);
+      Ts /= r;
+    }
+  }
+  GemmShape h;  // head: causal Conv1d(2048 -> 64, k=7) as a 7-tap GEMM
+  h.B = B; h.T = Ts; h.N = LAT; h.K = 2048; h.taps = 7; h.tap_shift0 = -6; h.tap_step = 1;
+  GemmEpi ep;
+  ep.bias = e->enc_head_b; ep.out_f32 = lat_dev; ep.ld_out = LAT;
+  CK(launch_gemm(st, 64, GemmA{ws.xh, 2048, 2048}, GemmW{e->enc_head_w, LAT, 7 * 2048}, h, ep));
 }
 
 struct VocTmp {  // stream-ordered temporaries for the stand-alone decode entry point
@@ -1029,7 +1117,7 @@ const char* stts_last_error(const stts_engine* e) { return e ? e->err.c_str() : 
 int stts_load_weight(stts_engine* e, int model, const char* name, const float* data, int ndim, const int64_t* shape) {
   if (!e) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
-    if (model < 0 || model > 1 || !name || !data || ndim < 0 || ndim > 4) throw Err(STTS_ERR_INVALID, "bad weight args");
+    if (model < 0 || model > 2 || !name || !data || ndim < 0 || ndim > 4) throw Err(STTS_ERR_INVALID, "bad weight args");
     RawTensor t;
     t.numel = 1;
     for (int i = 0; i < ndim; ++i) {
@@ -1216,6 +1304,34 @@ int stts_decode(stts_engine* e, const float* latents, int B, int T, int mem, flo
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&e->voc_ms[1], e->ev[4], e->ev[5]));
     CK(cudaEventElapsedTime(&e->voc_ms[0], e->ev[5], e->ev[6]));
+  });
+}
+
+int stts_encode_audio(stts_engine* e, const float* audio, int B, int N, int mem, float* latents) {
+  if (!e || !audio || !latents) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    need_ready(e);
+    if (!e->has_encoder) throw Err(STTS_ERR_WEIGHTS, "codec encoder weights (model 2) were not loaded");
+    if (B < 1 || N < STTS_HOP_SIZE || (N % STTS_HOP_SIZE) != 0) {
+      throw Err(STTS_ERR_INVALID, "audio length must be a positive multiple of the hop size (3200 samples)");
+    }
+    cudaStream_t st = e->st;
+    const int T = N / STTS_HOP_SIZE;
+    const long long na = static_cast<long long>(B) * N, nl = static_cast<long long>(B) * T * LAT;
+    Tmp<float> ha, lo;
+    const float* ad = to_dev(e, audio, static_cast<size_t>(na), mem, ha);
+    float* ld = latents;
+    if (mem == STTS_MEM_HOST) {
+      lo.alloc(st, nl);
+      ld = lo;
+    }
+    VocTmp vt(st, static_cast<long long>(B) * T);
+    CK(cudaEventRecord(e->ev[4], st));
+    encode_audio(e, ad, B, N, ld, vt.ws);
+    CK(cudaEventRecord(e->ev[5], st));
+    if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(latents, ld, nl * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&e->timing.codec_enc_ms, e->ev[4], e->ev[5]));
   });
 }
 

@@ -837,7 +837,55 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
   out[static_cast<long long>(b) * T + t] = acc;
 }
 
+// Codec encoder stem (hf:300-312): causal Conv1d(1 -> C, k=7) on raw audio.  One thread per sample; the thread
+// writes its C outputs as whole 128-byte lines.
+template <int C>
+__global__ void __launch_bounds__(256) audio_stem_conv_kernel(const float* __restrict__ audio, int N,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              float* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  __shared__ float sw[7 * C + C];
+  for (int i = threadIdx.x; i < 7 * C; i += 256) sw[(i % 7) * C + i / 7] = w[i];  // tap-major
+  for (int i = threadIdx.x; i < C; i += 256) sw[7 * C + i] = bias[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= N) return;
+  const float* a = audio + static_cast<long long>(b) * N;
+  float x[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) x[j] = (t - 6 + j >= 0) ? a[t - 6 + j] : 0.f;
+  float4* o = reinterpret_cast<float4*>(out + (static_cast<long long>(b) * N + t) * C);
+#pragma unroll
+  for (int c4 = 0; c4 < C / 4; ++c4) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float acc = sw[7 * C + 4 * c4 + k];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc = fmaf(sw[j * C + 4 * c4 + k], x[j], acc);
+      v[k] = acc;
+    }
+    o[c4] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // ------------------------------------------------------------------ packing
+// strided causal Conv1d weight [O, C, 2r] -> two-tap GEMM operand over rows regrouped r at a time:
+// dst[o, tap*r*C + j*C + c] = w[o, c, tap*r + j]
+__global__ void pack_conv_strided_kernel(const float* __restrict__ src, int O, int C, int r, bf16* __restrict__ dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per_o = static_cast<long long>(2) * r * C;
+  if (i >= O * per_o) return;
+  const int o = static_cast<int>(i / per_o);
+  const int rem = static_cast<int>(i % per_o);
+  const int tap = rem / (r * C), j = (rem % (r * C)) / C, c = rem % C;
+  dst[i] = __float2bfloat16_rn(src[(static_cast<long long>(o) * C + c) * (2 * r) + tap * r + j]);
+}
+
 __device__ __forceinline__ int map_row(int r, int mode) {
   if (mode == ROW_INTERLEAVE16_LO) return (r >> 4) * 32 + (r & 15);
   if (mode == ROW_INTERLEAVE16_HI) return (r >> 4) * 32 + 16 + (r & 15);
@@ -1150,6 +1198,18 @@ cudaError_t pack_conv_taps(cudaStream_t st, const float* src, int O, int cin, in
 
 cudaError_t pack_conv_dense_tiles(cudaStream_t st, const float* src, int taps, bf16* dst) {
   last_launch_status = launch_k(pack_conv_dense_tiles_kernel, dim3(blocks_for(static_cast<long long>(960) * 60 * taps, 256)), dim3(256), 0, st, src, taps, dst);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t audio_stem_conv(cudaStream_t st, const float* audio, int B, int N, int C, const float* w, const float* bias,
+                            float* out) {
+  if (C != 32) return cudaErrorInvalidValue;
+  last_launch_status = launch_k(audio_stem_conv_kernel<32>, dim3(blocks_for(N, 256), B), dim3(256), 0, st, audio, N, w, bias, out);
+  STTS_LAUNCH_OK();
+}
+
+cudaError_t pack_conv_strided(cudaStream_t st, const float* src, int O, int C, int r, bf16* dst) {
+  last_launch_status = launch_k(pack_conv_strided_kernel, dim3(blocks_for(static_cast<long long>(O) * 2 * r * C, 256)), dim3(256), 0, st, src, O, C, r, dst);
   STTS_LAUNCH_OK();
 }
 

@@ -94,6 +94,10 @@ cudaError_t convnext_fused(cudaStream_t st, const float* x, int B, int T, int C,
 cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, const float* w, const float* bias,
                       float* out);
 
+// codec encoder stem: causal Conv1d(1 -> C, k=7) (hf:300-312).  audio fp32 [B, N], w [C, 1, 7] -> out fp32 [B, N, C]
+cudaError_t audio_stem_conv(cudaStream_t st, const float* audio, int B, int N, int C, const float* w, const float* bias,
+                            float* out);
+
 // ---- weight packing (run once at stts_finalize_weights)
 enum PackRow : int { ROW_PLAIN = 0, ROW_INTERLEAVE16_LO = 1, ROW_INTERLEAVE16_HI = 2, ROW_GROUPPAD_60_64 = 3 };
 enum PackCol : int { COL_PLAIN = 0, COL_HEADPAD_120_128 = 1 };
@@ -106,6 +110,9 @@ cudaError_t pack_conv_taps(cudaStream_t st, const float* src, int O, int cin, in
 // Grouped Conv1d(960,960,k,groups=16) weight [960, 60, taps] -> 15 dense 64-column output tiles, each reading the two
 // adjacent 64-padded input groups it can touch: dst[o, tap*128 + (o/60 - o/64)*64 + c] = w[o, c, tap]  (dst [960, taps*128])
 cudaError_t pack_conv_dense_tiles(cudaStream_t st, const float* src, int taps, bf16* dst);
+// strided causal Conv1d weight [O, C, 2r] (hf:181-216, k = 2r, stride r) -> dst[o, tap*r*C + j*C + c] = w[o, c, tap*r + j]
+// (two taps over the input regrouped r rows at a time: [T, C] viewed as [T/r, r*C])
+cudaError_t pack_conv_strided(cudaStream_t st, const float* src, int O, int C, int r, bf16* dst);
 // ConvTranspose1d weight [Cin, Cout, 2r] -> dst[j*Cout + o, tap*Cin + c] = w[c, o, j + tap*r]
 cudaError_t pack_convtr(cudaStream_t st, const float* src, int cin, int cout, int r, bf16* dst);
 // fp32 vector helpers: dst[map(i) + off] = scale * src[i]

@@ -76,9 +76,11 @@ class Engine:
         self._ready = False
 
     # ------------------------------------------------------------------ weights
-    def load_state_dicts(self, dit_sd: Dict[str, "np.ndarray"], vocoder_sd: Dict[str, "np.ndarray"]) -> None:
-        """fp32 tensors under the reference's own key names (DiTModel.state_dict(), HF decoder state_dict())."""
-        for model, sd in ((0, dit_sd), (1, vocoder_sd)):
+    def load_state_dicts(self, dit_sd: Dict[str, "np.ndarray"], vocoder_sd: Dict[str, "np.ndarray"],
+                         encoder_sd: Optional[Dict[str, "np.ndarray"]] = None) -> None:
+        """fp32 tensors under the reference's own key names (DiTModel.state_dict(), HF decoder state_dict() and,
+        optionally, HF encoder state_dict() for the clone path)."""
+        for model, sd in ((0, dit_sd), (1, vocoder_sd), (2, encoder_sd or {})):
             for name, t in sd.items():
                 a = t.detach().cpu().numpy() if _is_torch(t) else np.asarray(t)
                 a = np.require(a, dtype=np.float32, requirements=["C"])  # keeps 0-d tensors 0-d
@@ -156,6 +158,21 @@ class Engine:
         out, op = self._out_like(noise, (B, T, LATENT_DIM), mem)
         _cabi.check(self._lib.stts_sample_teacher(self._h, cond3._h, C.c_void_p(fr.ctypes.data), B, T, steps,
                                                   cfg_text, cfg_speaker, np_, seed, mem, op), self._h)
+        return out
+
+    def encode_audio(self, audio):
+        """Codec encoder (codec/onnx.py:56-75): audio (B, N) or (B, 1, N) fp32 @ 24 kHz -> latents (B, N // 3200, 64).
+        A tail shorter than one hop is dropped (the encoder is causal and floors, so no latent changes)."""
+        if audio.ndim == 3:
+            audio = audio[:, 0]
+        B, N = audio.shape
+        n = (N // HOP_SIZE) * HOP_SIZE
+        if n == 0:
+            raise ValueError("audio shorter than one hop (3200 samples)")
+        audio = audio[:, :n]
+        ap, mem, keep = _buf(audio, np.float32, "audio")
+        out, op = self._out_like(audio, (B, n // HOP_SIZE, LATENT_DIM), mem)
+        _cabi.check(self._lib.stts_encode_audio(self._h, ap, B, n, mem, op), self._h)
         return out
 
     def decode(self, latents):

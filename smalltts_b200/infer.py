@@ -91,6 +91,7 @@ class SmallTTS:
         codec_decoder_path: str = "assets/codec/decoder.safetensors",
         providers: Optional[Iterable[str]] = None,  # accepted for call compatibility; the engine is CUDA-only
         *,
+        codec_encoder_path: Optional[str] = None,  # clone path (codec/onnx.py:56-75): HF encoder state_dict file
         device: int = 0,
         state_dicts: Optional[tuple] = None,
         num_steps: int = NUM_STEPS,
@@ -106,15 +107,33 @@ class SmallTTS:
             else:
                 dit = load_state_dict_file(cond_encoder_path)
             state_dicts = (dit, load_state_dict_file(codec_decoder_path))
+            if codec_encoder_path is not None:
+                state_dicts += (load_state_dict_file(codec_encoder_path),)
         self.engine = Engine(device)
         self.engine.load_state_dicts(*state_dicts)
 
     @classmethod
-    def synthetic(cls, dit_seed: int = 0, vocoder_seed: int = 1, **kw) -> "SmallTTS":
+    def synthetic(cls, dit_seed: int = 0, vocoder_seed: int = 1, encoder_seed: Optional[int] = None, **kw) -> "SmallTTS":
         """Engine on seeded random weights of the reference architecture (no checkpoint can be fetched offline)."""
         from . import synthetic
 
-        return cls(state_dicts=(synthetic.dit_state_dict(dit_seed), synthetic.vocoder_state_dict(vocoder_seed)), **kw)
+        sds = (synthetic.dit_state_dict(dit_seed), synthetic.vocoder_state_dict(vocoder_seed))
+        if encoder_seed is not None:
+            sds += (synthetic.encoder_state_dict(encoder_seed),)
+        return cls(state_dicts=sds, **kw)
+
+    def clone_voice(self, wav, sample_rate: int = SAMPLE_RATE):
+        """scripts/infer/clone.py:27-36: mono wav (N,) or (1,N) at `sample_rate` -> reference latents (R,64) on the
+        engine's codec encoder.  Resampling to 24 kHz (infer/utils.py:7-23, torchaudio kaiser sinc) stays on the host."""
+        import torch
+
+        x = torch.as_tensor(np.asarray(wav, dtype=np.float32)).reshape(1, -1)
+        if sample_rate != SAMPLE_RATE:
+            from torchaudio.transforms import Resample
+
+            x = Resample(orig_freq=sample_rate, new_freq=SAMPLE_RATE, resampling_method="sinc_interp_kaiser",
+                         lowpass_filter_width=1024, rolloff=0.94, beta=14.769656459379492)(x)
+        return self.engine.encode_audio(x.numpy())[0]
 
     # ------------------------------------------------------------------ reference API
     def synthesize(self, ref_latents: np.ndarray, phoneme_ids: List[int], duration_sec: float,

@@ -139,6 +139,30 @@ def vocoder_specs() -> List[Spec]:
     return s
 
 
+ENC_RATIOS = (2, 2, 4, 5, 5, 8)  # hf encoder config: downsampling_ratios
+ENC_DEPTHS = (3, 3, 3, 3, 3, 3, 8)
+ENC_CHANNELS = (32, 64, 128, 256, 512, 1024, 2048)
+
+
+def encoder_specs() -> List[Spec]:
+    """HF VibeVoiceAcousticTokenizerEncoderModel.state_dict() (hf:300-403): mirror of the decoder with strided
+    causal convolutions."""
+    s: List[Spec] = [
+        ("stem.conv.conv.weight", (32, 1, 7), "lin", 7),
+        ("stem.conv.conv.bias", (32,), "lin", 7),
+    ]
+    for l in range(ENC_DEPTHS[0]):
+        s += _convnext_specs(f"stem.stage.{l}.", 32)
+    for i, r in enumerate(ENC_RATIOS):
+        cin, cout = ENC_CHANNELS[i], ENC_CHANNELS[i + 1]
+        s.append((f"conv_layers.{i}.conv.conv.weight", (cout, cin, 2 * r), "lin", 2 * r * cin))
+        s.append((f"conv_layers.{i}.conv.conv.bias", (cout,), "lin", 2 * r * cin))
+        for l in range(ENC_DEPTHS[i + 1]):
+            s += _convnext_specs(f"conv_layers.{i}.stage.{l}.", cout)
+    s += [("head.conv.weight", (64, 2048, 7), "lin", 2048 * 7), ("head.conv.bias", (64,), "lin", 2048 * 7)]
+    return s
+
+
 def _draw(specs: List[Spec], seed: int) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
@@ -167,6 +191,10 @@ def dit_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
 
 def vocoder_state_dict(seed: int = 1) -> Dict[str, torch.Tensor]:
     return _draw(vocoder_specs(), seed)
+
+
+def encoder_state_dict(seed: int = 2) -> Dict[str, torch.Tensor]:
+    return _draw(encoder_specs(), seed)
 
 
 def synthetic_inputs(batch: int, frames, ref_frames, n_phonemes, seed: int = 20260217, steps: int = 4):

@@ -199,3 +199,62 @@ def test_teacher_sampler_guidance_identity(tts):
     cond.free()
     for b in range(2):
         assert rel_l2(x[b, : frames[b]], y[b, : frames[b]]) <= 2e-3
+
+
+@pytest.fixture(scope="module")
+def tts_enc(dit_sd, voc_sd):
+    """Engine that also carries the codec encoder (clone path, BASELINE config 3)."""
+    from smalltts_b200 import synthetic
+    from smalltts_b200.infer import SmallTTS
+
+    t = SmallTTS(state_dicts=(dit_sd, voc_sd, synthetic.encoder_state_dict(2)))
+    yield t
+    t.engine.close()
+
+
+def test_codec_encoder_vs_reference_fixture(tts_enc):
+    """stts_encode_audio vs transformers' VibeVoiceAcousticTokenizerEncoderModel fixture."""
+    g = _load("encoder_small.npz")
+    lat = tts_enc.engine.encode_audio(g["audio"])
+    assert lat.shape == g["latents"].shape
+    err = rel_l2(lat, g["latents"])
+    print("encoder latents rel_l2", err)
+    assert np.isfinite(lat).all() and err <= TOL_FP32
+
+
+def test_codec_encoder_vs_oracle_ragged_and_causal(tts_enc):
+    """3 s reference (clone.py): a tail shorter than one hop is floored away, and a prefix of the audio gives a prefix
+    of the latents (causal convolutions), checked against the CPU oracle on the full clip."""
+    import torch
+
+    from oracle import smalltts_oracle as O
+    from smalltts_b200 import synthetic
+
+    g = torch.Generator().manual_seed(5)
+    audio = 0.3 * torch.randn(1, 1, 7 * 3200 + 777, generator=g)
+    lat = tts_enc.engine.encode_audio(audio.numpy())
+    assert lat.shape == (1, 7, 64)
+    with torch.inference_mode():
+        want = O.codec_encode(synthetic.encoder_state_dict(2), audio).numpy()
+    assert rel_l2(lat, want) <= TOL_FP32
+    head = tts_enc.engine.encode_audio(audio.numpy()[:, :, : 4 * 3200])
+    assert rel_l2(head, lat[:, :4]) <= 1e-5
+
+
+def test_clone_path_config3(tts_enc):
+    """BASELINE config 3: one reference wav -> latents on the engine's encoder, shared by several prompts in one
+    batched call; each row must equal the same prompt synthesised alone with that voice."""
+    import torch
+
+    from smalltts_b200 import synthetic
+
+    g = torch.Generator().manual_seed(6)
+    wav = 0.2 * torch.randn(3 * 24000, generator=g).numpy()
+    ref = tts_enc.clone_voice(wav)
+    assert ref.shape == (22, 64)  # 3 s -> 22 whole hops
+    _, ids, frames, noise = synthetic.synthetic_inputs(3, [9, 6, 12], 1, [14, 9, 18], seed=21)
+    durs = [f * 3200 / 24000 + 1e-3 for f in frames]
+    both = tts_enc.synthesize_batch([ref] * 3, ids, durs, noise=noise.numpy())
+    solo = tts_enc.synthesize_batch([ref], ids[1:2], durs[1:2], noise=noise.numpy()[:, 1:2, : frames[1]])
+    assert both[1].shape == (1, frames[1] * 3200)
+    assert rel_l2(both[1], solo[0]) <= 2e-3

@@ -104,3 +104,18 @@ def test_teacher_sampler_matches_reference(dit_sd):
     x = O.sample_teacher(dit_sd, cond3, mask, noise, int(g["steps"]), s_text, s_spk)
     valid = mask[..., None].expand_as(x).numpy()  # padded frames are never attended to nor decoded
     _close(x.numpy()[valid], g["latents"][valid], atol=1e-3)
+
+
+@torch.inference_mode()
+def test_codec_encoder_matches_reference():
+    """codec encoder restatement vs transformers' VibeVoiceAcousticTokenizerEncoderModel
+    (oracle/make_golden_encoder.py), plus the causal-prefix property."""
+    from smalltts_b200 import synthetic
+
+    esd = synthetic.encoder_state_dict(2)
+    g = _load("encoder_small.npz")
+    lat = O.codec_encode(esd, torch.tensor(g["audio"]))
+    assert lat.shape == (2, 3, 64)
+    _close(lat, g["latents"], atol=2e-5)
+    lat1 = O.codec_encode(esd, torch.tensor(g["audio"][:, :, :3200 + 1234]))  # a ragged tail is floored away
+    _close(lat1, g["latents"][:, :1], atol=2e-5)
