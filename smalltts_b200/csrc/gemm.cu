@@ -9,6 +9,8 @@
 
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "launch.cuh"
@@ -147,53 +149,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   ptx::pdl_wait();
   ptx::pdl_trigger();
 
+  // Producer and MMA issuer are single threads running a dependent chain per k-iteration, so that chain is kept
+  // free of integer divisions and descriptor rebuilds (ring position / phase / tap counters are carried, the UMMA
+  // descriptors advance by a constant): measured ~690 clk per iteration before, independent of tile width and depth.
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t kidx = 0;  // ring position, continues across tiles
-      for (int li = 0; li < n_my; ++li) {
-        const int tile = first + li * stride;
-        const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
-        const int b = my / tiles_t, t0 = (my % tiles_t) * BM, n0 = nx * BN;
-        for (int it = 0; it < iters; ++it, ++kidx) {
-          const int st = kidx % kStages;
-          const uint32_t ph = (kidx / kStages) & 1;
-          const int tap = it / kchunks;
-          const int kc = it - tap * kchunks;
-          ptx::mbar_wait(&empty[st], ph ^ 1);
+    // The whole warp walks the loop (so ring state lives in uniform registers and the TMA / MMA instructions need no
+    // per-lane election loops); one elected lane issues.
+    uint32_t st = 0, ph = 0;  // ring position and phase, continue across tiles
+    for (int li = 0; li < n_my; ++li) {
+      const int tile = first + li * stride;
+      const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
+      const int b = my / tiles_t, t0 = (my % tiles_t) * BM, n0 = nx * BN;
+      const int a_col0 = g * s.a_group_koff, w_row = g * s.w_group_rows + n0;
+      int kc = 0, a_row = t0 + s.tap_shift0;
+      for (int it = 0; it < iters; ++it) {
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full[st], C::kABytes + C::kBBytes);
-          ptx::tma_load_3d(smA + st * C::kABytes, &tmA, &full[st], g * s.a_group_koff + kc * BK,
-                           t0 + s.tap_shift0 + tap * s.tap_step, b);
-          ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], (tap * kchunks + kc) * BK,
-                           g * s.w_group_rows + n0);
+          ptx::tma_load_3d(smA + st * C::kABytes, &tmA, &full[st], a_col0 + kc * BK, a_row, b);
+          ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], it * BK, w_row);
         }
+        __syncwarp();
+        if (++kc == kchunks) { kc = 0; a_row += s.tap_step; }
+        if (++st == static_cast<uint32_t>(kStages)) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // fp16 operands: clear the bf16 format bits of A and B
-      const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN) & (s.ab_f16 ? ~((1u << 7) | (1u << 10)) : ~0u);
-      uint32_t kidx = 0;
-      for (int li = 0; li < n_my; ++li) {
-        const int ab = li & 1;
-        // the epilogue warps must have drained this accumulator buffer (tile li-2)
-        ptx::mbar_wait(&acc_empty[ab], ((li >> 1) & 1) ^ 1);
+    // fp16 operands: clear the bf16 format bits of A and B
+    const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN) & (s.ab_f16 ? ~((1u << 7) | (1u << 10)) : ~0u);
+    const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(smA));
+    const uint64_t db0 = ptx::umma_desc_sw128(ptx::smem_u32(smB));
+    uint32_t st = 0, ph = 0;
+    for (int li = 0; li < n_my; ++li) {
+      const int ab = li & 1;
+      // the epilogue warps must have drained this accumulator buffer (tile li-2)
+      ptx::mbar_wait(&acc_empty[ab], ((li >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * BN;
+      for (int it = 0; it < iters; ++it) {
+        ptx::mbar_wait(&full[st], ph);
         ptx::tc_fence_after();
-        for (int it = 0; it < iters; ++it, ++kidx) {
-          const int st = kidx % kStages;
-          const uint32_t ph = (kidx / kStages) & 1;
-          ptx::mbar_wait(&full[st], ph);
-          ptx::tc_fence_after();
-          const uint64_t da = ptx::umma_desc_sw128(ptx::smem_u32(smA + st * C::kABytes));
-          const uint64_t db = ptx::umma_desc_sw128(ptx::smem_u32(smB + st * C::kBBytes));
+        if (ptx::elect_one()) {
+          // descriptor start-address field is (addr >> 4): stages are kABytes / kBBytes apart
+          const uint64_t da = da0 + static_cast<uint64_t>(st * (C::kABytes >> 4));
+          const uint64_t db = db0 + static_cast<uint64_t>(st * (C::kBBytes >> 4));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(tmem_base + ab * BN, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty[st]);  // frees this smem stage once the MMAs above have read it
         }
-        ptx::umma_commit(&acc_full[ab]);  // accumulator complete
+        __syncwarp();
+        if (++st == static_cast<uint32_t>(kStages)) { st = 0; ph ^= 1; }
       }
+      if (ptx::elect_one()) ptx::umma_commit(&acc_full[ab]);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue: 8 warps; warp w owns TMEM lanes [32(w%4), +32) = tile rows and every second
@@ -490,6 +501,14 @@ cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUten
   const int iters = s.taps * ((s.K + BK - 1) / BK);
   const long long ring = static_cast<long long>(iters) * ((total + grid - 1) / grid);
   int stages = ring < 2 ? 2 : (ring > Cfg<BN>::kMaxStages ? Cfg<BN>::kMaxStages : static_cast<int>(ring));
+  {
+    static int forced = -1;  // STTS_GEMM_STAGES=n: pipeline-depth experiments (tools/bench_gemm.py)
+    if (forced < 0) {
+      const char* ev = getenv("STTS_GEMM_STAGES");
+      forced = ev ? atoi(ev) : 0;
+    }
+    if (forced >= 2 && forced < stages) stages = forced;
+  }
   const cudaError_t le = launch_k(gemm_kernel<BN, ACT>, dim3(grid), dim3(kThreads), Cfg<BN>::smem_bytes(stages), stream,
                                   tmA, tmW, s, e, stages, n_tiles, m_tiles, static_cast<int>(total));
   ++g_launch_count;
