@@ -55,12 +55,27 @@ def tail_algorithmic_bytes(batch: int, frames: int) -> float:
 
 
 def measured_peaks():
+    """-> (hbm GB/s, bf16 TFLOP/s sustained, source)."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", 1400.0)), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained)"
+
+
+def tail_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tail group's kernels from the committed ncu capture
+    (profiles/r01_tail_traffic.json, same shapes as this bench); None if the capture is absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_tail_traffic.json")) as f:
+            return float(json.load(f)["traffic_bytes"])
+    except Exception:
+        return None
+
+
+# SURVEY.md 8(d): algorithmic FLOPs of one denoiser evaluation at B=8, T=75, R=15, P=120
+DENOISE_GFLOP_PER_STEP = 177.3
 
 
 class ClockSampler:
@@ -234,9 +249,10 @@ def main_ours(args, rank, local_rank, world):
     audio_s = BATCH * AUDIO_S_PER_UTT * world * args.steps
     value = audio_s / (dev_ms / 1e3)
     e2e_value = audio_s / (e2e_wall / 1e3)
-    peak, peak_src = measured_peaks()
+    peak, peak_tf, peak_src = measured_peaks()
     tail_bytes = tail_algorithmic_bytes(BATCH, T)
     achieved = tail_bytes / (tail_ms / 1e3) / 1e9
+    dit_tflops = DENOISE_GFLOP_PER_STEP * STEPS_DMD / stage["denoise_ms"]  # GFLOP / ms = TFLOP/s
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -263,8 +279,13 @@ def main_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": "vocoder tail (stages up3..up5 with C<=128 + head): token-mixer + "
                          "tcgen05 FFN GEMMs + transposed-conv GEMMs, CUDA events around the group on the engine stream",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes": tail_bytes, "ms": tail_ms, "traffic": None,
-                         "front_ms": front_ms},
+                         "peak_source": peak_src, "algorithmic_bytes": tail_bytes, "ms": tail_ms,
+                         "traffic": tail_dram_traffic(), "front_ms": front_ms},
+            # second regime of the path: the 4 denoiser evaluations are tensor-core work
+            "roofline_tensor": {"bound": "tensor", "kernel": "DMD loop: 4 denoiser evaluations (tcgen05 GEMMs + attention), "
+                                "CUDA events around the loop on the engine stream",
+                                "achieved": dit_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": dit_tflops / peak_tf,
+                                "algorithmic_gflop": DENOISE_GFLOP_PER_STEP * STEPS_DMD, "ms": stage["denoise_ms"]},
             "cpu_baseline": cpu,
         }
         print(json.dumps(out))
