@@ -144,10 +144,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail;
-  // from here on global memory written by it is read (A operand, residual) and its inputs may be overwritten.
-  ptx::pdl_wait();
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail.
+  // Weights never depend on the predecessor, so the producer also requests the W boxes of its first stages before
+  // waiting; everything else that touches global memory (A operand, residual, outputs) comes after the wait.
   ptx::pdl_trigger();
+  int w_pre = 0;  // stages of the first tile whose W box is already in flight (producer warp only)
+  if (warp == 0 && n_my > 0) {
+    w_pre = iters < kStages ? iters : kStages;
+    if (ptx::elect_one()) {
+      const int tile = first;
+      const int nx = tile % n_tiles, g = tile / (n_tiles * m_tiles);
+      for (int i = 0; i < w_pre; ++i) {
+        ptx::mbar_expect_tx(&full[i], C::kABytes + C::kBBytes);
+        ptx::tma_load_2d(smB + i * C::kBBytes, &tmW, &full[i], i * BK, g * s.w_group_rows + nx * BN);
+      }
+    }
+    __syncwarp();
+  }
+  ptx::pdl_wait();
 
   // Producer and MMA issuer are single threads running a dependent chain per k-iteration, so that chain is kept
   // free of integer divisions and descriptor rebuilds (ring position / phase / tap counters are carried, the UMMA
@@ -164,10 +178,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int kc = 0, a_row = t0 + s.tap_shift0;
       for (int it = 0; it < iters; ++it) {
         ptx::mbar_wait(&empty[st], ph ^ 1);
+        const bool w_done = li == 0 && it < w_pre;  // expect_tx + W box already issued ahead of the PDL wait
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&full[st], C::kABytes + C::kBBytes);
+          if (!w_done) ptx::mbar_expect_tx(&full[st], C::kABytes + C::kBBytes);
           ptx::tma_load_3d(smA + st * C::kABytes, &tmA, &full[st], a_col0 + kc * BK, a_row, b);
-          ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], it * BK, w_row);
+          if (!w_done) ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], it * BK, w_row);
         }
         __syncwarp();
         if (++kc == kchunks) { kc = 0; a_row += s.tap_step; }
