@@ -47,8 +47,18 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__
   if (row >= rows) return;
   const int nv = dim >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * dim);
-  float4 v[8];
+  // scale / shift do not depend on the row statistics: request them together with the row (one latency, not three)
+  const int bq = row / rpb;
+  const float4* scq = reinterpret_cast<const float4*>(scale + static_cast<long long>(kLayerNorm ? bq : 0) * ld_mod);
+  const float4* shq = kLayerNorm ? reinterpret_cast<const float4*>(shift + static_cast<long long>(bq) * ld_mod) : nullptr;
+  float4 v[8], wq[8], hq[8];
   float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + 32 * i;
+    wq[i] = idx < nv ? __ldg(scq + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    hq[i] = (kLayerNorm && idx < nv) ? __ldg(shq + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int idx = lane + 32 * i;
@@ -72,18 +82,15 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__
   } else {
     rstd = 1.0f / sqrtf(s / dim + eps);
   }
-  const int b = row / rpb;
-  const float4* sc = reinterpret_cast<const float4*>(scale + static_cast<long long>(kLayerNorm ? b : 0) * ld_mod);
-  const float4* sh = kLayerNorm ? reinterpret_cast<const float4*>(shift + static_cast<long long>(b) * ld_mod) : nullptr;
   uint2* o = reinterpret_cast<uint2*>(out + static_cast<long long>(row) * dim);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int idx = lane + 32 * i;
     if (idx < nv) {
-      const float4 w = sc[idx];
+      const float4 w = wq[i];
       float4 r;
       if (kLayerNorm) {
-        const float4 h = sh[idx];
+        const float4 h = hq[i];
         r.x = (v[i].x - mean) * rstd * (1.f + w.x) + h.x;
         r.y = (v[i].y - mean) * rstd * (1.f + w.y) + h.y;
         r.z = (v[i].z - mean) * rstd * (1.f + w.z) + h.z;
@@ -119,30 +126,51 @@ __device__ __forceinline__ void head_split_body(const float* __restrict__ in, in
   const int h = static_cast<int>(item % heads);
   const int d0 = lane * EPL;
   const float* src = in + static_cast<long long>(row) * ld_in + src_off + h * hd;
-  float v[EPL];
+  // every load of the item is requested up front (values, norm weights, rotary table): one memory latency instead of
+  // three dependent ones.  hd, src_off and ld_in are multiples of EPL (checked by the launcher), so lanes are either
+  // fully inside or fully outside the head.
+  const bool live = d0 < hd;
+  float v[EPL], nw[EPL], cs[EPL / 2], sn[EPL / 2];
+  const bool rotate = rot > 0 && d0 < rot;
+  if (EPL == 4) {
+    const float4 t = live ? *reinterpret_cast<const float4*>(src + d0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    if (norm_w != nullptr) {
+      const float4 w = live ? __ldg(reinterpret_cast<const float4*>(norm_w + h * hd + d0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      nw[0] = w.x; nw[1] = w.y; nw[2] = w.z; nw[3] = w.w;
+    }
+  } else {
+    const float2 t = live ? *reinterpret_cast<const float2*>(src + d0) : make_float2(0.f, 0.f);
+    v[0] = t.x; v[1] = t.y;
+    if (norm_w != nullptr) {
+      const float2 w = live ? __ldg(reinterpret_cast<const float2*>(norm_w + h * hd + d0)) : make_float2(0.f, 0.f);
+      nw[0] = w.x; nw[1] = w.y;
+    }
+  }
+  if (rotate) {
+    const int pos = row % rpb;
+#pragma unroll
+    for (int e = 0; e < EPL / 2; ++e) {
+      cs[e] = __ldg(cos_t + pos * (rot >> 1) + (d0 >> 1) + e);
+      sn[e] = __ldg(sin_t + pos * (rot >> 1) + (d0 >> 1) + e);
+    }
+  }
   float s = 0.f;
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) {
-    v[e] = (d0 + e < hd) ? src[d0 + e] : 0.f;
-    s += v[e] * v[e];
-  }
+  for (int e = 0; e < EPL; ++e) s += v[e] * v[e];
   if (norm_w != nullptr) {
     s = warp_sum(s);
     const float r = 1.0f / sqrtf(s / hd + eps);
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      if (d0 + e < hd) v[e] = v[e] * r * norm_w[h * hd + d0 + e];
-    }
+    for (int e = 0; e < EPL; ++e) v[e] = v[e] * r * nw[e];
   }
-  if (rot > 0 && d0 < rot) {
-    const int pos = row % rpb;
+  if (rotate) {
 #pragma unroll
     for (int e = 0; e < EPL; e += 2) {
-      const int i = (d0 + e) >> 1;
-      const float c = cos_t[pos * (rot >> 1) + i], sn = sin_t[pos * (rot >> 1) + i];
+      const float c = cs[e >> 1], sn_ = sn[e >> 1];
       const float x0 = v[e], x1 = v[e + 1];
-      v[e] = x0 * c - x1 * sn;
-      v[e + 1] = x1 * c + x0 * sn;
+      v[e] = x0 * c - x1 * sn_;
+      v[e + 1] = x1 * c + x0 * sn_;
     }
   }
   bf16* o = out + (static_cast<long long>(row) * heads + h) * (EPL * 32) + d0;
@@ -988,6 +1016,11 @@ cudaError_t head_split_launch(cudaStream_t st, const float* in, int ld_in, int r
                               int hd_pad, float eps, const float* cos_t, const float* sin_t, const HeadJobs& jobs,
                               int njobs) {
   dim3 grid(blocks_for(static_cast<long long>(rows) * heads, 8), njobs);
+  const int epl = hd_pad / 32;
+  if ((hd % epl) != 0 || (ld_in % epl) != 0 || (reinterpret_cast<uintptr_t>(in) & 15) != 0) return cudaErrorInvalidValue;
+  for (int j = 0; j < njobs; ++j) {
+    if ((jobs.src_off[j] % epl) != 0 || (jobs.rot[j] % epl) != 0) return cudaErrorInvalidValue;
+  }
   if (hd_pad == 128) {
     last_launch_status = launch_k(head_split_kernel<4>, grid, dim3(256), 0, st, in, ld_in, rows, rpb, heads, hd, eps, cos_t, sin_t, jobs);
   } else if (hd_pad == 64) {
@@ -1158,7 +1191,7 @@ cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, c
     STTS_LAUNCH_OK();
   }
   int TT = 16384 / C;
-  if (TT < 8) TT = 8;
+  if (TT < 4) TT = 4;  // C = 2048 (75 frames per utterance): 4-row tiles spread the stage over all SMs (19 x B CTAs)
   if (TT > 512) TT = 512;
   if (TT > T) TT = T;
   const int smem = ((TT + 6) * C + (TT + 6) + TT) * 4;
