@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("STTS_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DSTTS_FUSED_TRACE for tools/trace_fused.py
 
 
 def _nvcc() -> str:

@@ -65,7 +65,9 @@ struct FC {
   static constexpr int OFF_VEC = OFF_X + 2 * X_BYTES;
   static constexpr int OFF_INV = OFF_VEC + VEC_FLOATS * 4;
   static constexpr int OFF_BAR = ((OFF_INV + XR * 4 + 15) / 16) * 16;
-  static constexpr int SMEM = OFF_BAR + 17 * 8 + 16 + 1024;
+  static constexpr int OFF_STG = ((OFF_BAR + 17 * 8 + 16 + 127) / 128) * 128;  // 4 x 4 KB: out-warp transposition staging
+  static constexpr int SMEM = OFF_STG + 4 * 4096 + 1024;
+  static_assert(SMEM <= 232448, "fused ConvNeXt tile does not fit in shared memory");
 };
 
 // (fp32 reference form, kept for documentation) TWICE the erf-GELU: x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form (max abs err 2.6e-5 before
@@ -103,6 +105,23 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
 __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
   return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7))) << 4) + (k & 7) * 2);
 }
+
+#ifdef STTS_FUSED_TRACE
+// Role timeline of CTA 0 (debug builds only): g_fused_trace[tile][event] = clock64().
+//   0 mixer: tile data landed   1 mixer: conv done      2 mixer: a_full arrive
+//   3 mma: MMA1 issued          4 mma: last MMA2 issued (o_full commit)
+//   5 gelu(w0): h_full seen     6 gelu(w0): last chunk arrived
+//   7 out(w0): y copied/x_empty 8 out(w0): o_full seen  9 out(w0): stores issued
+__device__ long long g_fused_trace[64 * 16];
+#define TRACE(tile_it, ev)                                                              \
+  do {                                                                                  \
+    if (blockIdx.x == 0 && (tile_it) < 64) g_fused_trace[(tile_it) * 16 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define TRACE(tile_it, ev) \
+  do {                     \
+  } while (0)
+#endif
 
 template <int C>
 __global__ void __launch_bounds__(kThreadsFused, 1)
@@ -205,6 +224,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         ptx::cp_async_wait<0>();
       }
       ptx::named_bar_sync(1, NT);
+      if (tid == 0) TRACE(it, 0);
       float* xs = Xbuf(buf);
       // (1) 1/rms of every staged row: thread t owns row t
       if (tid < XR) {
@@ -249,6 +269,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         }
       }
       ptx::named_bar_sync(1, NT);
+      if (tid == 0) TRACE(it, 1);
       // (3) second RMSNorm -> bf16 A operand (UMMA K-major, 128B swizzle); A buffer must be free (MMA1 of it-2 done)
       if (it >= 2) ptx::mbar_wait(&a_empty[buf], ((it - 2) >> 1) & 1);
       if (tid < TM) {
@@ -277,6 +298,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       ptx::fence_proxy_async();
       ptx::named_bar_sync(1, NT);
       if (tid == 0) ptx::mbar_arrive(&a_full[buf]);
+      if (tid == 0) TRACE(it, 2);
     }
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer
@@ -304,6 +326,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem_base + buf * 256, dA + 2 * k, dW1 + 2 * k, idesc1, k > 0);
         ptx::umma_commit(&a_empty[buf]);
         ptx::umma_commit(&h_full[buf]);
+        TRACE(it, 3);
       };
       mma1(0);
       uint32_t gcount = 0;
@@ -328,6 +351,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           ptx::umma_commit(&g_empty[gb]);
         }
         ptx::umma_commit(&o_full[it & 1]);
+        TRACE(it, 4);
         if (!next_issued) mma1(it + 1);
       }
     }
@@ -341,18 +365,21 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     for (int it = 0; it < n_my; ++it) {
       ptx::mbar_wait(&h_full[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
+      if (gw == 0 && lane == 0) TRACE(it, 5);
       for (int c = 0; c < F::NCH; ++c, ++gcount) {
         const int gb = gcount & 1;
         if (gcount >= 2) ptx::mbar_wait(&g_empty[gb], ((gcount - 2) >> 1) & 1);
         uint32_t rr[32];
         ptx::tmem_ld_32x32(tmem_base + (it & 1) * 256 + (static_cast<uint32_t>(q * 32) << 16) + c * 64 + half * 32, rr);
-        ptx::tmem_ld_wait();
         const __half2* bb = reinterpret_cast<const __half2*>(b1h + c * 64 + half * 32);
+        uint4 bqs[4];  // 32 fp16 biases, in flight while the accumulator read completes
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bqs[j] = *reinterpret_cast<const uint4*>(bb + 4 * j);
+        ptx::tmem_ld_wait();
         uint8_t* Gs = Gbuf(gb);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint4 bq = *reinterpret_cast<const uint4*>(bb + 4 * j);  // 8 fp16 biases
-          const __half2* bh = reinterpret_cast<const __half2*>(&bq);
+          const __half2* bh = reinterpret_cast<const __half2*>(&bqs[j]);
           uint4 pk;
           pk.x = gelu2_half2(__uint_as_float(rr[8 * j + 0]), __uint_as_float(rr[8 * j + 1]), bh[0]);
           pk.y = gelu2_half2(__uint_as_float(rr[8 * j + 2]), __uint_as_float(rr[8 * j + 3]), bh[1]);
@@ -364,6 +391,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&g_full[gb]);  // the MMA warp proceeds once all 8 GELU warps have arrived
+        if (gw == 0 && lane == 0 && c == F::NCH - 1) TRACE(it, 6);
       }
     }
   } else {
@@ -385,8 +413,10 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       }
       ptx::named_bar_sync(3, 128);
       if (otid == 0) ptx::mbar_arrive(&x_empty[buf]);
+      if (otid == 0) TRACE(it, 7);
       ptx::mbar_wait(&o_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
+      if (otid == 0) TRACE(it, 8);
 #pragma unroll
       for (int cc = 0; cc < C / 32; ++cc) {
         uint32_t rr[32];
@@ -408,26 +438,38 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       ptx::tc_fence_before();
       ptx::named_bar_sync(3, 128);
       if (otid == 0) ptx::mbar_arrive(&tm_empty[buf]);  // TMEM buffer may be overwritten by MMA1 of tile it+2
-      // each thread owns one full output row: C contiguous floats (whole 128-byte lines)
+      // Each thread holds one full output row; storing it directly makes every store instruction touch 32 different
+      // lines (2048 LSU wavefronts per tile on a pipe the mixer and GELU warps also need: measured 4.4k cycles per
+      // tile).  The row block is transposed 32 columns at a time through a warp-private, XOR-swizzled staging buffer
+      // so that 8 consecutive lanes write one 128-byte row segment.
       const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * TM;
-      if (t0 + r < p.T) {
-        const long long o = (static_cast<long long>(b) * p.T + t0 + r) * C;
-        float4* dst = reinterpret_cast<float4*>(p.out + o);
+      const int nlive = p.T - (t0 + q * 32);  // rows of this warp inside the sequence
+      float4* stg = reinterpret_cast<float4*>(smem + F::OFF_STG + (warp - kOutWarp0) * 4096);
+      const int l8r = lane >> 3, l8c = lane & 7;
+      const long long obase = (static_cast<long long>(b) * p.T + t0 + q * 32) * C;
 #pragma unroll
-        for (int j = 0; j < C / 4; ++j) dst[j] = y[j];
-        if (p.out_bf16 != nullptr) {
-          uint4* dstb = reinterpret_cast<uint4*>(p.out_bf16 + o);
+      for (int cc = 0; cc < C / 32; ++cc) {
 #pragma unroll
-          for (int j = 0; j < C / 8; ++j) {
-            uint4 pk;
-            pk.x = bf2(y[2 * j].x, y[2 * j].y);
-            pk.y = bf2(y[2 * j].z, y[2 * j].w);
-            pk.z = bf2(y[2 * j + 1].x, y[2 * j + 1].y);
-            pk.w = bf2(y[2 * j + 1].z, y[2 * j + 1].w);
-            dstb[j] = pk;
+        for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = y[cc * 8 + j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = 4 * j + l8r;
+          const float4 v = stg[rr * 8 + (l8c ^ (rr & 7))];
+          if (rr < nlive) {
+            const long long o = obase + static_cast<long long>(rr) * C + cc * 32 + 4 * l8c;
+            *reinterpret_cast<float4*>(p.out + o) = v;
+            if (p.out_bf16 != nullptr) {
+              uint2 pk;
+              pk.x = bf2(v.x, v.y);
+              pk.y = bf2(v.z, v.w);
+              *reinterpret_cast<uint2*>(p.out_bf16 + o) = pk;
+            }
           }
         }
+        __syncwarp();
       }
+      if (otid == 0) TRACE(it, 9);
     }
   }
 
@@ -485,6 +527,12 @@ cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, 
 }
 
 }  // namespace
+
+#ifdef STTS_FUSED_TRACE
+extern "C" int stts_debug_fused_trace(long long* host_out /*[64*16]*/) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, g_fused_trace, sizeof(long long) * 64 * 16));
+}
+#endif
 
 cudaError_t convnext_fused(cudaStream_t st, const float* x, int B, int T, int C, const float* norm_w,
                            const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
