@@ -215,10 +215,19 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     if (n_my > 0) issue_load(first, 0);
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
+      // Prefetch of tile it+1 into the other x buffer, which last held tile it-1 and is released by the out warps once
+      // they hold y(it-1) in registers.  The out warps are the slowest role (role timeline, tools/trace_fused.py), so
+      // the mixer never BLOCKS on them before computing a tile whose data is already here: if the buffer is not free
+      // yet the prefetch is issued after this tile's token mixing instead.
+      bool issued_now = false;
       if (it + 1 < n_my) {
-        // the other x buffer was last used by iteration it-1: its out warps release it as soon as they hold y
-        if (it >= 1) ptx::mbar_wait(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
-        issue_load(first + (it + 1) * stride, buf ^ 1);
+        const bool free_now = it == 0 || ptx::mbar_test(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
+        if (ptx::named_bar_and(1, NT, free_now)) {  // uniform decision for the 256 mixer threads
+          issue_load(first + (it + 1) * stride, buf ^ 1);
+          issued_now = true;
+        }
+      }
+      if (issued_now) {
         ptx::cp_async_wait<1>();
       } else {
         ptx::cp_async_wait<0>();
@@ -299,6 +308,10 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       ptx::named_bar_sync(1, NT);
       if (tid == 0) ptx::mbar_arrive(&a_full[buf]);
       if (tid == 0) TRACE(it, 2);
+      if (it + 1 < n_my && !issued_now) {  // deferred prefetch: now the mixer has nothing better to do than wait
+        if (it >= 1) ptx::mbar_wait(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
+        issue_load(first + (it + 1) * stride, buf ^ 1);
+      }
     }
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer

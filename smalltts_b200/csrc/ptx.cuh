@@ -189,6 +189,19 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// barrier + AND-reduction of a per-thread predicate over the participating threads (every thread gets the result)
+__device__ __forceinline__ bool named_bar_and(uint32_t id, uint32_t nthreads, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %3, 0;\n\t"
+      "barrier.cta.red.and.pred p, %1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(out)
+      : "r"(id), "r"(nthreads), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+  return out != 0;
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
