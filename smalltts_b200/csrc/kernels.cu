@@ -3,6 +3,7 @@
 
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -1190,7 +1191,13 @@ cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, c
     }
     STTS_LAUNCH_OK();
   }
-  int TT = 16384 / C;
+  static int tt_elems = 0;  // STTS_MIX_TILE=<rows*C per CTA>: tile-size experiments
+  if (tt_elems == 0) {
+    const char* ev = getenv("STTS_MIX_TILE");
+    tt_elems = ev ? atoi(ev) : 8192;  // measured at BASELINE configs[1]: 8192 beats 16384 by 0.09 ms per step
+    if (tt_elems < 2048 || tt_elems > 24576) tt_elems = 8192;
+  }
+  int TT = tt_elems / C;
   if (TT < 4) TT = 4;  // C = 2048 (75 frames per utterance): 4-row tiles spread the stage over all SMs (19 x B CTAs)
   if (TT > 512) TT = 512;
   if (TT > T) TT = T;
