@@ -650,18 +650,29 @@ __global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restri
   const int sub = lane / lpr, sl = lane % lpr;
   const float* xb = x + static_cast<long long>(b) * T * C;
 
-  // phase 1: load rows t0-6 .. t0+nrows-1, per-row 1/rms
+  // phase 1: stage rows t0-6 .. t0+nrows-1 with cp.async (every 16-byte piece of the tile in flight at once: one
+  // memory round trip instead of one per row), then per-row 1/rms from shared memory
+  {
+    const uint32_t dst0 = ptx::smem_u32(tile);
+    for (int i = threadIdx.x; i < R * cv; i += 256) {
+      const int r = i / cv, c4 = i - r * cv;
+      const int t = t0 - 6 + r;
+      const bool live = t >= 0 && r < nrows + 6;
+      ptx::cp_async_16(dst0 + (r * C + c4 * 4) * 4, xb + static_cast<long long>(live ? t : 0) * C + c4 * 4, live ? 16u : 0u);
+    }
+    ptx::cp_async_commit();
+    ptx::cp_async_wait<0>();
+  }
+  __syncthreads();
   for (int r0 = warp * rpi; r0 < R; r0 += 8 * rpi) {
     const int r = r0 + sub;
     const int t = t0 - 6 + r;
     const bool live = r < R && t >= 0 && r < nrows + 6;
     float s = 0.f;
     if (r < R) {
-      float4* dst = reinterpret_cast<float4*>(tile + r * C);
+      const float4* src = reinterpret_cast<const float4*>(tile + r * C);
       for (int i = sl; i < cv; i += lpr) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) v = reinterpret_cast<const float4*>(xb + static_cast<long long>(t) * C)[i];
-        dst[i] = v;
+        const float4 v = src[i];
         s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       }
     }

@@ -258,3 +258,42 @@ def test_clone_path_config3(tts_enc):
     solo = tts_enc.synthesize_batch([ref], ids[1:2], durs[1:2], noise=noise.numpy()[:, 1:2, : frames[1]])
     assert both[1].shape == (1, frames[1] * 3200)
     assert rel_l2(both[1], solo[0]) <= 2e-3
+
+
+def test_edge_cases_single_frame_empty_text_and_long_utterance(tts, dit_sd, voc_sd):
+    """Edge cases of the path: a 1-frame utterance, a row without any phoneme (all keys of that source masked), a row
+    without reference frames, and a 30 s utterance (the cap of estimate_duration, infer/onnx.py:17-18) in one ragged
+    batch -- every row against the CPU oracle."""
+    import torch
+
+    from oracle import smalltts_oracle as O
+    from smalltts_b200 import synthetic
+
+    frames = [1, 7, 225, 12]
+    refs, ids, _, noise = synthetic.synthetic_inputs(4, frames, [3, 1, 15, 6], [2, 1, 40, 9], seed=31)
+    ids[1] = []          # no text at all
+    refs[3] = refs[3][:0]  # no reference audio at all
+    durs = [f * 3200 / 24000 + 1e-3 for f in frames]
+    got = tts.synthesize_batch(refs, ids, durs, noise=noise.numpy())
+    with torch.inference_mode():
+        want = O.synthesize_batch(dit_sd, voc_sd, refs, ids, frames, noise)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == (1, frames[i] * 3200) and np.isfinite(g).all()
+        err = rel_l2(g, w.numpy())
+        print("edge row", i, "frames", frames[i], "rel_l2", err)
+        assert err <= TOL_FP32
+
+
+def test_invalid_arguments_raise(tts):
+    """Error behaviour of the boundary: bad lengths / shapes come back as ValueError (status -1), never a crash."""
+    from smalltts_b200 import synthetic
+
+    refs, ids, frames, _ = synthetic.synthetic_inputs(1, 4, 3, 5, seed=1)
+    with pytest.raises(ValueError):
+        tts.synthesize_batch(refs, ids, [])  # empty batch
+    with pytest.raises(ValueError):
+        tts.engine.synthesize(np.zeros((1, 3, 64), np.float32), [4], np.zeros((1, 5), np.int64), [5], [4], 4)  # ref_len > R
+    with pytest.raises(ValueError):
+        tts.engine.synthesize(np.zeros((1, 3, 64), np.float32), [3], np.zeros((1, 5), np.int64), [5], [0], 4)  # 0 frames
+    with pytest.raises((ValueError, RuntimeError)):
+        tts.engine.encode_audio(np.zeros((1, 6400), np.float32))  # this engine carries no encoder weights
