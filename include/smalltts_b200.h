@@ -166,6 +166,9 @@ int stts_test_convnext_mix(stts_engine* e, const float* x, int B, int T, int C, 
                            const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
                            float* y, void* a_bf16);
 
+int stts_test_ffn_fused(stts_engine* e, const void* a_bf16, const float* y, long long M, int C, const void* w1_bf16,
+                        const float* b1, const void* w2_f16, const float* b2, const float* ffn_gamma, float* out,
+                        void* out_bf16);
 int stts_test_convnext_fused(stts_engine* e, const float* x, int B, int T, int C, const float* norm_w,
                              const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
                              const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2,

@@ -149,6 +149,7 @@ struct stts_engine {
   uint64_t use_counter = 0;
   bool use_graphs = true;
   bool test_async = false;  // test hooks return without synchronising (micro-benchmarks time many launches)
+  bool fused_ffn = true;   // STTS_NO_FUSED_FFN=1: C = 128 feed-forward as two GEMMs (debug / A-B timing)
   bool fused_tail = true;  // STTS_NO_FUSED_TAIL=1 falls back to mixer + two GEMMs for C <= 64 (debug / A-B timing)
   unsigned long long* seed_dev = nullptr;   // device u64 read by the Philox kernel
   unsigned long long* seed_host = nullptr;  // pinned staging for seed_dev
@@ -813,6 +814,10 @@ void convnext_layers(stts_engine* e, const std::vector<VocLayerW>& layers, float
   for (size_t l = 0; l < nl; ++l) {
     const VocLayerW& w = layers[l];
     CK(convnext_mix(st, cur, B, Ts, C, w.norm_w, w.conv_w, w.conv_b, w.gamma, w.ffn_norm_w, 1e-5f, oth, ws.a));
+    if (C == 128 && e->fused_ffn) {  // hidden activation stays on the SM
+      CK(ffn_fused(st, ws.a, oth, M, C, w.w1, w.b1, w.w2h, w.b2, w.ffn_gamma, cur, (bf16_copy && l + 1 == nl) ? ws.xh : nullptr));
+      continue;
+    }
     GemmEpi e1;
     e1.bias = w.b1; e1.act = ACT_GELU; e1.gelu2_f16 = 1; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
     linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1);
@@ -1078,6 +1083,8 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     e->use_graphs = !(ng && ng[0] == '1');
     const char* nf = getenv("STTS_NO_FUSED_TAIL");
     e->fused_tail = !(nf && nf[0] == '1');
+    const char* nff = getenv("STTS_NO_FUSED_FFN");
+    e->fused_ffn = !(nff && nff[0] == '1');
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, e->device));
     uint64_t thr = UINT64_MAX;
@@ -1503,6 +1510,17 @@ int stts_test_convnext_mix(stts_engine* e, const float* x, int B, int T, int C, 
   if (!e) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
     CK(convnext_mix(e->st, x, B, T, C, norm_w, conv_w, conv_b, gamma, ffn_norm_w, 1e-5f, y, static_cast<bf16*>(a_bf16)));
+    if (!e->test_async) CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+int stts_test_ffn_fused(stts_engine* e, const void* a_bf16, const float* y, long long M, int C, const void* w1_bf16,
+                        const float* b1, const void* w2_f16, const float* b2, const float* ffn_gamma, float* out,
+                        void* out_bf16) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    CK(ffn_fused(e->st, static_cast<const bf16*>(a_bf16), y, M, C, static_cast<const bf16*>(w1_bf16), b1, w2_f16, b2,
+                 ffn_gamma, out, static_cast<bf16*>(out_bf16)));
     if (!e->test_async) CK(cudaStreamSynchronize(e->st));
   });
 }

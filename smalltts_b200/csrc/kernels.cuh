@@ -90,6 +90,11 @@ cudaError_t convnext_fused(cudaStream_t st, const float* x, int B, int T, int C,
                            const float* conv_w, const float* conv_b, const float* gamma, const float* ffn_norm_w,
                            const bf16* w1, const float* b1, const void* w2_f16, const float* b2, const float* ffn_gamma,
                            float eps, float* out, bf16* out_bf16);
+// ConvNeXt feed-forward (hf:293-297) for C = 128 in one kernel; the 4C-wide hidden activation never leaves the SM:
+//   out = y + ffn_gamma * (W2 gelu(W1 a + b1) + b2),  a: bf16 [M, C] (FFN pre-norm output), y: fp32 [M, C] residual,
+// w1: bf16 [4C, C], w2: FP16 [C, 4C] pre-scaled by 0.5.  out must not alias y.
+cudaError_t ffn_fused(cudaStream_t st, const bf16* a, const float* y, long long M, int C, const bf16* w1, const float* b1,
+                      const void* w2_f16, const float* b2, const float* ffn_gamma, float* out, bf16* out_bf16);
 // vocoder head: causal Conv1d(C -> 1, k=7) (hf:484-489).  x fp32 [B, T, C], w [C, 7] -> out [B, T]
 cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, const float* w, const float* bias,
                       float* out);

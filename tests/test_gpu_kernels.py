@@ -264,3 +264,29 @@ def test_convnext_fused(eng, C_, T):
     want = y + fgamma * (h @ w2.float().t() + b2)
     _assert_close(out, want, tol=2e-3)
     _assert_close(out16, want, tol=1e-2)
+
+
+@pytest.mark.parametrize("M", [128, 1000, 37, 40000])
+def test_ffn_fused(eng, M):
+    """ConvNeXt feed-forward for C = 128 in one kernel (hidden activation in TMEM / shared memory only) vs torch fp32
+    on the same bf16 / fp16-rounded operands."""
+    from smalltts_b200 import _cabi
+
+    torch.manual_seed(12)
+    C_ = 128
+    a = _rand_bf16(M, C_)
+    y = torch.randn(M, C_, device="cuda")
+    w1 = _rand_bf16(4 * C_, C_, scale=C_ ** -0.5)
+    w2 = (torch.randn(C_, 4 * C_, device="cuda") * (4 * C_) ** -0.5).to(torch.float16)
+    b1, b2 = torch.randn(4 * C_, device="cuda") * 0.3, torch.randn(C_, device="cuda") * 0.3
+    fgamma = 0.1 + 0.1 * torch.rand(C_, device="cuda")
+    out = torch.zeros_like(y)
+    out16 = torch.zeros(M, C_, device="cuda", dtype=torch.bfloat16)
+    rc = _cabi.lib().stts_test_ffn_fused(eng._h, _p(a), _p(y), M, C_, _p(w1), _p(b1), _p((w2 * 0.5).contiguous()), _p(b2),
+                                         _p(fgamma), _p(out), _p(out16))  # kernel takes 0.5*W2
+    _cabi.check(rc, eng._h)
+    torch.cuda.synchronize()
+    h = torch.nn.functional.gelu(a.float() @ w1.float().t() + b1).to(torch.float16).float()
+    want = y + fgamma * (h @ w2.float().t() + b2)
+    _assert_close(out, want, tol=2e-3)
+    _assert_close(out16, want, tol=1e-2)
