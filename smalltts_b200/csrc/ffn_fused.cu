@@ -10,9 +10,11 @@
 //
 //   warp  0     TMA producer : A tile (2 K-atoms, double buffered) + weight-chunk ring; the first weight stages are
 //                              requested before the PDL dependency wait (weights never depend on the predecessor)
-//   warp  1     MMA issuer   : H[c] = A W1c^T (8 x tcgen05.mma N=64) one chunk ahead of O += G[c] W2c^T (4 x N=128)
+//   warp  1     MMA1 issuer  : H[c] = A W1c^T (8 x tcgen05.mma N=64), runs ahead as far as the two H buffers allow
 //   warps 2-9   GELU         : tcgen05.ld H chunk -> +b1 -> packed-fp16 2*gelu -> swizzled G chunk (double buffered)
 //   warps 10-13 out          : tcgen05.ld O -> transposition buffer -> y + ffn_gamma*(O + b2) on 128-byte row segments
+//   warp  14    MMA2 issuer  : O += G[c] W2c^T (4 x N=128).  Two issuing warps because one thread's wait -> issue ->
+//                              commit chain (~400 clk per step) would otherwise pace the whole tile.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -29,7 +31,8 @@ constexpr int TM = 128;   // rows per tile
 constexpr int HC = 64;    // hidden columns per chunk
 constexpr int kWStages = 3;
 constexpr int kGeluWarp0 = 2, kOutWarp0 = 10;
-constexpr int kThreadsFfn = 14 * 32;
+constexpr int kMma2Warp = 14;
+constexpr int kThreadsFfn = 15 * 32;
 
 struct FfnParams {
   const float* y;     // residual rows [M, C]
@@ -176,65 +179,65 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ================================================================== MMA issuer
+    // ================================================================== MMA1 issuer: H chunks
     constexpr uint32_t idesc1 = ptx::umma_idesc_bf16(TM, HC);
+    uint32_t ws = 0, wph = 0;
+    int gc = 0;  // global chunk counter (H buffer = gc & 1, use count = gc >> 1)
+    for (int tl = 0; tl < n_my; ++tl) {
+      const int ab = tl & 1;
+      ptx::mbar_wait(&a_full[ab], (tl >> 1) & 1);
+      const uint64_t dA = ptx::umma_desc_sw128(ptx::smem_u32(Abuf(ab)));
+      for (int c = 0; c < F::NCH; ++c, ++gc) {
+        const int hb = gc & 1, n = gc >> 1;
+        ptx::mbar_wait(&w_full[ws], wph);
+        ptx::mbar_wait(&h_empty[hb], (n & 1) ^ 1);  // GELU warps have drained this H buffer
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t dW = ptx::umma_desc_sw128(ptx::smem_u32(Wbuf(ws)));
+#pragma unroll
+          for (int ka = 0; ka < F::KA; ++ka) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ptx::umma_bf16(tmem_base + F::TM_H + hb * HC, dA + ka * ((TM * 128) >> 4) + 2 * k,
+                             dW + ka * ((HC * 128) >> 4) + 2 * k, idesc1, (ka | k) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(&h_full[hb]);
+          if (c + 1 == F::NCH) ptx::umma_commit(&a_empty[ab]);  // every MMA1 of the tile issued: A is free when they complete
+        }
+        __syncwarp();
+        if (++ws == kWStages) { ws = 0; wph ^= 1; }
+      }
+    }
+  } else if (warp == kMma2Warp) {
+    // ================================================================== MMA2 issuer: O += G W2c^T
     // MMA2 operands (G and W2) are fp16: clear the two bf16 format fields of the descriptor
     constexpr uint32_t idesc2 = ptx::umma_idesc_bf16(TM, C) & ~((1u << 7) | (1u << 10));
-    uint32_t ws1 = 0, wph1 = 0;  // ring position of the next MMA1 chunk
-    uint32_t ws2 = 0;            // ring position of the next MMA2 chunk
-    int gc1 = 0, gc2 = 0;        // global chunk counters (H / G buffer = counter & 1, use count = counter >> 1)
-    auto mma1 = [&](int ab) {
-      const int hb = gc1 & 1, n = gc1 >> 1;
-      ptx::mbar_wait(&w_full[ws1], wph1);
-      ptx::mbar_wait(&h_empty[hb], (n & 1) ^ 1);  // GELU warps have drained this H buffer
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint64_t dA = ptx::umma_desc_sw128(ptx::smem_u32(Abuf(ab)));
-        const uint64_t dW = ptx::umma_desc_sw128(ptx::smem_u32(Wbuf(ws1)));
-#pragma unroll
-        for (int ka = 0; ka < F::KA; ++ka) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            ptx::umma_bf16(tmem_base + F::TM_H + hb * HC, dA + ka * ((TM * 128) >> 4) + 2 * k,
-                           dW + ka * ((HC * 128) >> 4) + 2 * k, idesc1, (ka | k) != 0 ? 1u : 0u);
-          }
-        }
-        ptx::umma_commit(&h_full[hb]);
-      }
-      __syncwarp();
-      ++gc1;
-      if (++ws1 == kWStages) { ws1 = 0; wph1 ^= 1; }
-    };
+    uint32_t ws = 0, wph = 0;
+    int gc = 0;
     for (int tl = 0; tl < n_my; ++tl) {
-      const int ab = tl & 1, ob = tl & 1;
-      ptx::mbar_wait(&a_full[ab], (tl >> 1) & 1);
+      const int ob = tl & 1;
       ptx::mbar_wait(&o_empty[ob], ((tl >> 1) & 1) ^ 1);  // out warps have drained O of tile tl-2
-      ptx::tc_fence_after();
-      mma1(ab);
-      for (int c = 0; c < F::NCH; ++c) {
-        if (c + 1 < F::NCH) mma1(ab);  // keep the GELU warps one chunk ahead of the second GEMM
-        if (c + 1 == F::NCH - 1 || F::NCH == 1) {
-          // every MMA1 of this tile has been issued: the A buffer is free once they complete
-          if (ptx::elect_one()) ptx::umma_commit(&a_empty[ab]);
-          __syncwarp();
-        }
-        const int gb = gc2 & 1, n = gc2 >> 1;
+      for (int c = 0; c < F::NCH; ++c, ++gc) {
+        const int gb = gc & 1, n = gc >> 1;
+        ptx::mbar_wait(&w_full[ws], wph);  // already complete (MMA1 of this chunk waited for it); orders the W2c read
         ptx::mbar_wait(&g_full[gb], n & 1);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t dG = ptx::umma_desc_sw128(ptx::smem_u32(Gbuf(gb)));
-          const uint64_t dW2 = ptx::umma_desc_sw128(ptx::smem_u32(Wbuf(ws2) + F::W1C_BYTES));
+          const uint64_t dW2 = ptx::umma_desc_sw128(ptx::smem_u32(Wbuf(ws) + F::W1C_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             ptx::umma_bf16(tmem_base + F::TM_O + ob * C, dG + 2 * k, dW2 + 2 * k, idesc2, (c | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&w_empty[ws2]);
+          // MMA1 of this chunk completed long ago (its result went through the GELU warps), so this commit alone
+          // releases the weight stage
+          ptx::umma_commit(&w_empty[ws]);
           ptx::umma_commit(&g_empty[gb]);
           if (c + 1 == F::NCH) ptx::umma_commit(&o_full[ob]);
         }
         __syncwarp();
-        ++gc2;
-        if (++ws2 == kWStages) ws2 = 0;
+        if (++ws == kWStages) { ws = 0; wph ^= 1; }
       }
     }
   } else if (warp < kOutWarp0) {
@@ -276,7 +279,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) ptx::mbar_arrive(&g_full[hb]);
       }
     }
-  } else {
+  } else if (warp < kMma2Warp) {
     // ================================================================== out: O (TMEM) + y -> global
     ptx::pdl_wait();  // reads y and writes out: both belong to the predecessor until it has completed
     const int q = warp & 3;
