@@ -1377,7 +1377,6 @@ int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, co
     const bool default_ts = (ts == p->ts);
     std::vector<const float*> mods = default_ts ? p->mods : prepare_mods(e, ts);
     const float* nd = noise ? p->noise : nullptr;
-    float* ad = mem == STTS_MEM_DEVICE ? audio : p->audio;
 
     auto run_cond = [&] { encode_conditions_core(e, &p->cond, p->ref, p->ids); };
     auto run_sample = [&](const float* nz) { sample(e, &p->cond, p->frames_dev, B, T, ts, mods, nz, e->seed_dev, p->lat); };
@@ -1398,7 +1397,6 @@ int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, co
     // the graphs write the plan's own audio buffer; hand the result to the caller
     const cudaMemcpyKind out_kind = mem == STTS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     CK(cudaMemcpyAsync(audio, p->audio, na * sizeof(float), out_kind, st));
-    (void)ad;
     CK(cudaEventRecord(e->ev[3], st));
     CK(cudaStreamSynchronize(st));
     e->timing.codec_enc_ms = 0.f;

@@ -754,7 +754,6 @@ __global__ void __launch_bounds__(256) convnext_mix_rows_kernel(const float* __r
   constexpr int TT = 16384 / C;  // 128 or 64 output rows per CTA
   constexpr int R = TT + 6, P = C + 4, CV = C / 4;
   constexpr int NSEG = 256 / C > 0 ? 256 / C : 1;  // time segments per channel (2 or 1)
-  constexpr int CPT = C > 256 ? C / 256 : 1;       // channels per thread
   constexpr int SEGLEN = TT / NSEG;
   extern __shared__ __align__(16) float smr[];
   float* tile = smr;          // [R][P]
@@ -812,7 +811,6 @@ __global__ void __launch_bounds__(256) convnext_mix_rows_kernel(const float* __r
       a0 = fmaf(w[6], win[6], a0);
       tile[r * P + c] = fmaf(gm, a0 + a1, xv);
     }
-    (void)CPT;
   }
   __syncthreads();
   if (tid < TT) {
