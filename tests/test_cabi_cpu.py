@@ -83,3 +83,4 @@ def test_synthetic_weights_have_reference_shapes():
     assert sum(int(np.prod(s)) for _, s, _, _ in synthetic.dit_specs()) == 327_756_609
     assert sum(int(np.prod(s)) for _, s, _, _ in synthetic.vocoder_specs()) == 343_695_969
     assert len(synthetic.dit_specs()) == 592 and len(synthetic.vocoder_specs()) == 276
+    assert sum(int(np.prod(s)) for _, s, _, _ in synthetic.encoder_specs()) == 343_696_032  # hf encoder
