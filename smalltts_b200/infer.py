@@ -146,8 +146,10 @@ class SmallTTS:
         return self.synthesize_batch([ref_latents], [phoneme_ids], [duration_sec], noise=noise)[0]
 
     def synthesize_batch(self, ref_latents: Sequence, phoneme_ids: Sequence[Sequence[int]],
-                         durations: Sequence[float], noise=None, seed: Optional[int] = None) -> List[np.ndarray]:
-        """Ragged batch in one engine call.  noise: optional (steps, B, Tmax, 64).  Returns [(1, frames_i*3200)]."""
+                         durations: Sequence[float], noise=None, seed: Optional[int] = None,
+                         device_out: bool = False) -> List[np.ndarray]:
+        """Ragged batch in one engine call.  noise: optional (steps, B, Tmax, 64).  Returns [(1, frames_i*3200)]
+        (numpy; with ``device_out`` torch CUDA views of the engine's output, for device-side gathers)."""
         if not (len(ref_latents) == len(phoneme_ids) == len(durations)) or len(durations) == 0:
             raise ValueError("ref_latents, phoneme_ids and durations must be equally long and non-empty")
         frames = [frames_for(d) for d in durations]
@@ -156,6 +158,14 @@ class SmallTTS:
         if seed is None:
             seed = self._seed + self._calls
         self._calls += 1
+        if device_out:
+            import torch
+
+            dev = f"cuda:{self.engine.device}"
+            audio = self.engine.synthesize(torch.from_numpy(ref).to(dev), ref_len, torch.from_numpy(ids).to(dev), ph_len,
+                                           frames, T, noise=None if noise is None else torch.as_tensor(noise).to(dev),
+                                           seed=seed, steps=self.num_steps)
+            return [audio[i : i + 1, : frames[i] * HOP_SIZE] for i in range(len(frames))]
         audio = self.engine.synthesize(ref, ref_len, ids, ph_len, frames, T, noise=noise, seed=seed,
                                        steps=self.num_steps)
         return [audio[i : i + 1, : frames[i] * HOP_SIZE].copy() for i in range(len(frames))]

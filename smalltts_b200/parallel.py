@@ -58,32 +58,40 @@ def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], f
                        world: int, group=None, gather_to: int = 0):
     """Run ``synthesize_fn`` on this rank's shard and gather every waveform to ``gather_to`` in input order.
 
-    synthesize_fn(indices) -> list of (1, frames_i*3200) float32 arrays for those utterances (on a GPU rank this is
-    ``lambda idx: tts.synthesize_batch([refs[i] for i in idx], ...)``).  Returns the full list on ``gather_to``,
+    synthesize_fn(indices) -> list of (1, frames_i*3200) float32 arrays (numpy, or torch CUDA tensors when the engine
+    leaves its output in HBM) for those utterances (on a GPU rank this is
+    ``lambda idx: tts.synthesize_batch([refs[i] for i in idx], ..., device_out=True)``).  Returns the full list on ``gather_to``,
     None elsewhere.  world == 1 needs no process group."""
     shards = partition_lpt([utterance_cost(f) for f in frames], world)
     mine = shards[rank]
     results = {}
     for mb in length_buckets(mine, frames):
         for i, a in zip(mb, synthesize_fn(list(mb))):
-            a = np.asarray(a, dtype=np.float32)
-            if a.shape != (1, frames[i] * HOP_SIZE):
-                raise ValueError(f"utterance {i}: expected {(1, frames[i] * HOP_SIZE)}, got {a.shape}")
+            if tuple(a.shape) != (1, frames[i] * HOP_SIZE):
+                raise ValueError(f"utterance {i}: expected {(1, frames[i] * HOP_SIZE)}, got {tuple(a.shape)}")
             results[i] = a
+    on_device = any(type(a).__module__.startswith("torch") and a.is_cuda for a in results.values())
+
+    def to_numpy(a):
+        return np.asarray(a.detach().cpu().numpy() if type(a).__module__.startswith("torch") else a, dtype=np.float32)
+
     if world == 1:
-        return [results[i] for i in range(len(frames))]
+        return [to_numpy(results[i]) for i in range(len(frames))]
     import torch
     import torch.distributed as dist
 
-    # one flat fp32 buffer per rank, sizes are known on every rank from `frames` (no size exchange needed)
+    # one flat fp32 buffer per rank, sizes are known on every rank from `frames` (no size exchange needed).  When the
+    # engine left the waveforms in HBM they are concatenated and sent from there (NCCL over NVLink, no host round trip).
     sizes = [sum(frames[i] for i in s) * HOP_SIZE for s in shards]
-    flat = np.concatenate([results[i].ravel() for i in mine]) if mine else np.zeros(0, np.float32)
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    send = torch.from_numpy(flat).to(dev)
+    if on_device and dev.type == "cuda":
+        send = torch.cat([results[i].reshape(-1) for i in mine]) if mine else torch.zeros(0, device=dev)
+    else:
+        flat = np.concatenate([to_numpy(results[i]).ravel() for i in mine]) if mine else np.zeros(0, np.float32)
+        send = torch.from_numpy(flat).to(dev)
     if rank == gather_to:
-        bufs = [torch.empty(n, dtype=torch.float32, device=dev) for n in sizes]
-        bufs[rank].copy_(send)
+        bufs = [torch.empty(n, dtype=torch.float32, device=dev) if r != rank else send for r, n in enumerate(sizes)]
         reqs = [dist.irecv(bufs[r], src=r, group=group) for r in range(world) if r != rank and sizes[r] > 0]
         for q in reqs:
             q.wait()
@@ -92,7 +100,7 @@ def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], f
             off, host = 0, bufs[r].cpu().numpy()
             for i in shards[r]:
                 n = frames[i] * HOP_SIZE
-                out[i] = host[off : off + n].reshape(1, n).copy()
+                out[i] = host[off : off + n].reshape(1, n)
                 off += n
         return out
     if sizes[rank] > 0:

@@ -37,7 +37,8 @@ tts = SmallTTS.synthetic(device=local)
 
 
 def fn(idx):
-    return tts.synthesize_batch([refs[i] for i in idx], [ids[i] for i in idx], [durs[i] for i in idx], seed=7)
+    return tts.synthesize_batch([refs[i] for i in idx], [ids[i] for i in idx], [durs[i] for i in idx], seed=7,
+                                device_out=world > 1)
 
 
 def barrier():
