@@ -128,6 +128,14 @@ int stts_decode(stts_engine* e, const float* latents, int B, int T, int mem, flo
  * Sets stts_timing.codec_enc_ms. */
 int stts_encode_audio(stts_engine* e, const float* audio, int B, int N, int mem, float* latents);
 
+/* High-quality resampler of the clone path: replaces `resample_hq` (infer/utils.py:7-23 == torchaudio
+ * Resample(resampling_method="sinc_interp_kaiser", lowpass_filter_width=1024, rolloff=0.94,
+ * beta=14.769656459379492), called by scripts/infer/clone.py:32 before Encoder.encode).  audio: fp32 [B, N] at
+ * sr_from; out: fp32 [B, stts_resample_length(N, sr_from, sr_to)] at sr_to.  The polyphase filter bank of a rate pair
+ * is built on first use and cached in the engine.  sr_from == sr_to copies.  Needs no model weights. */
+int64_t stts_resample_length(int N, int sr_from, int sr_to); /* ceil(N * sr_to / sr_from); -1 on bad arguments */
+int stts_resample(stts_engine* e, const float* audio, int B, int N, int sr_from, int sr_to, int mem, float* out);
+
 /* == SmallTTS.synthesize for a padded batch; intermediates never leave the device. audio: [B, T*3200]. */
 int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* phonemes,
                     const int64_t* ph_len, const int64_t* frames, int B, int R, int P, int T, int steps,

@@ -439,6 +439,50 @@ def codec_encode(esd: SD, audio: Tensor) -> Tensor:
     return x.permute(0, 2, 1)
 
 
+# ---------------------------------------------------------------------------------------------- resample_hq
+def resample_bank(sr_from: int, sr_to: int, lowpass_filter_width: int = 1024, rolloff: float = 0.94,
+                  beta: float = 14.769656459379492):
+    """Polyphase filter bank of the reference's ``make_resampler`` (infer/utils.py:8-16): torchaudio's
+    ``_get_sinc_resample_kernel`` for ``sinc_interp_kaiser``, restated.  Returns (bank fp32 [up, K], width, down, up).
+
+    bank[j, k] = sinc(pi t) * kaiser(t) * base/down with t = clamp((-j/up + (k - width)/down) * base, +-lpw),
+    base = min(down, up) * rolloff, width = ceil(lpw * down / base), K = 2 width + down; fp64 arithmetic rounded to
+    fp32 at the end, except that torchaudio forms -j/up from an integer tensor (fp32 division) and holds beta in a
+    fp32 tensor."""
+    g = math.gcd(int(sr_from), int(sr_to))
+    down, up = int(sr_from) // g, int(sr_to) // g
+    base = min(down, up) * rolloff
+    width = math.ceil(lowpass_filter_width * down / base)
+    k = np.arange(-width, width + down, dtype=np.float64) / down
+    phase = (np.arange(0, -up, -1, dtype=np.float32) / np.float32(up)).astype(np.float64)
+    t = (phase[:, None] + k[None, :]) * base
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    b32 = torch.tensor(float(beta))  # fp32, like torchaudio's beta_tensor
+    win = torch.i0(b32.double() * torch.sqrt(1 - torch.from_numpy(t / lowpass_filter_width) ** 2)) / torch.i0(b32).double()
+    t = t * math.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sinc = np.where(t == 0, 1.0, np.sin(t) / t)
+    bank = sinc * win.numpy() * (base / down)
+    return bank.astype(np.float32), width, down, up
+
+
+def resample_hq(x: np.ndarray, sr: int, target: int) -> np.ndarray:
+    """infer/utils.py:19-23 (torchaudio ``_apply_sinc_resample_kernel``): x fp32 [B, N] at ``sr`` -> [B, ceil(N *
+    target / sr)] at ``target``.  out[n*up + j] = sum_k bank[j, k] * xpad[n*down + k], xpad = x with ``width`` zeros in
+    front and ``width + down`` behind; products accumulated in fp64, result rounded to fp32."""
+    x = np.asarray(x, dtype=np.float32)
+    if sr == target:
+        return x
+    bank, width, down, up = resample_bank(sr, target)
+    B, N = x.shape
+    K = bank.shape[1]
+    xp = np.pad(x.astype(np.float64), ((0, 0), (width, width + down)))
+    win = np.lib.stride_tricks.sliding_window_view(xp, K, axis=1)[:, ::down]  # [B, frames, K]
+    y = np.einsum("bfk,jk->bfj", win, bank.astype(np.float64)).reshape(B, -1)
+    n_out = -((-up * N) // down)
+    return y[:, :n_out].astype(np.float32)
+
+
 def frames_for(duration_sec: float) -> int:
     """infer/onnx.py:84."""
     return max(1, int(duration_sec * SAMPLE_RATE / HOP_SIZE))

@@ -44,6 +44,8 @@ SIGNATURES = {
                                       C.c_int, vp]),
     "stts_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "stts_encode_audio": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "stts_resample_length": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "stts_resample": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "stts_synthesize": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                   C.c_uint64, C.c_int, vp]),
     "stts_get_timings": (C.c_int, [vp, C.POINTER(Timing)]),

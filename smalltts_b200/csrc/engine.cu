@@ -115,7 +115,7 @@ struct stts_engine {
   std::string err;
   std::map<std::string, RawTensor> raw[3];  // 0 = DiT, 1 = codec decoder (vocoder), 2 = codec encoder (optional)
   std::vector<void*> owned;  // packed buffers
-  bool finalized = false;
+  bool finalized = false, packed_once = false;
 
   // packed DiT-side weights
   EncW style, text;
@@ -137,12 +137,19 @@ struct stts_engine {
   const float *head_w, *head_b;
 
   // packed codec-encoder weights (model 2; only when its tensors were loaded)
-  bool has_encoder = false;
+  bool has_encoder = false, has_dit = false, has_decoder = false;
   std::vector<std::vector<VocLayerW>> enc;  // [7 stages][depth]
   bf16* enc_down_w[6];
   const float* enc_down_b[6];
   bf16* enc_head_w = nullptr;
   const float *enc_head_b = nullptr, *enc_stem_w = nullptr, *enc_stem_b = nullptr;
+
+  // resampler filter banks per reduced (down, up) rate pair (built on first use, stts_resample)
+  struct ResampleBank {
+    int down, up, width, K;
+    float* d;
+  };
+  std::map<std::pair<int, int>, ResampleBank> banks;
 
   // per-shape persistent plans (buffers + CUDA graphs) used by stts_synthesize
   std::map<std::array<int, 5>, Plan*> plans;
@@ -335,7 +342,7 @@ void build_rope(stts_engine* e, int rot, float** cos_d, float** sin_d) {
   CK(cudaStreamSynchronize(e->st));
 }
 
-void finalize(stts_engine* e) {
+void finalize_dit(stts_engine* e) {
   cudaStream_t st = e->st;
   // ---- style encoder (style.py:118-174).  exp(log_scale) (style.py:167) is folded into in_proj.
   float log_scale = 0.f;
@@ -438,7 +445,11 @@ void finalize(stts_engine* e) {
   e->vel_b = e->W(0, "velocity.bias", {LAT}).d;
   build_rope(e, 64, &e->cos64, &e->sin64);
   build_rope(e, 128, &e->cos128, &e->sin128);
+  e->has_dit = true;
+}
 
+void finalize_decoder(stts_engine* e) {
+  cudaStream_t st = e->st;
   // ---- vocoder (hf:406-500)
   e->stem_w = e->dalloc<bf16>(static_cast<size_t>(2048) * 7 * 64);
   CK(pack_conv_taps(st, e->W(1, "stem.conv.conv.weight", {2048, 64, 7}).d, 2048, 64, 7, 64, 2048, 2048, e->stem_w, 7 * 64));
@@ -463,8 +474,17 @@ void finalize(stts_engine* e) {
   }
   e->head_w = e->W(1, "head.conv.weight", {1, 32, 7}).d;
   e->head_b = e->W(1, "head.conv.bias", {1}).d;
+  e->has_decoder = true;
+}
+
+// Each of the three models is packed iff any of its tensors was loaded (and then all of them must be there): a
+// codec-only engine serves the reference's standalone Decoder / Encoder (codec/onnx.py:34-75, used alone by sv.py:24).
+void finalize(stts_engine* e) {
+  if (e->raw[0].empty() && e->raw[1].empty() && e->raw[2].empty()) throw Err(STTS_ERR_WEIGHTS, "no weights were loaded");
+  if (!e->raw[0].empty()) finalize_dit(e);
+  if (!e->raw[1].empty()) finalize_decoder(e);
   if (!e->raw[2].empty()) finalize_encoder(e);
-  CK(cudaStreamSynchronize(st));
+  CK(cudaStreamSynchronize(e->st));
   e->finalized = true;
 }
 
@@ -1046,8 +1066,76 @@ int guard_impl(stts_engine* e, const std::function<void()>& fn) {
     return STTS_ERR_INVALID;
   }
 }
-void need_ready(stts_engine* e) {
+// ------------------------------------------------------------------ resampler (infer/utils.py:7-23)
+double bessel_i0(double x) {  // sum_k ((x/2)^k / k!)^2
+  const double q = 0.25 * x * x;
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < 500; ++k) {
+    term *= q / (static_cast<double>(k) * k);
+    sum += term;
+    if (term < 1e-17 * sum) break;
+  }
+  return sum;
+}
+
+int gcd_int(int a, int b) {
+  while (b) {
+    const int t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+// torchaudio.functional._get_sinc_resample_kernel with the reference's arguments (resampling_method
+// "sinc_interp_kaiser", lowpass_filter_width 1024, rolloff 0.94, beta 14.769656459379492), evaluated in fp64 and
+// rounded to fp32 like torchaudio does (dtype=None).  Two fp32 roundings of the original are kept: the phase offsets
+// -j/up come from an integer tensor divided in fp32, and beta is a fp32 tensor.
+const stts_engine::ResampleBank& resample_bank(stts_engine* e, int sr_from, int sr_to) {
+  const int g = gcd_int(sr_from, sr_to);
+  const int down = sr_from / g, up = sr_to / g;
+  auto it = e->banks.find({down, up});
+  if (it != e->banks.end()) return it->second;
+  const double lpw = 1024.0, rolloff = 0.94;
+  const double beta = static_cast<double>(static_cast<float>(14.769656459379492));
+  const double base_freq = static_cast<double>(down < up ? down : up) * rolloff;
+  const int width = static_cast<int>(ceil(lpw * down / base_freq));
+  const long long K = 2LL * width + down;
+  const long long smem = (31LL * down + K) * 4;
+  if (smem > 200 * 1024 || K * up > (64LL << 20)) {
+    throw Err(STTS_ERR_INVALID, "unsupported sample-rate pair: the reduced ratio " + std::to_string(down) + ":" +
+                                    std::to_string(up) + " needs a " + std::to_string(K) + "-tap x " + std::to_string(up) +
+                                    "-phase filter bank");
+  }
+  std::vector<float> h(static_cast<size_t>(K) * up);
+  const double i0b = bessel_i0(beta), scale = base_freq / down, pi = 3.14159265358979323846;
+  for (int j = 0; j < up; ++j) {
+    const double phase = static_cast<double>(static_cast<float>(-j) / static_cast<float>(up));
+    for (long long k = 0; k < K; ++k) {
+      double t = (phase + static_cast<double>(k - width) / down) * base_freq;
+      t = t < -lpw ? -lpw : (t > lpw ? lpw : t);
+      const double r = t / lpw;
+      const double win = bessel_i0(beta * sqrt(1.0 - r * r)) / i0b;
+      t *= pi;
+      const double sinc = t == 0.0 ? 1.0 : sin(t) / t;
+      h[static_cast<size_t>(j) * K + k] = static_cast<float>(sinc * win * scale);
+    }
+  }
+  stts_engine::ResampleBank bk;
+  bk.down = down;
+  bk.up = up;
+  bk.width = width;
+  bk.K = static_cast<int>(K);
+  bk.d = e->dalloc<float>(h.size(), false);
+  CK(cudaMemcpyAsync(bk.d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  CK(cudaStreamSynchronize(e->st));  // h goes out of scope
+  return e->banks.emplace(std::make_pair(down, up), bk).first->second;
+}
+
+void need_ready(stts_engine* e, bool dit = false, bool decoder = false) {
   if (!e->finalized) throw Err(STTS_ERR_WEIGHTS, "weights not finalized: call stts_finalize_weights first");
+  if (dit && !e->has_dit) throw Err(STTS_ERR_WEIGHTS, "DiT weights (model 0) were not loaded");
+  if (decoder && !e->has_decoder) throw Err(STTS_ERR_WEIGHTS, "codec decoder weights (model 1) were not loaded");
 }
 }  // namespace
 
@@ -1146,7 +1234,8 @@ int stts_finalize_weights(stts_engine* e) {
   if (!e) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
     if (e->finalized) return;
-    if (!e->blk.empty()) throw Err(STTS_ERR_WEIGHTS, "weights were already finalized once; create a new engine");
+    if (e->packed_once) throw Err(STTS_ERR_WEIGHTS, "weights were already finalized once; create a new engine");
+    e->packed_once = true;
     finalize(e);
   });
 }
@@ -1156,7 +1245,7 @@ int stts_encode_conditions(stts_engine* e, const float* ref, const int64_t* ref_
   if (!e || !out) return STTS_ERR_INVALID;
   *out = nullptr;
   return guard_impl(e, [&] {
-    need_ready(e);
+    need_ready(e, true);
     *out = encode_conditions(e, ref, ref_len, phonemes, ph_len, B, R, P, mem);
   });
 }
@@ -1193,7 +1282,7 @@ int stts_denoise_step(stts_engine* e, const stts_cond* c, const float* x_t, cons
                       int B, int T, int mem, float* velocity) {
   if (!e || !c || !x_t || !frames || !t || !velocity) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
-    need_ready(e);
+    need_ready(e, true);
     if (B != c->B || T < 1 || T > ROPE_MAX) throw Err(STTS_ERR_INVALID, "batch/T mismatch with conditions");
     cudaStream_t st = e->st;
     const long long n = static_cast<long long>(B) * T * LAT;
@@ -1235,7 +1324,7 @@ int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B
                 const float* timesteps, const float* noise, uint64_t seed, int mem, float* out_latents) {
   if (!e || !c || !frames || !out_latents) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
-    need_ready(e);
+    need_ready(e, true);
     if (B != c->B || T < 1 || T > ROPE_MAX || steps < 1) throw Err(STTS_ERR_INVALID, "bad sample arguments");
     cudaStream_t st = e->st;
     const long long n = static_cast<long long>(B) * T * LAT;
@@ -1262,7 +1351,7 @@ int stts_sample_teacher(stts_engine* e, const stts_cond* cond3, const int64_t* f
                         float* out_latents) {
   if (!e || !cond3 || !frames || !out_latents) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
-    need_ready(e);
+    need_ready(e, true);
     if (B < 1 || cond3->B != 3 * B || T < 1 || T > ROPE_MAX || steps < 1 || steps > 4096) {
       throw Err(STTS_ERR_INVALID, "bad teacher-sampler arguments (conditions must hold 3*B rows: cond | no text | no speaker)");
     }
@@ -1289,7 +1378,7 @@ int stts_sample_teacher(stts_engine* e, const stts_cond* cond3, const int64_t* f
 int stts_decode(stts_engine* e, const float* latents, int B, int T, int mem, float* audio) {
   if (!e || !latents || !audio) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
-    need_ready(e);
+    need_ready(e, false, true);
     if (B < 1 || T < 1) throw Err(STTS_ERR_INVALID, "bad decode arguments");
     cudaStream_t st = e->st;
     const long long n = static_cast<long long>(B) * T * LAT;
@@ -1342,12 +1431,46 @@ int stts_encode_audio(stts_engine* e, const float* audio, int B, int N, int mem,
   });
 }
 
+int64_t stts_resample_length(int N, int sr_from, int sr_to) {
+  if (N < 0 || sr_from < 1 || sr_to < 1) return -1;
+  const int g = gcd_int(sr_from, sr_to);
+  const long long down = sr_from / g, up = sr_to / g;
+  return (up * static_cast<long long>(N) + down - 1) / down;  // ceil(up * N / down), torchaudio target_length
+}
+
+int stts_resample(stts_engine* e, const float* audio, int B, int N, int sr_from, int sr_to, int mem, float* out) {
+  if (!e || !audio || !out) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    if (B < 1 || N < 1 || sr_from < 1 || sr_to < 1) throw Err(STTS_ERR_INVALID, "bad resample arguments");
+    cudaStream_t st = e->st;
+    const long long n_out = stts_resample_length(N, sr_from, sr_to);
+    if (n_out < 1 || n_out > 0x7fffffffLL) throw Err(STTS_ERR_INVALID, "resampled length out of range");
+    const size_t n_in_all = static_cast<size_t>(B) * N, n_out_all = static_cast<size_t>(B) * n_out;
+    if (sr_from == sr_to) {  // resample_hq returns its input (infer/utils.py:20-21)
+      CK(cudaMemcpyAsync(out, audio, n_in_all * sizeof(float), cudaMemcpyDefault, st));
+      CK(cudaStreamSynchronize(st));
+      return;
+    }
+    const stts_engine::ResampleBank& bk = resample_bank(e, sr_from, sr_to);
+    Tmp<float> hin, hout;
+    const float* xd = to_dev(e, audio, n_in_all, mem, hin);
+    float* od = out;
+    if (mem == STTS_MEM_HOST) {
+      hout.alloc(st, n_out_all);
+      od = hout;
+    }
+    CK(resample(st, xd, B, N, bk.d, bk.K, bk.width, bk.down, bk.up, od, static_cast<int>(n_out)));
+    if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(out, od, n_out_all * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
 int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, const int64_t* phonemes,
                     const int64_t* ph_len, const int64_t* frames, int B, int R, int P, int T, int steps,
                     const float* timesteps, const float* noise, uint64_t seed, int mem, float* audio) {
   if (!e || !ref || !ref_len || !phonemes || !ph_len || !frames || !audio) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
-    need_ready(e);
+    need_ready(e, true, true);
     if (B < 1 || R < 1 || P < 1 || R > ROPE_MAX || P > ROPE_MAX || T < 1 || T > ROPE_MAX || steps < 1) {
       throw Err(STTS_ERR_INVALID, "bad synthesize arguments");
     }

@@ -103,6 +103,11 @@ cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, cons
 cudaError_t audio_stem_conv(cudaStream_t st, const float* audio, int B, int N, int C, const float* w, const float* bias,
                             float* out);
 
+// polyphase FIR resampler (infer/utils.py:7-23 == torchaudio sinc_interp_kaiser): x fp32 [B, N] -> out fp32 [B, out_len],
+// out[n*up + j] = sum_k bank[j, k] * x[n*down + k - width];  bank fp32 [up, K], K = 2*width + down
+cudaError_t resample(cudaStream_t st, const float* x, int B, int N, const float* bank, int K, int width, int down, int up,
+                     float* out, int out_len);
+
 // ---- weight packing (run once at stts_finalize_weights)
 enum PackRow : int { ROW_PLAIN = 0, ROW_INTERLEAVE16_LO = 1, ROW_INTERLEAVE16_HI = 2, ROW_GROUPPAD_60_64 = 3 };
 enum PackCol : int { COL_PLAIN = 0, COL_HEADPAD_120_128 = 1 };

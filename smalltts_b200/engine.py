@@ -76,11 +76,13 @@ class Engine:
         self._ready = False
 
     # ------------------------------------------------------------------ weights
-    def load_state_dicts(self, dit_sd: Dict[str, "np.ndarray"], vocoder_sd: Dict[str, "np.ndarray"],
+    def load_state_dicts(self, dit_sd: Optional[Dict[str, "np.ndarray"]], vocoder_sd: Optional[Dict[str, "np.ndarray"]],
                          encoder_sd: Optional[Dict[str, "np.ndarray"]] = None) -> None:
         """fp32 tensors under the reference's own key names (DiTModel.state_dict(), HF decoder state_dict() and,
-        optionally, HF encoder state_dict() for the clone path)."""
-        for model, sd in ((0, dit_sd), (1, vocoder_sd), (2, encoder_sd or {})):
+        optionally, HF encoder state_dict() for the clone path).  Any model may be None: an engine with only the
+        codec models serves the standalone ``Decoder`` / ``Encoder`` (codec/onnx.py:34-75); operators of a model
+        that was not loaded raise."""
+        for model, sd in ((0, dit_sd or {}), (1, vocoder_sd or {}), (2, encoder_sd or {})):
             for name, t in sd.items():
                 a = t.detach().cpu().numpy() if _is_torch(t) else np.asarray(t)
                 a = np.require(a, dtype=np.float32, requirements=["C"])  # keeps 0-d tensors 0-d
@@ -173,6 +175,20 @@ class Engine:
         ap, mem, keep = _buf(audio, np.float32, "audio")
         out, op = self._out_like(audio, (B, n // HOP_SIZE, LATENT_DIM), mem)
         _cabi.check(self._lib.stts_encode_audio(self._h, ap, B, n, mem, op), self._h)
+        return out
+
+    def resample(self, audio, sr_from: int, sr_to: int = 24_000):
+        """``resample_hq`` (infer/utils.py:7-23) on the device: audio (B, N) fp32 at ``sr_from`` ->
+        (B, ceil(N * sr_to / sr_from)).  numpy in -> numpy out; cuda tensor in -> cuda tensor out."""
+        if audio.ndim != 2:
+            raise ValueError(f"audio must be (B, N), got {tuple(audio.shape)}")
+        B, N = audio.shape
+        n_out = int(self._lib.stts_resample_length(N, int(sr_from), int(sr_to)))
+        if n_out < 1:
+            raise ValueError("bad resample arguments")
+        ap, mem, keep = _buf(audio, np.float32, "audio")
+        out, op = self._out_like(audio, (B, n_out), mem)
+        _cabi.check(self._lib.stts_resample(self._h, ap, B, N, int(sr_from), int(sr_to), mem, op), self._h)
         return out
 
     def decode(self, latents):

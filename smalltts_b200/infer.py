@@ -4,9 +4,10 @@ B200 engine behind the C ABI (no onnxruntime, no PyTorch ops, no CPU fallback).
 
 Differences a caller can see, all additive:
   * the three path arguments point at weight files instead of ``.onnx`` graphs: ``cond_encoder_path`` /
-    ``denoiser_path`` name the DiT checkpoint (``.pt`` / ``.safetensors`` with ``DiTModel.state_dict()`` keys; both
-    graphs of the reference are exports of that one model, so the two paths normally coincide) and
-    ``codec_decoder_path`` the VibeVoice decoder weights (HF ``state_dict`` keys);
+    ``denoiser_path`` name the DiT checkpoint(s) -- ``.pt`` / ``.safetensors`` / ``.sttsw`` with
+    ``DiTModel.state_dict()`` keys, or the reference's own ``condition_encoder.onnx`` + ``denoiser.onnx``, whose
+    initialisers are read directly (``smalltts_b200/weights.py``; both graphs are exports of that one model) -- and
+    ``codec_decoder_path`` the VibeVoice decoder weights (HF ``state_dict`` keys or ``decoder.onnx``);
   * ``synthesize_batch`` runs a ragged batch in ONE engine call (the reference loops, infer/onnx.py:143-156);
   * ``noise=`` / ``seed=`` make the DMD loop reproducible (the reference draws from the global numpy RNG).
 """
@@ -35,38 +36,7 @@ def frames_for(duration_sec: float) -> int:
     return max(1, int(duration_sec * SAMPLE_RATE / HOP_SIZE))
 
 
-_PREFIXES = ("ema_model.", "module.", "_orig_mod.", "online_model.")  # scripts/train/dmd2/distill.py:39-57
-
-
-def load_state_dict_file(path: str, container_keys: Sequence[str] = ("student_model", "model", "state_dict")) -> Dict:
-    """Read a ``.pt`` / ``.safetensors`` checkpoint into {name: tensor}; strips the wrapper prefixes the reference's
-    trainers leave behind and drops their ``initted`` / ``step`` extras (distill.py:39-57,468-470)."""
-    if not os.path.exists(path):
-        raise FileNotFoundError(path)
-    if path.endswith(".safetensors"):
-        from safetensors.torch import load_file
-
-        sd = load_file(path)
-    else:
-        import torch
-
-        sd = torch.load(path, map_location="cpu", weights_only=True)
-        for k in container_keys:
-            if isinstance(sd, dict) and k in sd and isinstance(sd[k], dict):
-                sd = sd[k]
-                break
-    out = {}
-    for k, v in sd.items():
-        changed = True
-        while changed:
-            changed = False
-            for p in _PREFIXES:
-                if k.startswith(p):
-                    k, changed = k[len(p):], True
-        if k in ("initted", "step"):
-            continue
-        out[k] = v
-    return out
+from .weights import dit_exec_rank, load_model_weights, load_state_dict_file  # noqa: F401  (re-exported)
 
 
 def _tokens(x) -> List[int]:
@@ -101,14 +71,14 @@ class SmallTTS:
         self._seed = 0 if seed is None else int(seed)
         self._calls = 0
         if state_dicts is None:
-            if denoiser_path is not None and os.path.abspath(denoiser_path) != os.path.abspath(cond_encoder_path):
-                dit = load_state_dict_file(cond_encoder_path)
-                dit.update(load_state_dict_file(denoiser_path))
-            else:
-                dit = load_state_dict_file(cond_encoder_path)
-            state_dicts = (dit, load_state_dict_file(codec_decoder_path))
+            from . import synthetic
+
+            # both DiT graphs of the reference are exports of one DiTModel (infer/onnx.py:60-62): merge their tensors
+            dit_files = [cond_encoder_path] + ([denoiser_path] if denoiser_path is not None else [])
+            state_dicts = (load_model_weights(dit_files, synthetic.dit_specs(), "DiTModel", exec_rank=dit_exec_rank),
+                           load_model_weights([codec_decoder_path], synthetic.vocoder_specs(), "codec decoder"))
             if codec_encoder_path is not None:
-                state_dicts += (load_state_dict_file(codec_encoder_path),)
+                state_dicts += (load_model_weights([codec_encoder_path], synthetic.encoder_specs(), "codec encoder"),)
         self.engine = Engine(device)
         self.engine.load_state_dicts(*state_dicts)
 
@@ -123,17 +93,17 @@ class SmallTTS:
         return cls(state_dicts=sds, **kw)
 
     def clone_voice(self, wav, sample_rate: int = SAMPLE_RATE):
-        """scripts/infer/clone.py:27-36: mono wav (N,) or (1,N) at `sample_rate` -> reference latents (R,64) on the
-        engine's codec encoder.  Resampling to 24 kHz (infer/utils.py:7-23, torchaudio kaiser sinc) stays on the host."""
+        """scripts/infer/clone.py:27-36: wav (N,), (1,N) or (channels,N) at `sample_rate` -> reference latents (R,64).
+        Down-mix to mono (clone.py:29-30), ``resample_hq`` to 24 kHz (infer/utils.py:7-23) and the codec encoder all
+        run on the engine; the resampled audio never returns to the host."""
         import torch
 
-        x = torch.as_tensor(np.asarray(wav, dtype=np.float32)).reshape(1, -1)
+        x = torch.as_tensor(np.asarray(wav, dtype=np.float32))
+        x = x.reshape(1, -1) if x.ndim == 1 else x.mean(dim=0, keepdim=True)
+        x = x.to(f"cuda:{self.engine.device}")
         if sample_rate != SAMPLE_RATE:
-            from torchaudio.transforms import Resample
-
-            x = Resample(orig_freq=sample_rate, new_freq=SAMPLE_RATE, resampling_method="sinc_interp_kaiser",
-                         lowpass_filter_width=1024, rolloff=0.94, beta=14.769656459379492)(x)
-        return self.engine.encode_audio(x.numpy())[0]
+            x = self.engine.resample(x, sample_rate, SAMPLE_RATE)
+        return self.engine.encode_audio(x)[0].cpu().numpy()
 
     # ------------------------------------------------------------------ reference API
     def synthesize(self, ref_latents: np.ndarray, phoneme_ids: List[int], duration_sec: float,

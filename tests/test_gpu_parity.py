@@ -297,3 +297,99 @@ def test_invalid_arguments_raise(tts):
         tts.engine.synthesize(np.zeros((1, 3, 64), np.float32), [3], np.zeros((1, 5), np.int64), [5], [0], 4)  # 0 frames
     with pytest.raises((ValueError, RuntimeError)):
         tts.engine.encode_audio(np.zeros((1, 6400), np.float32))  # this engine carries no encoder weights
+
+
+# ------------------------------------------------------------------ clone path: resampler + standalone codec classes
+TOL_RESAMPLE = 2e-5  # abs, unit-amplitude signals: fp32 accumulation over ~4k filter taps (torchaudio itself: 2e-6 vs fp64)
+
+
+def test_resample_hq_vs_reference_fixture(tts):
+    """stts_resample vs the reference's own resample_hq outputs (tests/golden/resample_small.npz, made by
+    oracle/make_golden_resample.py) at the common wav rates; host and device buffers."""
+    import torch
+
+    g = _load("resample_small.npz")
+    for sr in (44100, 48000, 16000, 22050, 8000, 32000):
+        x, want = g[f"x_{sr}"], g[f"y_{sr}"]
+        y = tts.engine.resample(x, sr, 24000)
+        assert y.shape == want.shape and y.dtype == np.float32
+        err = float(np.abs(y - want).max())
+        print("resample", sr, "max abs err", err)
+        assert err <= TOL_RESAMPLE, sr
+        yd = tts.engine.resample(torch.from_numpy(x).cuda(), sr, 24000)
+        assert yd.is_cuda and float(np.abs(yd.cpu().numpy() - y).max()) <= 1e-7
+    same = tts.engine.resample(g["x_8000"], 24000, 24000)
+    assert np.array_equal(same, g["x_8000"])  # infer/utils.py:20-21
+
+
+def test_resample_hq_long_clip_vs_oracle_and_errors(tts):
+    """A 3 s clip at 44.1 kHz (clone.py's typical input; 80 phases x 4151 taps, several CTAs per phase group) against
+    the fp64 oracle; unsupported rate pairs fail loudly instead of allocating a gigantic filter bank."""
+    import torch
+
+    from oracle import smalltts_oracle as O
+
+    g = torch.Generator().manual_seed(77)
+    x = (0.3 * torch.randn(1, 3 * 44100 + 13, generator=g)).numpy()
+    y = tts.engine.resample(x, 44100, 24000)
+    want = O.resample_hq(x, 44100, 24000)
+    assert y.shape == want.shape == (1, 72008)
+    assert float(np.abs(y - want).max()) <= TOL_RESAMPLE
+    with pytest.raises(ValueError):
+        tts.engine.resample(x, 44101, 24000)  # coprime rates: a 24000-phase bank
+    with pytest.raises(ValueError):
+        tts.engine.resample(x[0], 44100, 24000)  # not (B, N)
+
+
+def test_clone_voice_resamples_on_device(tts_enc):
+    """clone.py:27-36 with a 44.1 kHz stereo wav: down-mix, resample_hq, encode -- all on the engine -- equals the
+    encoder applied to the oracle's resampled audio."""
+    import torch
+
+    from oracle import smalltts_oracle as O
+
+    g = torch.Generator().manual_seed(8)
+    wav = (0.2 * torch.randn(2, 2 * 44100, generator=g)).numpy()
+    ref = tts_enc.clone_voice(wav, sample_rate=44100)
+    mono24 = O.resample_hq(wav.mean(0, keepdims=True), 44100, 24000)
+    want = tts_enc.engine.encode_audio(mono24)[0]
+    assert ref.shape == want.shape == (15, 64)
+    assert rel_l2(ref, want) <= 1e-3
+
+    from smalltts_b200.utils import resample_hq
+
+    y = resample_hq(torch.from_numpy(wav), 44100, 24000, engine=tts_enc.engine)
+    assert tuple(y.shape) == (2, 48000) and y.dtype == torch.float32
+    assert resample_hq(y, 24000, 24000) is y
+
+
+def test_standalone_codec_classes_run_on_codec_only_engines(tts, tts_enc, voc_sd):
+    """codec/onnx.py:34-75: Decoder / Encoder are usable without a DiT (sv.py:24).  A codec-only engine gives the
+    same audio as the full engine and refuses the DiT operators loudly."""
+    import torch
+
+    from smalltts_b200 import synthetic
+    from smalltts_b200.codec import Decoder, Encoder
+
+    g = torch.Generator().manual_seed(9)
+    lat = torch.randn(2, 4, 64, generator=g)
+    dec = Decoder(state_dict=voc_sd)
+    audio = dec.decode(lat)
+    assert tuple(audio.shape) == (2, 1, 4 * 3200)
+    assert rel_l2(audio[:, 0].numpy(), tts.engine.decode(lat.numpy())) <= 1e-6
+    with pytest.raises(RuntimeError, match="not loaded"):
+        dec.engine.encode_conditions(np.zeros((1, 2, 64), np.float32), [2], np.ones((1, 3), np.int64), [3])
+    with pytest.raises(RuntimeError, match="not loaded"):
+        dec.engine.encode_audio(np.zeros((1, 3200), np.float32))
+    dec.engine.close()
+
+    enc = Encoder(state_dict=synthetic.encoder_state_dict(2))
+    wav = 0.3 * torch.randn(1, 1, 2 * 3200, generator=g)
+    lat2 = enc.encode(wav)
+    assert tuple(lat2.shape) == (1, 2, 64)
+    assert rel_l2(lat2.numpy(), tts_enc.engine.encode_audio(wav.numpy())) <= 1e-6
+    with pytest.raises(RuntimeError, match="not loaded"):
+        enc.engine.decode(lat.numpy())
+    enc.engine.close()
+    shared = Decoder(engine=tts.engine)
+    assert rel_l2(shared.decode(lat.cuda()).cpu().numpy(), audio.numpy()) <= 1e-6

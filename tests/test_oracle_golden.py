@@ -119,3 +119,28 @@ def test_codec_encoder_matches_reference():
     _close(lat, g["latents"], atol=2e-5)
     lat1 = O.codec_encode(esd, torch.tensor(g["audio"][:, :, :3200 + 1234]))  # a ragged tail is floored away
     _close(lat1, g["latents"][:, :1], atol=2e-5)
+
+
+def test_resample_hq_oracle_vs_reference_fixture():
+    """infer/utils.py:7-23: the fixture was produced by the reference's own resample_hq (torchaudio, fp32 conv1d);
+    the restatement accumulates in fp64, so the difference is torchaudio's fp32 summation error over ~4k taps."""
+    g = np.load(os.path.join(GOLDEN, "resample_small.npz"))
+    for sr in (44100, 48000, 16000, 22050, 8000, 32000):
+        y = O.resample_hq(g[f"x_{sr}"], sr, 24000)
+        assert y.shape == g[f"y_{sr}"].shape, sr
+        assert float(np.abs(y - g[f"y_{sr}"]).max()) <= 5e-6, sr
+    x = g["x_16000"]
+    assert O.resample_hq(x, 24000, 24000) is not None and np.array_equal(O.resample_hq(x, 24000, 24000), x)
+
+
+def test_resample_bank_shape_and_dc_gain():
+    """Filter-bank facts the CUDA side relies on: K = 2*width + down taps per phase, `up` phases, and every phase
+    sums to ~1 (unit DC gain: a constant signal stays constant away from the edges)."""
+    for a, b in ((44100, 24000), (48000, 24000), (16000, 24000), (22050, 24000)):
+        bank, width, down, up = O.resample_bank(a, b)
+        assert bank.shape == (up, 2 * width + down) and bank.dtype == np.float32
+        assert np.allclose(bank.astype(np.float64).sum(1), 1.0, atol=2e-3), (a, b)
+    n = 30000
+    y = O.resample_hq(np.ones((1, n), np.float32), 44100, 24000)
+    mid = y[0, 4000:-4000]
+    assert np.abs(mid - 1.0).max() < 2e-3
