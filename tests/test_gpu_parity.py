@@ -393,3 +393,37 @@ def test_standalone_codec_classes_run_on_codec_only_engines(tts, tts_enc, voc_sd
     enc.engine.close()
     shared = Decoder(engine=tts.engine)
     assert rel_l2(shared.decode(lat.cuda()).cpu().numpy(), audio.numpy()) <= 1e-6
+
+
+def test_serving_pipeline_and_microbatcher(tts_enc):
+    """pipeline.rs:60-112 on the engine: synthesize_timed returns ceil(duration*7.5) frames of audio and the stage
+    timings; requests submitted together share one engine pass and each equals its solo result (same seed)."""
+    import torch
+
+    from smalltts_b200 import serve
+
+    g = torch.Generator().manual_seed(31)
+    refs = [(0.2 * torch.randn(n, generator=g)).numpy() for n in (2 * 24000, 24000 + 500, 3 * 24000)]
+    toks = [[5, 9, 20, 33], [7, 7, 12], [101, 3, 44, 9, 2]]
+    durs = [1.01, 0.5, 2.0]
+    pipe = serve.Pipeline(tts_enc)
+    tts_enc._seed, tts_enc._calls = 123, 0
+    audio, tm = pipe.synthesize_timed(refs[0], toks[0], durs[0])
+    assert audio.shape == (8 * 3200,) and np.isfinite(audio).all()  # ceil(1.01 * 7.5) = 8 frames
+    assert tm.codec_enc_ms > 0 and tm.cond_enc_ms > 0 and tm.denoise_ms > 0 and tm.codec_dec_ms > 0
+    assert tm.total_ms >= tm.codec_enc_ms + tm.cond_enc_ms + tm.denoise_ms + tm.codec_dec_ms - 1e-3
+
+    tts_enc._calls = 0
+    many, tm3 = pipe.synthesize_many(refs, toks, durs)
+    assert [a.shape[0] for a in many] == [8 * 3200, 4 * 3200, 15 * 3200] and tm3.batch == 3
+
+    b = serve.MicroBatcher(pipe.synthesize_many, max_batch=4, max_wait_ms=500)
+    try:
+        tts_enc._calls = 0
+        futs = [b.submit(r, t, d) for r, t, d in zip(refs, toks, durs)]
+        res = [f.result(120) for f in futs]
+    finally:
+        b.close()
+    assert b.batches_run == 1 and res[0][1].batch == 3
+    for (a, _), want in zip(res, many):
+        assert rel_l2(a, want) <= 1e-6  # same seed, same batch composition -> same pass
