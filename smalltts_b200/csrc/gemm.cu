@@ -29,11 +29,15 @@ constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr int kActGelu2 = 100;  // kernel-internal: ACT_GELU with GemmEpi::gelu2_f16 (own instantiation, no general path)
 constexpr int kStageBytes = 4096;  // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled (no padding)
 
-template <int BN>
+// CTAS = 2: a CTA pair (cluster of two CTAs on the SMs of one TPC) computes a 256 x BN tile with cta_group::2 MMAs; each
+// CTA stages its own 128 rows of A and BN/2 rows of W, so one SM ingests 16 KB + BN*64 B per k-iteration instead of
+// 16 KB + BN*128 B for the same 128 x BN x 64 MMA work (the per-SM L2 pull rate is what limits the large GEMMs).
+template <int BN, int CTAS = 1>
 struct Cfg {
-  static constexpr int kMaxStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);  // one persistent CTA per SM
+  static constexpr int kBRows = BN / CTAS;  // W rows staged by one CTA
+  static constexpr int kMaxStages = (kBRows == 256) ? 4 : (kBRows == 128 ? 6 : 8);  // one persistent CTA per SM
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int smem_bytes(int stages) {
     // <= 12 barriers + slot, then 4 KB of transposition staging per epilogue warp
     return stages * (kABytes + kBBytes) + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kStageBytes;
@@ -98,11 +102,15 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
 // Persistent CTA: walks output tiles (tile = blockIdx.x + i * gridDim.x; n fastest, so concurrently running CTAs share
 // A rows in L2).  The smem ring runs ahead across tile boundaries and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
-template <int BN, int ACT>
+template <int BN, int ACT, int CTAS = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmShape s,
             const GemmEpi e, const int kStages, const int n_tiles, const int m_tiles, const int total_tiles) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
+  constexpr int BMS = BM * CTAS;  // rows of the (pair's) tile
+  // pair mode: rank 0 is the leader (issues the MMAs, owns the barriers the issuer waits on); both CTAs walk the
+  // same tile sequence, CTA `rank` owns rows [rank*128, +128) of each 256-row tile and W rows [rank*BN/2, +BN/2)
+  const uint32_t rank = CTAS == 2 ? ptx::cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -118,10 +126,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_t = (s.T + BM - 1) / BM;
+  const int tiles_t = (s.T + BMS - 1) / BMS;
   const int kchunks = (s.K + BK - 1) / BK;
   const int iters = s.taps * kchunks;
-  const int first = blockIdx.x, stride = gridDim.x;
+  const int first = blockIdx.x / CTAS, stride = gridDim.x / CTAS;
   const int n_my = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
 
   if (warp == 0 && lane == 0) {
@@ -133,15 +141,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&acc_empty[i], kEpiWarps);
+      ptx::mbar_init(&acc_empty[i], kEpiWarps * CTAS);  // pair: the epilogue warps of both CTAs release the leader's copy
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc<2 * BN>(tmem_slot);
+    if constexpr (CTAS == 2) ptx::tmem_alloc_pair<2 * BN>(tmem_slot);
+    else ptx::tmem_alloc<2 * BN>(tmem_slot);
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) ptx::cluster_sync();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail.
@@ -149,7 +159,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // waiting; everything else that touches global memory (A operand, residual, outputs) comes after the wait.
   ptx::pdl_trigger();
   int w_pre = 0;  // stages of the first tile whose W box is already in flight (producer warp only)
-  if (warp == 0 && n_my > 0) {
+  if (CTAS == 1 && warp == 0 && n_my > 0) {
     w_pre = iters < kStages ? iters : kStages;
     if (ptx::elect_one()) {
       const int tile = first;
@@ -173,16 +183,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int li = 0; li < n_my; ++li) {
       const int tile = first + li * stride;
       const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
-      const int b = my / tiles_t, t0 = (my % tiles_t) * BM, n0 = nx * BN;
-      const int a_col0 = g * s.a_group_koff, w_row = g * s.w_group_rows + n0;
+      const int b = my / tiles_t, t0 = (my % tiles_t) * BMS + static_cast<int>(rank) * BM, n0 = nx * BN;
+      const int a_col0 = g * s.a_group_koff, w_row = g * s.w_group_rows + n0 + static_cast<int>(rank) * C::kBRows;
       int kc = 0, a_row = t0 + s.tap_shift0;
       for (int it = 0; it < iters; ++it) {
         ptx::mbar_wait(&empty[st], ph ^ 1);
         const bool w_done = li == 0 && it < w_pre;  // expect_tx + W box already issued ahead of the PDL wait
         if (ptx::elect_one()) {
-          if (!w_done) ptx::mbar_expect_tx(&full[st], C::kABytes + C::kBBytes);
-          ptx::tma_load_3d(smA + st * C::kABytes, &tmA, &full[st], a_col0 + kc * BK, a_row, b);
-          if (!w_done) ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], it * BK, w_row);
+          if constexpr (CTAS == 2) {
+            // the leader's barrier counts the bytes of both CTAs; the peer's copies may complete before the leader
+            // arrives (the phase cannot flip until it does)
+            if (rank == 0) ptx::mbar_expect_tx(&full[st], 2 * (C::kABytes + C::kBBytes));
+            ptx::tma_load_3d_pair(smA + st * C::kABytes, &tmA, &full[st], a_col0 + kc * BK, a_row, b);
+            ptx::tma_load_2d_pair(smB + st * C::kBBytes, &tmW, &full[st], it * BK, w_row);
+          } else {
+            if (!w_done) ptx::mbar_expect_tx(&full[st], C::kABytes + C::kBBytes);
+            ptx::tma_load_3d(smA + st * C::kABytes, &tmA, &full[st], a_col0 + kc * BK, a_row, b);
+            if (!w_done) ptx::tma_load_2d(smB + st * C::kBBytes, &tmW, &full[st], it * BK, w_row);
+          }
         }
         __syncwarp();
         if (++kc == kchunks) { kc = 0; a_row += s.tap_step; }
@@ -190,8 +208,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
+    if (CTAS == 2 && rank != 0) {
+      // the peer's MMA warp only allocates / frees TMEM; the leader issues for both
+    } else {
     // fp16 operands: clear the bf16 format bits of A and B
-    const uint32_t idesc = ptx::umma_idesc_bf16(BM, BN) & (s.ab_f16 ? ~((1u << 7) | (1u << 10)) : ~0u);
+    const uint32_t idesc = ptx::umma_idesc_bf16(BMS, BN) & (s.ab_f16 ? ~((1u << 7) | (1u << 10)) : ~0u);
     const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(smA));
     const uint64_t db0 = ptx::umma_desc_sw128(ptx::smem_u32(smB));
     uint32_t st = 0, ph = 0;
@@ -211,15 +232,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            if constexpr (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&empty[st]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if constexpr (CTAS == 2) ptx::umma_commit_pair(&empty[st]);
+          else ptx::umma_commit(&empty[st]);
         }
         __syncwarp();
         if (++st == static_cast<uint32_t>(kStages)) { st = 0; ph ^= 1; }
       }
-      if (ptx::elect_one()) ptx::umma_commit(&acc_full[ab]);  // accumulator complete
+      if (ptx::elect_one()) {  // accumulator complete (pair: in both CTAs' TMEM, signalled to both epilogues)
+        if constexpr (CTAS == 2) ptx::umma_commit_pair(&acc_full[ab]);
+        else ptx::umma_commit(&acc_full[ab]);
+      }
       __syncwarp();
+    }
     }
   } else {
     // ---------------- epilogue: 8 warps; warp w owns TMEM lanes [32(w%4), +32) = tile rows and every second
@@ -237,7 +265,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int li = 0; li < n_my; ++li) {
       const int tile = first + li * stride;
       const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
-      const int b = my / tiles_t, t0 = (my % tiles_t) * BM, n0 = nx * BN;
+      const int b = my / tiles_t, t0 = (my % tiles_t) * BMS + static_cast<int>(rank) * BM, n0 = nx * BN;
       const int ab = li & 1;
       const int t = t0 + row;
       const bool row_ok = t < s.T;
@@ -442,14 +470,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // this warp is done reading the accumulator buffer
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
+      if (lane == 0) {
+        if constexpr (CTAS == 2) ptx::mbar_arrive_leader(&acc_empty[ab]);
+        else ptx::mbar_arrive(&acc_empty[ab]);
+      }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  // pair: neither CTA may free its TMEM / leave while the other still reads its shared memory or signals its barriers
+  if constexpr (CTAS == 2) ptx::cluster_sync();
+  else __syncthreads();
   if (warp == 1) {
-    ptx::tmem_dealloc<2 * BN>(tmem_base);
+    if constexpr (CTAS == 2) ptx::tmem_dealloc_pair<2 * BN>(tmem_base);
+    else ptx::tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 
@@ -491,17 +525,18 @@ bool make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int ACT>
+template <int BN, int ACT, int CTAS = 1>
 cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
                         const GemmEpi& e) {
+  using C = Cfg<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<BN>::smem_bytes(Cfg<BN>::kMaxStages));
+    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, ACT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           C::smem_bytes(C::kMaxStages));
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
-  const int tiles_t = (s.T + BM - 1) / BM;
+  const int tiles_t = (s.T + BM * CTAS - 1) / (BM * CTAS);
   const int n_tiles = (s.N + BN - 1) / BN, m_tiles = s.B * tiles_t;
   const long long total = static_cast<long long>(n_tiles) * m_tiles * s.groups;
   if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -511,11 +546,12 @@ cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUten
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = total < num_sms ? static_cast<int>(total) : num_sms;
+  const int slots = num_sms / CTAS;  // persistent CTAs (CTA pairs)
+  const int grid = total < slots ? static_cast<int>(total) : slots;
   // deep ring (the producer runs ahead into the next tile); short reductions of small problems need fewer stages
   const int iters = s.taps * ((s.K + BK - 1) / BK);
   const long long ring = static_cast<long long>(iters) * ((total + grid - 1) / grid);
-  int stages = ring < 2 ? 2 : (ring > Cfg<BN>::kMaxStages ? Cfg<BN>::kMaxStages : static_cast<int>(ring));
+  int stages = ring < 2 ? 2 : (ring > C::kMaxStages ? C::kMaxStages : static_cast<int>(ring));
   {
     static int forced = -1;  // STTS_GEMM_STAGES=n: pipeline-depth experiments (tools/bench_gemm.py)
     if (forced < 0) {
@@ -524,10 +560,22 @@ cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUten
     }
     if (forced >= 2 && forced < stages) stages = forced;
   }
-  const cudaError_t le = launch_k(gemm_kernel<BN, ACT>, dim3(grid), dim3(kThreads), Cfg<BN>::smem_bytes(stages), stream,
-                                  tmA, tmW, s, e, stages, n_tiles, m_tiles, static_cast<int>(total));
+  const cudaError_t le =
+      CTAS == 2 ? launch_k_pair(gemm_kernel<BN, ACT, CTAS>, dim3(2 * grid), dim3(kThreads), C::smem_bytes(stages), stream, tmA,
+                                tmW, s, e, stages, n_tiles, m_tiles, static_cast<int>(total))
+                : launch_k(gemm_kernel<BN, ACT, CTAS>, dim3(grid), dim3(kThreads), C::smem_bytes(stages), stream, tmA, tmW,
+                           s, e, stages, n_tiles, m_tiles, static_cast<int>(total));
   ++g_launch_count;
   return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+// CTA-pair instantiations exist for the epilogues of the large vocoder GEMMs only (ACT_NONE and the fp16 2*gelu form).
+template <int BN>
+cudaError_t launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
+                        const GemmEpi& e) {
+  if (e.act == ACT_NONE) return launch_inst<BN, ACT_NONE, 2>(stream, tmA, tmW, s, e);
+  if (e.act == ACT_GELU && e.gelu2_f16) return launch_inst<BN, kActGelu2, 2>(stream, tmA, tmW, s, e);
+  return cudaErrorInvalidValue;
 }
 
 template <int BN>
@@ -566,6 +614,22 @@ cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const 
   if (!aligned16(e.bias) || !aligned16(e.colscale) || !aligned16(e.rowgate) || (e.ld_gate % 4) != 0) {
     return cudaErrorInvalidValue;
   }
+  // CTA-pair variant: requested explicitly (block_n | kGemmPairFlag: tests, micro-benchmarks) or, with
+  // STTS_GEMM_2CTA=1, wherever it measured faster in isolation (tools/bench_gemm.py, profiles/r01_gemm_microbench_pair.txt):
+  // reductions of >= 16 k-iterations (K*taps >= 1024: -4..-12 %; shorter ones are epilogue-bound and lose), same tile
+  // width as the single-CTA choice, enough tiles to occupy all 74 pairs.
+  bool pair = (block_n & kGemmPairFlag) != 0;
+  block_n &= ~kGemmPairFlag;
+  if (!pair && (block_n == 128 || block_n == 256) && (e.act == ACT_NONE || (e.act == ACT_GELU && e.gelu2_f16))) {
+    static int env = -1;
+    if (env < 0) {
+      const char* ev = getenv("STTS_GEMM_2CTA");
+      env = (ev && ev[0] == '1') ? 1 : 0;
+    }
+    const long long tiles2 = static_cast<long long>(s.B) * ((s.T + 255) / 256) * ((s.N + block_n - 1) / block_n) * s.groups;
+    pair = env == 1 && s.taps * ((s.K + BK - 1) / BK) >= 16 && tiles2 >= 60;
+  }
+  if (pair && block_n != 128 && block_n != 256) return cudaErrorInvalidValue;
   CUtensorMap tmA, tmW;
   {
     uint64_t dims[3] = {static_cast<uint64_t>(a.cols), static_cast<uint64_t>(s.T), static_cast<uint64_t>(s.B)};
@@ -576,9 +640,10 @@ cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const 
   {
     uint64_t dims[2] = {static_cast<uint64_t>(w.ld), static_cast<uint64_t>(w.rows)};
     uint64_t str[1] = {static_cast<uint64_t>(w.ld) * 2};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(block_n)};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(pair ? block_n / 2 : block_n)};
     if (!make_tmap(&tmW, w.ptr, 2, dims, str, box)) return cudaErrorInvalidValue;
   }
+  if (pair) return block_n == 256 ? launch_pair<256>(stream, tmA, tmW, s, e) : launch_pair<128>(stream, tmA, tmW, s, e);
   switch (block_n) {
     case 32:
       return launch_bn<32>(stream, tmA, tmW, s, e);

@@ -68,6 +68,10 @@ struct GemmW {
   int ld;    // row pitch in elements = taps*Kp (multiple of 8)
 };
 
+// `block_n | kGemmPairFlag` (block_n 128 or 256) runs the CTA-pair variant: clusters of two CTAs compute 256 x block_n
+// tiles with cta_group::2 MMAs (ACT_NONE and the fp16 2*gelu epilogue only).
+constexpr int kGemmPairFlag = 0x1000;
+
 // Returns cudaSuccess or the first CUDA error; `block_n` in {32, 64, 128, 256}.
 cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const GemmW& w, const GemmShape& s,
                         const GemmEpi& e);

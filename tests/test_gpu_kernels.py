@@ -2,6 +2,7 @@
 on the same bf16-rounded operands in fp32, so tolerances only cover accumulation order and the bf16 rounding of
 outputs where the kernel emits bf16."""
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -60,6 +61,42 @@ def test_linear(eng, bn, M, N, K):
     bias = torch.randn(N, device="cuda")
     out, _ = run_gemm(eng, a, w, B=1, T=M, N=N, K=K, bn=bn, bias=bias)
     _assert_close(out, a.float() @ w.float().t() + bias)
+
+
+PAIR = 0x1000  # gemm.cuh kGemmPairFlag: clusters of two CTAs, 256 x bn tiles, cta_group::2 MMAs
+# The engine uses the pair variant only with STTS_GEMM_2CTA=1 (measured: wins on long reductions in isolation, no
+# end-to-end gain yet); the kernel itself is always tested.  STTS_TEST_PAIR=0 skips (e.g. a part without 2-SM TPCs).
+pair_only = pytest.mark.skipif(os.environ.get("STTS_TEST_PAIR") == "0", reason="CTA-pair GEMM tests disabled: STTS_TEST_PAIR=0")
+
+
+@pair_only
+
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(600, 960, 960), (75, 256, 64), (20000, 1024, 256), (1000, 4096, 512), (130, 960, 2400)])
+def test_linear_cta_pair(eng, bn, M, N, K):
+    """CTA-pair variant of the GEMM (each CTA stages 128 rows of A and bn/2 rows of W; the leader issues M = 256 MMAs):
+    ragged M (tiles whose second half is empty), N not a multiple of bn, several tiles per pair."""
+    torch.manual_seed(0)
+    a, w = _rand_bf16(M, K), _rand_bf16(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    out, _ = run_gemm(eng, a, w, B=1, T=M, N=N, K=K, bn=bn | PAIR, bias=bias, residual=res)
+    _assert_close(out, a.float() @ w.float().t() + bias + res)
+
+
+@pair_only
+def test_conv_taps_and_batches_cta_pair(eng):
+    """7-tap causal conv over B batches of T rows (the vocoder stem's shape family) on CTA pairs: 256-row tiles must
+    not cross batch boundaries and rows shifted before the start of a batch read zero."""
+    torch.manual_seed(4)
+    B, T, Cin, Cout = 3, 300, 64, 512
+    x = _rand_bf16(B, T, Cin)
+    wc = _rand_bf16(Cout, Cin, 7, scale=(7 * Cin) ** -0.5)
+    bias = torch.randn(Cout, device="cuda")
+    w = wc.permute(0, 2, 1).reshape(Cout, 7 * Cin).contiguous()
+    out, _ = run_gemm(eng, x, w, B=B, T=T, N=Cout, K=Cin, bn=256 | PAIR, taps=7, shift0=-6, step=1, bias=bias)
+    want = torch.nn.functional.conv1d(torch.nn.functional.pad(x.float().transpose(1, 2), (6, 0)), wc.float(), bias)
+    _assert_close(out.view(B, T, Cout), want.transpose(1, 2))
 
 
 def test_small_k_box_exceeds_extent(eng):

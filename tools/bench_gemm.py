@@ -14,6 +14,7 @@ import torch
 from smalltts_b200 import _cabi
 from smalltts_b200.engine import Engine
 
+PAIR = 0x1000  # gemm.cuh kGemmPairFlag: CTA-pair variant (cta_group::2), printed as bn + 4096
 ACT = dict(none=0, gelu=1, mish=2, swiglu=4, gelu2=1 + 16, none_f16=0 + 32)
 
 
@@ -46,7 +47,7 @@ def main():
     ]
     print(f"{'shape':10s} {'M':>7s} {'N':>5s} {'K':>5s} {'bn':>4s} {'warm us':>9s} {'TF/s':>7s} {'coldW us':>9s} {'TF/s':>7s}")
     for name, M, N, K, act, res, out in shapes:
-        if only and only not in name:
+        if only and not any(o in name for o in only.split(",")):
             continue
         torch.manual_seed(0)
         a = (torch.randn(M, K, device="cuda")).to(torch.bfloat16)
@@ -59,9 +60,11 @@ def main():
         o16 = torch.zeros(M, ncol, device="cuda", dtype=torch.bfloat16) if out == "bf16" else None
         r = torch.randn(M, ncol, device="cuda") if res else None
         flops = 2.0 * M * N * K
-        for bn in (32, 64, 128, 256):
-            if bn > N or (bn == 32 and M > 5000):
+        for bn in (32, 64, 128, 256, 128 | PAIR, 256 | PAIR):
+            if (bn & ~PAIR) > N or (bn == 32 and M > 5000):
                 continue
+            if bn & PAIR and act not in ("none", "none_f16", "gelu2"):
+                continue  # pair instantiations: ACT_NONE and the fp16 2*gelu epilogue
 
             def run(w):
                 rc = lib.stts_test_gemm(eng._h, bn, p(a), 1, M, K, K, p(w), N, K, N, K, 1, 0, 1, 1, 0, 0, 0, p(bias),
