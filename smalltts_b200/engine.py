@@ -28,6 +28,9 @@ def _buf(x, dtype, name: str):
             raise ValueError(f"{name}: expected dtype {want}, got {x.dtype}")
         x = x.contiguous()
         if x.is_cuda:
+            # the engine works on its own non-blocking CUDA stream: whatever torch still has in flight for this tensor
+            # (the kernel that produces it, the H2D copy behind .cuda()) must be complete before the engine reads it
+            torch.cuda.current_stream(x.device).synchronize()
             return C.c_void_p(x.data_ptr()), _cabi.MEM_DEVICE, x
         x = x.numpy()
     a = np.ascontiguousarray(x, dtype=dtype)
@@ -265,6 +268,8 @@ class Engine:
             import torch
 
             out = torch.empty(shape, dtype=torch.float32, device=f"cuda:{self.device}")
+            # the caching allocator may hand out memory whose previous user is still running on torch's stream
+            torch.cuda.current_stream(out.device).synchronize()
             return out, C.c_void_p(out.data_ptr())
         out = np.empty(shape, dtype=np.float32)
         return out, C.c_void_p(out.ctypes.data)

@@ -22,7 +22,12 @@ def eng():
 
 
 def _p(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Raw device pointer for a C-ABI test hook.  The engine runs on its own non-blocking stream, so everything torch
+    has queued for this tensor (randn, zeros, casts) must have finished before the hook launches: synchronise here."""
+    if t is None:
+        return None
+    torch.cuda.current_stream(t.device).synchronize()
+    return C.c_void_p(t.data_ptr())
 
 
 def run_gemm(eng, a, w, *, B, T, N, K, bn, taps=1, shift0=0, step=1, groups=1, a_koff=0, w_grows=0, out_gcols=0,

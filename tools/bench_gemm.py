@@ -60,6 +60,7 @@ def main():
         o16 = torch.zeros(M, ncol, device="cuda", dtype=torch.bfloat16) if out == "bf16" else None
         r = torch.randn(M, ncol, device="cuda") if res else None
         flops = 2.0 * M * N * K
+        torch.cuda.synchronize()  # the engine stream does not wait for torch's
         for bn in (32, 64, 128, 256, 128 | PAIR, 256 | PAIR):
             if (bn & ~PAIR) > N or (bn == 32 and M > 5000):
                 continue
