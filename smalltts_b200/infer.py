@@ -56,13 +56,14 @@ class SmallTTS:
 
     def __init__(
         self,
-        cond_encoder_path: str = "assets/dmd/model.safetensors",
-        denoiser_path: Optional[str] = None,
-        codec_decoder_path: str = "assets/codec/decoder.safetensors",
+        cond_encoder_path: str = "assets/dmd/condition_encoder.onnx",  # the reference's defaults (infer/onnx.py:55-57)
+        denoiser_path: Optional[str] = "assets/dmd/denoiser.onnx",
+        codec_decoder_path: str = "assets/codec/decoder.onnx",
         providers: Optional[Iterable[str]] = None,  # accepted for call compatibility; the engine is CUDA-only
         *,
-        codec_encoder_path: Optional[str] = None,  # clone path (codec/onnx.py:56-75): HF encoder state_dict file
+        codec_encoder_path: Optional[str] = None,  # clone path (codec/onnx.py:56-75): encoder.onnx / HF state_dict file
         device: int = 0,
+        devices: Optional[Sequence[int]] = None,  # several GPUs from one process: replicas + batch split
         state_dicts: Optional[tuple] = None,
         num_steps: int = NUM_STEPS,
         seed: Optional[int] = None,
@@ -70,6 +71,9 @@ class SmallTTS:
         self.num_steps = num_steps
         self._seed = 0 if seed is None else int(seed)
         self._calls = 0
+        devs = [int(d) for d in devices] if devices is not None else [int(device)]
+        if not devs or len(set(devs)) != len(devs):
+            raise ValueError("devices must be a non-empty list of distinct CUDA ordinals")
         if state_dicts is None:
             from . import synthetic
 
@@ -79,8 +83,11 @@ class SmallTTS:
                            load_model_weights([codec_decoder_path], synthetic.vocoder_specs(), "codec decoder"))
             if codec_encoder_path is not None:
                 state_dicts += (load_model_weights([codec_encoder_path], synthetic.encoder_specs(), "codec encoder"),)
-        self.engine = Engine(device)
+        self.engine = Engine(devs[0])
         self.engine.load_state_dicts(*state_dicts)
+        # one replica (own engine, own weights copy, own host thread per call) per extra GPU; utterances are independent
+        self._replicas = [SmallTTS(state_dicts=state_dicts, device=d, num_steps=num_steps, seed=self._seed + 7919 * (k + 1))
+                          for k, d in enumerate(devs[1:])]
 
     @classmethod
     def synthetic(cls, dit_seed: int = 0, vocoder_seed: int = 1, encoder_seed: Optional[int] = None, **kw) -> "SmallTTS":
@@ -123,6 +130,8 @@ class SmallTTS:
         if not (len(ref_latents) == len(phoneme_ids) == len(durations)) or len(durations) == 0:
             raise ValueError("ref_latents, phoneme_ids and durations must be equally long and non-empty")
         frames = [frames_for(d) for d in durations]
+        if self._replicas and len(frames) > 1 and not device_out:
+            return self._synthesize_on_devices(ref_latents, phoneme_ids, durations, frames, noise, seed)
         T = max(frames)
         ref, ref_len, ids, ph_len = pad_batch(ref_latents, phoneme_ids, frames)
         if seed is None:
@@ -139,6 +148,34 @@ class SmallTTS:
         audio = self.engine.synthesize(ref, ref_len, ids, ph_len, frames, T, noise=noise, seed=seed,
                                        steps=self.num_steps)
         return [audio[i : i + 1, : frames[i] * HOP_SIZE].copy() for i in range(len(frames))]
+
+    def _synthesize_on_devices(self, ref_latents, phoneme_ids, durations, frames, noise, seed) -> List[np.ndarray]:
+        """``devices=[...]``: longest-processing-time split of the utterances over the GPUs, length-bucketed micro-batches
+        per GPU, one host thread per GPU (parallel.synthesize_on_workers).  With ``noise`` the result is independent of
+        the split; the on-device Philox streams are keyed per (seed, device, micro-batch) and are not."""
+        from .parallel import synthesize_on_workers
+
+        noise = None if noise is None else np.asarray(noise, dtype=np.float32)
+
+        def worker(tts: "SmallTTS", k: int):
+            calls = [0]
+
+            def run(idx: List[int]) -> List[np.ndarray]:
+                tl = max(frames[i] for i in idx)
+                nz = None if noise is None else np.ascontiguousarray(noise[:, idx, :tl])
+                sd = None if seed is None else int(seed) + 7919 * k + calls[0]
+                calls[0] += 1
+                return SmallTTS.synthesize_batch(tts, [ref_latents[i] for i in idx], [phoneme_ids[i] for i in idx],
+                                                 [durations[i] for i in idx], noise=nz, seed=sd)
+
+            return run
+
+        members = [self] + self._replicas
+        saved, self._replicas = self._replicas, []  # the primary serves its own shard locally
+        try:
+            return synthesize_on_workers([worker(t, k) for k, t in enumerate(members)], frames)
+        finally:
+            self._replicas = saved
 
     def synthesize_teacher(self, ref_latents: Sequence, phoneme_ids: Sequence[Sequence[int]], durations: Sequence[float],
                            steps: int = 128, cfg_scale_text: float = 2.0, cfg_scale_speaker: float = 1.5, noise=None,

@@ -54,6 +54,39 @@ def length_buckets(indices: Sequence[int], frames: Sequence[int], max_batch: int
     return out
 
 
+def synthesize_on_workers(workers: Sequence[Callable[[List[int]], List[np.ndarray]]], frames: Sequence[int],
+                          max_batch: int = 16) -> List[np.ndarray]:
+    """Single-process variant of the batch split (``SmallTTS(devices=[0, 1, ...])``): worker k is bound to GPU k's engine
+    (``fn(indices) -> [(1, frames_i*3200)]``) and is driven by its own host thread -- the C-ABI calls release the GIL and
+    every engine handle is used by exactly one thread.  Same partitioning as :func:`synthesize_sharded`; the waveforms
+    come back in input order.  The first worker exception is re-raised after all threads have finished."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    if not workers:
+        raise ValueError("no workers")
+    shards = partition_lpt([utterance_cost(f) for f in frames], len(workers))
+    results: List[np.ndarray] = [None] * len(frames)  # type: ignore[list-item]
+
+    def run(k: int) -> None:
+        for mb in length_buckets(shards[k], frames, max_batch=max_batch):
+            for i, a in zip(mb, workers[k](list(mb))):
+                if tuple(a.shape) != (1, frames[i] * HOP_SIZE):
+                    raise ValueError(f"utterance {i}: expected {(1, frames[i] * HOP_SIZE)}, got {tuple(a.shape)}")
+                results[i] = a
+
+    busy = [k for k in range(len(workers)) if shards[k]]
+    if len(busy) == 1:
+        run(busy[0])
+    else:
+        with ThreadPoolExecutor(max_workers=len(busy), thread_name_prefix="stts-dev") as pool:
+            futs = [pool.submit(run, k) for k in busy]
+            errs = [f.exception() for f in futs]
+        for e in errs:
+            if e is not None:
+                raise e
+    return results
+
+
 def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], frames: Sequence[int], rank: int,
                        world: int, group=None, gather_to: int = 0):
     """Run ``synthesize_fn`` on this rank's shard and gather every waveform to ``gather_to`` in input order.

@@ -66,3 +66,54 @@ def test_sharded_gather_world2_gloo():
         assert p.exitcode == 0
     for g, w in zip(got, want):
         assert g[-1] == w.shape[1] and np.allclose(g[:3], w[0, :3])
+
+
+def test_single_process_multi_device_split_orders_results_and_uses_one_thread_per_worker():
+    """SmallTTS(devices=[...]) host logic (parallel.synthesize_on_workers) with fake per-GPU workers."""
+    import threading
+    import time
+
+    import numpy as np
+
+    from smalltts_b200.parallel import HOP_SIZE, synthesize_on_workers
+
+    frames = [75, 15, 40, 75, 22, 60, 15, 33, 75, 50]
+    seen = [set() for _ in range(3)]
+    served = [[] for _ in range(3)]
+
+    def make(k):
+        def fn(idx):
+            seen[k].add(threading.get_ident())
+            served[k] += idx
+            time.sleep(0.01)
+            return [np.full((1, frames[i] * HOP_SIZE), float(i), np.float32) for i in idx]
+
+        return fn
+
+    out = synthesize_on_workers([make(k) for k in range(3)], frames)
+    assert [int(a[0, 0]) for a in out] == list(range(len(frames)))
+    assert all(a.shape == (1, f * HOP_SIZE) for a, f in zip(out, frames))
+    assert sorted(sum(served, [])) == list(range(len(frames)))  # every utterance exactly once
+    assert all(len(s) == 1 for s in seen) and len(set.union(*seen)) == 3  # one host thread per worker
+    loads = [sum(frames[i] for i in s) for s in served]
+    assert max(loads) - min(loads) <= 75  # LPT balance
+
+    # a failing worker surfaces after the others finished; a wrong shape is rejected
+    def boom(idx):
+        raise RuntimeError("device 1 failed")
+
+    try:
+        synthesize_on_workers([make(0), boom], frames)
+        raise AssertionError("expected RuntimeError")
+    except RuntimeError as e:
+        assert "device 1" in str(e)
+    try:
+        synthesize_on_workers([lambda idx: [np.zeros((1, 5), np.float32) for _ in idx]], [3])
+        raise AssertionError("expected ValueError")
+    except ValueError:
+        pass
+    # fewer utterances than workers: idle workers are never called
+    calls = []
+    out = synthesize_on_workers([lambda idx: calls.append(0) or [np.zeros((1, 2 * HOP_SIZE), np.float32)],
+                                 lambda idx: calls.append(1) or []], [2])
+    assert calls == [0] and out[0].shape == (1, 2 * HOP_SIZE)
