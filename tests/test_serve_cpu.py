@@ -156,3 +156,30 @@ def test_http_front_routes_and_status_codes():
         httpd.shutdown()
         httpd.server_close()
         b.close()
+
+
+def test_replicas_run_batches_concurrently_and_shut_down_cleanly():
+    """One worker thread per engine replica: two batches are in flight at the same time, every request is served
+    exactly once, close() stops every worker."""
+    gate = threading.Barrier(2, timeout=5)
+    fakes = [FakePipeline(), FakePipeline()]
+
+    def make(f):
+        def run(refs, tokens, durations):
+            gate.wait()  # only passes if BOTH replicas are inside a pass at the same time
+            return f(refs, tokens, durations)
+
+        return run
+
+    b = serve.MicroBatcher([make(f) for f in fakes], max_batch=2, max_wait_ms=20)
+    try:
+        futs = [b.submit(REF, [i + 1], 1.0) for i in range(4)]
+        res = [f.result(10) for f in futs]
+    finally:
+        b.close()
+    assert [int(a[0]) for a, _ in res] == [1, 2, 3, 4]
+    assert sorted(c[0] for f in fakes for c in f.calls) == [2, 2] and all(len(f.calls) == 1 for f in fakes)
+    assert b.batches_run == 2 and b.requests_run == 4
+    assert not any(w.is_alive() for w in b._workers)
+    with pytest.raises(ValueError):
+        serve.MicroBatcher([])

@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Throughput of N engine replicas on ONE GPU (N host threads, N non-blocking streams): does a second in-flight batch
+fill the SMs the latency-bound DiT GEMMs (75-150 tiles at M = 600) leave idle?   usage: bench_concurrent.py [steps]"""
+import os
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from smalltts_b200 import synthetic
+from smalltts_b200.engine import Engine, pad_batch
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+sds = (synthetic.dit_state_dict(0), synthetic.vocoder_state_dict(1))
+refs, ids, frames, _ = synthetic.synthetic_inputs(8, 75, 15, 120)
+ref, ref_len, idt, ph_len = pad_batch(refs, ids, frames)
+engines = []
+for n in (1, 2, 3):
+    while len(engines) < n:
+        e = Engine(0)
+        e.load_state_dicts(*sds)
+        dev = [torch.from_numpy(ref).cuda(), torch.from_numpy(idt).cuda()]
+        out = torch.empty(8, 75 * 3200, device="cuda")
+        for i in range(3):
+            e.synthesize(dev[0], ref_len, dev[1], ph_len, frames, 75, seed=i, out=out)
+        engines.append((e, dev, out))
+    torch.cuda.synchronize()
+
+    def work(k):
+        e, dev, out = engines[k]
+        for i in range(steps):
+            e.synthesize(dev[0], ref_len, dev[1], ph_len, frames, 75, seed=10 + i, out=out)
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(n)]
+    t0 = time.perf_counter()
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    dt = time.perf_counter() - t0
+    print(f"replicas={n}: {n * steps} batches of 8 x 10 s in {dt * 1e3:.1f} ms -> {n * steps * 80 / dt:.0f} audio-s/s "
+          f"({dt * 1e3 / (n * steps):.2f} ms per batch)", flush=True)
