@@ -254,6 +254,40 @@ def main_ours(args, rank, local_rank, world):
     achieved = tail_bytes / (tail_ms / 1e3) / 1e9
     dit_tflops = DENOISE_GFLOP_PER_STEP * STEPS_DMD / stage["denoise_ms"]  # GFLOP / ms = TFLOP/s
 
+    # optional: throughput with N batches in flight on this GPU (N engine replicas, one host thread and stream each;
+    # same loop as tools/bench_concurrent.py).  Not part of the headline: BASELINE's metric is one batch at a time.
+    in_flight = None
+    if args.in_flight > 1 and world == 1:
+        import threading
+
+        sds = (synthetic.dit_state_dict(0), synthetic.vocoder_state_dict(1))
+        reps = [(eng, d_out)]
+        for _ in range(args.in_flight - 1):
+            e2 = Engine(local_rank)
+            e2.load_state_dicts(*sds)
+            reps.append((e2, torch.empty_like(d_out)))
+        for e2, o2 in reps:
+            for i in range(max(3, args.warmup)):
+                e2.synthesize(d_ref, ref_len, d_ids, ph_len, frames, T, seed=i, steps=STEPS_DMD, out=o2)
+        torch.cuda.synchronize()
+
+        def work(k):
+            e2, o2 = reps[k]
+            for i in range(args.steps):
+                e2.synthesize(d_ref, ref_len, d_ids, ph_len, frames, T, seed=2000 + i, steps=STEPS_DMD, out=o2)
+
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(len(reps))]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n_batches = len(reps) * args.steps
+        in_flight = {"batches_in_flight": len(reps), "value": n_batches * BATCH * AUDIO_S_PER_UTT / dt, "unit": UNIT,
+                     "ms_per_batch": dt * 1e3 / n_batches, "timing": "wall clock around all threads"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, per_step, cores = cpu_reference_run(3, 1)
@@ -288,6 +322,8 @@ def main_ours(args, rank, local_rank, world):
                                 "algorithmic_gflop": DENOISE_GFLOP_PER_STEP * STEPS_DMD, "ms": stage["denoise_ms"]},
             "cpu_baseline": cpu,
         }
+        if in_flight is not None:
+            out["in_flight"] = in_flight
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
@@ -301,6 +337,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=1,
+                    help="additionally report throughput with this many batches in flight on one GPU (N=1 only)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":

@@ -319,7 +319,7 @@ def make_handler(batcher: MicroBatcher, resample: Callable[[np.ndarray, int], np
                     return self._send(400, b"missing 'text'")
                 wav, sr = decode_wav(fields["audio"])
                 ref = resample(wav, sr)
-            except (KeyError, ValueError, wave.Error, EOFError) as exc:
+            except (KeyError, ValueError, wave.Error, EOFError, struct.error) as exc:
                 return self._send(400, f"bad request: {exc}".encode())
             try:
                 audio, _ = batcher.submit(ref, tokens, duration).result()
