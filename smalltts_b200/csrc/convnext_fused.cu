@@ -523,11 +523,12 @@ bool tmap_2d(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, ui
 
 template <int C>
 cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, const void* w2, int num_sms) {
-  static bool once = false;
-  if (!once) {
-    cudaError_t e = cudaFuncSetAttribute(convnext_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC<C>::SMEM);
+  static PerDeviceOnce once;
+  {
+    const cudaError_t e = once.run([] {
+      return cudaFuncSetAttribute(convnext_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC<C>::SMEM);
+    });
     if (e != cudaSuccess) return e;
-    once = true;
   }
   CUtensorMap m1, m2;
   if (!tmap_2d(&m1, w1, C, 4 * C, 4 * C)) return cudaErrorInvalidValue;  // W1 [4C, C]: one box of all rows, K padded to 64

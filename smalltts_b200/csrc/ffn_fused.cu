@@ -371,11 +371,12 @@ cudaError_t ffn_fused(cudaStream_t st, const bf16* a, const float* y, long long 
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   using F = FF<128>;
-  static bool once = false;
-  if (!once) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
+  static PerDeviceOnce once;
+  {
+    const cudaError_t e = once.run([] {
+      return cudaFuncSetAttribute(ffn_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM);
+    });
     if (e != cudaSuccess) return e;
-    once = true;
   }
   CUtensorMap mA, m1, m2;
   if (!map2d(&mA, a, C, static_cast<uint64_t>(M), TM)) return cudaErrorInvalidValue;  // A [M, C]: K atoms of 128 rows

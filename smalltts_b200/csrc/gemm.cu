@@ -529,12 +529,13 @@ template <int BN, int ACT, int CTAS = 1>
 cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
                         const GemmEpi& e) {
   using C = Cfg<BN, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_kernel<BN, ACT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           C::smem_bytes(C::kMaxStages));
+  static PerDeviceOnce attr_set;
+  {
+    const cudaError_t err = attr_set.run([] {
+      return cudaFuncSetAttribute(gemm_kernel<BN, ACT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::smem_bytes(C::kMaxStages));
+    });
     if (err != cudaSuccess) return err;
-    attr_set = true;
   }
   const int tiles_t = (s.T + BM * CTAS - 1) / (BM * CTAS);
   const int n_tiles = (s.N + BN - 1) / BN, m_tiles = s.B * tiles_t;

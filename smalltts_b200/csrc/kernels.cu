@@ -1143,21 +1143,19 @@ cudaError_t attention_bf16(cudaStream_t st, const bf16* q, int B, int tq, int H,
   };
   if (hd_pad == 128) {
     const int smem = smem_for(128);
-    static bool once = false;
-    if (!once) {
-      cudaError_t e = cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      once = true;
-    }
+    static PerDeviceOnce once;
+    const cudaError_t e = once.run([smem] {
+      return cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    });
+    if (e != cudaSuccess) return e;
     last_launch_status = launch_k(attention_kernel<128>, dim3(grid), dim3(kAttThreads), smem, st, maps, lens, tq, H, hd, nseg, gate, ld_gate, gate_off, scale_log2, out);
   } else {
     const int smem = smem_for(64);
-    static bool once = false;
-    if (!once) {
-      cudaError_t e = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      once = true;
-    }
+    static PerDeviceOnce once;
+    const cudaError_t e = once.run([smem] {
+      return cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    });
+    if (e != cudaSuccess) return e;
     last_launch_status = launch_k(attention_kernel<64>, dim3(grid), dim3(kAttThreads), smem, st, maps, lens, tq, H, hd, nseg, gate, ld_gate, gate_off, scale_log2, out);
   }
   STTS_LAUNCH_OK();
@@ -1227,13 +1225,13 @@ cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, c
   if (C == 128 || C == 256) {
     const int TTr = 16384 / C;
     const int smem_r = ((TTr + 6) * (C + 4) + (TTr + 6) + TTr) * 4;
-    static bool once_r = false;
-    if (!once_r) {
+    static PerDeviceOnce once_r;
+    const cudaError_t er = once_r.run([] {
       cudaError_t e1 = cudaFuncSetAttribute(convnext_mix_rows_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
       cudaError_t e2 = cudaFuncSetAttribute(convnext_mix_rows_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-      if (e1 != cudaSuccess || e2 != cudaSuccess) return e1 != cudaSuccess ? e1 : e2;
-      once_r = true;
-    }
+      return e1 != cudaSuccess ? e1 : e2;
+    });
+    if (er != cudaSuccess) return er;
     dim3 gr((T + TTr - 1) / TTr, B);
     if (C == 128) {
       last_launch_status = launch_k(convnext_mix_rows_kernel<128>, gr, dim3(256), smem_r, st, x, T, norm_w, conv_w, conv_b, gamma, ffn_norm_w, eps, y, a);
@@ -1253,11 +1251,12 @@ cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, c
   if (TT > 512) TT = 512;
   if (TT > T) TT = T;
   const int smem = ((TT + 6) * C + (TT + 6) + TT) * 4;
-  static bool once = false;
-  if (!once) {
-    cudaError_t e = cudaFuncSetAttribute(convnext_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+  static PerDeviceOnce once;
+  {
+    const cudaError_t e = once.run([] {
+      return cudaFuncSetAttribute(convnext_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    });
     if (e != cudaSuccess) return e;
-    once = true;
   }
   dim3 grid((T + TT - 1) / TT, B);
   last_launch_status = launch_k(convnext_mix_kernel, dim3(grid), dim3(256), smem, st, x, T, C, TT, norm_w, conv_w, conv_b, gamma, ffn_norm_w, eps, y, a);
@@ -1303,11 +1302,12 @@ cudaError_t resample(cudaStream_t st, const float* x, int B, int N, const float*
                      float* out, int out_len) {
   const size_t smem = (static_cast<size_t>(31) * down + K) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  static size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static PerDeviceOnce attr_set;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = attr_set.run([] {
+      return cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
     if (e != cudaSuccess) return e;
-    attr_set = 200 * 1024;
   }
   const long long frames = (static_cast<long long>(out_len) + up - 1) / up;
   last_launch_status = launch_k(resample_kernel, dim3(blocks_for(frames, 32), blocks_for(up, 8), B), dim3(256), smem, st, x, N,

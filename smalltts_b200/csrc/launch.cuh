@@ -8,9 +8,35 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
 #include <utility>
 
 namespace stts {
+
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) belong to the current device: a process that drives
+// several GPUs (SmallTTS(devices=[...])) has to set them once per device, and engine replicas launch from several host
+// threads.  `static PerDeviceOnce once; once.run([&] { return cudaFuncSetAttribute(...); })` does both.
+class PerDeviceOnce {
+ public:
+  template <typename F>
+  cudaError_t run(F&& fn) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    std::lock_guard<std::mutex> g(m_);
+    if (done_.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+    e = fn();
+    if (e == cudaSuccess) done_.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+
+ private:
+  std::mutex m_;
+  std::atomic<unsigned long long> done_{0};
+};
 
 inline bool pdl_enabled() {
   static int v = -1;
