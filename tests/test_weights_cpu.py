@@ -255,3 +255,22 @@ def test_spec_tables_match_survey_counts():
     assert n(synthetic.dit_specs()) == 327_756_609
     assert n(synthetic.vocoder_specs()) == 343_695_969
     assert n(synthetic.encoder_specs()) == 343_696_032
+
+
+def test_convert_weights_cli_roundtrip(tmp_path, monkeypatch):
+    """tools/convert_weights.py: an exported .onnx -> .sttsw (bf16 matrices) -> load_model_weights again."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "convert_weights", os.path.join(os.path.dirname(__file__), "..", "tools", "convert_weights.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ref = np.load(os.path.join(GOLDEN, "tiny_codec_decoder.npz"))
+    specs = [(k, ref[k].shape) for k in ref.files]
+    monkeypatch.setattr(synthetic, "vocoder_specs", lambda: specs)
+    out = str(tmp_path / "dec.sttsw")
+    assert mod.main(["decoder", os.path.join(GOLDEN, "tiny_codec_decoder.onnx"), "-o", out, "--bf16"]) == 0
+    sd = weights.load_model_weights([out], specs, "tiny decoder")
+    for k in ref.files:
+        want = ref[k] if ref[k].ndim < 2 else torch.from_numpy(ref[k]).to(torch.bfloat16).float().numpy()
+        np.testing.assert_array_equal(np.asarray(sd[k]), want, err_msg=k)
