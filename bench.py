@@ -254,39 +254,24 @@ def main_ours(args, rank, local_rank, world):
     achieved = tail_bytes / (tail_ms / 1e3) / 1e9
     dit_tflops = DENOISE_GFLOP_PER_STEP * STEPS_DMD / stage["denoise_ms"]  # GFLOP / ms = TFLOP/s
 
-    # optional: throughput with N batches in flight on this GPU (N engine replicas, one host thread and stream each;
-    # same loop as tools/bench_concurrent.py).  Not part of the headline: BASELINE's metric is one batch at a time.
+    # Informational, not the headline (BASELINE's metric is one batch at a time): throughput with several batches in
+    # flight on this GPU -- N engine replicas, one host thread and stream each (tools/bench_concurrent.py).  Runs in a
+    # child process after the measurements above, so nothing it does can disturb them; any failure just drops the key.
     in_flight = None
-    if args.in_flight > 1 and world == 1:
-        import threading
+    if rank == 0 and world == 1 and args.in_flight > 1:
+        try:
+            import subprocess
 
-        sds = (synthetic.dit_state_dict(0), synthetic.vocoder_state_dict(1))
-        reps = [(eng, d_out)]
-        for _ in range(args.in_flight - 1):
-            e2 = Engine(local_rank)
-            e2.load_state_dicts(*sds)
-            reps.append((e2, torch.empty_like(d_out)))
-        for e2, o2 in reps:
-            for i in range(max(3, args.warmup)):
-                e2.synthesize(d_ref, ref_len, d_ids, ph_len, frames, T, seed=i, steps=STEPS_DMD, out=o2)
-        torch.cuda.synchronize()
-
-        def work(k):
-            e2, o2 = reps[k]
-            for i in range(args.steps):
-                e2.synthesize(d_ref, ref_len, d_ids, ph_len, frames, T, seed=2000 + i, steps=STEPS_DMD, out=o2)
-
-        ths = [threading.Thread(target=work, args=(k,)) for k in range(len(reps))]
-        t0 = time.perf_counter()
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        n_batches = len(reps) * args.steps
-        in_flight = {"batches_in_flight": len(reps), "value": n_batches * BATCH * AUDIO_S_PER_UTT / dt, "unit": UNIT,
-                     "ms_per_batch": dt * 1e3 / n_batches, "timing": "wall clock around all threads"}
+            tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "bench_concurrent.py")
+            r = subprocess.run([sys.executable, tool, str(max(5, min(args.steps, 20))), str(args.in_flight), str(local_rank)],
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=240)
+            rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+            if rows:
+                in_flight = {"by_batches_in_flight": {str(x["batches_in_flight"]): round(x["value"], 1) for x in rows},
+                             "unit": UNIT, "timing": "wall clock around all replica threads, device-resident inputs",
+                             "note": "N engine replicas on one GPU; the headline value above is 1 batch at a time"}
+        except Exception:  # noqa: BLE001 - strictly optional
+            in_flight = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -337,8 +322,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=1,
-                    help="additionally report throughput with this many batches in flight on one GPU (N=1 only)")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="also report throughput with up to this many batches in flight on one GPU (N=1 only; 0 = skip)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
