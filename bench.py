@@ -264,7 +264,7 @@ def main_ours(args, rank, local_rank, world):
 
             tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "bench_concurrent.py")
             r = subprocess.run([sys.executable, tool, str(max(5, min(args.steps, 20))), str(args.in_flight), str(local_rank)],
-                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=240)
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=150)
             rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
             if rows:
                 in_flight = {"by_batches_in_flight": {str(x["batches_in_flight"]): round(x["value"], 1) for x in rows},
