@@ -76,6 +76,11 @@ typedef struct stts_timing {
 
 int stts_create(const stts_config* cfg, stts_engine** out);
 void stts_destroy(stts_engine* e);
+/* A second handle on the same device that SHARES the finalized weights of `src` (no copy) and owns its own streams,
+ * per-shape plans / CUDA graphs and timers: two handles may run calls concurrently from two host threads, which is how
+ * a server keeps two batches in flight (the reference serialises on one mutex, main.rs:25).  Destroy every clone before
+ * `src`; loading or finalizing weights through a clone is not allowed. */
+int stts_engine_clone(stts_engine* src, stts_engine** out);
 const char* stts_last_error(const stts_engine* e);
 
 /* Weights: fp32 tensors under the reference's own state-dict names.

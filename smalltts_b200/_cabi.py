@@ -32,6 +32,7 @@ class Timing(C.Structure):
 SIGNATURES = {
     "stts_create": (C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
     "stts_destroy": (None, [vp]),
+    "stts_engine_clone": (C.c_int, [vp, C.POINTER(vp)]),
     "stts_last_error": (C.c_char_p, [vp]),
     "stts_load_weight": (C.c_int, [vp, C.c_int, C.c_char_p, vp, C.c_int, c_i64p]),
     "stts_finalize_weights": (C.c_int, [vp]),

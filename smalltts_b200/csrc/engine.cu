@@ -116,6 +116,7 @@ struct stts_engine {
   std::map<std::string, RawTensor> raw[3];  // 0 = DiT, 1 = codec decoder (vocoder), 2 = codec encoder (optional)
   std::vector<void*> owned;  // packed buffers
   bool finalized = false, packed_once = false;
+  bool owns_weights = true;  // false for stts_engine_clone handles: weight memory belongs to the source engine
 
   // packed DiT-side weights
   EncW style, text;
@@ -1139,6 +1140,20 @@ void need_ready(stts_engine* e, bool dit = false, bool decoder = false) {
 }
 }  // namespace
 
+namespace {
+// Streams, events and the seed staging buffers: what every handle (created or cloned) owns for itself.
+void init_instance(stts_engine* e) {
+  CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+  CK(cudaEventCreate(&e->ev_stop));
+  CK(cudaMalloc(reinterpret_cast<void**>(&e->seed_dev), sizeof(unsigned long long)));
+  CK(cudaHostAlloc(reinterpret_cast<void**>(&e->seed_host), sizeof(unsigned long long), cudaHostAllocDefault));
+}
+}  // namespace
+
 extern "C" {
 
 int stts_create(const stts_config* cfg, stts_engine** out) {
@@ -1159,14 +1174,7 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
                                         ", this engine is built for sm_100a (B200) only");
     }
     CK(cudaSetDevice(e->device));
-    CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-    for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
-    CK(cudaEventCreate(&e->ev_stop));
-    CK(cudaMalloc(reinterpret_cast<void**>(&e->seed_dev), sizeof(unsigned long long)));
-    CK(cudaHostAlloc(reinterpret_cast<void**>(&e->seed_host), sizeof(unsigned long long), cudaHostAllocDefault));
+    init_instance(e);
     const char* ng = getenv("STTS_NO_GRAPH");
     e->use_graphs = !(ng && ng[0] == '1');
     const char* nf = getenv("STTS_NO_FUSED_TAIL");
@@ -1190,7 +1198,9 @@ void stts_destroy(stts_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
-  for (auto& m : e->raw) for (auto& kv : m) cudaFree(kv.second.d);
+  if (e->owns_weights) {
+    for (auto& m : e->raw) for (auto& kv : m) cudaFree(kv.second.d);
+  }
   for (void* p : e->owned) cudaFree(p);
   for (auto& kv : e->plans) {
     kv.second->destroy();
@@ -1207,12 +1217,46 @@ void stts_destroy(stts_engine* e) {
   delete e;
 }
 
+int stts_engine_clone(stts_engine* src, stts_engine** out) {
+  if (!src || !out) return STTS_ERR_INVALID;
+  *out = nullptr;
+  stts_engine* c = nullptr;
+  const int rc = guard_impl(src, [&] {
+    need_ready(src);
+    CK(cudaStreamSynchronize(src->st));
+    c = new stts_engine(*src);  // every packed-weight pointer and the raw-tensor table, by value
+    c->owns_weights = false;
+    c->owned.clear();      // what the clone allocates from here on (adaLN tables, filter banks) is its own
+    c->plans.clear();
+    c->mod_cache.clear();
+    c->banks.clear();
+    c->err.clear();
+    c->use_counter = 0;
+    c->test_async = false;
+    c->timing = stts_timing{0, 0, 0, 0, 0};
+    c->voc_ms[0] = c->voc_ms[1] = 0;
+    c->st = c->st2 = nullptr;
+    c->ev_fork = c->ev_join = c->ev_stop = nullptr;
+    for (auto& ev : c->ev) ev = nullptr;
+    c->seed_dev = nullptr;
+    c->seed_host = nullptr;
+    init_instance(c);
+  });
+  if (rc != STTS_OK) {
+    if (c) stts_destroy(c);  // tolerates the handles init_instance did not get to
+    return rc;
+  }
+  *out = c;
+  return STTS_OK;
+}
+
 const char* stts_last_error(const stts_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
 
 int stts_load_weight(stts_engine* e, int model, const char* name, const float* data, int ndim, const int64_t* shape) {
   if (!e) return STTS_ERR_INVALID;
   return guard_impl(e, [&] {
     if (model < 0 || model > 2 || !name || !data || ndim < 0 || ndim > 4) throw Err(STTS_ERR_INVALID, "bad weight args");
+    if (!e->owns_weights) throw Err(STTS_ERR_WEIGHTS, "this handle is a clone: load weights through its source engine");
     RawTensor t;
     t.numel = 1;
     for (int i = 0; i < ndim; ++i) {

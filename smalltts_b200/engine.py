@@ -78,6 +78,15 @@ class Engine:
         self.device = device
         self._ready = False
 
+    def clone(self) -> "Engine":
+        """A second handle that shares this engine's weights (no copy) and has its own streams / plans: run it from
+        another host thread to keep two batches in flight on the GPU (stts_engine_clone).  Close clones first."""
+        h = C.c_void_p()
+        _cabi.check(self._lib.stts_engine_clone(self._h, C.byref(h)), self._h)
+        c = Engine.__new__(Engine)
+        c._lib, c._h, c.device, c._ready, c._parent = self._lib, h, self.device, True, self  # parent outlives the clone
+        return c
+
     # ------------------------------------------------------------------ weights
     def load_state_dicts(self, dit_sd: Optional[Dict[str, "np.ndarray"]], vocoder_sd: Optional[Dict[str, "np.ndarray"]],
                          encoder_sd: Optional[Dict[str, "np.ndarray"]] = None) -> None:

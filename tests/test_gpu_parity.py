@@ -454,3 +454,36 @@ def test_devices_kwarg_splits_the_batch_over_gpus(tts, dit_sd, voc_sd):
     assert [g.shape for g in got] == [w.shape for w in want]
     for g, w in zip(got, want):
         assert rel_l2(g, w) <= 2e-3  # batch composition changes tile shapes, not the arithmetic per row
+
+
+@pytest.mark.skipif(os.environ.get("STTS_TEST_EXPERIMENTAL") != "1",
+                    reason="stts_engine_clone has not been exercised on a GPU yet: STTS_TEST_EXPERIMENTAL=1")
+def test_engine_clone_shares_weights_and_runs_concurrently(tts):
+    """stts_engine_clone: same weights, own streams / plans.  Same inputs + same noise -> same audio as the source; two
+    handles driven from two host threads at once give the same results as one after the other."""
+    import threading
+
+    from smalltts_b200 import synthetic
+    from smalltts_b200.engine import pad_batch
+
+    refs, ids, frames, noise = synthetic.synthetic_inputs(3, [9, 6, 12], [4, 6, 3], [14, 9, 18], seed=33)
+    ref, ref_len, idt, ph_len = pad_batch(refs, ids, frames)
+    want = tts.engine.synthesize(ref, ref_len, idt, ph_len, frames, 12, noise=noise.numpy())
+    clone = tts.engine.clone()
+    try:
+        got = clone.synthesize(ref, ref_len, idt, ph_len, frames, 12, noise=noise.numpy())
+        assert rel_l2(got, want) <= 1e-6
+        with pytest.raises(RuntimeError, match="clone"):
+            clone.load_state_dicts({"x": np.zeros(1, np.float32)}, None)
+        outs = {}
+
+        def work(name, eng):
+            for _ in range(5):
+                outs[name] = eng.synthesize(ref, ref_len, idt, ph_len, frames, 12, noise=noise.numpy())
+
+        ths = [threading.Thread(target=work, args=(n, e)) for n, e in (("a", tts.engine), ("b", clone))]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        assert rel_l2(outs["a"], want) <= 1e-6 and rel_l2(outs["b"], want) <= 1e-6
+    finally:
+        clone.close()

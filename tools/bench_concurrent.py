@@ -24,8 +24,11 @@ ref, ref_len, idt, ph_len = pad_batch(refs, ids, frames)
 engines = []
 for n in range(1, max_replicas + 1):
     while len(engines) < n:
-        e = Engine(device)
-        e.load_state_dicts(*sds)
+        if engines and os.environ.get("STTS_CLONE") == "1":
+            e = engines[0][0].clone()  # shares the first engine's weights (stts_engine_clone)
+        else:
+            e = Engine(device)
+            e.load_state_dicts(*sds)
         dev = [torch.from_numpy(ref).cuda(), torch.from_numpy(idt).cuda()]
         out = torch.empty(8, 75 * 3200, device="cuda")
         for i in range(3):
