@@ -431,6 +431,8 @@ def test_serving_pipeline_and_microbatcher(tts_enc):
         assert rel_l2(a, want) <= 1e-6  # same seed, same batch composition -> same pass
 
 
+@pytest.mark.skipif(os.environ.get("STTS_TEST_EXPERIMENTAL") != "1",
+                    reason="single-process multi-GPU split has not run on a 2-GPU box yet: STTS_TEST_EXPERIMENTAL=1")
 def test_devices_kwarg_splits_the_batch_over_gpus(tts, dit_sd, voc_sd):
     """SmallTTS(devices=[0, 1]) (replicas + batch split, no data-path collective): with supplied noise
     the waveforms equal the single-GPU ones.  Needs two visible GPUs."""
