@@ -237,7 +237,9 @@ def onnx_state_dict(path: str, specs: Optional[Iterable[Tuple]] = None, exec_ran
     whose consumer is named after the *owning* module only (``/decoder/stem/stage.0/Mul_1``).  With ``specs`` (the
     architecture's (name, shape, ...) list) they are resolved too: the anonymous operands of elementwise nodes in
     module scope M are assigned, in execution order, to the still-unmatched direct parameters ``M.<leaf>`` of the
-    same element count, in declaration order.
+    same element count, in declaration order.  One parameter is not used as it is: ``style_encoder.log_scale`` enters
+    as ``x * exp(log_scale)`` (style.py:167), so a folded graph holds ``exp(log_scale)`` as the Mul operand; the log is
+    taken back.
 
     Graphs traced through direct method calls (``DiTModel.denoise_step`` calls ``self.dit.forward_cached(...)``, not
     ``self.dit(...)``, models/backbone/model.py:97-100) lose the outer scopes: their nodes are called
@@ -340,6 +342,9 @@ def onnx_state_dict(path: str, specs: Optional[Iterable[Tuple]] = None, exec_ran
                     a = g.tensors[src]
                     for i, (pname, shape) in enumerate(pending[owner]):
                         if int(np.prod(shape, dtype=np.int64)) == a.size:
+                            if pname.endswith("log_scale") and op == "Mul":
+                                # style.py:167 multiplies by exp(log_scale); a folding exporter leaves exp(.) behind
+                                a = np.log(np.asarray(a, dtype=np.float64)).astype(np.float32)
                             out[pname] = a.reshape(shape)
                             used.add(src)
                             del pending[owner][i]

@@ -130,6 +130,25 @@ def test_onnx_scopeless_graph_bias_pairing_and_execution_order(tmp_path):
         np.testing.assert_array_equal(np.asarray(sd[n + ".weight"]), W[n], err_msg=n)
 
 
+def test_folded_log_scale_is_recovered_as_a_logarithm(tmp_path):
+    """style.py:167: x * exp(log_scale).  Constant folding leaves exp(log_scale) as an anonymous scalar Mul operand in
+    the style encoder's scope; an unfolded graph keeps the named parameter.  Both must load as log_scale = -1.8."""
+    folded = _model(
+        [_node("/style_encoder/Mul", "Mul", ["h", "onnx::Mul_7"], ["hs"])],
+        [_tensor("onnx::Mul_7", [], 1, raw=np.array(np.exp(-1.8), "<f4").tobytes())])
+    named = _model(
+        [_node("/style_encoder/Exp", "Exp", ["m.style_encoder.log_scale"], ["s"]),
+         _node("/style_encoder/Mul", "Mul", ["h", "s"], ["hs"])],
+        [_tensor("m.style_encoder.log_scale", [], 1, raw=np.array(-1.8, "<f4").tobytes())])
+    specs = [("style_encoder.log_scale", ())]
+    for name, blob in (("folded", folded), ("named", named)):
+        path = tmp_path / f"{name}.onnx"
+        path.write_bytes(blob)
+        sd = weights.load_model_weights([str(path)], specs, name)
+        assert np.asarray(sd["style_encoder.log_scale"]).shape == ()
+        assert abs(float(sd["style_encoder.log_scale"]) + 1.8) < 1e-6, name
+
+
 def test_dit_exec_rank_follows_the_reference_forward():
     r = weights.dit_exec_rank
     assert r("style_encoder.blocks.11.mlp.w2.weight") < r("phoneme_embedding.blocks.0.attention.wq.weight")
