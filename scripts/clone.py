@@ -32,6 +32,10 @@ def tokens_for(text, tokens):
 def load_tts(args) -> SmallTTS:
     if args.synthetic:
         return SmallTTS.synthetic(encoder_seed=2)
+    if all(str(p).startswith("assets/") for p in (args.dit, args.denoiser, args.decoder, args.encoder)):
+        from smalltts_b200.assets import ensure_assets  # like the reference scripts (clone.py:14)
+
+        ensure_assets(["codec", "dmd"])
     return SmallTTS(args.dit, args.denoiser, args.decoder, codec_encoder_path=args.encoder)
 
 

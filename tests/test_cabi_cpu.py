@@ -84,3 +84,28 @@ def test_synthetic_weights_have_reference_shapes():
     assert sum(int(np.prod(s)) for _, s, _, _ in synthetic.vocoder_specs()) == 343_695_969
     assert len(synthetic.dit_specs()) == 592 and len(synthetic.vocoder_specs()) == 276
     assert sum(int(np.prod(s)) for _, s, _, _ in synthetic.encoder_specs()) == 343_696_032  # hf encoder
+
+
+def test_ensure_assets_offline_behaviour(tmp_path, monkeypatch):
+    """assets/ensure.py:20-41 mirror: an existing folder is left alone; a missing one without a reachable Hub is a
+    FileNotFoundError that names the files to provide (there is no network in the build / bench environment)."""
+    import sys
+    import types
+
+    from smalltts_b200.assets import ensure_assets
+
+    (tmp_path / "dmd").mkdir()
+    ensure_assets(["dmd", ""], root=str(tmp_path))  # nothing to do
+    fake = types.ModuleType("huggingface_hub")
+
+    def snapshot_download(**kw):
+        raise OSError("network unreachable")
+
+    fake.snapshot_download = snapshot_download
+    monkeypatch.setitem(sys.modules, "huggingface_hub", fake)
+    with pytest.raises(FileNotFoundError, match="codec/decoder.onnx"):
+        ensure_assets("codec", root=str(tmp_path))
+    calls = []
+    fake.snapshot_download = lambda **kw: calls.append(kw) or (tmp_path / "codec").mkdir()
+    ensure_assets("codec", root=str(tmp_path))
+    assert calls[0]["repo_id"] == "smallbraineng/smalltts" and calls[0]["allow_patterns"] == ["codec/*"]
