@@ -295,12 +295,15 @@ class Engine:
             pass
 
 
-def pad_batch(ref_list, ids_list: Sequence[Sequence[int]], frames: Sequence[int]):
-    """Ragged python inputs -> padded numpy batch (ref [B,R,64], ref_len, ids [B,P], ph_len)."""
+def pad_batch(ref_list, ids_list: Sequence[Sequence[int]], frames: Sequence[int], r_mult: int = 1, p_mult: int = 1):
+    """Ragged python inputs -> padded numpy batch (ref [B,R,64], ref_len, ids [B,P], ph_len).  ``r_mult`` / ``p_mult``
+    round the padded widths up to a multiple (the padding is masked by the lengths): fewer distinct shapes, so the
+    engine re-uses its per-shape plans / CUDA graphs instead of building new ones."""
     B = len(ref_list)
     refs = [np.asarray(r.detach().cpu().numpy() if _is_torch(r) else r, dtype=np.float32) for r in ref_list]
     R = max(r.shape[0] for r in refs)
     P = max(1, max(len(p) for p in ids_list))
+    R, P = -(-R // r_mult) * r_mult, -(-P // p_mult) * p_mult
     ref = np.zeros((B, R, LATENT_DIM), dtype=np.float32)
     ids = np.zeros((B, P), dtype=np.int64)
     for i in range(B):

@@ -67,8 +67,12 @@ class SmallTTS:
         state_dicts: Optional[tuple] = None,
         num_steps: int = NUM_STEPS,
         seed: Optional[int] = None,
+        shape_buckets: Optional[Sequence[int]] = None,  # (R, P, T) multiples the padded batch shape is rounded up to
     ) -> None:
         self.num_steps = num_steps
+        self.shape_buckets = tuple(int(x) for x in shape_buckets) if shape_buckets is not None else None
+        if self.shape_buckets is not None and (len(self.shape_buckets) != 3 or min(self.shape_buckets) < 1):
+            raise ValueError("shape_buckets must be three positive integers (R, P, T multiples)")
         self._seed = 0 if seed is None else int(seed)
         self._calls = 0
         devs = [int(d) for d in devices] if devices is not None else [int(device)]
@@ -86,8 +90,8 @@ class SmallTTS:
         self.engine = Engine(devs[0])
         self.engine.load_state_dicts(*state_dicts)
         # one replica (own engine, own weights copy, own host thread per call) per extra GPU; utterances are independent
-        self._replicas = [SmallTTS(state_dicts=state_dicts, device=d, num_steps=num_steps, seed=self._seed + 7919 * (k + 1))
-                          for k, d in enumerate(devs[1:])]
+        self._replicas = [SmallTTS(state_dicts=state_dicts, device=d, num_steps=num_steps, seed=self._seed + 7919 * (k + 1),
+                                   shape_buckets=shape_buckets) for k, d in enumerate(devs[1:])]
 
     @classmethod
     def synthetic(cls, dit_seed: int = 0, vocoder_seed: int = 1, encoder_seed: Optional[int] = None, **kw) -> "SmallTTS":
@@ -133,7 +137,10 @@ class SmallTTS:
         if self._replicas and len(frames) > 1 and not device_out:
             return self._synthesize_on_devices(ref_latents, phoneme_ids, durations, frames, noise, seed)
         T = max(frames)
-        ref, ref_len, ids, ph_len = pad_batch(ref_latents, phoneme_ids, frames)
+        rb, pb, tb = self.shape_buckets or (1, 1, 1)
+        if noise is None:  # supplied noise fixes T; the on-device stream does not care
+            T = -(-T // tb) * tb
+        ref, ref_len, ids, ph_len = pad_batch(ref_latents, phoneme_ids, frames, rb, pb)
         if seed is None:
             seed = self._seed + self._calls
         self._calls += 1

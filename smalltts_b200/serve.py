@@ -63,8 +63,12 @@ class Pipeline:
     ``tts`` is a :class:`smalltts_b200.infer.SmallTTS` whose engine carries the codec encoder (the server always
     encodes the posted reference audio, pipeline.rs:74-76)."""
 
-    def __init__(self, tts) -> None:
+    def __init__(self, tts, shape_buckets: Optional[Sequence[int]] = (8, 16, 5)) -> None:
         self.tts = tts
+        # requests come in every shape: round the padded (R, P, T) up so that the engine's per-shape plans (buffers +
+        # CUDA graphs, an LRU of 6) are re-used instead of rebuilt; T costs vocoder work, hence the small multiple
+        if shape_buckets is not None and getattr(tts, "shape_buckets", None) is None:
+            tts.shape_buckets = tuple(int(x) for x in shape_buckets)
 
     @classmethod
     def load(cls, cond_encoder_path: str = "assets/dmd/condition_encoder.onnx",

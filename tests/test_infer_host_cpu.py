@@ -19,8 +19,10 @@ class FakeEngine:
 
     def synthesize(self, ref, ref_len, ids, ph_len, frames, T, noise=None, seed=0, steps=4, timesteps=None, out=None):
         B = ref.shape[0]
-        assert ref.shape == (B, max(ref_len), 64) and ids.shape == (B, max(1, max(ph_len)))
-        assert T == max(frames) and all(1 <= f <= T for f in frames)
+        assert ref.shape[0] == B and ref.shape[1] >= max(ref_len) and ref.shape[2] == 64
+        assert ids.shape[0] == B and ids.shape[1] >= max(1, max(ph_len))
+        self.last_shape = (ref.shape[1], ids.shape[1])
+        assert T >= max(frames) and all(1 <= f <= T for f in frames)
         if noise is not None:
             assert noise.shape == (steps, B, T, 64)
         self.calls.append(dict(B=B, T=T, frames=list(frames), seed=seed, steps=steps, noise=noise is not None,
@@ -110,3 +112,21 @@ def test_devices_split_uses_every_gpu_and_keeps_the_order(fake):
         _tts(devices=[1, 1])
     with pytest.raises(ValueError):
         _tts(devices=[])
+
+
+def test_shape_buckets_round_the_padded_shape_up(fake):
+    """Fewer distinct (R, P, T) -> the engine re-uses its per-shape plans; lengths still mask the padding and every
+    utterance keeps its own number of samples."""
+    tts = _tts(shape_buckets=(8, 16, 5))
+    rng = np.random.default_rng(3)
+    refs = [rng.standard_normal((r, 64)).astype(np.float32) for r in (3, 9)]
+    out = tts.synthesize_batch(refs, [[5, 6], [7] * 17], [1.0, 2.2])  # frames 7 and 16
+    c = fake.instances[0].calls[-1]
+    assert c["T"] == 20 and c["frames"] == [7, 16] and c["ref_len"] == [3, 9] and c["ph_len"] == [2, 17]
+    assert [a.shape for a in out] == [(1, 7 * 3200), (1, 16 * 3200)]
+    assert fake.instances[0].last_shape == (16, 32)  # R 9 -> 16, P 17 -> 32
+    noise = np.zeros((4, 2, 16, 64), np.float32)
+    tts.synthesize_batch(refs, [[5, 6], [7] * 17], [1.0, 2.2], noise=noise)  # supplied noise pins T
+    assert fake.instances[0].calls[-1]["T"] == 16
+    with pytest.raises(ValueError):
+        _tts(shape_buckets=(8, 16))
