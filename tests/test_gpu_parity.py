@@ -408,7 +408,7 @@ def test_serving_pipeline_and_microbatcher(tts_enc):
     refs = [(0.2 * torch.randn(n, generator=g)).numpy() for n in (2 * 24000, 24000 + 500, 3 * 24000)]
     toks = [[5, 9, 20, 33], [7, 7, 12], [101, 3, 44, 9, 2]]
     durs = [1.01, 0.5, 2.0]
-    pipe = serve.Pipeline(tts_enc)
+    pipe = serve.Pipeline(tts_enc, shape_buckets=None)  # exact shapes here; bucketing has its own test below
     tts_enc._seed, tts_enc._calls = 123, 0
     audio, tm = pipe.synthesize_timed(refs[0], toks[0], durs[0])
     assert audio.shape == (8 * 3200,) and np.isfinite(audio).all()  # ceil(1.01 * 7.5) = 8 frames
@@ -489,3 +489,27 @@ def test_engine_clone_shares_weights_and_runs_concurrently(tts):
         assert rel_l2(outs["a"], want) <= 1e-6 and rel_l2(outs["b"], want) <= 1e-6
     finally:
         clone.close()
+
+
+@pytest.mark.skipif(os.environ.get("STTS_TEST_EXPERIMENTAL") != "1",
+                    reason="shape bucketing (T padded beyond every utterance) has not run on a GPU yet: STTS_TEST_EXPERIMENTAL=1")
+def test_shape_buckets_do_not_change_the_audio(dit_sd, voc_sd):
+    """Rounding the padded (R, P, T) up only adds masked rows: with supplied noise (which pins T) the audio equals the
+    unbucketed run; with the on-device stream every utterance still gets its own length."""
+    from smalltts_b200 import synthetic
+    from smalltts_b200.infer import SmallTTS
+
+    refs, ids, frames, noise = synthetic.synthetic_inputs(3, [9, 6, 12], [4, 6, 3], [14, 9, 18], seed=41)
+    durs = [f * 3200 / 24000 + 1e-3 for f in frames]
+    plain = SmallTTS(state_dicts=(dit_sd, voc_sd))
+    bucketed = SmallTTS(state_dicts=(dit_sd, voc_sd), shape_buckets=(8, 16, 5))
+    try:
+        a = plain.synthesize_batch(refs, ids, durs, noise=noise.numpy())
+        b = bucketed.synthesize_batch(refs, ids, durs, noise=noise.numpy())
+        for x, y in zip(a, b):
+            assert rel_l2(y, x) <= 2e-3
+        c = bucketed.synthesize_batch(refs, ids, durs, seed=5)  # T 12 -> 15: padded beyond every utterance
+        assert [x.shape for x in c] == [(1, f * 3200) for f in frames] and all(np.isfinite(x).all() for x in c)
+    finally:
+        plain.engine.close()
+        bucketed.engine.close()
