@@ -12,8 +12,12 @@ bench.rs:69-71), aggregated over all GPUs.
   value : device-timed (CUDA events on the engine stream), inputs resident in HBM, output left in HBM
   e2e   : the same through the public Python API / C ABI with pinned HOST buffers; H2D of inputs and D2H of the
           waveform are inside the timed region
-  --impl reference : the reference's own CPU path (PyTorch fp32 restatement in oracle/, all host threads), a bounded
-          sample of the same workload per step (1 utterance x 10 s; the reference is sequential per utterance)
+  --impl reference : the reference's own CPU path (PyTorch fp32 restatement in oracle/, all host threads) on the SAME
+          config: every step runs all 8 utterances x 10 s, one after the other like the reference's batch loop
+          (infer/onnx.py:143-156, bench.rs:29); --steps / --warmup are honoured exactly
+
+N > 1 additionally runs BASELINE configs[3] (64 mixed 2-10 s prompts sharded over the N GPUs, smalltts_b200/parallel.py)
+after the headline measurement and reports it under "config4" (a STRONG-scaling figure: the job is fixed).
 
 N > 1: one process per GPU (torchrun), utterance batches are independent -> weak scaling, no data-path collective;
 NCCL only for the barrier and the max-over-ranks of the timings.
@@ -55,23 +59,29 @@ def tail_algorithmic_bytes(batch: int, frames: int) -> float:
 
 
 def measured_peaks():
-    """-> (hbm GB/s, bf16 TFLOP/s sustained, source)."""
+    """-> (hbm GB/s, bf16 TFLOP/s sustained, bf16 TFLOP/s burst, source)."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", 1400.0)), "measured (MEASURED_PEAKS.json)"
+        return (float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", 1400.0)), float(p.get("bf16_tflops", 1650.0)),
+                "measured (MEASURED_PEAKS.json)")
     except Exception:
-        return 6650.0, 1400.0, "fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained)"
+        return 6650.0, 1400.0, 1650.0, "fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained)"
+
+
+TRAFFIC_FILE = "r02_tail_traffic.json"
 
 
 def tail_dram_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the tail group's kernels from the committed ncu capture
-    (profiles/r01_tail_traffic.json, same shapes as this bench); None if the capture is absent."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tail group's kernels, per launch group, from the ncu capture
+    committed under profiles/ (tools/ncu_tail.sh writes it together with the commit it was taken at; same shapes as
+    this bench).  -> (bytes, provenance) or (None, None)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_tail_traffic.json")) as f:
-            return float(json.load(f)["traffic_bytes"])
+        with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
+            j = json.load(f)
+        return float(j["traffic_bytes"]), f"profiles/{TRAFFIC_FILE} (ncu --set full, captured at commit {j.get('commit', '?')})"
     except Exception:
-        return None
+        return None, None
 
 
 # SURVEY.md 8(d): algorithmic FLOPs of one denoiser evaluation at B=8, T=75, R=15, P=120
@@ -128,11 +138,12 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_reference_run(steps: int, warmup: int):
+def cpu_reference_run(steps: int, warmup: int, utterances: int = BATCH, batched: bool = False):
     """The reference's own CPU implementation of the path, restated in oracle/ (PyTorch fp32, torch threads = all
-    host cores).  Each step = ONE utterance of the workload (10 s, R=15, P=120): the reference processes a batch as a
-    sequential loop over utterances (infer/onnx.py:143-156, bench.rs:29), so its batch throughput equals its
-    single-utterance throughput."""
+    host cores).  One step = `utterances` utterances of the workload (10 s, R=15, P=120), processed one after the other
+    like the reference's batch loop (infer/onnx.py:143-156, bench.rs:29,57-63), or as one padded batch (`batched`: what
+    the reference's mask-aware PyTorch model could do but none of its entry points does).
+    -> (audio-s/s, seconds per step, threads)."""
     import torch
 
     from oracle import smalltts_oracle as O
@@ -140,34 +151,102 @@ def cpu_reference_run(steps: int, warmup: int):
 
     torch.set_num_threads(os.cpu_count() or 1)
     sd, vsd = synthetic.dit_state_dict(0), synthetic.vocoder_state_dict(1)
-    refs, ids, frames, noise = synthetic.synthetic_inputs(1, T, R, P)
+    refs, ids, frames, noise = synthetic.synthetic_inputs(utterances, T, R, P)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.synthesize_batch(sd, vsd, refs, ids, frames, noise)
+        if batched:
+            O.synthesize_batch(sd, vsd, refs, ids, frames, noise)
+        else:
+            for u in range(utterances):
+                O.synthesize_batch(sd, vsd, refs[u : u + 1], ids[u : u + 1], frames[u : u + 1], noise[:, u : u + 1])
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     per_step = float(np.mean(times))
-    return AUDIO_S_PER_UTT / per_step, per_step, torch.get_num_threads()
+    return utterances * AUDIO_S_PER_UTT / per_step, per_step, torch.get_num_threads()
 
 
 def main_reference(args, rank, world):
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    steps, warmup = args.steps, args.warmup
     value, per_step, cores = cpu_reference_run(steps, warmup)
-    sample = f"{steps} steps x 1 utterance x 10 s (T=75,R=15,P=120), {warmup} warm-up; sequential per utterance like the reference"
+    sample = (f"{steps} steps x {BATCH} utterances x 10 s (T=75,R=15,P=120) after {warmup} warm-up steps; sequential per "
+              "utterance like the reference's batch loop")
+    batched, _, _ = cpu_reference_run(1, 0, batched=True)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_path": "PyTorch fp32 CPU restatement (oracle/); onnxruntime and the "
-                   ".onnx assets are not available offline"},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "dmd_steps": STEPS_DMD,
+                   "reference_path": "PyTorch fp32 CPU restatement (oracle/); onnxruntime and the .onnx assets are not "
+                   "available offline"},
         "rtf": 1.0 / value,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "batched_value": batched,
+                         "batched_sample": f"1 step, the {BATCH} utterances as ONE padded batch (not a reference entry point)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs[3]
+def run_config4(eng, rank, world, local_rank, dist, reps: int = 3):
+    """64 mixed 2-10 s prompts (T ~ U{15..75}, R ~ U{8..64}, P = round(1.53 T)) sharded over the ranks
+    (smalltts_b200/parallel.py: length-sorted contiguous split, length-bucketed micro-batches per rank), waveforms
+    gathered to rank 0 from HBM over NCCL.  The job is fixed, so across N this is STRONG scaling.  Wall clock around the
+    whole job including the host-side partition, padding, H2D and the gather; best of `reps` after one warm-up pass
+    (which builds the per-shape plans / CUDA graphs)."""
+    import torch
+
+    from smalltts_b200 import parallel, synthetic
+    from smalltts_b200.infer import SmallTTS
+
+    rng = np.random.default_rng(20260217)
+    n = 64
+    frames = rng.integers(15, 76, n).tolist()
+    refs_n = rng.integers(8, 65, n).tolist()
+    phon_n = [int(round(1.53 * f)) for f in frames]
+    refs, ids, _, _ = synthetic.synthetic_inputs(n, frames, refs_n, phon_n, steps=1)
+    durs = [f * 3200 / 24000 + 1e-3 for f in frames]
+    tts = SmallTTS(engine=eng)
+
+    def fn(idx):
+        return tts.synthesize_batch([refs[i] for i in idx], [ids[i] for i in idx], [durs[i] for i in idx], seed=7,
+                                    device_out=world > 1)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    best, best_stats, out = None, None, None
+    for rep in range(1 + reps):
+        stats = {}
+        barrier()
+        t0 = time.perf_counter()
+        out = parallel.synthesize_sharded(fn, frames, rank, world, stats=stats)
+        barrier()
+        dt = time.perf_counter() - t0
+        if rep > 0 and (best is None or dt < best):
+            best, best_stats = dt, stats
+    t = torch.tensor([best, best_stats["compute_s"], best_stats["gather_s"] if rank == 0 else 0.0], dtype=torch.float64,
+                     device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    assert all(a.shape == (1, f * 3200) and np.isfinite(a).all() for a, f in zip(out, frames))
+    shards = parallel.partition_sorted(frames, world)
+    pads = [(max(frames[i] for i in mb) * len(mb), sum(frames[i] for i in mb))
+            for s in shards for mb in parallel.length_buckets(s, frames)]
+    audio_s = sum(frames) * 3200 / 24000
+    return {"workload": "configs[3]: 64 mixed 2-10 s prompts sharded over the GPUs (strong scaling: fixed job)",
+            "audio_s_per_s": audio_s / t[0].item(), "wall_ms": t[0].item() * 1e3, "audio_seconds": audio_s,
+            "compute_ms_max_rank": t[1].item() * 1e3, "gather_ms": t[2].item() * 1e3, "micro_batches": len(pads),
+            "micro_batches_per_rank": [len(parallel.length_buckets(s, frames)) for s in shards],
+            "padding_frac": 1 - sum(u for _, u in pads) / sum(p for p, _ in pads),
+            "timing": f"wall clock incl. host partition/padding, H2D and the gather to rank 0; best of {reps} after a warm-up pass"}
 
 
 # ------------------------------------------------------------------------------------------ our arm (B200)
@@ -249,7 +328,8 @@ def main_ours(args, rank, local_rank, world):
     audio_s = BATCH * AUDIO_S_PER_UTT * world * args.steps
     value = audio_s / (dev_ms / 1e3)
     e2e_value = audio_s / (e2e_wall / 1e3)
-    peak, peak_tf, peak_src = measured_peaks()
+    peak, peak_tf, peak_tf_burst, peak_src = measured_peaks()
+    traffic, traffic_src = tail_dram_traffic()
     tail_bytes = tail_algorithmic_bytes(BATCH, T)
     achieved = tail_bytes / (tail_ms / 1e3) / 1e9
     dit_tflops = DENOISE_GFLOP_PER_STEP * STEPS_DMD / stage["denoise_ms"]  # GFLOP / ms = TFLOP/s
@@ -273,12 +353,22 @@ def main_ours(args, rank, local_rank, world):
         except Exception:  # noqa: BLE001 - strictly optional
             in_flight = None
 
+    config4 = None
+    if not args.no_config4:
+        try:
+            config4 = run_config4(eng, rank, world, local_rank, dist)
+        except Exception as exc:  # noqa: BLE001 - the headline line must still be printed
+            config4 = {"error": repr(exc)} if rank == 0 else None
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, per_step, cores = cpu_reference_run(3, 1)
+        v, per_step, cores = cpu_reference_run(2, 1)
+        vb, _, _ = cpu_reference_run(1, 0, batched=True)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "3 steps x 1 utterance x 10 s (T=75,R=15,P=120) after 1 warm-up; reference semantics "
-                         "(sequential per utterance), PyTorch fp32 oracle"}
+               "sample": f"2 steps x {BATCH} utterances x 10 s (T=75,R=15,P=120) after 1 warm-up step; reference "
+                         "semantics (sequential per utterance), PyTorch fp32 oracle",
+               "batched_value": vb,
+               "batched_sample": f"1 step, the {BATCH} utterances as ONE padded batch (not a reference entry point)"}
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -299,16 +389,19 @@ def main_ours(args, rank, local_rank, world):
                          "tcgen05 FFN GEMMs + transposed-conv GEMMs, CUDA events around the group on the engine stream",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes": tail_bytes, "ms": tail_ms,
-                         "traffic": tail_dram_traffic(), "front_ms": front_ms},
+                         "traffic": traffic, "traffic_source": traffic_src, "front_ms": front_ms},
             # second regime of the path: the 4 denoiser evaluations are tensor-core work
             "roofline_tensor": {"bound": "tensor", "kernel": "DMD loop: 4 denoiser evaluations (tcgen05 GEMMs + attention), "
                                 "CUDA events around the loop on the engine stream",
                                 "achieved": dit_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": dit_tflops / peak_tf,
+                                "peak_burst": peak_tf_burst, "frac_of_burst": dit_tflops / peak_tf_burst,
                                 "algorithmic_gflop": DENOISE_GFLOP_PER_STEP * STEPS_DMD, "ms": stage["denoise_ms"]},
             "cpu_baseline": cpu,
         }
         if in_flight is not None:
             out["in_flight"] = in_flight
+        if config4 is not None:
+            out["config4"] = config4
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
@@ -322,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the configs[3] (64 mixed prompts, sharded) figure")
     ap.add_argument("--in-flight", type=int, default=2,
                     help="also report throughput with up to this many batches in flight on one GPU (N=1 only; 0 = skip)")
     args = ap.parse_args()

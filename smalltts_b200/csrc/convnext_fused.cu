@@ -536,7 +536,7 @@ cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, 
   const int ntiles = p.B * ((p.T + TM - 1) / TM);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   const cudaError_t le = launch_k(convnext_fused_kernel<C>, dim3(grid), dim3(kThreadsFused), FC<C>::SMEM, st, m1, m2, p);
-  ++g_launch_count;
+  count_launch();
   return le != cudaSuccess ? le : cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@
 #include "../../include/smalltts_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "launch.cuh"
 
 using namespace stts;
 
@@ -849,8 +850,10 @@ void convnext_layers(stts_engine* e, const std::vector<VocLayerW>& layers, float
   }
 }
 
-// Launch-only (graph-capturable).  FRONT = stem + stages with C >= 256 (tensor-bound) incl. the upsampler into
-// C = 128; TAIL = stages with C <= 128 + head (HBM-bound).  Stage s works in buffer (s even ? xa : xb).
+// Launch-only (graph-capturable).  FRONT = stem + the ConvNeXt layers of the stages with C >= 256 and the upsamplers
+// between them (tensor-bound); TAIL = the upsampler into C = 128, stages with C <= 128 and the head (HBM-bound: this is
+// SURVEY 8(d)'s up3 + up4 + up5 + head group, whose 753.6 MB per 10 s utterance bench.py's roofline is quoted on).
+// Stage s works in buffer `cur`; every transposed convolution writes `oth` and swaps.
 void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev, const VocWs& ws, int part) {
   cudaStream_t st = e->st;
   const long long frames = static_cast<long long>(B) * T;
@@ -864,15 +867,20 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
     CK(launch_gemm(st, pick_bn(frames, 2048, 7), GemmA{ws.latb, LAT, LAT}, GemmW{e->stem_w, 2048, 7 * 64}, s, ep));
   }
   int Ts = T;
-  float* cur = ws.xa;  // activations of the current stage (every stage ends with one swap, see below)
+  float* cur = ws.xa;
   float* oth = ws.xb;
   for (int s = 0; s < 7; ++s) {
     const int C = VOC_C[s];
     const long long M = static_cast<long long>(B) * Ts;
-    const bool mine = (s < 4) ? (part & VOC_FRONT) != 0 : (part & VOC_TAIL) != 0;
-    if (mine) {
+    const bool layers_mine = (s < 4) ? (part & VOC_FRONT) != 0 : (part & VOC_TAIL) != 0;
+    const bool up_mine = (s < 3) ? (part & VOC_FRONT) != 0 : (part & VOC_TAIL) != 0;
+    if (layers_mine) {
       convnext_layers(e, e->voc[s], cur, oth, ws, B, Ts, C, /*bf16_copy=*/s < 6);
-      if (s < 6) {  // causal ConvTranspose1d(k=2r, stride=r) as a 2-tap GEMM with N = r*Cout (hf:219-260)
+    } else if (C <= 64 && e->fused_tail && (VOC_DEPTH[s] & 1)) {
+      std::swap(cur, oth);  // the other part's fused layers ping-pong between the buffers: follow them
+    }
+    if (s < 6) {  // causal ConvTranspose1d(k=2r, stride=r) as a 2-tap GEMM with N = r*Cout (hf:219-260)
+      if (up_mine) {
         const int r = VOC_R[s], cout = VOC_C[s + 1];
         GemmShape g;
         g.B = B; g.T = Ts; g.N = r * cout; g.K = C; g.taps = 2; g.tap_shift0 = 0; g.tap_step = -1;
@@ -880,10 +888,8 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
         ep.bias = e->up_b[s]; ep.out_f32 = oth; ep.ld_out = r * cout;
         CK(launch_gemm(st, pick_bn(M, r * cout, 2 * ((C + 63) / 64)), GemmA{ws.xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
       }
-    }
-    if (s < 6) {
       Ts *= VOC_R[s];
-      if (mine || !(C <= 64 && e->fused_tail)) std::swap(cur, oth);
+      std::swap(cur, oth);
     }
   }
   if (part & VOC_TAIL) CK(head_conv(st, cur, B, Ts, 32, e->head_w, e->head_b, audio_dev));
@@ -1027,18 +1033,31 @@ Plan* get_plan(stts_engine* e, int B, int R, int P, int T, int steps) {
 template <typename F>
 cudaGraphExec_t capture(stts_engine* e, F&& fn, unsigned long long* n_kernels) {
   cudaGraph_t graph = nullptr;
-  const unsigned long long before = g_launch_count;
   CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeRelaxed));
+  ++tl_capturing;  // launches below are recorded, not executed: the launch counter ignores them
   try {
     fn();
   } catch (...) {
+    --tl_capturing;
     cudaStreamEndCapture(e->st, &graph);
     if (graph) cudaGraphDestroy(graph);
     throw;
   }
+  --tl_capturing;
   CK(cudaStreamEndCapture(e->st, &graph));
-  *n_kernels = g_launch_count - before;  // recorded, not executed: replays add this to the launch counter
-  g_launch_count = before;
+  {  // kernels per replay = kernel nodes of the graph
+    size_t n = 0;
+    CK(cudaGraphGetNodes(graph, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n) CK(cudaGraphGetNodes(graph, nodes.data(), &n));
+    unsigned long long k = 0;
+    for (size_t i = 0; i < n; ++i) {
+      cudaGraphNodeType ty;
+      CK(cudaGraphNodeGetType(nodes[i], &ty));
+      if (ty == cudaGraphNodeTypeKernel) ++k;
+    }
+    *n_kernels = k;
+  }
   cudaGraphExec_t exec = nullptr;
   cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -1552,7 +1571,7 @@ int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, co
 
     const bool graphs = e->use_graphs && default_ts && p->graph_state == 1;
     CK(cudaEventRecord(e->ev[0], st));
-    if (graphs) g_launch_count += p->n_cond + p->n_sample[noise ? 1 : 0] + p->n_front + p->n_tail;
+    if (graphs) g_launch_count.fetch_add(p->n_cond + p->n_sample[noise ? 1 : 0] + p->n_front + p->n_tail, std::memory_order_relaxed);
     if (graphs) CK(cudaGraphLaunch(p->g_cond, st)); else run_cond();
     CK(cudaEventRecord(e->ev[1], st));
     if (graphs) CK(cudaGraphLaunch(p->g_sample[noise ? 1 : 0], st)); else run_sample(nd);
@@ -1597,7 +1616,7 @@ int stts_get_timings(const stts_engine* e, stts_timing* out) {
   return STTS_OK;
 }
 
-uint64_t stts_launch_count(void) { return g_launch_count; }
+uint64_t stts_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 float stts_last_vocoder_ms(const stts_engine* e, int which) {
   return (e && which >= 0 && which < 2) ? e->voc_ms[which] : -1.f;

@@ -388,7 +388,7 @@ cudaError_t ffn_fused(cudaStream_t st, const bf16* a, const float* y, long long 
   const int ntiles = static_cast<int>((M + TM - 1) / TM);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   const cudaError_t le = launch_k(ffn_fused_kernel<128>, dim3(grid), dim3(kThreadsFfn), F::SMEM, st, mA, m1, m2, p);
-  ++g_launch_count;
+  count_launch();
   return le != cudaSuccess ? le : cudaGetLastError();
 }
 

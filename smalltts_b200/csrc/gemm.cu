@@ -18,7 +18,8 @@
 
 namespace stts {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
+thread_local int tl_capturing = 0;
 
 namespace {
 
@@ -566,7 +567,7 @@ cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUten
                                 tmW, s, e, stages, n_tiles, m_tiles, static_cast<int>(total))
                 : launch_k(gemm_kernel<BN, ACT, CTAS>, dim3(grid), dim3(kThreads), C::smem_bytes(stages), stream, tmA, tmW,
                            s, e, stages, n_tiles, m_tiles, static_cast<int>(total));
-  ++g_launch_count;
+  count_launch();
   return le != cudaSuccess ? le : cudaGetLastError();
 }
 

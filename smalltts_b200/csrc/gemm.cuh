@@ -76,7 +76,5 @@ constexpr int kGemmPairFlag = 0x1000;
 cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const GemmW& w, const GemmShape& s,
                         const GemmEpi& e);
 
-// Number of kernels launched by this translation unit since process start (bench.py's gpu_launches).
-extern unsigned long long g_launch_count;
 
 }  // namespace stts

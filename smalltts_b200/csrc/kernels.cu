@@ -16,7 +16,7 @@ namespace {
 thread_local cudaError_t last_launch_status = cudaSuccess;
 #define STTS_LAUNCH_OK()                                                         \
   do {                                                                           \
-    ++g_launch_count;                                                            \
+    count_launch();                                                              \
     const cudaError_t _e = last_launch_status;                                   \
     return _e != cudaSuccess ? _e : cudaGetLastError();                          \
   } while (0)
@@ -1168,7 +1168,7 @@ cudaError_t gemv_rows(cudaStream_t st, const float* x, int rows, int k, const fl
     const int nr = rows - r0 < 8 ? rows - r0 : 8;
     last_launch_status = launch_k(gemv_rows_kernel<8>, dim3(blocks_for(n, 8)), dim3(256), 0, st, x + static_cast<long long>(r0) * k, nr, k, w, b, n, pre, post,
                                                          chunk, tanh_chunks, y + static_cast<long long>(r0) * ld_y, ld_y);
-    ++g_launch_count;
+    count_launch();
   }
   return cudaGetLastError();
 }

@@ -130,6 +130,5 @@ cudaError_t pack_vector(cudaStream_t st, const float* src, int n, float scale, i
 cudaError_t tile_vector(cudaStream_t st, const float* src, int n, int reps, float* dst);  // dst[j*n+i] = src[i]
 cudaError_t cast_f16(cudaStream_t st, const float* src, long long n, float scale, void* dst_f16);  // dst = fp16(scale*src)
 
-extern unsigned long long g_launch_count;
 
 }  // namespace stts

@@ -38,6 +38,16 @@ class PerDeviceOnce {
   std::atomic<unsigned long long> done_{0};
 };
 
+// Kernels launched (really executed) by this library since process start: bench.py's gpu_launches.  Engines may be driven
+// from several host threads (replicas, SmallTTS(devices=[...])), hence atomic.  Launches recorded into a CUDA graph
+// during stream capture do not run, so they are not counted here; a graph replay adds the number of kernel nodes the
+// graph holds (engine.cu: capture()).
+extern std::atomic<unsigned long long> g_launch_count;
+extern thread_local int tl_capturing;  // > 0 while this host thread records a graph
+inline void count_launch() {
+  if (tl_capturing == 0) g_launch_count.fetch_add(1, std::memory_order_relaxed);
+}
+
 inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {

@@ -232,6 +232,13 @@ class Engine:
         if out is None:
             out, op = self._out_like(ref, (B, T * HOP_SIZE), mem)
         else:
+            # the engine writes B*T*3200 floats straight through this pointer: never accept a buffer it could overrun
+            # and never let a silent copy (non-contiguous / wrong dtype) swallow the result
+            ok_dtype = str(out.dtype).endswith("float32")
+            contiguous = out.is_contiguous() if _is_torch(out) else bool(out.flags["C_CONTIGUOUS"])
+            if tuple(out.shape) != (B, T * HOP_SIZE) or not ok_dtype or not contiguous:
+                raise ValueError(f"out must be a C-contiguous float32 buffer of shape {(B, T * HOP_SIZE)}, got "
+                                 f"{tuple(out.shape)} {out.dtype}")
             op, mo, _ = _buf(out, np.float32, "out")
             if mo != mem:
                 raise ValueError("out must live in the same memory space as the inputs")

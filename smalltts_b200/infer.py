@@ -68,6 +68,7 @@ class SmallTTS:
         num_steps: int = NUM_STEPS,
         seed: Optional[int] = None,
         shape_buckets: Optional[Sequence[int]] = None,  # (R, P, T) multiples the padded batch shape is rounded up to
+        engine: Optional[Engine] = None,  # adopt an engine whose weights are already loaded (no second copy)
     ) -> None:
         self.num_steps = num_steps
         self.shape_buckets = tuple(int(x) for x in shape_buckets) if shape_buckets is not None else None
@@ -78,6 +79,11 @@ class SmallTTS:
         devs = [int(d) for d in devices] if devices is not None else [int(device)]
         if not devs or len(set(devs)) != len(devs):
             raise ValueError("devices must be a non-empty list of distinct CUDA ordinals")
+        if engine is not None:
+            if devices is not None:
+                raise ValueError("engine= adopts ONE loaded engine; it cannot be combined with devices=")
+            self.engine, self._replicas = engine, []
+            return
         if state_dicts is None:
             from . import synthetic
 
@@ -128,7 +134,7 @@ class SmallTTS:
 
     def synthesize_batch(self, ref_latents: Sequence, phoneme_ids: Sequence[Sequence[int]],
                          durations: Sequence[float], noise=None, seed: Optional[int] = None,
-                         device_out: bool = False) -> List[np.ndarray]:
+                         device_out: bool = False, shape_buckets: Optional[Sequence[int]] = None) -> List[np.ndarray]:
         """Ragged batch in one engine call.  noise: optional (steps, B, Tmax, 64).  Returns [(1, frames_i*3200)]
         (numpy; with ``device_out`` torch CUDA views of the engine's output, for device-side gathers)."""
         if not (len(ref_latents) == len(phoneme_ids) == len(durations)) or len(durations) == 0:
@@ -137,7 +143,7 @@ class SmallTTS:
         if self._replicas and len(frames) > 1 and not device_out:
             return self._synthesize_on_devices(ref_latents, phoneme_ids, durations, frames, noise, seed)
         T = max(frames)
-        rb, pb, tb = self.shape_buckets or (1, 1, 1)
+        rb, pb, tb = shape_buckets or self.shape_buckets or (1, 1, 1)
         if noise is None:  # supplied noise fixes T; the on-device stream does not care
             T = -(-T // tb) * tb
         ref, ref_len, ids, ph_len = pad_batch(ref_latents, phoneme_ids, frames, rb, pb)

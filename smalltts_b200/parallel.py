@@ -7,7 +7,7 @@ infer/onnx.py:143-156, scripts/infer/batch.py:31-45); this module is the host-si
 """
 from __future__ import annotations
 
-from typing import Callable, List, Sequence
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
@@ -33,6 +33,82 @@ def partition_lpt(costs: Sequence[float], n_ranks: int) -> List[List[int]]:
         out[r].append(i)
         loads[r] += costs[i]
     return out
+
+
+# Cost of one engine pass over a padded micro-batch, in frame units: the DiT loop is latency-bound (about the same
+# time for 100 or 600 rows) while the vocoder is linear in padded frames.  Measured on B200 (profiles/r02_summary.md):
+# ~3.5 ms + 8.5 us per padded frame, i.e. the fixed part is worth ~400 frames.
+PASS_FIXED_FRAMES = 400.0
+
+
+def pass_cost(indices: Sequence[int], frames: Sequence[int]) -> float:
+    return PASS_FIXED_FRAMES + len(indices) * max(frames[i] for i in indices)
+
+
+def shard_cost(indices: Sequence[int], frames: Sequence[int], max_batch: int = 16) -> float:
+    return sum(pass_cost(mb, frames) for mb in length_buckets(indices, frames, max_batch=max_batch)) if indices else 0.0
+
+
+class _ShardScan:
+    """Incremental :func:`shard_cost` of a growing contiguous shard (the micro-batching of length_buckets is a left-to-
+    right greedy scan, so extending a shard by one utterance is O(1))."""
+
+    def __init__(self, frames: Sequence[int], max_batch: int, max_pad_frac: float = 0.25) -> None:
+        self.frames, self.max_batch, self.max_pad_frac = frames, max_batch, max_pad_frac
+        self.cost, self.n_cur, self.used, self.tmax = 0.0, 0, 0, 0
+
+    def extended(self, i: int):
+        """-> (cost, n_cur, used, tmax) after appending utterance i; does not modify the scan."""
+        f = self.frames[i]
+        if self.n_cur and not (self.n_cur >= self.max_batch
+                               or 1.0 - (self.used + f) / (self.tmax * (self.n_cur + 1)) > self.max_pad_frac):
+            return self.cost + self.tmax, self.n_cur + 1, self.used + f, self.tmax
+        return self.cost + PASS_FIXED_FRAMES + f, 1, f, f
+
+    def push(self, state) -> None:
+        self.cost, self.n_cur, self.used, self.tmax = state
+
+
+def partition_sorted(frames: Sequence[int], n_ranks: int, max_batch: int = 16) -> List[List[int]]:
+    """Contiguous split of the utterances, sorted by decreasing length, into ``n_ranks`` shards that minimises the most
+    expensive shard (cost = the engine passes the shard needs, :func:`shard_cost`; bisection on that bound with a greedy
+    feasibility scan, O(n log) on the host).  Each rank gets utterances of similar length, so a shard is few, well-
+    filled micro-batches: with 64 mixed prompts on 8 GPUs that is ONE pass per GPU, where a length-mixing LPT split
+    needs two or three half-empty ones."""
+    if n_ranks < 1:
+        raise ValueError("n_ranks must be >= 1")
+    n = len(frames)
+    order = sorted(range(n), key=lambda i: (-frames[i], i))
+    if n_ranks == 1 or n == 0:
+        return [order] + [[] for _ in range(n_ranks - 1)]
+
+    def split(bound: float):
+        """Greedy: fill shard after shard up to `bound`; -> cut points, or None if more than n_ranks shards are needed."""
+        cuts, scan = [], _ShardScan(frames, max_batch)
+        for pos, i in enumerate(order):
+            st = scan.extended(i)
+            if st[0] > bound and scan.n_cur:
+                cuts.append(pos)
+                if len(cuts) >= n_ranks:
+                    return None
+                scan = _ShardScan(frames, max_batch)
+                st = scan.extended(i)
+            scan.push(st)
+        return cuts
+
+    lo, hi = 0.0, shard_cost(order, frames, max_batch)
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        if split(mid) is None:
+            lo = mid
+        else:
+            hi = mid
+        if hi - lo < 0.5:
+            break
+    cuts = split(hi) or []
+    edges = [0] + cuts + [n]
+    shards = [order[edges[k] : edges[k + 1]] for k in range(len(edges) - 1)]
+    return shards + [[] for _ in range(n_ranks - len(shards))]
 
 
 def length_buckets(indices: Sequence[int], frames: Sequence[int], max_batch: int = 16,
@@ -64,7 +140,7 @@ def synthesize_on_workers(workers: Sequence[Callable[[List[int]], List[np.ndarra
 
     if not workers:
         raise ValueError("no workers")
-    shards = partition_lpt([utterance_cost(f) for f in frames], len(workers))
+    shards = partition_sorted(frames, len(workers), max_batch=max_batch)
     results: List[np.ndarray] = [None] * len(frames)  # type: ignore[list-item]
 
     def run(k: int) -> None:
@@ -88,14 +164,20 @@ def synthesize_on_workers(workers: Sequence[Callable[[List[int]], List[np.ndarra
 
 
 def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], frames: Sequence[int], rank: int,
-                       world: int, group=None, gather_to: int = 0):
+                       world: int, group=None, gather_to: int = 0, shards: Optional[List[List[int]]] = None,
+                       stats: Optional[dict] = None):
     """Run ``synthesize_fn`` on this rank's shard and gather every waveform to ``gather_to`` in input order.
 
     synthesize_fn(indices) -> list of (1, frames_i*3200) float32 arrays (numpy, or torch CUDA tensors when the engine
     leaves its output in HBM) for those utterances (on a GPU rank this is
     ``lambda idx: tts.synthesize_batch([refs[i] for i in idx], ..., device_out=True)``).  Returns the full list on ``gather_to``,
-    None elsewhere.  world == 1 needs no process group."""
-    shards = partition_lpt([utterance_cost(f) for f in frames], world)
+    None elsewhere.  world == 1 needs no process group.  ``shards`` overrides the split (default: :func:`partition_sorted`,
+    the same on every rank); ``stats`` receives ``compute_s`` and ``gather_s`` of this rank."""
+    import time
+
+    t0 = time.perf_counter()
+    if shards is None:
+        shards = partition_sorted(frames, world)
     mine = shards[rank]
     results = {}
     for mb in length_buckets(mine, frames):
@@ -104,6 +186,13 @@ def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], f
                 raise ValueError(f"utterance {i}: expected {(1, frames[i] * HOP_SIZE)}, got {tuple(a.shape)}")
             results[i] = a
     on_device = any(type(a).__module__.startswith("torch") and a.is_cuda for a in results.values())
+    if on_device:
+        import torch
+
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if stats is not None:
+        stats["compute_s"], stats["gather_s"] = t1 - t0, 0.0
 
     def to_numpy(a):
         return np.asarray(a.detach().cpu().numpy() if type(a).__module__.startswith("torch") else a, dtype=np.float32)
@@ -135,7 +224,11 @@ def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], f
                 n = frames[i] * HOP_SIZE
                 out[i] = host[off : off + n].reshape(1, n)
                 off += n
+        if stats is not None:
+            stats["gather_s"] = time.perf_counter() - t1
         return out
     if sizes[rank] > 0:
         dist.send(send, dst=gather_to, group=group)
+    if stats is not None:
+        stats["gather_s"] = time.perf_counter() - t1
     return None

@@ -29,6 +29,7 @@ import numpy as np
 
 SAMPLE_RATE = 24_000  # pipeline.rs:11
 HOP_SIZE = 3_200  # pipeline.rs:12
+ENGINE_MAX_LEN = 4096  # frames / reference hops / tokens one engine call accepts (RoPE table size, dit.py:139)
 
 
 @dataclass
@@ -63,12 +64,13 @@ class Pipeline:
     ``tts`` is a :class:`smalltts_b200.infer.SmallTTS` whose engine carries the codec encoder (the server always
     encodes the posted reference audio, pipeline.rs:74-76)."""
 
-    def __init__(self, tts, shape_buckets: Optional[Sequence[int]] = (8, 16, 5)) -> None:
+    def __init__(self, tts, shape_buckets: Optional[Sequence[int]] = None) -> None:
         self.tts = tts
-        # requests come in every shape: round the padded (R, P, T) up so that the engine's per-shape plans (buffers +
-        # CUDA graphs, an LRU of 6) are re-used instead of rebuilt; T costs vocoder work, hence the small multiple
-        if shape_buckets is not None and getattr(tts, "shape_buckets", None) is None:
-            tts.shape_buckets = tuple(int(x) for x in shape_buckets)
+        # Requests come in every shape.  Rounding the padded (R, P, T) up lets the engine's per-shape plans (buffers +
+        # CUDA graphs, an LRU of 6) be re-used instead of rebuilt; T costs vocoder work, hence the small multiple in
+        # e.g. (8, 16, 5).  Off by default; the buckets live on the Pipeline (the caller's SmallTTS is not modified)
+        # and are applied per call.
+        self.shape_buckets = None if shape_buckets is None else tuple(int(x) for x in shape_buckets)
 
     @classmethod
     def load(cls, cond_encoder_path: str = "assets/dmd/condition_encoder.onnx",
@@ -104,7 +106,8 @@ class Pipeline:
         # the server's frame count rounds up (pipeline.rs:71); SmallTTS.synthesize_batch floors durations
         frames = [seq_len_for(d) for d in durations]
         durs = [(f + 0.5) * HOP_SIZE / SAMPLE_RATE for f in frames]
-        audio = self.tts.synthesize_batch(refs, [list(map(int, t)) for t in token_ids], durs)
+        audio = self.tts.synthesize_batch(refs, [list(map(int, t)) for t in token_ids], durs,
+                                          shape_buckets=self.shape_buckets)
         tm = eng.timings()
         timing = Timing(codec_enc_ms, tm["cond_enc_ms"], tm["denoise_ms"], tm["codec_dec_ms"],
                         (time.perf_counter() - t0) * 1e3, len(ref_audios))
@@ -152,6 +155,10 @@ class MicroBatcher:
             req.future.set_exception(ValueError("duration must be a positive number of seconds"))
         elif len(req.ref_audio) < HOP_SIZE:
             req.future.set_exception(ValueError("reference audio shorter than one codec hop (3200 samples at 24 kHz)"))
+        elif not (1 <= len(req.token_ids) <= ENGINE_MAX_LEN):
+            req.future.set_exception(ValueError(f"between 1 and {ENGINE_MAX_LEN} phoneme tokens are required"))
+        elif len(req.ref_audio) // HOP_SIZE > ENGINE_MAX_LEN or seq_len_for(req.duration_sec) > ENGINE_MAX_LEN:
+            req.future.set_exception(ValueError(f"reference audio and duration are limited to {ENGINE_MAX_LEN} codec frames"))
         else:
             self._q.put(req)
         return req.future
@@ -207,17 +214,37 @@ class MicroBatcher:
                 batch = self._take_batch()
             if batch is None:
                 break
-            try:
-                audio, timing = run([r.ref_audio for r in batch], [r.token_ids for r in batch],
-                                    [r.duration_sec for r in batch])
-                for r, a in zip(batch, audio):
-                    r.future.set_result((a, timing))
-                with self._stats:  # not _form: an idle worker holds that one while it waits for the next request
-                    self.batches_run += 1
-                    self.requests_run += len(batch)
-            except Exception as exc:  # inference failed: every request of the pass gets the error (HTTP 500)
+            self._run_batch(run, batch)
+
+    @staticmethod
+    def _resolve(fut: Future, result=None, exc: Optional[BaseException] = None) -> None:
+        """A client may have cancelled its future; never let that take the worker thread down."""
+        try:
+            if fut.done():
+                return
+            if exc is not None:
+                fut.set_exception(exc)
+            else:
+                fut.set_result(result)
+        except Exception:  # noqa: BLE001 - InvalidStateError from a race with cancel()
+            pass
+
+    def _run_batch(self, run, batch: List[Request]) -> None:
+        try:
+            audio, timing = run([r.ref_audio for r in batch], [r.token_ids for r in batch],
+                                [r.duration_sec for r in batch])
+        except Exception as exc:  # noqa: BLE001
+            if len(batch) == 1:  # this request is the offender (HTTP 400/500 for it alone)
+                self._resolve(batch[0].future, exc=exc)
+            else:  # the reference serves requests independently: retry one at a time so only the offender fails
                 for r in batch:
-                    r.future.set_exception(exc)
+                    self._run_batch(run, [r])
+            return
+        for r, a in zip(batch, audio):
+            self._resolve(r.future, result=(a, timing))
+        with self._stats:  # not _form: an idle worker holds that one while it waits for the next request
+            self.batches_run += 1
+            self.requests_run += len(batch)
 
 
 # ---------------------------------------------------------------------------------------------- WAV + HTTP front

@@ -20,6 +20,31 @@ def test_partition_lpt_balances_and_covers():
     assert parallel.partition_lpt(costs, 2) == parallel.partition_lpt(costs, 2)  # deterministic
 
 
+def test_partition_sorted_minimises_the_most_expensive_shard():
+    """Contiguous split of the length-sorted list: covers every utterance once, deterministic, never worse than the
+    length-mixing LPT split under the pass-cost model, and optimal against brute force on small cases."""
+    import itertools
+
+    rng = np.random.default_rng(20260217)
+    frames = rng.integers(15, 76, 64).tolist()  # BASELINE configs[3]
+    for world in (1, 2, 4, 8):
+        shards = parallel.partition_sorted(frames, world)
+        assert len(shards) == world and sorted(i for s in shards for i in s) == list(range(64))
+        lpt = parallel.partition_lpt([parallel.utterance_cost(f) for f in frames], world)
+        assert max(parallel.shard_cost(s, frames) for s in shards) <= max(parallel.shard_cost(s, frames) for s in lpt)
+    assert [len(parallel.length_buckets(s, frames)) for s in parallel.partition_sorted(frames, 8)] == [1] * 8
+    assert parallel.partition_sorted(frames, 4) == parallel.partition_sorted(frames, 4)
+    for _ in range(30):
+        n, world = int(rng.integers(1, 9)), int(rng.integers(1, 4))
+        fr = rng.integers(1, 226, n).tolist()
+        shards = parallel.partition_sorted(fr, world)
+        assert len(shards) == world and sorted(i for s in shards for i in s) == list(range(n))
+        order = sorted(range(n), key=lambda i: (-fr[i], i))
+        best = min(max(parallel.shard_cost(order[a:b], fr) for a, b in zip((0,) + cuts, cuts + (n,)))
+                   for cuts in itertools.combinations_with_replacement(range(n + 1), world - 1))
+        assert max(parallel.shard_cost(s, fr) for s in shards) <= best + 0.5
+
+
 def test_length_buckets_bound_padding():
     frames = [75, 74, 70, 40, 38, 15, 15, 14]
     order = sorted(range(len(frames)), key=lambda i: -frames[i])
@@ -95,8 +120,8 @@ def test_single_process_multi_device_split_orders_results_and_uses_one_thread_pe
     assert all(a.shape == (1, f * HOP_SIZE) for a, f in zip(out, frames))
     assert sorted(sum(served, [])) == list(range(len(frames)))  # every utterance exactly once
     assert all(len(s) == 1 for s in seen) and len(set.union(*seen)) == 3  # one host thread per worker
-    loads = [sum(frames[i] for i in s) for s in served]
-    assert max(loads) - min(loads) <= 75  # LPT balance
+    costs = [parallel.shard_cost(sorted(s, key=lambda i: -frames[i]), frames) for s in served]
+    assert max(costs) <= 1.5 * (sum(costs) / 3)  # the split balances engine passes, not utterance counts
 
     # a failing worker surfaces after the others finished; a wrong shape is rejected
     def boom(idx):

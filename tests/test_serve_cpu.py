@@ -96,6 +96,51 @@ def test_errors_reach_the_right_futures_and_the_worker_survives():
         b.submit(REF, [1], 1.0).result(1)
 
 
+def test_one_bad_request_does_not_fail_its_batch_mates():
+    """The reference serves requests independently (main.rs:138-147): when a batched pass fails, its requests are
+    retried one at a time so only the offender gets the error; limits of the engine are checked at submit()."""
+    fake = FakePipeline(delay=0.02, fail_on=13)
+    b = serve.MicroBatcher(fake, max_batch=4, max_wait_ms=200)
+    try:
+        futs = [b.submit(REF, [t], 1.0) for t in (5, 13, 7)]
+        assert futs[0].result(10)[0][0] == 5 and futs[2].result(10)[0][0] == 7
+        with pytest.raises(RuntimeError, match="boom"):
+            futs[1].result(10)
+        assert [c[0] for c in fake.calls] == [3, 1, 1, 1]
+        with pytest.raises(ValueError, match="tokens"):
+            b.submit(REF, list(range(serve.ENGINE_MAX_LEN + 1)), 1.0).result(1)
+        with pytest.raises(ValueError, match="tokens"):
+            b.submit(REF, [], 1.0).result(1)
+        with pytest.raises(ValueError, match="codec frames"):
+            b.submit(REF, [1], 4096 * 3200 / 24000 + 1).result(1)
+    finally:
+        b.close()
+
+
+def test_cancelled_future_does_not_kill_the_worker():
+    fake = FakePipeline(delay=0.1)
+    b = serve.MicroBatcher(fake, max_batch=1, max_wait_ms=1)
+    try:
+        first = b.submit(REF, [1], 1.0)
+        second = b.submit(REF, [2], 1.0)
+        assert second.cancel()  # still queued behind the first pass
+        assert first.result(10)[0][0] == 1
+        assert b.submit(REF, [3], 1.0).result(10)[0][0] == 3  # the worker thread is still alive
+    finally:
+        b.close()
+
+
+def test_pipeline_keeps_buckets_to_itself():
+    class T:  # SmallTTS stand-in
+        shape_buckets = None
+
+    t = T()
+    p = serve.Pipeline(t)
+    assert p.shape_buckets is None and t.shape_buckets is None  # bucketing is off by default
+    p = serve.Pipeline(t, shape_buckets=(8, 16, 5))
+    assert p.shape_buckets == (8, 16, 5) and t.shape_buckets is None  # the caller's object is not modified
+
+
 def test_wav_roundtrip_pcm16_and_float():
     x = (0.5 * np.sin(np.arange(2400) * 0.05)).astype(np.float32)
     data = serve.encode_wav(x)
