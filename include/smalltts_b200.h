@@ -187,6 +187,25 @@ int stts_test_convnext_fused(stts_engine* e, const float* x, int B, int T, int C
                              const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2,
                              const float* ffn_gamma, float* out, void* out_bf16);
 
+
+/* Chained DiT GEMM kernel (csrc/dit_chain.cuh): weights of the 12 blocks stacked per GEMM type, activation buffers of
+ * one denoiser evaluation and up to four dependent GEMM phases (kind: 0 q|k|v|gate, 1 to_out, 2 w1|w3, 3 w2, 4 velocity).
+ * `ready` must hold zeroed counters (4 per 128-row block + 1, rounded up to 16 ints). */
+typedef struct stts_test_chain_args {
+  const void *wqkvg, *wo, *w13, *w2, *wvel;                 /* bf16 */
+  const float *bqkvg, *b13, *b2, *bvel, *qn, *kn, *cos_t, *sin_t;
+  float* x; void* xb; float* stats; void* qkv; float* gate; const void* ob; void* hb; float* vel; int32_t* ready;
+  const int32_t* frames; const float* mod; const float* fold;
+  int32_t M, T, n_phases;
+  int32_t kind[4];
+  int32_t blk[4];
+} stts_test_chain_args;
+int stts_test_chain(stts_engine* e, const stts_test_chain_args* a);
+/* fold table [stts_test_chain_fold_floats()] of the timestep whose adaLN table is a->mod, from the weights in `a` */
+int stts_test_chain_fold(stts_engine* e, const stts_test_chain_args* a, float* fold_out);
+int64_t stts_test_chain_fold_floats(void);
+int stts_test_chain_stats_cast(stts_engine* e, const float* x, int M, const float* scale, void* xb, float* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,16 @@ class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("codec_enc_ms", "cond_enc_ms", "denoise_ms", "codec_dec_ms", "total_ms")]
 
 
+class ChainArgs(C.Structure):
+    """stts_test_chain_args (include/smalltts_b200.h)."""
+
+    _fields_ = ([(n, vp) for n in ("wqkvg", "wo", "w13", "w2", "wvel", "bqkvg", "b13", "b2", "bvel", "qn", "kn", "cos_t",
+                                   "sin_t", "x", "xb", "stats", "qkv", "gate", "ob", "hb", "vel", "ready", "frames", "mod",
+                                   "fold")]
+                + [("M", C.c_int32), ("T", C.c_int32), ("n_phases", C.c_int32), ("kind", C.c_int32 * 4),
+                   ("blk", C.c_int32 * 4)])
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header is exported
 SIGNATURES = {
     "stts_create": (C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
@@ -64,6 +74,10 @@ SIGNATURES = {
                                       vp, C.c_int, vp, C.c_int, vp]),
     "stts_test_convnext_mix": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "stts_test_ffn_fused": (C.c_int, [vp, vp, vp, C.c_longlong, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "stts_test_chain": (C.c_int, [vp, C.POINTER(ChainArgs)]),
+    "stts_test_chain_fold": (C.c_int, [vp, C.POINTER(ChainArgs), vp]),
+    "stts_test_chain_fold_floats": (C.c_int64, []),
+    "stts_test_chain_stats_cast": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
     "stts_test_convnext_fused": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
 }
 

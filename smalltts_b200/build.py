@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmalltts_b200.so")
-SOURCES = ["gemm.cu", "kernels.cu", "convnext_fused.cu", "ffn_fused.cu", "engine.cu"]
+SOURCES = ["gemm.cu", "kernels.cu", "convnext_fused.cu", "ffn_fused.cu", "dit_chain.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -1,0 +1,819 @@
+// Chained DiT GEMMs on tcgen05 (see dit_chain.cuh for what is fused and why).
+//
+// Persistent CTAs (one per SM) pull 128 x bn output tiles from ONE global queue: tiles are numbered phase by phase
+// (phase = one GEMM of the chain) and claimed in that order with an atomic counter.  A tile only depends on tiles with
+// smaller numbers, and a claimed tile is always in the hands of a resident CTA, so the kernel makes progress with ANY
+// number of resident CTAs (two engines sharing a GPU cannot deadlock each other) and the tail of one phase overlaps the
+// head of the next.  The claiming warp hands the tile numbers to the other roles through a small shared-memory FIFO:
+//   warp 0      W producer : claims tiles (one ahead), TMA boxes of the weight tile (no dependency: runs ahead through
+//                            the ring, also across phase boundaries and ahead of the PDL wait)
+//   warp 1      A producer : waits until the row block it needs has been completed by the previous phase (a counter in
+//                            global memory, bumped by the epilogue warps of the producing tiles), then TMA-loads A
+//   warp 2      MMA issuer : tcgen05.mma 128 x bn x 16, fp32 accumulators double-buffered in TMEM (2 x 256 columns)
+//   warps 4-11  epilogue   : tcgen05.ld -> LayerNorm fold / head RMSNorm + RoPE / SwiGLU / gated residual + LayerNorm
+//                            partials -> global; then release the accumulator and bump the row block's counter
+// The tile width is a per-tile value (64 / 128 / 192): it only changes the instruction descriptor, the number of
+// 64-row weight boxes per stage and the epilogue's chunk count, so one launch mixes widths to keep every phase at or
+// below one tile per SM at the benchmark shape (q|k|v: 24 head tiles of 128 + 5 gate tiles of 192 per row block).
+//
+// Memory model notes: data that another CTA wrote earlier in the SAME launch is read either by TMA (A operands; the
+// A producer acquires the counter at gpu scope and crosses to the async proxy with fence.proxy.async) or with
+// ld.global.cg (residual rows, LayerNorm partials: L1 may hold lines from an earlier phase).  Write-after-read hazards
+// between phases are excluded by the chain itself: a buffer's next writer depends transitively on all of its readers.
+#include "dit_chain.cuh"
+
+#include <cuda.h>
+
+#include "launch.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace stts {
+
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2;    // 16 KB
+constexpr int kWBytes = 192 * BK * 2;   // 24 KB: widest tile
+constexpr int kEpiWarps = 8;
+constexpr int kEpiWarp0 = 4;
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kStgBytes = 4096;         // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
+constexpr int kAccCols = 256;           // TMEM columns per accumulator buffer
+constexpr int kTq = 4;                  // depth of the tile FIFO between the claiming warp and the other roles
+constexpr int kTqReaders = 2 + kEpiWarps;  // A producer, MMA issuer, epilogue warps
+constexpr int kSmem = kStages * (kABytes + kWBytes) + 256 + kEpiWarps * kStgBytes + 2 * 2 * BM * 4 + 1024;
+
+struct ChainMaps {
+  CUtensorMap a[3];  // xb [M, 960], ob [M, 1024], hb [M, 2400]: box 64 x 128 rows
+  CUtensorMap w[5];  // per ChainKind, all blocks stacked: box 64 x 64 rows
+};
+
+struct ChainDev {
+  ChainWeights w;
+  ChainBuffers b;
+  ChainCall c;
+  int m_tiles;
+};
+
+// ---------------------------------------------------------------- static shape tables
+__device__ __forceinline__ int kind_ntiles(int kind) {
+  return kind == CHAIN_QKVG ? 29 : (kind == CHAIN_W13 ? 25 : (kind == CHAIN_VEL ? 1 : 15));
+}
+__device__ __forceinline__ int kind_kiters(int kind) {
+  return kind == CHAIN_OUT ? 16 : (kind == CHAIN_W2 ? 38 : 15);
+}
+__device__ __forceinline__ int kind_wrows(int kind) {  // weight rows per block
+  return kind == CHAIN_QKVG ? kChainQKVG : (kind == CHAIN_W13 ? kChainW13 : (kind == CHAIN_VEL ? 0 : kChainD));
+}
+__device__ __forceinline__ int kind_amap(int kind) { return kind == CHAIN_OUT ? 1 : (kind == CHAIN_W2 ? 2 : 0); }
+__device__ __forceinline__ void tile_cols(int kind, int n, int& n0, int& bn) {
+  if (kind == CHAIN_QKVG) {
+    if (n < 24) { n0 = n * 128; bn = 128; } else { n0 = 3072 + (n - 24) * 192; bn = 192; }
+  } else if (kind == CHAIN_W13) {
+    n0 = n * 192; bn = 192;
+  } else {
+    n0 = n * 64; bn = 64;
+  }
+}
+
+struct Tile {
+  int p, kind, blk, m, n;
+};
+// global tile number -> (phase, row block, column tile); phases are numbered back to back, n fastest inside a phase
+__device__ __forceinline__ Tile decode_tile(int g, const ChainCall& c, int m_tiles) {
+  Tile t;
+  t.p = 0;
+  for (;;) {
+    const int total = kind_ntiles(c.kind[t.p]) * m_tiles;
+    if (g < total || t.p + 1 >= c.n_phases) break;
+    g -= total;
+    ++t.p;
+  }
+  t.kind = c.kind[t.p];
+  t.blk = c.blk[t.p];
+  const int nt = kind_ntiles(t.kind);
+  t.m = g / nt;
+  t.n = g % nt;
+  return t;
+}
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded like ptx::mbar_wait: a scheduling bug traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_ready(const int* p, int target) {
+  uint32_t spins = 0;
+  while (ld_acquire(p) < target) {
+    __nanosleep(40);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
+__device__ __forceinline__ uint32_t bf2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x));
+}
+
+// ---------------------------------------------------------------- epilogue building blocks
+struct Epi {
+  int q, half, lane;    // TMEM lane quarter, chunk parity of this warp, lane
+  float* stg;           // warp-private staging (4 KB)
+  float* ssx;           // [2][2][128] head RMSNorm exchange between the two warps of a lane quarter
+  uint32_t acc;         // TMEM address of this tile's accumulator at this warp's lane quarter
+  int m0;               // global row of this warp's first TMEM lane
+  uint32_t okbits;      // rows of this warp inside [0, M)
+};
+
+// mean / rstd of LayerNorm(x[row]) from the 30 partials the producing epilogue left (dit.py:16, eps 1e-6)
+__device__ __forceinline__ void row_stats(const float* __restrict__ stats, int grow, bool ok, float& mean, float& rstd) {
+  float s1 = 0.f, s2 = 0.f;
+  if (ok) {
+    const float4* p = reinterpret_cast<const float4*>(stats + static_cast<long long>(grow) * (2 * kChainParts));
+#pragma unroll
+    for (int i = 0; i < kChainParts / 2; ++i) {
+      const float4 v = __ldcg(p + i);
+      s1 += v.x + v.z;
+      s2 += v.y + v.w;
+    }
+  }
+  mean = s1 * (1.0f / kChainD);
+  const float var = fmaxf(s2 * (1.0f / kChainD) - mean * mean, 0.f);
+  rstd = rsqrtf(var + 1e-6f);
+}
+
+// v = rstd * (acc - mean * cs) + b  on one 32-column chunk held in row form
+__device__ __forceinline__ void ln_chunk(const uint32_t (&r)[32], float (&v)[32], float mean, float rstd,
+                                         const float* __restrict__ cs, const float* __restrict__ bb) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs) + i);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bb) + i);
+    v[4 * i + 0] = fmaf(rstd, fmaf(-mean, c4.x, __uint_as_float(r[4 * i + 0])), b4.x);
+    v[4 * i + 1] = fmaf(rstd, fmaf(-mean, c4.y, __uint_as_float(r[4 * i + 1])), b4.y);
+    v[4 * i + 2] = fmaf(rstd, fmaf(-mean, c4.z, __uint_as_float(r[4 * i + 2])), b4.z);
+    v[4 * i + 3] = fmaf(rstd, fmaf(-mean, c4.w, __uint_as_float(r[4 * i + 3])), b4.w);
+  }
+}
+
+// 32 rows x 32 bf16 (row form) -> global rows of pitch ld (elements), 64-byte row segments per 4 lanes
+__device__ __forceinline__ void store_bf16_chunk(const Epi& e, const float (&v)[32], bf16* __restrict__ out, long long ld,
+                                                 int col0) {
+  uint4* srow = reinterpret_cast<uint4*>(e.stg) + e.lane * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 pk;
+    pk.x = bf2(v[8 * i + 0], v[8 * i + 1]);
+    pk.y = bf2(v[8 * i + 2], v[8 * i + 3]);
+    pk.z = bf2(v[8 * i + 4], v[8 * i + 5]);
+    pk.w = bf2(v[8 * i + 6], v[8 * i + 7]);
+    srow[i ^ ((e.lane >> 1) & 3)] = pk;
+  }
+  __syncwarp();
+  const int l4r = e.lane >> 2, l4c = e.lane & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int rr = 8 * j + l4r;
+    const uint4 pk = reinterpret_cast<const uint4*>(e.stg)[rr * 4 + (l4c ^ ((rr >> 1) & 3))];
+    if ((e.okbits >> rr) & 1u) {
+      *reinterpret_cast<uint4*>(out + static_cast<long long>(e.m0 + rr) * ld + col0 + 8 * l4c) = pk;
+    }
+  }
+  __syncwarp();
+}
+
+// 32 rows x 32 fp32 (row form) -> global, 128-byte row segments per 8 lanes
+__device__ __forceinline__ void store_f32_chunk(const Epi& e, const float (&v)[32], float* __restrict__ out, long long ld,
+                                                int col0) {
+  float4* srow = reinterpret_cast<float4*>(e.stg) + e.lane * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) srow[i ^ (e.lane & 7)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  __syncwarp();
+  const int l8r = e.lane >> 3, l8c = e.lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int rr = 4 * j + l8r;
+    const float4 x = reinterpret_cast<const float4*>(e.stg)[rr * 8 + (l8c ^ (rr & 7))];
+    if ((e.okbits >> rr) & 1u) {
+      *reinterpret_cast<float4*>(out + static_cast<long long>(e.m0 + rr) * ld + col0 + 4 * l8c) = x;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainDev d) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smA = smem;
+  uint8_t* smW = smem + kStages * kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smW + kStages * kWBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint64_t* tq_full = acc_empty + 2;     // [kTq]
+  uint64_t* tq_empty = tq_full + kTq;    // [kTq]
+  int* tileq = reinterpret_cast<int*>(tq_empty + kTq);  // [kTq]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tileq + kTq);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full) + 256;
+  float* ssx = reinterpret_cast<float*>(stage_base + kEpiWarps * kStgBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const ChainCall& c = d.c;
+  const int m_tiles = d.m_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 3; ++i) ptx::prefetch_tmap(&maps.a[i]);
+    for (int i = 0; i < 5; ++i) ptx::prefetch_tmap(&maps.w[i]);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full[i], 2);  // W producer + A producer (each arrives with its own byte count)
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], kEpiWarps);
+    }
+    for (int i = 0; i < kTq; ++i) {
+      ptx::mbar_init(&tq_full[i], 1);
+      ptx::mbar_init(&tq_empty[i], kTqReaders);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<2 * kAccCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_trigger();
+
+  int total_tiles = 0;
+  for (int p = 0; p < c.n_phases; ++p) total_tiles += kind_ntiles(c.kind[p]) * m_tiles;
+  int* const next_tile = d.b.ready + 4 * m_tiles;  // the launch's claim counter sits behind its ready counters
+
+  // Consumer side of the tile FIFO: calls fn(tile) for every tile this CTA claimed, in claim order.
+  auto walk = [&](auto&& fn) {
+    uint32_t slot = 0, tph = 0;
+    for (;;) {
+      ptx::mbar_wait(&tq_full[slot], tph);
+      const int g = tileq[slot];
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tq_empty[slot]);
+      if (g < 0) break;
+      fn(decode_tile(g, c, m_tiles));
+      if (++slot == kTq) { slot = 0; tph ^= 1; }
+    }
+  };
+
+  if (warp == 0) {
+    // ================================================================== W producer + tile claims
+    uint32_t st = 0, ph = 0, slot = 0, tph = 0;
+    int issued = 0;
+    bool waited = false;
+    auto claim = [&]() {  // the whole warp gets the next global tile number
+      int g = 0;
+      if (lane == 0) g = atomicAdd(next_tile, 1);
+      return __shfl_sync(0xffffffffu, g, 0);
+    };
+    int g = claim();
+    for (;;) {
+      const bool live = g < total_tiles;
+      ptx::mbar_wait(&tq_empty[slot], tph ^ 1);
+      if (lane == 0) {
+        tileq[slot] = live ? g : -1;
+        ptx::mbar_arrive(&tq_full[slot]);  // release: the tile number is visible to whoever sees this phase complete
+      }
+      __syncwarp();
+      if (++slot == kTq) { slot = 0; tph ^= 1; }
+      if (!live) break;
+      const Tile t = decode_tile(g, c, m_tiles);
+      g = claim();  // one ahead: the round trip to L2 hides behind this tile's loads
+      int n0, bn;
+      tile_cols(t.kind, t.n, n0, bn);
+      const int wrow = t.blk * kind_wrows(t.kind) + n0;
+      const int iters = kind_kiters(t.kind);
+      const CUtensorMap* tm = &maps.w[t.kind];
+      for (int it = 0; it < iters; ++it) {
+        // weights never depend on the predecessor kernel: the first ring's worth of boxes is requested before the
+        // PDL wait; the wait itself must still happen before this kernel can be considered complete
+        if (!waited && issued == kStages) {
+          ptx::pdl_wait();
+          waited = true;
+        }
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full[st], static_cast<uint32_t>(bn) * 128u);
+          for (int r = 0; r < bn / 64; ++r) {
+            ptx::tma_load_2d(smW + st * kWBytes + r * 8192, tm, &full[st], it * BK, wrow + r * 64);
+          }
+        }
+        __syncwarp();
+        ++issued;
+        if (++st == kStages) { st = 0; ph ^= 1; }
+      }
+    }
+    if (!waited) ptx::pdl_wait();
+  } else if (warp == 1) {
+    // ================================================================== A producer
+    ptx::pdl_wait();
+    uint32_t st = 0, ph = 0;
+    walk([&](const Tile& t) {
+      const int p = t.p, kind = t.kind, m = t.m;
+      if (p > 0) {
+        // all tiles of the previous phase that write rows [128 m, +128) must be done (8 epilogue warps each)
+        if (lane == 0) wait_ready(d.b.ready + (p - 1) * m_tiles + m, kind_ntiles(c.kind[p - 1]) * kEpiWarps);
+        __syncwarp();
+        fence_proxy_async_all();  // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
+      }
+      const int iters = kind_kiters(kind);
+      const CUtensorMap* tm = &maps.a[kind_amap(kind)];
+      for (int it = 0; it < iters; ++it) {
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full[st], kABytes);
+          ptx::tma_load_2d(smA + st * kABytes, tm, &full[st], it * BK, m * BM);
+        }
+        __syncwarp();
+        if (++st == kStages) { st = 0; ph ^= 1; }
+      }
+    });
+  } else if (warp == 2) {
+    // ================================================================== MMA issuer
+    ptx::pdl_wait();
+    const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(smA));
+    const uint64_t db0 = ptx::umma_desc_sw128(ptx::smem_u32(smW));
+    uint32_t st = 0, ph = 0;
+    int li = 0;
+    walk([&](const Tile& t) {
+      const int kind = t.kind;
+      int n0, bn;
+      tile_cols(kind, t.n, n0, bn);
+      const uint32_t idesc = ptx::umma_idesc_bf16(BM, static_cast<uint32_t>(bn));
+      const int iters = kind_kiters(kind);
+      const int ab = li & 1;
+      ptx::mbar_wait(&acc_empty[ab], ((li >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * kAccCols;
+      for (int it = 0; it < iters; ++it) {
+        ptx::mbar_wait(&full[st], ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t da = da0 + static_cast<uint64_t>(st * (kABytes >> 4));
+          const uint64_t db = db0 + static_cast<uint64_t>(st * (kWBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty[st]);
+        }
+        __syncwarp();
+        if (++st == kStages) { st = 0; ph ^= 1; }
+      }
+      if (ptx::elect_one()) ptx::umma_commit(&acc_full[ab]);
+      __syncwarp();
+      ++li;
+    });
+  } else if (warp >= kEpiWarp0) {
+    // ================================================================== epilogue (8 warps)
+    ptx::pdl_wait();
+    Epi e;
+    e.q = warp & 3;
+    e.half = (warp - kEpiWarp0) >> 2;
+    e.lane = lane;
+    e.stg = reinterpret_cast<float*>(stage_base + (warp - kEpiWarp0) * kStgBytes);
+    e.ssx = ssx;
+    const int l8r = lane >> 3, l8c = lane & 7;
+    int li = 0, hcount = 0;
+    walk([&](const Tile& t) {
+      const int p = t.p, kind = t.kind, blk = t.blk, m = t.m, n = t.n;
+      int n0, bn;
+      tile_cols(kind, n, n0, bn);
+      const int ab = li & 1;
+      e.acc = tmem_base + ab * kAccCols + (static_cast<uint32_t>(e.q * 32) << 16);
+      e.m0 = m * BM + e.q * 32;
+      const int grow = e.m0 + lane;  // row this thread owns in row form
+      const bool row_ok = grow < c.M;
+      e.okbits = __ballot_sync(0xffffffffu, row_ok);
+      ptx::mbar_wait(&acc_full[ab], (li >> 1) & 1);
+      ptx::tc_fence_after();
+
+      if (e.okbits != 0u) {
+        if (kind == CHAIN_QKVG || kind == CHAIN_W13 || kind == CHAIN_VEL) {
+          float mean, rstd;
+          row_stats(d.b.stats, grow, row_ok, mean, rstd);
+          if (kind == CHAIN_QKVG && n < 24) {
+            // ---- one head of q (kind3 0), k (1) or v (2): LayerNorm fold, per-head RMSNorm, RoPE, bf16 head layout
+            const int kind3 = n >> 3, head = n & 7;
+            const float* cs = c.fold + kFoldCsQ + blk * kChainQKVG + n0;
+            const float* bb = c.fold + kFoldBq + blk * kChainQKVG + n0;
+            float rn = 1.0f;
+            if (kind3 < 2) {
+              float ss = 0.f;
+#pragma unroll 1
+              for (int cc = e.half; cc < 4; cc += 2) {
+                uint32_t r[32];
+                float v[32];
+                ptx::tmem_ld_32x32(e.acc + cc * 32, r);
+                ptx::tmem_ld_wait();
+                ln_chunk(r, v, mean, rstd, cs + cc * 32, bb + cc * 32);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);  // pad columns are exactly 0 (zero weights, cs, b)
+              }
+              float* sx = e.ssx + (hcount & 1) * (2 * BM);
+              sx[e.half * BM + e.q * 32 + lane] = ss;
+              ptx::named_bar_sync(1 + e.q, 64);  // the two warps of this lane quarter
+              const float tot = sx[e.q * 32 + lane] + sx[BM + e.q * 32 + lane];
+              rn = rsqrtf(tot * (1.0f / kChainHD) + 1e-6f);
+              ++hcount;
+            }
+            const float* nw = (kind3 == 0 ? d.w.qn : d.w.kn) + blk * (kChainH * kChainHD) + head * kChainHD;
+            const int pos = grow % c.T;
+            bf16* out = d.b.qkv + static_cast<long long>(kind3) * c.M * (kChainH * kChainHDP) + head * kChainHDP;
+#pragma unroll 1
+            for (int cc = e.half; cc < 4; cc += 2) {
+              uint32_t r[32];
+              float v[32];
+              ptx::tmem_ld_32x32(e.acc + cc * 32, r);
+              ptx::tmem_ld_wait();
+              ln_chunk(r, v, mean, rstd, cs + cc * 32, bb + cc * 32);
+              if (kind3 < 2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (cc * 32 + 4 * i < kChainHD) w4 = __ldg(reinterpret_cast<const float4*>(nw + cc * 32) + i);
+                  v[4 * i + 0] *= rn * w4.x; v[4 * i + 1] *= rn * w4.y;
+                  v[4 * i + 2] *= rn * w4.z; v[4 * i + 3] *= rn * w4.w;
+                }
+                if (cc < 2) {  // interleaved-pair rotation of dims [0, 64): pair j of this chunk uses angle index 16 cc + j
+                  const float4* cp = reinterpret_cast<const float4*>(d.w.cos_t + static_cast<long long>(pos) * 32 + cc * 16);
+                  const float4* sp = reinterpret_cast<const float4*>(d.w.sin_t + static_cast<long long>(pos) * 32 + cc * 16);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 c4 = __ldg(cp + i), s4 = __ldg(sp + i);
+                    const float cj[4] = {c4.x, c4.y, c4.z, c4.w}, sj[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
+                      v[8 * i + 2 * j] = x0 * cj[j] - x1 * sj[j];
+                      v[8 * i + 2 * j + 1] = x1 * cj[j] + x0 * sj[j];
+                    }
+                  }
+                }
+              }
+              store_bf16_chunk(e, v, out, kChainH * kChainHDP, cc * 32);
+            }
+          } else if (kind == CHAIN_QKVG) {
+            // ---- attention gate columns (dit.py:111): LayerNorm fold only, fp32 (the attention kernel applies sigmoid)
+            const float* cs = c.fold + kFoldCsQ + blk * kChainQKVG + n0;
+            const float* bb = c.fold + kFoldBq + blk * kChainQKVG + n0;
+#pragma unroll 1
+            for (int cc = e.half; cc < 6; cc += 2) {
+              uint32_t r[32];
+              float v[32];
+              ptx::tmem_ld_32x32(e.acc + cc * 32, r);
+              ptx::tmem_ld_wait();
+              ln_chunk(r, v, mean, rstd, cs + cc * 32, bb + cc * 32);
+              store_f32_chunk(e, v, d.b.gate, kChainD, n0 - 3072 + cc * 32);
+            }
+          } else if (kind == CHAIN_W13) {
+            // ---- SwiGLU hidden (dit.py:186): chunk = 16 w1 columns | 16 w3 columns
+            const float* cs = c.fold + kFoldCs13 + blk * kChainW13 + n0;
+            const float* bb = c.fold + kFoldB13 + blk * kChainW13 + n0;
+#pragma unroll 1
+            for (int cc = e.half; cc < 6; cc += 2) {
+              uint32_t r[32];
+              float v[32];
+              ptx::tmem_ld_32x32(e.acc + cc * 32, r);
+              ptx::tmem_ld_wait();
+              ln_chunk(r, v, mean, rstd, cs + cc * 32, bb + cc * 32);
+              uint4 pk[2];
+              uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float a0 = v[2 * i], a1 = v[2 * i + 1];
+                pw[i] = bf2(a0 * fast_sigmoid(a0) * v[16 + 2 * i], a1 * fast_sigmoid(a1) * v[16 + 2 * i + 1]);
+              }
+              // 32 rows x 16 bf16: 32-byte rows staged, two lanes per row store 16 bytes each
+              uint4* srow = reinterpret_cast<uint4*>(e.stg) + lane * 2;
+              srow[0 ^ ((lane >> 2) & 1)] = pk[0];
+              srow[1 ^ ((lane >> 2) & 1)] = pk[1];
+              __syncwarp();
+              const int hcol = (n0 + cc * 32) >> 1;
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int rr = 16 * j + (lane >> 1), hf = lane & 1;
+                const uint4 x = reinterpret_cast<const uint4*>(e.stg)[rr * 2 + (hf ^ ((rr >> 2) & 1))];
+                if ((e.okbits >> rr) & 1u) {
+                  *reinterpret_cast<uint4*>(d.b.hb + static_cast<long long>(e.m0 + rr) * kChainFF + hcol + 8 * hf) = x;
+                }
+              }
+              __syncwarp();
+            }
+          } else {
+            // ---- velocity head (model.py:100) behind the final adaLN (dit.py:35-39): one chunk per warp
+            uint32_t r[32];
+            float v[32];
+            ptx::tmem_ld_32x32(e.acc + e.half * 32, r);
+            ptx::tmem_ld_wait();
+            ln_chunk(r, v, mean, rstd, c.fold + kFoldCsV + e.half * 32, c.fold + kFoldBv + e.half * 32);
+            store_f32_chunk(e, v, d.b.vel, 64, e.half * 32);
+          }
+        } else {
+          // ---- to_out / w2: x += tanh(gate) * (acc + b) with padded query rows masked for to_out (dit.py:115-118,
+          // 198,201); writes x, its LayerNorm partials and the next GEMM's operand bf16(x * (1 + scale)).
+          const bool is_out = kind == CHAIN_OUT;
+          bool masked = false;
+          if (is_out && row_ok) masked = (grow % c.T) >= __ldg(c.frames + grow / c.T);
+          const uint32_t mkbits = __ballot_sync(0xffffffffu, masked);
+          const float* mblk = c.mod + blk * 6 * kChainD;
+          const float* gatev = mblk + (is_out ? 2 : 5) * kChainD;
+          // scale of the LayerNorm that consumes this x: scale_mlp of this block | scale_msa of the next | final scale
+          const float* scalev = is_out ? mblk + 4 * kChainD
+                                       : (blk + 1 < kChainBlocks ? mblk + 7 * kChainD : c.mod + kChainBlocks * 6 * kChainD);
+          const int col = n0 + e.half * 32 + 4 * l8c;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(e.acc + e.half * 32, r);
+          ptx::tmem_ld_wait();
+          {
+            uint4* srow = reinterpret_cast<uint4*>(e.stg) + lane * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) srow[i ^ (lane & 7)] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          }
+          __syncwarp();
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!is_out) bias4 = __ldg(reinterpret_cast<const float4*>(d.w.b2 + blk * kChainD + col));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gatev + col));
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(scalev + col));
+          float4 xr[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + l8r;
+            xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((e.okbits >> rr) & 1u) {
+              xr[j] = __ldcg(reinterpret_cast<const float4*>(d.b.x + static_cast<long long>(e.m0 + rr) * kChainD + col));
+            }
+          }
+          const int part = (n0 >> 5) + e.half;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + l8r;
+            const bool ok = (e.okbits >> rr) & 1u;
+            float4 v = reinterpret_cast<const float4*>(e.stg)[rr * 8 + (l8c ^ (rr & 7))];
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if ((mkbits >> rr) & 1u) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            v.x = fmaf(v.x, g4.x, xr[j].x); v.y = fmaf(v.y, g4.y, xr[j].y);
+            v.z = fmaf(v.z, g4.z, xr[j].z); v.w = fmaf(v.w, g4.w, xr[j].w);
+            float s1 = (v.x + v.y) + (v.z + v.w);
+            float s2 = fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (ok) {
+              const long long off = static_cast<long long>(e.m0 + rr) * kChainD + col;
+              *reinterpret_cast<float4*>(d.b.x + off) = v;
+              uint2 pk;
+              pk.x = bf2(v.x * (1.0f + s4.x), v.y * (1.0f + s4.y));
+              pk.y = bf2(v.z * (1.0f + s4.z), v.w * (1.0f + s4.w));
+              *reinterpret_cast<uint2*>(d.b.xb + off) = pk;
+              if (l8c == 0) {
+                *reinterpret_cast<float2*>(d.b.stats + (static_cast<long long>(e.m0 + rr) * kChainParts + part) * 2) =
+                    make_float2(s1, s2);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else if (kind == CHAIN_QKVG && n < 24 && (n >> 3) < 2) {
+        // no live row in this quarter, but the partner-warp barrier of the head epilogue is unconditional
+        ptx::named_bar_sync(1 + e.q, 64);
+        ++hcount;
+      }
+      // this warp is done with the accumulator buffer ...
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
+      // ... and with its share of the tile: publish (release at gpu scope; the consumer crosses to the async proxy)
+      __threadfence();
+      fence_proxy_async_all();
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(d.b.ready + p * m_tiles + m, 1);
+      }
+      ++li;
+    });
+  } else {
+    ptx::pdl_wait();  // warp 3: idle
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<2 * kAccCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------- per-timestep folded vectors
+// One warp per output row j of a GEMM whose input is LayerNorm(x) * (1 + scale) + shift:
+//   cs[j] = sum_k W[j,k] (1 + scale[k]),   b'[j] = b[j] + sum_k W[j,k] shift[k]          (W as packed: bf16)
+__global__ void __launch_bounds__(256) chain_fold_kernel(const ChainWeights w, const float* __restrict__ mod,
+                                                         float* __restrict__ fold) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  constexpr long long nq = static_cast<long long>(kChainBlocks) * kChainQKVG, n13 = static_cast<long long>(kChainBlocks) * kChainW13;
+  if (row >= nq + n13 + 64) return;
+  const bf16* wr;
+  const float *scale, *shift;
+  float bias;
+  float *ocs, *ob;
+  if (row < nq) {
+    const int blk = static_cast<int>(row / kChainQKVG);
+    wr = w.wqkvg + row * kChainD;
+    shift = mod + blk * 6 * kChainD;            // shift_msa
+    scale = shift + kChainD;                    // scale_msa
+    bias = w.bqkvg[row];
+    ocs = fold + kFoldCsQ + row;
+    ob = fold + kFoldBq + row;
+  } else if (row < nq + n13) {
+    const long long r = row - nq;
+    const int blk = static_cast<int>(r / kChainW13);
+    wr = w.w13 + r * kChainD;
+    shift = mod + blk * 6 * kChainD + 3 * kChainD;  // shift_mlp
+    scale = shift + kChainD;                        // scale_mlp
+    bias = w.b13[r];
+    ocs = fold + kFoldCs13 + r;
+    ob = fold + kFoldB13 + r;
+  } else {
+    const long long r = row - nq - n13;
+    wr = w.wvel + r * kChainD;
+    scale = mod + kChainBlocks * 6 * kChainD;  // final adaLN: [scale, shift] (dit.py:37)
+    shift = scale + kChainD;
+    bias = w.bvel[r];
+    ocs = fold + kFoldCsV + r;
+    ob = fold + kFoldBv + r;
+  }
+  float a = 0.f, b = 0.f;
+  const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(wr);
+  for (int i = lane; i < kChainD / 2; i += 32) {
+    const float2 wv = __bfloat1622float2(w2[i]);
+    const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * i);
+    const float2 sh = *reinterpret_cast<const float2*>(shift + 2 * i);
+    a = fmaf(wv.x, 1.0f + sc.x, fmaf(wv.y, 1.0f + sc.y, a));
+    b = fmaf(wv.x, sh.x, fmaf(wv.y, sh.y, b));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    *ocs = a;
+    *ob = b + bias;
+  }
+}
+
+// x [M][960] fp32 -> xb = bf16(x (1 + scale)), stats[M][30][2]; one warp per row, 8 lanes per 32-column chunk
+__global__ void __launch_bounds__(256) chain_stats_cast_kernel(const float* __restrict__ x, int M,
+                                                               const float* __restrict__ scale, bf16* __restrict__ xb,
+                                                               float* __restrict__ stats) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * kChainD);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * 32 + lane;  // float4 index, 240 per row
+    const bool live = idx < kChainD / 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), s = v;
+    if (live) {
+      v = xr[idx];
+      s = __ldg(reinterpret_cast<const float4*>(scale) + idx);
+    }
+    float s1 = (v.x + v.y) + (v.z + v.w);
+    float s2 = fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (live) {
+      uint2 pk;
+      pk.x = bf2(v.x * (1.0f + s.x), v.y * (1.0f + s.y));
+      pk.y = bf2(v.z * (1.0f + s.z), v.w * (1.0f + s.w));
+      reinterpret_cast<uint2*>(xb + static_cast<long long>(row) * kChainD)[idx] = pk;
+      if ((lane & 7) == 0) {
+        *reinterpret_cast<float2*>(stats + (static_cast<long long>(row) * kChainParts + (idx >> 3)) * 2) = make_float2(s1, s2);
+      }
+    }
+  }
+}
+
+__global__ void pack_rows_headpad_kernel(const float* __restrict__ src, int rows, int cols, int row_off,
+                                         bf16* __restrict__ dst, int ld_dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols) return;
+  const int r = static_cast<int>(i / cols), cc = static_cast<int>(i % cols);
+  const int dr = (r / kChainHD) * kChainHDP + r % kChainHD + row_off;
+  dst[static_cast<long long>(dr) * ld_dst + cc] = __float2bfloat16_rn(src[i]);
+}
+__global__ void pack_vec_headpad_kernel(const float* __restrict__ src, int n, int off, float* __restrict__ dst) {
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[(i / kChainHD) * kChainHDP + i % kChainHD + off] = src[i];
+}
+
+bool make_map(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t str[1] = {cols * 2};
+  const uint32_t box[2] = {BK, box_rows};
+  return tmap_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ptr, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace
+
+cudaError_t launch_dit_chain(cudaStream_t st, const ChainWeights& w, const ChainBuffers& b, const ChainCall& c) {
+  if (c.M < 1 || c.T < 1 || c.n_phases < 1 || c.n_phases > 4 || !c.mod || !c.fold || !b.ready) return cudaErrorInvalidValue;
+  for (int p = 0; p < c.n_phases; ++p) {
+    if (c.kind[p] < CHAIN_QKVG || c.kind[p] > CHAIN_VEL || c.blk[p] < 0 || c.blk[p] >= kChainBlocks) return cudaErrorInvalidValue;
+  }
+  static PerDeviceOnce attr_set;
+  {
+    const cudaError_t err = attr_set.run(
+        [] { return cudaFuncSetAttribute(dit_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); });
+    if (err != cudaSuccess) return err;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  ChainMaps maps;
+  const uint64_t M = static_cast<uint64_t>(c.M);
+  bool ok = make_map(&maps.a[0], b.xb, kChainD, M, BM) && make_map(&maps.a[1], b.ob, kChainH * kChainHDP, M, BM) &&
+            make_map(&maps.a[2], b.hb, kChainFF, M, BM) &&
+            make_map(&maps.w[CHAIN_QKVG], w.wqkvg, kChainD, static_cast<uint64_t>(kChainBlocks) * kChainQKVG, 64) &&
+            make_map(&maps.w[CHAIN_OUT], w.wo, kChainH * kChainHDP, static_cast<uint64_t>(kChainBlocks) * kChainD, 64) &&
+            make_map(&maps.w[CHAIN_W13], w.w13, kChainD, static_cast<uint64_t>(kChainBlocks) * kChainW13, 64) &&
+            make_map(&maps.w[CHAIN_W2], w.w2, kChainFF, static_cast<uint64_t>(kChainBlocks) * kChainD, 64) &&
+            make_map(&maps.w[CHAIN_VEL], w.wvel, kChainD, 64, 64);
+  if (!ok) return cudaErrorInvalidValue;
+  ChainDev d;
+  d.w = w;
+  d.b = b;
+  d.c = c;
+  d.m_tiles = (c.M + BM - 1) / BM;
+  // every CTA must be resident at the same time (the phases wait on each other): one CTA per SM, never more
+  int most = 0;
+  for (int p = 0; p < c.n_phases; ++p) {
+    const int nt = c.kind[p] == CHAIN_QKVG ? 29 : (c.kind[p] == CHAIN_W13 ? 25 : (c.kind[p] == CHAIN_VEL ? 1 : 15));
+    most = nt * d.m_tiles > most ? nt * d.m_tiles : most;
+  }
+  const int grid = most < num_sms ? most : num_sms;
+  const cudaError_t le = launch_k(dit_chain_kernel, dim3(grid), dim3(kThreads), kSmem, st, maps, d);
+  count_launch();
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+cudaError_t chain_fold_table(cudaStream_t st, const ChainWeights& w, const float* mod, float* fold) {
+  const long long rows = static_cast<long long>(kChainBlocks) * (kChainQKVG + kChainW13) + 64;
+  const cudaError_t le = launch_k(chain_fold_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, st, w, mod, fold);
+  count_launch();
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+cudaError_t chain_stats_cast(cudaStream_t st, const float* x, int M, const float* scale, bf16* xb, float* stats) {
+  const cudaError_t le = launch_k(chain_stats_cast_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, M, scale, xb, stats);
+  count_launch();
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+cudaError_t pack_rows_headpad(cudaStream_t st, const float* src, int rows, int cols, int row_off, bf16* dst, int ld_dst) {
+  const long long n = static_cast<long long>(rows) * cols;
+  const cudaError_t le = launch_k(pack_rows_headpad_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, src,
+                                  rows, cols, row_off, dst, ld_dst);
+  count_launch();
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+cudaError_t pack_vec_headpad(cudaStream_t st, const float* src, int n, int off, float* dst) {
+  const cudaError_t le = launch_k(pack_vec_headpad_kernel, dim3((n + 255) / 256), dim3(256), 0, st, src, n, off, dst);
+  count_launch();
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+}  // namespace stts

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/smalltts_b200.h"
+#include "dit_chain.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -129,6 +130,11 @@ struct stts_engine {
   std::vector<DitBlockW> blk;
   float *cos64, *sin64, *cos128, *sin128;
   std::map<uint32_t, float*> mod_cache;  // timestep bits -> device adaLN table [MOD_LD]
+  // chained DiT path (dit_chain.cu): the 12 blocks' GEMM weights stacked per type + folded LayerNorm vectors per timestep
+  ChainWeights chain_w;
+  std::map<uint32_t, float*> fold_cache;  // timestep bits -> device fold table [kFoldFloats]
+  bool use_chain = true;    // STTS_NO_CHAIN=1: generic 8-launches-per-block path (also used for per-utterance timesteps)
+  bool chain_split = false; // STTS_CHAIN_SPLIT=1: one GEMM per chain launch (debug / A-B timing of the in-kernel dependencies)
 
   // packed vocoder weights
   bf16* stem_w;
@@ -406,29 +412,53 @@ void finalize_dit(stts_engine* e) {
   e->bkv_ref = e->dalloc<float>(NBLK * 2 * D);
   e->bkv_text = e->dalloc<float>(NBLK * 2 * D);
   e->knorm_cross = e->dalloc<float>(NBLK * H * HD);
+  // GEMM weights of the 12 blocks live stacked per type (one TMA tensor map per type in the chained kernel); the
+  // per-block pointers of the generic path point into the same memory.
+  bf16* wo_all = e->dalloc<bf16>(static_cast<size_t>(NBLK) * D * H * HDP);
+  bf16* w13_all = e->dalloc<bf16>(static_cast<size_t>(NBLK) * 2 * FF * D);
+  bf16* w2_all = e->dalloc<bf16>(static_cast<size_t>(NBLK) * D * FF);
+  bf16* wqkvg_pad = e->dalloc<bf16>(static_cast<size_t>(NBLK) * kChainQKVG * D);  // q|k|v head-padded 120 -> 128, then gate
+  float* bqkvg_pad = e->dalloc<float>(static_cast<size_t>(NBLK) * kChainQKVG);
+  float* b13_all = e->dalloc<float>(static_cast<size_t>(NBLK) * 2 * FF);
+  float* b2_all = e->dalloc<float>(static_cast<size_t>(NBLK) * D);
+  float* qn_all = e->dalloc<float>(static_cast<size_t>(NBLK) * H * HD);
+  float* kn_all = e->dalloc<float>(static_cast<size_t>(NBLK) * H * HD);
   for (int i = 0; i < NBLK; ++i) {
     const std::string p = "dit.transformer_blocks." + std::to_string(i) + ".";
     DitBlockW b;
     b.wqkvg = e->dalloc<bf16>(static_cast<size_t>(4) * D * D);
     b.bqkvg = e->dalloc<float>(4 * D);
     const char* names[4] = {"to_q", "to_k_self", "to_v_self", "gate"};
+    bf16* wq_pad = wqkvg_pad + static_cast<size_t>(i) * kChainQKVG * D;
+    float* bq_pad = bqkvg_pad + static_cast<size_t>(i) * kChainQKVG;
     for (int j = 0; j < 4; ++j) {
-      pack_lin(e, e->W(0, p + "attn." + names[j] + ".weight", {D, D}), D, D, b.wqkvg, D, j * D);
-      if (j < 3) CK(pack_vector(st, e->W(0, p + "attn." + names[j] + ".bias", {D}).d, D, 1.f, ROW_PLAIN, j * D, b.bqkvg));
+      const RawTensor& wj = e->W(0, p + "attn." + names[j] + ".weight", {D, D});
+      pack_lin(e, wj, D, D, b.wqkvg, D, j * D);
+      if (j < 3) {
+        const float* bj = e->W(0, p + "attn." + names[j] + ".bias", {D}).d;
+        CK(pack_vector(st, bj, D, 1.f, ROW_PLAIN, j * D, b.bqkvg));
+        CK(pack_rows_headpad(st, wj.d, D, D, j * H * HDP, wq_pad, D));
+        CK(pack_vec_headpad(st, bj, D, j * H * HDP, bq_pad));
+      } else {
+        pack_lin(e, wj, D, D, wq_pad, D, 3 * H * HDP);
+      }
     }
     // to_out consumes head-padded (120 -> 128) attention output: K = 8 * 128
-    b.wo = e->dalloc<bf16>(static_cast<size_t>(D) * H * HDP);
+    b.wo = wo_all + static_cast<size_t>(i) * D * H * HDP;
     pack_lin(e, e->W(0, p + "attn.to_out.0.weight", {D, D}), D, D, b.wo, H * HDP, 0, ROW_PLAIN, COL_HEADPAD_120_128);
-    b.w13 = e->dalloc<bf16>(static_cast<size_t>(2) * FF * D);
-    b.b13 = e->dalloc<float>(2 * FF);
+    b.w13 = w13_all + static_cast<size_t>(i) * 2 * FF * D;
+    b.b13 = b13_all + static_cast<size_t>(i) * 2 * FF;
     pack_lin(e, e->W(0, p + "ff.w1.weight", {FF, D}), FF, D, b.w13, D, 0, ROW_INTERLEAVE16_LO);
     pack_lin(e, e->W(0, p + "ff.w3.weight", {FF, D}), FF, D, b.w13, D, 0, ROW_INTERLEAVE16_HI);
     CK(pack_vector(st, e->W(0, p + "ff.w1.bias", {FF}).d, FF, 1.f, ROW_INTERLEAVE16_LO, 0, b.b13));
     CK(pack_vector(st, e->W(0, p + "ff.w3.bias", {FF}).d, FF, 1.f, ROW_INTERLEAVE16_HI, 0, b.b13));
-    b.w2 = pack_lin(e, e->W(0, p + "ff.w2.weight", {D, FF}), D, FF);
+    b.w2 = pack_lin(e, e->W(0, p + "ff.w2.weight", {D, FF}), D, FF, w2_all + static_cast<size_t>(i) * D * FF);
     b.b2 = e->W(0, p + "ff.w2.bias", {D}).d;
     b.qn = e->W(0, p + "attn.q_norm.weight", {H, HD}).d;
     b.kn = e->W(0, p + "attn.k_norm.weight", {H, HD}).d;
+    CK(cudaMemcpyAsync(b2_all + static_cast<size_t>(i) * D, b.b2, D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(qn_all + static_cast<size_t>(i) * H * HD, b.qn, H * HD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(kn_all + static_cast<size_t>(i) * H * HD, b.kn, H * HD * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(e->knorm_cross + static_cast<size_t>(i) * H * HD, e->W(0, p + "attn.k_norm_cross.weight", {H, HD}).d,
                        H * HD * sizeof(float), cudaMemcpyDeviceToDevice, st));
     b.ada_w = e->W(0, p + "attn_norm.linear.weight", {6 * D, D}).d;
@@ -447,6 +477,10 @@ void finalize_dit(stts_engine* e) {
   e->vel_b = e->W(0, "velocity.bias", {LAT}).d;
   build_rope(e, 64, &e->cos64, &e->sin64);
   build_rope(e, 128, &e->cos128, &e->sin128);
+  e->chain_w.wqkvg = wqkvg_pad; e->chain_w.wo = wo_all; e->chain_w.w13 = w13_all; e->chain_w.w2 = w2_all;
+  e->chain_w.wvel = e->vel_w; e->chain_w.bqkvg = bqkvg_pad; e->chain_w.b13 = b13_all; e->chain_w.b2 = b2_all;
+  e->chain_w.bvel = e->vel_b; e->chain_w.qn = qn_all; e->chain_w.kn = kn_all;
+  e->chain_w.cos_t = e->cos64; e->chain_w.sin_t = e->sin64;
   e->has_dit = true;
 }
 
@@ -648,20 +682,45 @@ const float* cached_mod(stts_engine* e, float t) {
   return table;
 }
 
+// Folded LayerNorm vectors of the chained DiT path for timestep t (dit_chain.cuh); nullptr when that path is off.
+const float* cached_fold(stts_engine* e, float t) {
+  if (!e->use_chain) return nullptr;
+  uint32_t bits;
+  memcpy(&bits, &t, 4);
+  auto it = e->fold_cache.find(bits);
+  if (it != e->fold_cache.end()) return it->second;
+  const float* mod = cached_mod(e, t);
+  float* fold = nullptr;
+  CK(cudaMalloc(reinterpret_cast<void**>(&fold), static_cast<size_t>(kFoldFloats) * sizeof(float)));
+  e->owned.push_back(fold);
+  CK(chain_fold_table(e->st, e->chain_w, mod, fold));
+  CK(cudaStreamSynchronize(e->st));
+  e->fold_cache[bits] = fold;
+  return fold;
+}
+
 // ------------------------------------------------------------------ denoiser (dit.py:316-327, model.py:97-100)
+constexpr int kChainLaunches = NBLK + 1;  // q|k|v|gate of block 0, then one launch per block (the last ends in the velocity head)
 struct DenoiseWs {
-  Tmp<float> h, x, qkvg, v;
-  Tmp<bf16> hm, c1, a, qb, kb, vb, ob, hb;
+  Tmp<float> h, x, qkvg, v, stats;
+  Tmp<bf16> hm, c1, a, qkv, ob, hb;
+  Tmp<int> ready;
+  bf16 *qb = nullptr, *kb = nullptr, *vb = nullptr;  // views of qkv: [3][M][8][128]
   void alloc(cudaStream_t st, long long M) {
     h.alloc(st, M * D); x.alloc(st, M * D); qkvg.alloc(st, M * 4 * D);
     hm.alloc(st, M * DP); c1.alloc(st, M * DP); a.alloc(st, M * D);
-    qb.alloc(st, M * H * HDP); kb.alloc(st, M * H * HDP); vb.alloc(st, M * H * HDP); ob.alloc(st, M * H * HDP);
+    qkv.alloc(st, 3 * M * H * HDP); ob.alloc(st, M * H * HDP);
+    qb = qkv.p; kb = qb + M * H * HDP; vb = kb + M * H * HDP;
     hb.alloc(st, M * FF);
+    stats.alloc(st, M * 2 * kChainParts);
+    ready.alloc(st, static_cast<size_t>(kChainLaunches) * chain_ready_ints(static_cast<int>(M)));
   }
 };
 
+// `fold` (cached_fold of the same timestep, shared by all rows) selects the chained path: per block one attention launch
+// and one persistent GEMM-chain launch (dit_chain.cu) instead of eight kernels.
 void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_bf16, const int* frames_dev,
-             const float* mod, int ld_mod, int B, int T, float* v_out) {
+             const float* mod, int ld_mod, const float* fold, int B, int T, float* v_out) {
   cudaStream_t st = e->st;
   const long long M = static_cast<long long>(B) * T;
   // input embedding: h = proj(x); hm = masked bf16 copy; x = mask(mish(conv2(mask(mish(conv1(hm)))))) + h
@@ -685,6 +744,45 @@ void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_b
     e2.bias = e->conv2_b; e2.act = ACT_MISH; e2.row_len = frames_dev; e2.residual = ws.h; e2.ld_res = D;
     e2.out_f32 = ws.x; e2.ld_out = D;
     CK(launch_gemm(st, 64, GemmA{ws.c1, DP, DP}, GemmW{e->conv2_w, D, 31 * 128}, s, e2));
+  }
+  if (fold != nullptr && ld_mod == 0 && e->use_chain) {
+    const int Mi = static_cast<int>(M);
+    const int ready_ints = chain_ready_ints(Mi);
+    ChainBuffers cb;
+    cb.x = ws.x; cb.xb = ws.a; cb.stats = ws.stats; cb.qkv = ws.qkv; cb.gate = ws.qkvg; cb.ob = ws.ob; cb.hb = ws.hb;
+    cb.vel = v_out;
+    ChainCall cc;
+    cc.M = Mi; cc.T = T; cc.frames = frames_dev; cc.mod = mod; cc.fold = fold;
+    CK(cudaMemsetAsync(ws.ready, 0, static_cast<size_t>(kChainLaunches) * ready_ints * sizeof(int), st));
+    CK(chain_stats_cast(st, ws.x, Mi, mod + D /*scale_msa of block 0*/, ws.a, ws.stats));
+    int launch = 0;
+    auto run = [&](std::initializer_list<std::pair<int, int>> phases) {
+      cb.ready = ws.ready + launch * ready_ints;
+      if (e->chain_split) {  // one GEMM per launch: kernel boundaries instead of the in-kernel ready counters
+        for (const auto& ph : phases) {
+          cc.n_phases = 1; cc.kind[0] = ph.first; cc.blk[0] = ph.second;
+          CK(launch_dit_chain(st, e->chain_w, cb, cc));
+        }
+      } else {
+        cc.n_phases = 0;
+        for (const auto& ph : phases) { cc.kind[cc.n_phases] = ph.first; cc.blk[cc.n_phases] = ph.second; ++cc.n_phases; }
+        CK(launch_dit_chain(st, e->chain_w, cb, cc));
+      }
+      ++launch;
+    };
+    run({{CHAIN_QKVG, 0}});
+    for (int i = 0; i < NBLK; ++i) {
+      AttnSeg segs[3];
+      segs[0].k = ws.kb; segs[0].v = ws.vb; segs[0].len = frames_dev; segs[0].n_max = T;
+      segs[1].k = c->kv_ref + (2 * i) * c->ref_stride(); segs[1].v = c->kv_ref + (2 * i + 1) * c->ref_stride();
+      segs[1].len = c->ref_len; segs[1].n_max = c->R;
+      segs[2].k = c->kv_text + (2 * i) * c->text_stride(); segs[2].v = c->kv_text + (2 * i + 1) * c->text_stride();
+      segs[2].len = c->ph_len; segs[2].n_max = c->P;
+      CK(attention_bf16(st, ws.qb, B, T, H, HD, HDP, segs, 3, ws.qkvg, D, 0, ws.ob));
+      if (i + 1 < NBLK) run({{CHAIN_OUT, i}, {CHAIN_W13, i}, {CHAIN_W2, i}, {CHAIN_QKVG, i + 1}});
+      else run({{CHAIN_OUT, i}, {CHAIN_W13, i}, {CHAIN_W2, i}, {CHAIN_VEL, 0}});
+    }
+    return;
   }
   for (int i = 0; i < NBLK; ++i) {
     const DitBlockW& w = e->blk[i];
@@ -751,10 +849,16 @@ std::vector<const float*> prepare_mods(stts_engine* e, const std::vector<float>&
   return mods;
 }
 
+std::vector<const float*> prepare_folds(stts_engine* e, const std::vector<float>& ts) {
+  std::vector<const float*> folds(ts.size());
+  for (size_t s = 0; s < ts.size(); ++s) folds[s] = cached_fold(e, ts[s]);
+  return folds;
+}
+
 // Launch-only (graph-capturable).  seed_dev: device u64 read by the Philox kernel when noise_dev is null.
 void sample(stts_engine* e, const stts_cond* c, const int* frames_dev, int B, int T, const std::vector<float>& ts,
-            const std::vector<const float*>& mods, const float* noise_dev, const unsigned long long* seed_dev,
-            float* x_pred) {
+            const std::vector<const float*>& mods, const std::vector<const float*>& folds, const float* noise_dev,
+            const unsigned long long* seed_dev, float* x_pred) {
   cudaStream_t st = e->st;
   const int steps = static_cast<int>(ts.size());
   const long long n = static_cast<long long>(B) * T * LAT;
@@ -770,7 +874,7 @@ void sample(stts_engine* e, const stts_cond* c, const int* frames_dev, int B, in
     const float* nzs = noise_dev ? noise_dev + s * n : nz.p;
     if (noise_dev == nullptr) CK(philox_normal(st, seed_dev, static_cast<unsigned long long>(s), n, nz));
     CK(noise_mix(st, x_pred, nzs, alpha, sigma, n, xt, xtb));
-    denoise(e, c, ws, xtb, frames_dev, mods[s], 0, B, T, v);
+    denoise(e, c, ws, xtb, frames_dev, mods[s], 0, folds[s], B, T, v);
     CK(dmd_update(st, xt, v, alpha, sigma, n, x_pred));
   }
 }
@@ -788,6 +892,7 @@ void sample_teacher(stts_engine* e, const stts_cond* c3, const int* frames3_dev,
   std::vector<float> ts(steps + 1);
   for (int s = 0; s <= steps; ++s) ts[s] = static_cast<float>(1.0 - static_cast<double>(s) / steps);
   const std::vector<const float*> mods = prepare_mods(e, std::vector<float>(ts.begin(), ts.end() - 1));
+  const std::vector<const float*> folds = prepare_folds(e, std::vector<float>(ts.begin(), ts.end() - 1));
   DenoiseWs ws;
   ws.alloc(st, static_cast<long long>(3) * B * T);
   Tmp<float> v3(st, 3 * n);
@@ -802,7 +907,7 @@ void sample_teacher(stts_engine* e, const stts_cond* c3, const int* frames3_dev,
     alpha_sigma(ts[s], &a, &sg);
     alpha_sigma(ts[s + 1], &an, &sn);
     CK(repeat_cast_bf16(st, x, n, 3, xb));
-    denoise(e, c3, ws, xb, frames3_dev, mods[s], 0, 3 * B, T, v3);
+    denoise(e, c3, ws, xb, frames3_dev, mods[s], 0, folds[s], 3 * B, T, v3);
     CK(cfg_ddim_update(st, x, v3, n, cfg_text, cfg_spk, an * a + sn * sg, sn * a - an * sg));
   }
 }
@@ -954,7 +1059,7 @@ struct Plan {
   VocWs voc;
   std::vector<void*> owned;
   std::vector<float> ts;
-  std::vector<const float*> mods;
+  std::vector<const float*> mods, folds;
   cudaGraphExec_t g_cond = nullptr, g_sample[2] = {nullptr, nullptr}, g_front = nullptr, g_tail = nullptr;
   unsigned long long n_cond = 0, n_sample[2] = {0, 0}, n_front = 0, n_tail = 0;  // kernels per graph
   int graph_state = 0;  // 0 = not captured yet, 1 = captured, -1 = capture failed: stay eager
@@ -1018,6 +1123,7 @@ Plan* get_plan(stts_engine* e, int B, int R, int P, int T, int steps) {
     CK(cudaHostAlloc(reinterpret_cast<void**>(&p->h_lens), 3 * B * sizeof(int), cudaHostAllocDefault));
     p->ts = resolve_timesteps(steps, nullptr);
     p->mods = prepare_mods(e, p->ts);
+    p->folds = prepare_folds(e, p->ts);
   } catch (...) {
     p->destroy();
     delete p;
@@ -1200,6 +1306,10 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     e->fused_tail = !(nf && nf[0] == '1');
     const char* nff = getenv("STTS_NO_FUSED_FFN");
     e->fused_ffn = !(nff && nff[0] == '1');
+    const char* nc = getenv("STTS_NO_CHAIN");
+    e->use_chain = !(nc && nc[0] == '1');
+    const char* cs = getenv("STTS_CHAIN_SPLIT");
+    e->chain_split = cs && cs[0] == '1';
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, e->device));
     uint64_t thr = UINT64_MAX;
@@ -1248,6 +1358,7 @@ int stts_engine_clone(stts_engine* src, stts_engine** out) {
     c->owned.clear();      // what the clone allocates from here on (adaLN tables, filter banks) is its own
     c->plans.clear();
     c->mod_cache.clear();
+    c->fold_cache.clear();
     c->banks.clear();
     c->err.clear();
     c->use_counter = 0;
@@ -1360,8 +1471,10 @@ int stts_denoise_step(stts_engine* e, const stts_cond* c, const float* x_t, cons
     Tmp<float> table, td;
     const float* mod;
     int ld_mod = 0;
+    const float* fold = nullptr;
     if (same) {
       mod = cached_mod(e, t[0]);
+      fold = cached_fold(e, t[0]);
     } else {
       td.alloc(st, B);
       table.alloc(st, static_cast<size_t>(B) * MOD_LD);
@@ -1377,7 +1490,7 @@ int stts_denoise_step(stts_engine* e, const stts_cond* c, const float* x_t, cons
       vout.alloc(st, n);
       vd = vout;
     }
-    denoise(e, c, ws, xb, fr, mod, ld_mod, B, T, vd);
+    denoise(e, c, ws, xb, fr, mod, ld_mod, fold, B, T, vd);
     if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(velocity, vd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   });
@@ -1395,6 +1508,7 @@ int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B
     lens_to_dev(e, frames, B, T, fr);
     const std::vector<float> ts = resolve_timesteps(steps, timesteps);
     const std::vector<const float*> mods = prepare_mods(e, ts);
+    const std::vector<const float*> folds = prepare_folds(e, ts);
     set_seed(e, seed);
     Tmp<float> hn, xo;
     const float* nd = noise ? to_dev(e, noise, static_cast<size_t>(steps) * n, mem, hn) : nullptr;
@@ -1403,7 +1517,7 @@ int stts_sample(stts_engine* e, const stts_cond* c, const int64_t* frames, int B
       xo.alloc(st, n);
       xd = xo;
     }
-    sample(e, c, fr, B, T, ts, mods, nd, e->seed_dev, xd);
+    sample(e, c, fr, B, T, ts, mods, folds, nd, e->seed_dev, xd);
     if (mem == STTS_MEM_HOST) CK(cudaMemcpyAsync(out_latents, xd, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   });
@@ -1562,10 +1676,11 @@ int stts_synthesize(stts_engine* e, const float* ref, const int64_t* ref_len, co
     std::vector<float> ts = resolve_timesteps(steps, timesteps);
     const bool default_ts = (ts == p->ts);
     std::vector<const float*> mods = default_ts ? p->mods : prepare_mods(e, ts);
+    std::vector<const float*> folds = default_ts ? p->folds : prepare_folds(e, ts);
     const float* nd = noise ? p->noise : nullptr;
 
     auto run_cond = [&] { encode_conditions_core(e, &p->cond, p->ref, p->ids); };
-    auto run_sample = [&](const float* nz) { sample(e, &p->cond, p->frames_dev, B, T, ts, mods, nz, e->seed_dev, p->lat); };
+    auto run_sample = [&](const float* nz) { sample(e, &p->cond, p->frames_dev, B, T, ts, mods, folds, nz, e->seed_dev, p->lat); };
     auto run_front = [&] { decode(e, p->lat, B, T, p->audio, p->voc, VOC_FRONT); };
     auto run_tail = [&] { decode(e, p->lat, B, T, p->audio, p->voc, VOC_TAIL); };
 
@@ -1717,6 +1832,50 @@ int stts_test_convnext_fused(stts_engine* e, const float* x, int B, int T, int C
   return guard_impl(e, [&] {
     CK(convnext_fused(e->st, x, B, T, C, norm_w, conv_w, conv_b, gamma, ffn_norm_w, static_cast<const bf16*>(w1_bf16), b1,
                       w2_f16, b2, ffn_gamma, 1e-5f, out, static_cast<bf16*>(out_bf16)));
+    if (!e->test_async) CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+
+namespace {
+ChainWeights chain_weights_of(const stts_test_chain_args* a) {
+  ChainWeights w;
+  w.wqkvg = static_cast<const bf16*>(a->wqkvg); w.wo = static_cast<const bf16*>(a->wo);
+  w.w13 = static_cast<const bf16*>(a->w13); w.w2 = static_cast<const bf16*>(a->w2); w.wvel = static_cast<const bf16*>(a->wvel);
+  w.bqkvg = a->bqkvg; w.b13 = a->b13; w.b2 = a->b2; w.bvel = a->bvel; w.qn = a->qn; w.kn = a->kn;
+  w.cos_t = a->cos_t; w.sin_t = a->sin_t;
+  return w;
+}
+}  // namespace
+
+int stts_test_chain(stts_engine* e, const stts_test_chain_args* a) {
+  if (!e || !a) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    ChainBuffers b;
+    b.x = a->x; b.xb = static_cast<bf16*>(a->xb); b.stats = a->stats; b.qkv = static_cast<bf16*>(a->qkv); b.gate = a->gate;
+    b.ob = static_cast<const bf16*>(a->ob); b.hb = static_cast<bf16*>(a->hb); b.vel = a->vel; b.ready = a->ready;
+    ChainCall c;
+    c.M = a->M; c.T = a->T; c.frames = a->frames; c.mod = a->mod; c.fold = a->fold; c.n_phases = a->n_phases;
+    for (int i = 0; i < 4; ++i) { c.kind[i] = a->kind[i]; c.blk[i] = a->blk[i]; }
+    CK(launch_dit_chain(e->st, chain_weights_of(a), b, c));
+    if (!e->test_async) CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+int stts_test_chain_fold(stts_engine* e, const stts_test_chain_args* a, float* fold_out) {
+  if (!e || !a || !fold_out) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    CK(chain_fold_table(e->st, chain_weights_of(a), a->mod, fold_out));
+    if (!e->test_async) CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+int64_t stts_test_chain_fold_floats(void) { return kFoldFloats; }
+
+int stts_test_chain_stats_cast(stts_engine* e, const float* x, int M, const float* scale, void* xb, float* stats) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    CK(chain_stats_cast(e->st, x, M, scale, static_cast<bf16*>(xb), stats));
     if (!e->test_async) CK(cudaStreamSynchronize(e->st));
   });
 }
