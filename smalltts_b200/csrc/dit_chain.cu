@@ -100,18 +100,22 @@ __device__ __forceinline__ Tile decode_tile(int g, const ChainCall& c, int m_til
 }
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ int ld_acquire(const int* p) {
+__device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Bounded like ptx::mbar_wait: a scheduling bug traps instead of hanging the GPU.
-__device__ __forceinline__ void wait_ready(const int* p, int target) {
-  uint32_t spins = 0;
-  while (ld_acquire(p) < target) {
-    __nanosleep(40);
-    if (++spins > (1u << 24)) __trap();
+// Wait until *p != 0.  Polls with relaxed loads (an acquire load per poll would invalidate this SM's L1 every time,
+// under the feet of the epilogue warps) and backs off, then acquires once.  Bounded like ptx::mbar_wait: a scheduling
+// bug traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_flag(const int* p) {
+  uint32_t spins = 0, ns = 64;
+  while (ld_relaxed(p) == 0) {
+    __nanosleep(ns);
+    if (ns < 512) ns += ns;
+    if (++spins > (1u << 23)) __trap();
   }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
@@ -229,7 +233,6 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int G = gridDim.x;
   const ChainCall& c = d.c;
   const int m_tiles = d.m_tiles;
 
@@ -259,7 +262,12 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
 
   int total_tiles = 0;
   for (int p = 0; p < c.n_phases; ++p) total_tiles += kind_ntiles(c.kind[p]) * m_tiles;
-  int* const next_tile = d.b.ready + 4 * m_tiles;  // the launch's claim counter sits behind its ready counters
+  // counters of this launch (dit_chain.cuh chain_ready_ints): tile-completion counts per (phase, row block), the
+  // "row block complete" flags the consumers poll (kept on other cache lines than the atomics), the claim counter
+  const int cstride = (4 * m_tiles + 31) & ~31;
+  int* const done_cnt = d.b.ready;
+  int* const done_flag = d.b.ready + cstride;
+  int* const next_tile = d.b.ready + 2 * cstride;
 
   // Consumer side of the tile FIFO: calls fn(tile) for every tile this CTA claimed, in claim order.
   auto walk = [&](auto&& fn) {
@@ -297,7 +305,6 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       if (++slot == kTq) { slot = 0; tph ^= 1; }
       if (!live) break;
       const Tile t = decode_tile(g, c, m_tiles);
-      g = claim();  // one ahead: the round trip to L2 hides behind this tile's loads
       int n0, bn;
       tile_cols(t.kind, t.n, n0, bn);
       const int wrow = t.blk * kind_wrows(t.kind) + n0;
@@ -310,6 +317,9 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
           ptx::pdl_wait();
           waited = true;
         }
+        // Claim the next tile late: close to when this CTA can really start it (so that tiles go to whoever is free),
+        // but a ring's depth before the end of this tile's loads, which hides the round trip of the atomic.
+        if (it == (iters > kStages ? iters - kStages : 0)) g = claim();
         ptx::mbar_wait(&empty[st], ph ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full[st], static_cast<uint32_t>(bn) * 128u);
@@ -330,8 +340,8 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
     walk([&](const Tile& t) {
       const int p = t.p, kind = t.kind, m = t.m;
       if (p > 0) {
-        // all tiles of the previous phase that write rows [128 m, +128) must be done (8 epilogue warps each)
-        if (lane == 0) wait_ready(d.b.ready + (p - 1) * m_tiles + m, kind_ntiles(c.kind[p - 1]) * kEpiWarps);
+        // all tiles of the previous phase that write rows [128 m, +128) must be done
+        if (lane == 0) wait_flag(done_flag + (p - 1) * m_tiles + m);
         __syncwarp();
         fence_proxy_async_all();  // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
       }
@@ -602,13 +612,19 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
-      // ... and with its share of the tile: publish (release at gpu scope; the consumer crosses to the async proxy)
+      // ... and with its share of the tile.  Publish the tile once all eight warps are done: every warp's stores are
+      // ordered before the barrier (gpu-scope fence + cross-proxy fence: the consumer reads them with TMA), one thread
+      // counts the tile, and whoever completes the row block raises its flag.
       __threadfence();
       fence_proxy_async_all();
-      __syncwarp();
-      if (lane == 0) {
+      ptx::named_bar_sync(5, kEpiWarps * 32);
+      if (warp == kEpiWarp0 && lane == 0) {
         __threadfence();
-        atomicAdd(d.b.ready + p * m_tiles + m, 1);
+        const int done = atomicAdd(done_cnt + p * m_tiles + m, 1) + 1;
+        if (done == kind_ntiles(kind)) {
+          __threadfence();
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done_flag + p * m_tiles + m), "r"(1) : "memory");
+        }
       }
       ++li;
     });

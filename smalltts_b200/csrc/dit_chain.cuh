@@ -62,7 +62,7 @@ struct ChainBuffers {  // activations of one denoiser evaluation, M = B*T rows
   const bf16* ob = nullptr;  // [M][1024] gated attention output (written by the attention kernel)
   bf16* hb = nullptr;      // [M][2400] SwiGLU hidden
   float* vel = nullptr;    // [M][64]
-  int* ready = nullptr;    // zero-initialised counters of THIS launch: [4][m_tiles] ready + 1 tile-claim counter
+  int* ready = nullptr;    // zero-initialised counters of THIS launch (chain_ready_ints of them)
 };
 
 struct ChainCall {
@@ -75,8 +75,9 @@ struct ChainCall {
   int blk[4] = {0, 0, 0, 0};
 };
 
-// Number of int counters one launch needs (4 phases x row blocks, + the tile-claim counter; padded to 16 ints).
-inline int chain_ready_ints(int M) { return (4 * ((M + 127) / 128) + 1 + 15) / 16 * 16; }
+// Number of int counters one launch needs: completed tiles per (phase, row block) | "row block complete" flags | the
+// tile-claim counter, each group on its own 128-byte lines.
+inline int chain_ready_ints(int M) { return 2 * ((4 * ((M + 127) / 128) + 31) / 32 * 32) + 32; }
 
 cudaError_t launch_dit_chain(cudaStream_t st, const ChainWeights& w, const ChainBuffers& b, const ChainCall& c);
 

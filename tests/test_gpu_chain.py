@@ -118,7 +118,7 @@ class Case:
                   "stats", "qkv", "gate", "ob", "hb", "vel", "frames", "mod", "fold"):
             t = getattr(self, n)
             setattr(a, n, None if t is None else _ptr(t))
-        n_ready = (4 * ((self.M + 127) // 128) + 1 + 15) // 16 * 16
+        n_ready = 2 * ((4 * ((self.M + 127) // 128) + 31) // 32 * 32) + 32  # dit_chain.cuh chain_ready_ints
         self.ready = torch.zeros(n_ready, dtype=torch.int32, device="cuda")
         a.ready = _ptr(self.ready)
         a.M, a.T, a.n_phases = self.M, self.T, len(phases)
