@@ -196,6 +196,7 @@ typedef struct stts_test_chain_args {
   const float *bqkvg, *b13, *b2, *bvel, *qn, *kn, *cos_t, *sin_t;
   float* x; void* xb; float* stats; void* qkv; float* gate; const void* ob; void* hb; float* vel; int32_t* ready;
   const int32_t* frames; const float* mod; const float* fold;
+  uint64_t* trace; /* optional role timeline [CTAs][64][16] (tools/trace_chain.py), else NULL */
   int32_t M, T, n_phases;
   int32_t kind[4];
   int32_t blk[4];

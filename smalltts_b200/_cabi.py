@@ -33,7 +33,7 @@ class ChainArgs(C.Structure):
 
     _fields_ = ([(n, vp) for n in ("wqkvg", "wo", "w13", "w2", "wvel", "bqkvg", "b13", "b2", "bvel", "qn", "kn", "cos_t",
                                    "sin_t", "x", "xb", "stats", "qkv", "gate", "ob", "hb", "vel", "ready", "frames", "mod",
-                                   "fold")]
+                                   "fold", "trace")]
                 + [("M", C.c_int32), ("T", C.c_int32), ("n_phases", C.c_int32), ("kind", C.c_int32 * 4),
                    ("blk", C.c_int32 * 4)])
 

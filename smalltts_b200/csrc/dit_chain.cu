@@ -79,11 +79,12 @@ __device__ __forceinline__ void tile_cols(int kind, int n, int& n0, int& bn) {
 }
 
 struct Tile {
-  int p, kind, blk, m, n;
+  int p, kind, blk, m, n, g;
 };
 // global tile number -> (phase, row block, column tile); phases are numbered back to back, n fastest inside a phase
 __device__ __forceinline__ Tile decode_tile(int g, const ChainCall& c, int m_tiles) {
   Tile t;
+  t.g = g;
   t.p = 0;
   for (;;) {
     const int total = kind_ntiles(c.kind[t.p]) * m_tiles;
@@ -116,6 +117,16 @@ __device__ __forceinline__ void wait_flag(const int* p) {
     if (++spins > (1u << 23)) __trap();
   }
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+// Optional role timeline (ChainBuffers::trace != nullptr, tools/trace_chain.py): trace[(cta * 64 + seq) * 16 + ev] =
+// globaltimer ns; ev 0 tile published | 1 A producer at the flag | 2 flag seen | 3 first operands landed | 4 MMAs issued
+// | 5 epilogue sees the accumulator | 6 epilogue stores issued | 7 tile counted; slot 15 = global tile number + 1.
+__device__ __forceinline__ void trace_ev(unsigned long long* trace, int seq, int ev, long long val = -1) {
+  if (trace == nullptr || seq >= 64) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  trace[(static_cast<size_t>(blockIdx.x) * 64 + seq) * 16 + ev] = val >= 0 ? static_cast<unsigned long long>(val) : t;
 }
 
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
@@ -293,7 +304,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       if (lane == 0) g = atomicAdd(next_tile, 1);
       return __shfl_sync(0xffffffffu, g, 0);
     };
-    int g = claim();
+    int g = claim(), g_raw = 0, wseq = 0;
     for (;;) {
       const bool live = g < total_tiles;
       ptx::mbar_wait(&tq_empty[slot], tph ^ 1);
@@ -305,6 +316,8 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       if (++slot == kTq) { slot = 0; tph ^= 1; }
       if (!live) break;
       const Tile t = decode_tile(g, c, m_tiles);
+      if (lane == 0) { trace_ev(d.b.trace, wseq, 0); trace_ev(d.b.trace, wseq, 15, g + 1); }
+      ++wseq;
       int n0, bn;
       tile_cols(t.kind, t.n, n0, bn);
       const int wrow = t.blk * kind_wrows(t.kind) + n0;
@@ -319,7 +332,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         }
         // Claim the next tile late: close to when this CTA can really start it (so that tiles go to whoever is free),
         // but a ring's depth before the end of this tile's loads, which hides the round trip of the atomic.
-        if (it == (iters > kStages ? iters - kStages : 0)) g = claim();
+        if (it == (iters > kStages ? iters - kStages : 0) && lane == 0) g_raw = atomicAdd(next_tile, 1);
         ptx::mbar_wait(&empty[st], ph ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&full[st], static_cast<uint32_t>(bn) * 128u);
@@ -331,20 +344,25 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         ++issued;
         if (++st == kStages) { st = 0; ph ^= 1; }
       }
+      g = __shfl_sync(0xffffffffu, g_raw, 0);  // the atomic's result is first needed here
     }
     if (!waited) ptx::pdl_wait();
   } else if (warp == 1) {
     // ================================================================== A producer
     ptx::pdl_wait();
     uint32_t st = 0, ph = 0;
+    int aseq = 0;
     walk([&](const Tile& t) {
       const int p = t.p, kind = t.kind, m = t.m;
+      if (lane == 0) trace_ev(d.b.trace, aseq, 1);
       if (p > 0) {
         // all tiles of the previous phase that write rows [128 m, +128) must be done
         if (lane == 0) wait_flag(done_flag + (p - 1) * m_tiles + m);
         __syncwarp();
         fence_proxy_async_all();  // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
       }
+      if (lane == 0) trace_ev(d.b.trace, aseq, 2);
+      ++aseq;
       const int iters = kind_kiters(kind);
       const CUtensorMap* tm = &maps.a[kind_amap(kind)];
       for (int it = 0; it < iters; ++it) {
@@ -377,6 +395,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       for (int it = 0; it < iters; ++it) {
         ptx::mbar_wait(&full[st], ph);
         ptx::tc_fence_after();
+        if (it == 0 && lane == 0) trace_ev(d.b.trace, li, 3);
         if (ptx::elect_one()) {
           const uint64_t da = da0 + static_cast<uint64_t>(st * (kABytes >> 4));
           const uint64_t db = db0 + static_cast<uint64_t>(st * (kWBytes >> 4));
@@ -389,6 +408,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       }
       if (ptx::elect_one()) ptx::umma_commit(&acc_full[ab]);
       __syncwarp();
+      if (lane == 0) trace_ev(d.b.trace, li, 4);
       ++li;
     });
   } else if (warp >= kEpiWarp0) {
@@ -414,6 +434,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       e.okbits = __ballot_sync(0xffffffffu, row_ok);
       ptx::mbar_wait(&acc_full[ab], (li >> 1) & 1);
       ptx::tc_fence_after();
+      if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, li, 5);
 
       if (e.okbits != 0u) {
         if (kind == CHAIN_QKVG || kind == CHAIN_W13 || kind == CHAIN_VEL) {
@@ -615,6 +636,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       // ... and with its share of the tile.  Publish the tile once all eight warps are done: every warp's stores are
       // ordered before the barrier (gpu-scope fence + cross-proxy fence: the consumer reads them with TMA), one thread
       // counts the tile, and whoever completes the row block raises its flag.
+      if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, li, 6);
       __threadfence();
       fence_proxy_async_all();
       ptx::named_bar_sync(5, kEpiWarps * 32);
@@ -625,6 +647,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
           __threadfence();
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done_flag + p * m_tiles + m), "r"(1) : "memory");
         }
+        trace_ev(d.b.trace, li, 7);
       }
       ++li;
     });

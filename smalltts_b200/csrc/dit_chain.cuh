@@ -63,6 +63,7 @@ struct ChainBuffers {  // activations of one denoiser evaluation, M = B*T rows
   bf16* hb = nullptr;      // [M][2400] SwiGLU hidden
   float* vel = nullptr;    // [M][64]
   int* ready = nullptr;    // zero-initialised counters of THIS launch (chain_ready_ints of them)
+  unsigned long long* trace = nullptr;  // optional role timeline [grid][64 tiles][16] (tools/trace_chain.py)
 };
 
 struct ChainCall {

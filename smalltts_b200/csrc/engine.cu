@@ -1854,6 +1854,7 @@ int stts_test_chain(stts_engine* e, const stts_test_chain_args* a) {
     ChainBuffers b;
     b.x = a->x; b.xb = static_cast<bf16*>(a->xb); b.stats = a->stats; b.qkv = static_cast<bf16*>(a->qkv); b.gate = a->gate;
     b.ob = static_cast<const bf16*>(a->ob); b.hb = static_cast<bf16*>(a->hb); b.vel = a->vel; b.ready = a->ready;
+    b.trace = reinterpret_cast<unsigned long long*>(a->trace);
     ChainCall c;
     c.M = a->M; c.T = a->T; c.frames = a->frames; c.mod = a->mod; c.fold = a->fold; c.n_phases = a->n_phases;
     for (int i = 0; i < 4; ++i) { c.kind[i] = a->kind[i]; c.blk[i] = a->blk[i]; }
