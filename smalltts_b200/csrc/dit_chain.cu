@@ -43,7 +43,9 @@ constexpr int kStgBytes = 4096;         // per epilogue warp: 32 rows x 32 fp32,
 constexpr int kAccCols = 256;           // TMEM columns per accumulator buffer
 constexpr int kTq = 4;                  // depth of the tile FIFO between the claiming warp and the other roles
 constexpr int kTqReaders = 2 + kEpiWarps;  // A producer, MMA issuer, epilogue warps
-constexpr int kSmem = kStages * (kABytes + kWBytes) + 256 + kEpiWarps * kStgBytes + 2 * 2 * BM * 4 + 1024;
+constexpr int kColvecFloats = 192;         // per epilogue warp: 3 chunks x (cs | b') or 2 chunks x (cs | b') + norm weights
+constexpr int kSmem = kStages * (kABytes + kWBytes) + 256 + kEpiWarps * kStgBytes + 2 * 2 * BM * 4 +
+                      kEpiWarps * kColvecFloats * 4 + 1024;
 
 struct ChainMaps {
   CUtensorMap a[3];  // xb [M, 960], ob [M, 1024], hb [M, 2400]: box 64 x 128 rows
@@ -169,8 +171,8 @@ __device__ __forceinline__ void ln_chunk(const uint32_t (&r)[32], float (&v)[32]
                                          const float* __restrict__ cs, const float* __restrict__ bb) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs) + i);
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bb) + i);
+    const float4 c4 = reinterpret_cast<const float4*>(cs)[i];  // shared memory, same address in every lane: broadcast
+    const float4 b4 = reinterpret_cast<const float4*>(bb)[i];
     v[4 * i + 0] = fmaf(rstd, fmaf(-mean, c4.x, __uint_as_float(r[4 * i + 0])), b4.x);
     v[4 * i + 1] = fmaf(rstd, fmaf(-mean, c4.y, __uint_as_float(r[4 * i + 1])), b4.y);
     v[4 * i + 2] = fmaf(rstd, fmaf(-mean, c4.z, __uint_as_float(r[4 * i + 2])), b4.z);
@@ -241,6 +243,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tileq + kTq);
   uint8_t* stage_base = reinterpret_cast<uint8_t*>(full) + 256;
   float* ssx = reinterpret_cast<float*>(stage_base + kEpiWarps * kStgBytes);
+  float* colvec = ssx + 2 * 2 * BM;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -421,6 +424,8 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
     e.stg = reinterpret_cast<float*>(stage_base + (warp - kEpiWarp0) * kStgBytes);
     e.ssx = ssx;
     const int l8r = lane >> 3, l8c = lane & 7;
+    // warp-private column vectors of the current tile (fold vectors, head norm weights): fetched BEFORE the waits
+    float* cv = colvec + (warp - kEpiWarp0) * kColvecFloats;
     int li = 0, hcount = 0;
     walk([&](const Tile& t) {
       const int p = t.p, kind = t.kind, blk = t.blk, m = t.m, n = t.n;
@@ -432,144 +437,193 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       const int grow = e.m0 + lane;  // row this thread owns in row form
       const bool row_ok = grow < c.M;
       e.okbits = __ballot_sync(0xffffffffu, row_ok);
+      const bool ln_kind = kind == CHAIN_QKVG || kind == CHAIN_W13 || kind == CHAIN_VEL;
+      const bool head_tile = kind == CHAIN_QKVG && n < 24;
+      const int kind3 = n >> 3, head = n & 7;  // head tiles: q (0) | k (1) | v (2)
+      const int nch = kind == CHAIN_VEL ? 1 : (bn == 192 ? 3 : (bn == 128 ? 2 : 1));  // chunks of this warp
+
+      // ---- (1) everything that does not depend on earlier phases, requested before any wait: the tile's fold vectors
+      // (cs | b' per chunk) and head norm weights go to warp-private shared memory, per-lane vectors to registers.
+      float4 rc4[4], rs4[4];   // RoPE cos / sin of this thread's row (head tiles, rotated chunk = chunk `half`)
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, s4 = bias4;  // to_out / w2: bias, tanh(gate), scale
+      const int col = n0 + e.half * 32 + 4 * l8c;  // to_out / w2: this lane's float4 column
+      if (ln_kind) {
+        const float* cs = kind == CHAIN_QKVG ? c.fold + kFoldCsQ + blk * kChainQKVG + n0
+                                             : (kind == CHAIN_W13 ? c.fold + kFoldCs13 + blk * kChainW13 + n0 : c.fold + kFoldCsV);
+        const float* bb = kind == CHAIN_QKVG ? c.fold + kFoldBq + blk * kChainQKVG + n0
+                                             : (kind == CHAIN_W13 ? c.fold + kFoldB13 + blk * kChainW13 + n0 : c.fold + kFoldBv);
+        // layout: chunk j of this warp (columns 32 (half + 2 j)) -> cv[64 j .. +32) = cs, cv[64 j + 32 .. +32) = b'
+        for (int i = lane; i < nch * 16; i += 32) {
+          const int j = i >> 4, w = (i >> 3) & 1, f = i & 7;
+          const float* src = (w ? bb : cs) + (e.half + 2 * j) * 32;
+          reinterpret_cast<float4*>(cv + j * 64 + w * 32)[f] = __ldg(reinterpret_cast<const float4*>(src) + f);
+        }
+        if (head_tile && kind3 < 2) {
+          const float* nw = (kind3 == 0 ? d.w.qn : d.w.kn) + blk * (kChainH * kChainHD) + head * kChainHD;
+          if (lane < 16) {  // cv[128 + 32 j .. +32): norm weights of chunk j, zero beyond the 120 real dims
+            const int j = lane >> 3, f = lane & 7, cc = e.half + 2 * j;
+            float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cc * 32 + 4 * f < kChainHD) w4 = __ldg(reinterpret_cast<const float4*>(nw + cc * 32) + f);
+            reinterpret_cast<float4*>(cv + 128 + j * 32)[f] = w4;
+          }
+          const int pos = grow % c.T;  // rotated dims [0, 64) = chunks 0 and 1: chunk `half` of this warp
+          const float4* cp = reinterpret_cast<const float4*>(d.w.cos_t + static_cast<long long>(pos) * 32 + e.half * 16);
+          const float4* sp = reinterpret_cast<const float4*>(d.w.sin_t + static_cast<long long>(pos) * 32 + e.half * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { rc4[i] = __ldg(cp + i); rs4[i] = __ldg(sp + i); }
+        }
+      } else {
+        const bool is_out = kind == CHAIN_OUT;
+        const float* mblk = c.mod + blk * 6 * kChainD;
+        const float* gatev = mblk + (is_out ? 2 : 5) * kChainD;
+        // scale of the LayerNorm that consumes this x: scale_mlp of this block | scale_msa of the next | final scale
+        const float* scalev = is_out ? mblk + 4 * kChainD
+                                     : (blk + 1 < kChainBlocks ? mblk + 7 * kChainD : c.mod + kChainBlocks * 6 * kChainD);
+        if (!is_out) bias4 = __ldg(reinterpret_cast<const float4*>(d.w.b2 + blk * kChainD + col));
+        g4 = __ldg(reinterpret_cast<const float4*>(gatev + col));
+        s4 = __ldg(reinterpret_cast<const float4*>(scalev + col));
+      }
+      __syncwarp();
+
+      // ---- (2) what earlier phases of this launch produced (LayerNorm partials, residual rows): the row block's flag
+      // first -- the MMAs of this tile cannot start before it either, so this wait is off the critical path
+      if (p > 0) {
+        if (lane == 0) wait_flag(done_flag + (p - 1) * m_tiles + m);
+        __syncwarp();
+      }
+      float mean = 0.f, rstd = 0.f;
+      float4 xr[8];
+      uint32_t mkbits = 0u;
+      if (ln_kind) {
+        row_stats(d.b.stats, grow, row_ok, mean, rstd);
+      } else {
+        bool masked = false;
+        if (kind == CHAIN_OUT && row_ok) masked = (grow % c.T) >= __ldg(c.frames + grow / c.T);
+        mkbits = __ballot_sync(0xffffffffu, masked);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = 4 * j + l8r;
+          xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((e.okbits >> rr) & 1u) {
+            xr[j] = __ldcg(reinterpret_cast<const float4*>(d.b.x + static_cast<long long>(e.m0 + rr) * kChainD + col));
+          }
+        }
+      }
+
+      // ---- (3) the accumulator
       ptx::mbar_wait(&acc_full[ab], (li >> 1) & 1);
       ptx::tc_fence_after();
       if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, li, 5);
 
       if (e.okbits != 0u) {
-        if (kind == CHAIN_QKVG || kind == CHAIN_W13 || kind == CHAIN_VEL) {
-          float mean, rstd;
-          row_stats(d.b.stats, grow, row_ok, mean, rstd);
-          if (kind == CHAIN_QKVG && n < 24) {
-            // ---- one head of q (kind3 0), k (1) or v (2): LayerNorm fold, per-head RMSNorm, RoPE, bf16 head layout
-            const int kind3 = n >> 3, head = n & 7;
-            const float* cs = c.fold + kFoldCsQ + blk * kChainQKVG + n0;
-            const float* bb = c.fold + kFoldBq + blk * kChainQKVG + n0;
-            float rn = 1.0f;
-            if (kind3 < 2) {
-              float ss = 0.f;
+        if (head_tile) {
+          // ---- one head of q, k or v: LayerNorm fold, per-head RMSNorm, RoPE, bf16 head layout
+          float rn = 1.0f;
+          if (kind3 < 2) {
+            float ss = 0.f;
 #pragma unroll 1
-              for (int cc = e.half; cc < 4; cc += 2) {
-                uint32_t r[32];
-                float v[32];
-                ptx::tmem_ld_32x32(e.acc + cc * 32, r);
-                ptx::tmem_ld_wait();
-                ln_chunk(r, v, mean, rstd, cs + cc * 32, bb + cc * 32);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);  // pad columns are exactly 0 (zero weights, cs, b)
-              }
-              float* sx = e.ssx + (hcount & 1) * (2 * BM);
-              sx[e.half * BM + e.q * 32 + lane] = ss;
-              ptx::named_bar_sync(1 + e.q, 64);  // the two warps of this lane quarter
-              const float tot = sx[e.q * 32 + lane] + sx[BM + e.q * 32 + lane];
-              rn = rsqrtf(tot * (1.0f / kChainHD) + 1e-6f);
-              ++hcount;
-            }
-            const float* nw = (kind3 == 0 ? d.w.qn : d.w.kn) + blk * (kChainH * kChainHD) + head * kChainHD;
-            const int pos = grow % c.T;
-            bf16* out = d.b.qkv + static_cast<long long>(kind3) * c.M * (kChainH * kChainHDP) + head * kChainHDP;
-#pragma unroll 1
-            for (int cc = e.half; cc < 4; cc += 2) {
+            for (int j = 0; j < 2; ++j) {
               uint32_t r[32];
               float v[32];
-              ptx::tmem_ld_32x32(e.acc + cc * 32, r);
+              ptx::tmem_ld_32x32(e.acc + (e.half + 2 * j) * 32, r);
               ptx::tmem_ld_wait();
-              ln_chunk(r, v, mean, rstd, cs + cc * 32, bb + cc * 32);
-              if (kind3 < 2) {
+              ln_chunk(r, v, mean, rstd, cv + j * 64, cv + j * 64 + 32);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (cc * 32 + 4 * i < kChainHD) w4 = __ldg(reinterpret_cast<const float4*>(nw + cc * 32) + i);
-                  v[4 * i + 0] *= rn * w4.x; v[4 * i + 1] *= rn * w4.y;
-                  v[4 * i + 2] *= rn * w4.z; v[4 * i + 3] *= rn * w4.w;
-                }
-                if (cc < 2) {  // interleaved-pair rotation of dims [0, 64): pair j of this chunk uses angle index 16 cc + j
-                  const float4* cp = reinterpret_cast<const float4*>(d.w.cos_t + static_cast<long long>(pos) * 32 + cc * 16);
-                  const float4* sp = reinterpret_cast<const float4*>(d.w.sin_t + static_cast<long long>(pos) * 32 + cc * 16);
+              for (int i = 0; i < 32; ++i) ss = fmaf(v[i], v[i], ss);  // pad columns are exactly 0 (zero weights, cs, b)
+            }
+            float* sx = e.ssx + (hcount & 1) * (2 * BM);
+            sx[e.half * BM + e.q * 32 + lane] = ss;
+            ptx::named_bar_sync(1 + e.q, 64);  // the two warps of this lane quarter
+            const float tot = sx[e.q * 32 + lane] + sx[BM + e.q * 32 + lane];
+            rn = rsqrtf(tot * (1.0f / kChainHD) + 1e-6f);
+            ++hcount;
+          }
+          bf16* out = d.b.qkv + static_cast<long long>(kind3) * c.M * (kChainH * kChainHDP) + head * kChainHDP;
+#pragma unroll 1
+          for (int j = 0; j < 2; ++j) {
+            const int cc = e.half + 2 * j;
+            uint32_t r[32];
+            float v[32];
+            ptx::tmem_ld_32x32(e.acc + cc * 32, r);
+            ptx::tmem_ld_wait();
+            ln_chunk(r, v, mean, rstd, cv + j * 64, cv + j * 64 + 32);
+            if (kind3 < 2) {
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float4 c4 = __ldg(cp + i), s4 = __ldg(sp + i);
-                    const float cj[4] = {c4.x, c4.y, c4.z, c4.w}, sj[4] = {s4.x, s4.y, s4.z, s4.w};
+              for (int i = 0; i < 8; ++i) {
+                const float4 w4 = reinterpret_cast<const float4*>(cv + 128 + j * 32)[i];
+                v[4 * i + 0] *= rn * w4.x; v[4 * i + 1] *= rn * w4.y;
+                v[4 * i + 2] *= rn * w4.z; v[4 * i + 3] *= rn * w4.w;
+              }
+              if (j == 0) {  // interleaved-pair rotation of dims [0, 64): pair i of chunk cc uses angle index 16 cc + i
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
-                      v[8 * i + 2 * j] = x0 * cj[j] - x1 * sj[j];
-                      v[8 * i + 2 * j + 1] = x1 * cj[j] + x0 * sj[j];
-                    }
+                for (int i = 0; i < 4; ++i) {
+                  const float cj[4] = {rc4[i].x, rc4[i].y, rc4[i].z, rc4[i].w}, sj[4] = {rs4[i].x, rs4[i].y, rs4[i].z, rs4[i].w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float x0 = v[8 * i + 2 * k], x1 = v[8 * i + 2 * k + 1];
+                    v[8 * i + 2 * k] = x0 * cj[k] - x1 * sj[k];
+                    v[8 * i + 2 * k + 1] = x1 * cj[k] + x0 * sj[k];
                   }
                 }
               }
-              store_bf16_chunk(e, v, out, kChainH * kChainHDP, cc * 32);
             }
-          } else if (kind == CHAIN_QKVG) {
-            // ---- attention gate columns (dit.py:111): LayerNorm fold only, fp32 (the attention kernel applies sigmoid)
-            const float* cs = c.fold + kFoldCsQ + blk * kChainQKVG + n0;
-            const float* bb = c.fold + kFoldBq + blk * kChainQKVG + n0;
+            store_bf16_chunk(e, v, out, kChainH * kChainHDP, cc * 32);
+          }
+        } else if (kind == CHAIN_QKVG) {
+          // ---- attention gate columns (dit.py:111): LayerNorm fold only, fp32 (the attention kernel applies sigmoid)
 #pragma unroll 1
-            for (int cc = e.half; cc < 6; cc += 2) {
-              uint32_t r[32];
-              float v[32];
-              ptx::tmem_ld_32x32(e.acc + cc * 32, r);
-              ptx::tmem_ld_wait();
-              ln_chunk(r, v, mean, rstd, cs + cc * 32, bb + cc * 32);
-              store_f32_chunk(e, v, d.b.gate, kChainD, n0 - 3072 + cc * 32);
-            }
-          } else if (kind == CHAIN_W13) {
-            // ---- SwiGLU hidden (dit.py:186): chunk = 16 w1 columns | 16 w3 columns
-            const float* cs = c.fold + kFoldCs13 + blk * kChainW13 + n0;
-            const float* bb = c.fold + kFoldB13 + blk * kChainW13 + n0;
-#pragma unroll 1
-            for (int cc = e.half; cc < 6; cc += 2) {
-              uint32_t r[32];
-              float v[32];
-              ptx::tmem_ld_32x32(e.acc + cc * 32, r);
-              ptx::tmem_ld_wait();
-              ln_chunk(r, v, mean, rstd, cs + cc * 32, bb + cc * 32);
-              uint4 pk[2];
-              uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float a0 = v[2 * i], a1 = v[2 * i + 1];
-                pw[i] = bf2(a0 * fast_sigmoid(a0) * v[16 + 2 * i], a1 * fast_sigmoid(a1) * v[16 + 2 * i + 1]);
-              }
-              // 32 rows x 16 bf16: 32-byte rows staged, two lanes per row store 16 bytes each
-              uint4* srow = reinterpret_cast<uint4*>(e.stg) + lane * 2;
-              srow[0 ^ ((lane >> 2) & 1)] = pk[0];
-              srow[1 ^ ((lane >> 2) & 1)] = pk[1];
-              __syncwarp();
-              const int hcol = (n0 + cc * 32) >> 1;
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const int rr = 16 * j + (lane >> 1), hf = lane & 1;
-                const uint4 x = reinterpret_cast<const uint4*>(e.stg)[rr * 2 + (hf ^ ((rr >> 2) & 1))];
-                if ((e.okbits >> rr) & 1u) {
-                  *reinterpret_cast<uint4*>(d.b.hb + static_cast<long long>(e.m0 + rr) * kChainFF + hcol + 8 * hf) = x;
-                }
-              }
-              __syncwarp();
-            }
-          } else {
-            // ---- velocity head (model.py:100) behind the final adaLN (dit.py:35-39): one chunk per warp
+          for (int j = 0; j < 3; ++j) {
             uint32_t r[32];
             float v[32];
-            ptx::tmem_ld_32x32(e.acc + e.half * 32, r);
+            ptx::tmem_ld_32x32(e.acc + (e.half + 2 * j) * 32, r);
             ptx::tmem_ld_wait();
-            ln_chunk(r, v, mean, rstd, c.fold + kFoldCsV + e.half * 32, c.fold + kFoldBv + e.half * 32);
-            store_f32_chunk(e, v, d.b.vel, 64, e.half * 32);
+            ln_chunk(r, v, mean, rstd, cv + j * 64, cv + j * 64 + 32);
+            store_f32_chunk(e, v, d.b.gate, kChainD, n0 - 3072 + (e.half + 2 * j) * 32);
           }
+        } else if (kind == CHAIN_W13) {
+          // ---- SwiGLU hidden (dit.py:186): chunk = 16 w1 columns | 16 w3 columns
+#pragma unroll 1
+          for (int j = 0; j < 3; ++j) {
+            const int cc = e.half + 2 * j;
+            uint32_t r[32];
+            float v[32];
+            ptx::tmem_ld_32x32(e.acc + cc * 32, r);
+            ptx::tmem_ld_wait();
+            ln_chunk(r, v, mean, rstd, cv + j * 64, cv + j * 64 + 32);
+            uint4 pk[2];
+            uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a0 = v[2 * i], a1 = v[2 * i + 1];
+              pw[i] = bf2(a0 * fast_sigmoid(a0) * v[16 + 2 * i], a1 * fast_sigmoid(a1) * v[16 + 2 * i + 1]);
+            }
+            // 32 rows x 16 bf16: 32-byte rows staged, two lanes per row store 16 bytes each
+            uint4* srow = reinterpret_cast<uint4*>(e.stg) + lane * 2;
+            srow[0 ^ ((lane >> 2) & 1)] = pk[0];
+            srow[1 ^ ((lane >> 2) & 1)] = pk[1];
+            __syncwarp();
+            const int hcol = (n0 + cc * 32) >> 1;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int rr = 16 * k + (lane >> 1), hf = lane & 1;
+              const uint4 x = reinterpret_cast<const uint4*>(e.stg)[rr * 2 + (hf ^ ((rr >> 2) & 1))];
+              if ((e.okbits >> rr) & 1u) {
+                *reinterpret_cast<uint4*>(d.b.hb + static_cast<long long>(e.m0 + rr) * kChainFF + hcol + 8 * hf) = x;
+              }
+            }
+            __syncwarp();
+          }
+        } else if (kind == CHAIN_VEL) {
+          // ---- velocity head (model.py:100) behind the final adaLN (dit.py:35-39): one chunk per warp
+          uint32_t r[32];
+          float v[32];
+          ptx::tmem_ld_32x32(e.acc + e.half * 32, r);
+          ptx::tmem_ld_wait();
+          ln_chunk(r, v, mean, rstd, cv, cv + 32);
+          store_f32_chunk(e, v, d.b.vel, 64, e.half * 32);
         } else {
           // ---- to_out / w2: x += tanh(gate) * (acc + b) with padded query rows masked for to_out (dit.py:115-118,
           // 198,201); writes x, its LayerNorm partials and the next GEMM's operand bf16(x * (1 + scale)).
-          const bool is_out = kind == CHAIN_OUT;
-          bool masked = false;
-          if (is_out && row_ok) masked = (grow % c.T) >= __ldg(c.frames + grow / c.T);
-          const uint32_t mkbits = __ballot_sync(0xffffffffu, masked);
-          const float* mblk = c.mod + blk * 6 * kChainD;
-          const float* gatev = mblk + (is_out ? 2 : 5) * kChainD;
-          // scale of the LayerNorm that consumes this x: scale_mlp of this block | scale_msa of the next | final scale
-          const float* scalev = is_out ? mblk + 4 * kChainD
-                                       : (blk + 1 < kChainBlocks ? mblk + 7 * kChainD : c.mod + kChainBlocks * 6 * kChainD);
-          const int col = n0 + e.half * 32 + 4 * l8c;
           uint32_t r[32];
           ptx::tmem_ld_32x32(e.acc + e.half * 32, r);
           ptx::tmem_ld_wait();
@@ -579,19 +633,6 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
             for (int i = 0; i < 8; ++i) srow[i ^ (lane & 7)] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
           }
           __syncwarp();
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!is_out) bias4 = __ldg(reinterpret_cast<const float4*>(d.w.b2 + blk * kChainD + col));
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gatev + col));
-          const float4 s4 = __ldg(reinterpret_cast<const float4*>(scalev + col));
-          float4 xr[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = 4 * j + l8r;
-            xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((e.okbits >> rr) & 1u) {
-              xr[j] = __ldcg(reinterpret_cast<const float4*>(d.b.x + static_cast<long long>(e.m0 + rr) * kChainD + col));
-            }
-          }
           const int part = (n0 >> 5) + e.half;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -624,7 +665,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
           }
           __syncwarp();
         }
-      } else if (kind == CHAIN_QKVG && n < 24 && (n >> 3) < 2) {
+      } else if (head_tile && kind3 < 2) {
         // no live row in this quarter, but the partner-warp barrier of the head epilogue is unconditional
         ptx::named_bar_sync(1 + e.q, 64);
         ++hcount;
@@ -633,11 +674,11 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
-      // ... and with its share of the tile.  Publish the tile once all eight warps are done: every warp's stores are
-      // ordered before the barrier (gpu-scope fence + cross-proxy fence: the consumer reads them with TMA), one thread
-      // counts the tile, and whoever completes the row block raises its flag.
+      // ... and with its share of the tile.  Publish the tile once all eight warps are done: each thread makes its
+      // global writes visible to the async proxy (the consumer reads them with TMA), the barrier orders them before
+      // thread 0, whose gpu-scope fence + atomic is the (cumulative) release; whoever completes the row block raises
+      // its flag.
       if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, li, 6);
-      __threadfence();
       fence_proxy_async_all();
       ptx::named_bar_sync(5, kEpiWarps * 32);
       if (warp == kEpiWarp0 && lane == 0) {

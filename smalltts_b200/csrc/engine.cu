@@ -761,6 +761,7 @@ void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_b
       if (e->chain_split) {  // one GEMM per launch: kernel boundaries instead of the in-kernel ready counters
         for (const auto& ph : phases) {
           cc.n_phases = 1; cc.kind[0] = ph.first; cc.blk[0] = ph.second;
+          CK(cudaMemsetAsync(cb.ready, 0, ready_ints * sizeof(int), st));  // every launch claims its tiles from zero
           CK(launch_dit_chain(st, e->chain_w, cb, cc));
         }
       } else {
