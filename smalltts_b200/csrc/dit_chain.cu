@@ -34,18 +34,21 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int kStages = 4;
-constexpr int kABytes = BM * BK * 2;    // 16 KB
-constexpr int kWBytes = 192 * BK * 2;   // 24 KB: widest tile
+constexpr int kABytes = BM * BK * 2;    // 16 KB: one k-block (64 columns) of the A tile
+// One ring slot = 48 KB.  Wide tiles (bn 128 / 192) put one k-block in it (A 16 KB | W <= 24 KB); the narrow tiles of
+// to_out / w2 / velocity (bn 64) put TWO (A0 | A1 | W0 8 KB | W1 8 KB): the mainloop is paced by the bytes in flight per
+// SM (ring bytes / L2 latency), so the 24 KB stages of a narrow tile would leave half of the ring empty.
+constexpr int kSlotBytes = 48 * 1024;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiWarp0 = 4;
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
-constexpr int kStgBytes = 4096;         // per epilogue warp: 32 rows x 32 fp32, XOR-swizzled
+constexpr int kStgBytes = 2048;         // per epilogue warp: 32 rows x 16 fp32 (or 32 bf16), XOR-swizzled
 constexpr int kAccCols = 256;           // TMEM columns per accumulator buffer
 constexpr int kTq = 4;                  // depth of the tile FIFO between the claiming warp and the other roles
 constexpr int kTqReaders = 2 + kEpiWarps;  // A producer, MMA issuer, epilogue warps
 constexpr int kColvecFloats = 192;         // per epilogue warp: 3 chunks x (cs | b') or 2 chunks x (cs | b') + norm weights
-constexpr int kSmem = kStages * (kABytes + kWBytes) + 256 + kEpiWarps * kStgBytes + 2 * 2 * BM * 4 +
-                      kEpiWarps * kColvecFloats * 4 + 1024;
+constexpr int kSmem = kStages * kSlotBytes + 256 + kEpiWarps * kStgBytes + 2 * 2 * BM * 4 + kEpiWarps * kColvecFloats * 4 + 1024;
+static_assert(kSmem <= 232448, "chain kernel does not fit in shared memory");
 
 struct ChainMaps {
   CUtensorMap a[3];  // xb [M, 960], ob [M, 1024], hb [M, 2400]: box 64 x 128 rows
@@ -79,6 +82,8 @@ __device__ __forceinline__ void tile_cols(int kind, int n, int& n0, int& bn) {
     n0 = n * 64; bn = 64;
   }
 }
+
+__device__ __forceinline__ int slot_kblocks(int bn) { return bn == 64 ? 2 : 1; }
 
 struct Tile {
   int p, kind, blk, m, n, g;
@@ -206,23 +211,28 @@ __device__ __forceinline__ void store_bf16_chunk(const Epi& e, const float (&v)[
   __syncwarp();
 }
 
-// 32 rows x 32 fp32 (row form) -> global, 128-byte row segments per 8 lanes
+// 32 rows x 32 fp32 (row form) -> global: two passes of 16 columns, 64-byte row segments per 4 lanes
 __device__ __forceinline__ void store_f32_chunk(const Epi& e, const float (&v)[32], float* __restrict__ out, long long ld,
                                                 int col0) {
-  float4* srow = reinterpret_cast<float4*>(e.stg) + e.lane * 8;
+  const int l4r = e.lane >> 2, l4c = e.lane & 3;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) srow[i ^ (e.lane & 7)] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  __syncwarp();
-  const int l8r = e.lane >> 3, l8c = e.lane & 7;
+  for (int h = 0; h < 2; ++h) {
+    float4* srow = reinterpret_cast<float4*>(e.stg) + e.lane * 4;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int rr = 4 * j + l8r;
-    const float4 x = reinterpret_cast<const float4*>(e.stg)[rr * 8 + (l8c ^ (rr & 7))];
-    if ((e.okbits >> rr) & 1u) {
-      *reinterpret_cast<float4*>(out + static_cast<long long>(e.m0 + rr) * ld + col0 + 4 * l8c) = x;
+    for (int i = 0; i < 4; ++i) {
+      srow[i ^ ((e.lane >> 1) & 3)] = make_float4(v[16 * h + 4 * i], v[16 * h + 4 * i + 1], v[16 * h + 4 * i + 2], v[16 * h + 4 * i + 3]);
     }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = 8 * j + l4r;
+      const float4 x = reinterpret_cast<const float4*>(e.stg)[rr * 4 + (l4c ^ ((rr >> 1) & 3))];
+      if ((e.okbits >> rr) & 1u) {
+        *reinterpret_cast<float4*>(out + static_cast<long long>(e.m0 + rr) * ld + col0 + 16 * h + 4 * l4c) = x;
+      }
+    }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -231,15 +241,15 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* smA = smem;
-  uint8_t* smW = smem + kStages * kABytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smW + kStages * kWBytes);
+  uint8_t* ring = smem;  // kStages slots of kSlotBytes
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kStages * kSlotBytes);
   uint64_t* empty = full + kStages;
   uint64_t* acc_full = empty + kStages;  // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint64_t* tq_full = acc_empty + 2;     // [kTq]
   uint64_t* tq_empty = tq_full + kTq;    // [kTq]
-  int* tileq = reinterpret_cast<int*>(tq_empty + kTq);  // [kTq]
+  uint64_t* dep_full = tq_empty + kTq;   // [kTq] the A producer has seen the row block's flag for the tile in this FIFO slot
+  int* tileq = reinterpret_cast<int*>(dep_full + kTq);  // [kTq]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tileq + kTq);
   uint8_t* stage_base = reinterpret_cast<uint8_t*>(full) + 256;
   float* ssx = reinterpret_cast<float*>(stage_base + kEpiWarps * kStgBytes);
@@ -264,6 +274,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
     for (int i = 0; i < kTq; ++i) {
       ptx::mbar_init(&tq_full[i], 1);
       ptx::mbar_init(&tq_empty[i], kTqReaders);
+      ptx::mbar_init(&dep_full[i], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -283,16 +294,18 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   int* const done_flag = d.b.ready + cstride;
   int* const next_tile = d.b.ready + 2 * cstride;
 
-  // Consumer side of the tile FIFO: calls fn(tile) for every tile this CTA claimed, in claim order.
+  // Consumer side of the tile FIFO: calls fn(tile, slot, parity) for every tile this CTA claimed, in claim order.  The
+  // slot is handed back only after the tile has been processed, so per-slot state (dep_full) cannot be recycled early.
   auto walk = [&](auto&& fn) {
     uint32_t slot = 0, tph = 0;
     for (;;) {
       ptx::mbar_wait(&tq_full[slot], tph);
       const int g = tileq[slot];
       __syncwarp();
+      if (g >= 0) fn(decode_tile(g, c, m_tiles), slot, tph);
+      __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tq_empty[slot]);
       if (g < 0) break;
-      fn(decode_tile(g, c, m_tiles));
       if (++slot == kTq) { slot = 0; tph ^= 1; }
     }
   };
@@ -324,7 +337,8 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       int n0, bn;
       tile_cols(t.kind, t.n, n0, bn);
       const int wrow = t.blk * kind_wrows(t.kind) + n0;
-      const int iters = kind_kiters(t.kind);
+      const int kblocks = kind_kiters(t.kind), kpb = slot_kblocks(bn);
+      const int iters = (kblocks + kpb - 1) / kpb;  // ring slots of this tile
       const CUtensorMap* tm = &maps.w[t.kind];
       for (int it = 0; it < iters; ++it) {
         // weights never depend on the predecessor kernel: the first ring's worth of boxes is requested before the
@@ -338,9 +352,13 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         if (it == (iters > kStages ? iters - kStages : 0) && lane == 0) g_raw = atomicAdd(next_tile, 1);
         ptx::mbar_wait(&empty[st], ph ^ 1);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&full[st], static_cast<uint32_t>(bn) * 128u);
-          for (int r = 0; r < bn / 64; ++r) {
-            ptx::tma_load_2d(smW + st * kWBytes + r * 8192, tm, &full[st], it * BK, wrow + r * 64);
+          const int nkb = kblocks - it * kpb < kpb ? kblocks - it * kpb : kpb;
+          uint8_t* wdst = ring + st * kSlotBytes + (kpb == 2 ? 2 * kABytes : kABytes);
+          ptx::mbar_expect_tx(&full[st], static_cast<uint32_t>(bn * 128 * nkb));
+          for (int kb = 0; kb < nkb; ++kb) {
+            for (int r = 0; r < bn / 64; ++r) {
+              ptx::tma_load_2d(wdst + kb * (bn * 128) + r * 8192, tm, &full[st], (it * kpb + kb) * BK, wrow + r * 64);
+            }
           }
         }
         __syncwarp();
@@ -355,7 +373,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
     ptx::pdl_wait();
     uint32_t st = 0, ph = 0;
     int aseq = 0;
-    walk([&](const Tile& t) {
+    walk([&](const Tile& t, uint32_t slot, uint32_t) {
       const int p = t.p, kind = t.kind, m = t.m;
       if (lane == 0) trace_ev(d.b.trace, aseq, 1);
       if (p > 0) {
@@ -364,15 +382,23 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         __syncwarp();
         fence_proxy_async_all();  // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
       }
+      // one poller per CTA: the epilogue warps learn about the flag through shared memory
+      if (lane == 0) ptx::mbar_arrive(&dep_full[slot]);
       if (lane == 0) trace_ev(d.b.trace, aseq, 2);
       ++aseq;
-      const int iters = kind_kiters(kind);
+      int n0, bn;
+      tile_cols(kind, t.n, n0, bn);
+      const int kblocks = kind_kiters(kind), kpb = slot_kblocks(bn);
+      const int iters = (kblocks + kpb - 1) / kpb;
       const CUtensorMap* tm = &maps.a[kind_amap(kind)];
       for (int it = 0; it < iters; ++it) {
         ptx::mbar_wait(&empty[st], ph ^ 1);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&full[st], kABytes);
-          ptx::tma_load_2d(smA + st * kABytes, tm, &full[st], it * BK, m * BM);
+          const int nkb = kblocks - it * kpb < kpb ? kblocks - it * kpb : kpb;
+          ptx::mbar_expect_tx(&full[st], static_cast<uint32_t>(kABytes * nkb));
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::tma_load_2d(ring + st * kSlotBytes + kb * kABytes, tm, &full[st], (it * kpb + kb) * BK, m * BM);
+          }
         }
         __syncwarp();
         if (++st == kStages) { st = 0; ph ^= 1; }
@@ -381,16 +407,16 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   } else if (warp == 2) {
     // ================================================================== MMA issuer
     ptx::pdl_wait();
-    const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(smA));
-    const uint64_t db0 = ptx::umma_desc_sw128(ptx::smem_u32(smW));
+    const uint64_t d0 = ptx::umma_desc_sw128(ptx::smem_u32(ring));
     uint32_t st = 0, ph = 0;
     int li = 0;
-    walk([&](const Tile& t) {
+    walk([&](const Tile& t, uint32_t, uint32_t) {
       const int kind = t.kind;
       int n0, bn;
       tile_cols(kind, t.n, n0, bn);
       const uint32_t idesc = ptx::umma_idesc_bf16(BM, static_cast<uint32_t>(bn));
-      const int iters = kind_kiters(kind);
+      const int kblocks = kind_kiters(kind), kpb = slot_kblocks(bn);
+      const int iters = (kblocks + kpb - 1) / kpb;
       const int ab = li & 1;
       ptx::mbar_wait(&acc_empty[ab], ((li >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
@@ -400,10 +426,18 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         ptx::tc_fence_after();
         if (it == 0 && lane == 0) trace_ev(d.b.trace, li, 3);
         if (ptx::elect_one()) {
-          const uint64_t da = da0 + static_cast<uint64_t>(st * (kABytes >> 4));
-          const uint64_t db = db0 + static_cast<uint64_t>(st * (kWBytes >> 4));
+          const int nkb = kblocks - it * kpb < kpb ? kblocks - it * kpb : kpb;
+          // descriptor start-address field is (addr >> 4)
+          const uint64_t ds = d0 + static_cast<uint64_t>(st * (kSlotBytes >> 4));
+          const uint32_t w_off = (kpb == 2 ? 2 * kABytes : kABytes) >> 4;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint64_t da = ds + static_cast<uint64_t>(kb * (kABytes >> 4));
+            const uint64_t db = ds + w_off + static_cast<uint64_t>(kb * ((bn * 128) >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | kb | k) != 0 ? 1u : 0u);
+            }
+          }
           ptx::umma_commit(&empty[st]);
         }
         __syncwarp();
@@ -423,11 +457,10 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
     e.lane = lane;
     e.stg = reinterpret_cast<float*>(stage_base + (warp - kEpiWarp0) * kStgBytes);
     e.ssx = ssx;
-    const int l8r = lane >> 3, l8c = lane & 7;
     // warp-private column vectors of the current tile (fold vectors, head norm weights): fetched BEFORE the waits
     float* cv = colvec + (warp - kEpiWarp0) * kColvecFloats;
     int li = 0, hcount = 0;
-    walk([&](const Tile& t) {
+    walk([&](const Tile& t, uint32_t slot, uint32_t tph) {
       const int p = t.p, kind = t.kind, blk = t.blk, m = t.m, n = t.n;
       int n0, bn;
       tile_cols(kind, n, n0, bn);
@@ -445,8 +478,12 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       // ---- (1) everything that does not depend on earlier phases, requested before any wait: the tile's fold vectors
       // (cs | b' per chunk) and head norm weights go to warp-private shared memory, per-lane vectors to registers.
       float4 rc4[4], rs4[4];   // RoPE cos / sin of this thread's row (head tiles, rotated chunk = chunk `half`)
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, s4 = bias4;  // to_out / w2: bias, tanh(gate), scale
-      const int col = n0 + e.half * 32 + 4 * l8c;  // to_out / w2: this lane's float4 column
+      // to_out / w2 work on 64-byte row segments: lane (l4r, l4c) owns rows 8 j + l4r and, in pass h, the float4 column
+      // n0 + 32 half + 16 h + 4 l4c.  Per-column vectors of both passes: bias, tanh(gate), scale of the consuming norm.
+      const int l4r = lane >> 2, l4c = lane & 3;
+      const int col = n0 + e.half * 32 + 4 * l4c;
+      float4 bias4[2], g4[2], s4[2];
+      bias4[0] = bias4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ln_kind) {
         const float* cs = kind == CHAIN_QKVG ? c.fold + kFoldCsQ + blk * kChainQKVG + n0
                                              : (kind == CHAIN_W13 ? c.fold + kFoldCs13 + blk * kChainW13 + n0 : c.fold + kFoldCsV);
@@ -479,18 +516,19 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         // scale of the LayerNorm that consumes this x: scale_mlp of this block | scale_msa of the next | final scale
         const float* scalev = is_out ? mblk + 4 * kChainD
                                      : (blk + 1 < kChainBlocks ? mblk + 7 * kChainD : c.mod + kChainBlocks * 6 * kChainD);
-        if (!is_out) bias4 = __ldg(reinterpret_cast<const float4*>(d.w.b2 + blk * kChainD + col));
-        g4 = __ldg(reinterpret_cast<const float4*>(gatev + col));
-        s4 = __ldg(reinterpret_cast<const float4*>(scalev + col));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (!is_out) bias4[h] = __ldg(reinterpret_cast<const float4*>(d.w.b2 + blk * kChainD + col + 16 * h));
+          g4[h] = __ldg(reinterpret_cast<const float4*>(gatev + col + 16 * h));
+          s4[h] = __ldg(reinterpret_cast<const float4*>(scalev + col + 16 * h));
+        }
       }
       __syncwarp();
 
       // ---- (2) what earlier phases of this launch produced (LayerNorm partials, residual rows): the row block's flag
       // first -- the MMAs of this tile cannot start before it either, so this wait is off the critical path
-      if (p > 0) {
-        if (lane == 0) wait_flag(done_flag + (p - 1) * m_tiles + m);
-        __syncwarp();
-      }
+      ptx::mbar_wait(&dep_full[slot], tph);  // raised by the A producer once it has seen the flag (one poller per CTA)
+      if (p > 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
       float mean = 0.f, rstd = 0.f;
       float4 xr[8];
       uint32_t mkbits = 0u;
@@ -501,11 +539,11 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         if (kind == CHAIN_OUT && row_ok) masked = (grow % c.T) >= __ldg(c.frames + grow / c.T);
         mkbits = __ballot_sync(0xffffffffu, masked);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = 4 * j + l8r;
-          xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) {  // i = 4 h + j: pass h, row 8 j + l4r
+          const int rr = 8 * (i & 3) + l4r;
+          xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if ((e.okbits >> rr) & 1u) {
-            xr[j] = __ldcg(reinterpret_cast<const float4*>(d.b.x + static_cast<long long>(e.m0 + rr) * kChainD + col));
+            xr[i] = __ldcg(reinterpret_cast<const float4*>(d.b.x + static_cast<long long>(e.m0 + rr) * kChainD + col + 16 * (i >> 2)));
           }
         }
       }
@@ -627,43 +665,51 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
           uint32_t r[32];
           ptx::tmem_ld_32x32(e.acc + e.half * 32, r);
           ptx::tmem_ld_wait();
-          {
-            uint4* srow = reinterpret_cast<uint4*>(e.stg) + lane * 8;
+          float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};  // LayerNorm partials of rows 8 j + l4r
 #pragma unroll
-            for (int i = 0; i < 8; ++i) srow[i ^ (lane & 7)] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-          }
-          __syncwarp();
-          const int part = (n0 >> 5) + e.half;
+          for (int h = 0; h < 2; ++h) {
+            {
+              uint4* srow = reinterpret_cast<uint4*>(e.stg) + lane * 4;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = 4 * j + l8r;
-            const bool ok = (e.okbits >> rr) & 1u;
-            float4 v = reinterpret_cast<const float4*>(e.stg)[rr * 8 + (l8c ^ (rr & 7))];
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            if ((mkbits >> rr) & 1u) v = make_float4(0.f, 0.f, 0.f, 0.f);
-            v.x = fmaf(v.x, g4.x, xr[j].x); v.y = fmaf(v.y, g4.y, xr[j].y);
-            v.z = fmaf(v.z, g4.z, xr[j].z); v.w = fmaf(v.w, g4.w, xr[j].w);
-            float s1 = (v.x + v.y) + (v.z + v.w);
-            float s2 = fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            if (ok) {
-              const long long off = static_cast<long long>(e.m0 + rr) * kChainD + col;
-              *reinterpret_cast<float4*>(d.b.x + off) = v;
-              uint2 pk;
-              pk.x = bf2(v.x * (1.0f + s4.x), v.y * (1.0f + s4.y));
-              pk.y = bf2(v.z * (1.0f + s4.z), v.w * (1.0f + s4.w));
-              *reinterpret_cast<uint2*>(d.b.xb + off) = pk;
-              if (l8c == 0) {
-                *reinterpret_cast<float2*>(d.b.stats + (static_cast<long long>(e.m0 + rr) * kChainParts + part) * 2) =
-                    make_float2(s1, s2);
+              for (int i = 0; i < 4; ++i) {
+                srow[i ^ ((lane >> 1) & 3)] = make_uint4(r[16 * h + 4 * i], r[16 * h + 4 * i + 1], r[16 * h + 4 * i + 2], r[16 * h + 4 * i + 3]);
               }
             }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = 8 * j + l4r;
+              float4 v = reinterpret_cast<const float4*>(e.stg)[rr * 4 + (l4c ^ ((rr >> 1) & 3))];
+              const float4 xv = xr[4 * h + j];
+              v.x += bias4[h].x; v.y += bias4[h].y; v.z += bias4[h].z; v.w += bias4[h].w;
+              if ((mkbits >> rr) & 1u) v = make_float4(0.f, 0.f, 0.f, 0.f);
+              v.x = fmaf(v.x, g4[h].x, xv.x); v.y = fmaf(v.y, g4[h].y, xv.y);
+              v.z = fmaf(v.z, g4[h].z, xv.z); v.w = fmaf(v.w, g4[h].w, xv.w);
+              p1[j] += (v.x + v.y) + (v.z + v.w);
+              p2[j] += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+              if ((e.okbits >> rr) & 1u) {
+                const long long off = static_cast<long long>(e.m0 + rr) * kChainD + col + 16 * h;
+                *reinterpret_cast<float4*>(d.b.x + off) = v;
+                uint2 pk;
+                pk.x = bf2(v.x * (1.0f + s4[h].x), v.y * (1.0f + s4[h].y));
+                pk.y = bf2(v.z * (1.0f + s4[h].z), v.w * (1.0f + s4[h].w));
+                *reinterpret_cast<uint2*>(d.b.xb + off) = pk;
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          const int part = (n0 >> 5) + e.half;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float s1 = p1[j], s2 = p2[j];
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            const int rr = 8 * j + l4r;
+            if (l4c == 0 && ((e.okbits >> rr) & 1u)) {
+              *reinterpret_cast<float2*>(d.b.stats + (static_cast<long long>(e.m0 + rr) * kChainParts + part) * 2) =
+                  make_float2(s1, s2);
+            }
+          }
         }
       } else if (head_tile && kind3 < 2) {
         // no live row in this quarter, but the partner-warp barrier of the head epilogue is unconditional
