@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsmalltts_b200.so")
+# STTS_LIB_PATH: load another build of the library (A/B experiments with compile-time variants, tools/build_variant.py)
+LIB_PATH = os.environ.get("STTS_LIB_PATH") or os.path.join(HERE, "libsmalltts_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 OK = 0

@@ -83,7 +83,10 @@ __device__ __forceinline__ void tile_cols(int kind, int n, int& n0, int& bn) {
   }
 }
 
-__device__ __forceinline__ int slot_kblocks(int bn) { return bn == 64 ? 2 : 1; }
+#ifndef STTS_CHAIN_KPB
+#define STTS_CHAIN_KPB 2  // k-blocks per ring slot for the narrow (bn 64) tiles; 1 = A/B experiments
+#endif
+__device__ __forceinline__ int slot_kblocks(int bn) { return bn == 64 ? STTS_CHAIN_KPB : 1; }
 
 struct Tile {
   int p, kind, blk, m, n, g;
@@ -113,12 +116,12 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// Wait until *p != 0.  Polls with relaxed loads (an acquire load per poll would invalidate this SM's L1 every time,
+// Wait until *p >= target.  Polls with relaxed loads (an acquire load per poll would invalidate this SM's L1 every time,
 // under the feet of the epilogue warps) and backs off, then acquires once.  Bounded like ptx::mbar_wait: a scheduling
 // bug traps instead of hanging the GPU.
-__device__ __forceinline__ void wait_flag(const int* p) {
+__device__ __forceinline__ void wait_flag(const int* p, int target) {
   uint32_t spins = 0, ns = 64;
-  while (ld_relaxed(p) == 0) {
+  while (ld_relaxed(p) < target) {
     __nanosleep(ns);
     if (ns < 512) ns += ns;
     if (++spins > (1u << 23)) __trap();
@@ -291,7 +294,6 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   // "row block complete" flags the consumers poll (kept on other cache lines than the atomics), the claim counter
   const int cstride = (4 * m_tiles + 31) & ~31;
   int* const done_cnt = d.b.ready;
-  int* const done_flag = d.b.ready + cstride;
   int* const next_tile = d.b.ready + 2 * cstride;
 
   // Consumer side of the tile FIFO: calls fn(tile, slot, parity) for every tile this CTA claimed, in claim order.  The
@@ -378,7 +380,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       if (lane == 0) trace_ev(d.b.trace, aseq, 1);
       if (p > 0) {
         // all tiles of the previous phase that write rows [128 m, +128) must be done
-        if (lane == 0) wait_flag(done_flag + (p - 1) * m_tiles + m);
+        if (lane == 0) wait_flag(done_cnt + (p - 1) * m_tiles + m, kind_ntiles(c.kind[p - 1]));
         __syncwarp();
         fence_proxy_async_all();  // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
       }
@@ -722,18 +724,13 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
       // ... and with its share of the tile.  Publish the tile once all eight warps are done: each thread makes its
       // global writes visible to the async proxy (the consumer reads them with TMA), the barrier orders them before
-      // thread 0, whose gpu-scope fence + atomic is the (cumulative) release; whoever completes the row block raises
-      // its flag.
+      // thread 0, whose gpu-scope fence + atomic is the (cumulative) release.
       if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, li, 6);
       fence_proxy_async_all();
       ptx::named_bar_sync(5, kEpiWarps * 32);
       if (warp == kEpiWarp0 && lane == 0) {
         __threadfence();
-        const int done = atomicAdd(done_cnt + p * m_tiles + m, 1) + 1;
-        if (done == kind_ntiles(kind)) {
-          __threadfence();
-          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(done_flag + p * m_tiles + m), "r"(1) : "memory");
-        }
+        atomicAdd(done_cnt + p * m_tiles + m, 1);  // the consumers' (one per CTA) pollers watch this count
         trace_ev(d.b.trace, li, 7);
       }
       ++li;
