@@ -633,13 +633,26 @@ __global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ ffn_norm_w, float eps,
                                                            float* __restrict__ y, bf16* __restrict__ a) {
-  ptx::pdl_wait();
-  ptx::pdl_trigger();
   extern __shared__ __align__(16) float smx[];
   const int R = TT + 6;
   float* tile = smx;               // [R][C]
   float* inv1 = smx + R * C;       // [R]
   float* inv2 = inv1 + R;          // [TT]
+  // per-channel parameters, staged BEFORE the dependency wait (weights do not depend on the predecessor): the conv
+  // loop below walks C / 256 channels per thread, and a dependent global-load round trip per channel was most of this
+  // kernel's time at C = 2048 (19 us for 5 MB of activations)
+  float* cw = inv2 + ((TT + 3) & ~3);  // [C][7]
+  float* cbs = cw + 7 * C;             // [C] conv bias
+  float* gms = cbs + C;                // [C] layer scale
+  float* nws = gms + C;                // [C] norm weight
+  for (int i = threadIdx.x; i < 7 * C; i += 256) cw[i] = conv_w[i];
+  for (int i = threadIdx.x; i < C; i += 256) {
+    cbs[i] = conv_b[i];
+    gms[i] = gamma[i];
+    nws[i] = norm_w[i];
+  }
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * TT;
   const int nrows = min(TT, T - t0);
@@ -690,8 +703,8 @@ __global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restri
   for (int c = (C >= 256 ? threadIdx.x : threadIdx.x % C); c < C; c += 256) {
     float w[7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) w[j] = conv_w[c * 7 + j];
-    const float cb = conv_b[c], gm = gamma[c], nw = norm_w[c];
+    for (int j = 0; j < 7; ++j) w[j] = cw[c * 7 + j];  // stride 7 words across lanes: conflict-free
+    const float cb = cbs[c], gm = gms[c], nw = nws[c];
     float win[7];
     win[0] = 0.f;
 #pragma unroll
@@ -1247,17 +1260,21 @@ cudaError_t convnext_mix(cudaStream_t st, const float* x, int B, int T, int C, c
     if (tt_elems < 2048 || tt_elems > 24576) tt_elems = 8192;
   }
   int TT = tt_elems / C;
-  if (TT < 4) TT = 4;  // C = 2048 (75 frames per utterance): 4-row tiles spread the stage over all SMs (19 x B CTAs)
+  if (TT < 4) TT = 4;
+  // C = 2048 (75 frames per utterance): the tile + the staged parameters allow one CTA per SM, and 5-row tiles give
+  // 15 x B = 120 CTAs at batch 8 -- a single wave (4-row tiles: 152 CTAs, two waves)
+  if (C == 2048 && TT < 5) TT = 5;
   if (TT > 512) TT = 512;
   if (TT > T) TT = T;
-  const int smem = ((TT + 6) * C + (TT + 6) + TT) * 4;
+  const int smem = ((TT + 6) * C + (TT + 6) + ((TT + 3) & ~3) + 10 * C) * 4;
   static PerDeviceOnce once;
   {
     const cudaError_t e = once.run([] {
-      return cudaFuncSetAttribute(convnext_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+      return cudaFuncSetAttribute(convnext_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     });
     if (e != cudaSuccess) return e;
   }
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
   dim3 grid((T + TT - 1) / TT, B);
   last_launch_status = launch_k(convnext_mix_kernel, dim3(grid), dim3(256), smem, st, x, T, C, TT, norm_w, conv_w, conv_b, gamma, ffn_norm_w, eps, y, a);
   STTS_LAUNCH_OK();
