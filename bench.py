@@ -84,6 +84,9 @@ def tail_dram_traffic():
         return None, None
 
 
+PRECISION_NOTE = {"fast": "bf16 GEMM / attention operands, fp32 accumulation (stated tolerance 2e-2 rel-L2 vs the fp32 reference)",
+                  "tight": "fp16 operands (11-bit significand like TF32), fp32 accumulation (stated tolerance 2e-3 rel-L2)"}
+
 # algorithmic FLOPs of one denoiser evaluation at B=8, T=75, R=15, P=120
 DENOISE_GFLOP_PER_STEP = 177.3
 
@@ -263,7 +266,7 @@ def main_ours(args, rank, local_rank, world):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = f"cuda:{local_rank}"
-    eng = Engine(local_rank)
+    eng = Engine(local_rank, precision=args.precision)
     eng.load_state_dicts(synthetic.dit_state_dict(0), synthetic.vocoder_state_dict(1))
 
     # per-rank batch: same shapes, rank-dependent content
@@ -353,6 +356,27 @@ def main_ours(args, rank, local_rank, world):
         except Exception:  # noqa: BLE001 - strictly optional
             in_flight = None
 
+    # The other precision mode on the same workload (device-resident inputs, CUDA events on the engine stream): the
+    # headline build feeds bf16 operands to the tensor cores, the parity build fp16 (11-bit significand like TF32).
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_precision:
+        try:
+            oname = "tight" if args.precision == "fast" else "fast"
+            eng2 = Engine(local_rank, precision=oname)
+            eng2.load_state_dicts(synthetic.dit_state_dict(0), synthetic.vocoder_state_dict(1))
+            for i in range(3):
+                eng2.synthesize(d_ref, ref_len, d_ids, ph_len, frames, T, seed=1 + i, steps=STEPS_DMD, out=d_out)
+            n2 = 10
+            eng2.timer_start()
+            for i in range(n2):
+                eng2.synthesize(d_ref, ref_len, d_ids, ph_len, frames, T, seed=10 + i, steps=STEPS_DMD, out=d_out)
+            ms2 = eng2.timer_stop()
+            other = {"precision": oname, "value": BATCH * AUDIO_S_PER_UTT * n2 / (ms2 / 1e3), "unit": UNIT,
+                     "ms_per_step": ms2 / n2, "steps": n2, "warmup": 3}
+            eng2.close()
+        except Exception as exc:  # noqa: BLE001 - informational
+            other = {"error": repr(exc)}
+
     config4 = None
     if not args.no_config4:
         try:
@@ -373,8 +397,9 @@ def main_ours(args, rank, local_rank, world):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16" if args.precision == "fast" else "fp16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "dmd_steps": STEPS_DMD, "noise": "on-device Philox",
+                       "precision": f"{args.precision}: {PRECISION_NOTE[args.precision]}",
                        "l2": "no explicit flush: per-step working set (1.3 GB bf16 weights + >1 GB activations) >> 126 MB L2",
                        "weights": "seeded random init of the reference architecture (328 M DiT + 344 M vocoder params)"},
             "rtf": (dev_ms / 1e3) / audio_s,
@@ -398,6 +423,8 @@ def main_ours(args, rank, local_rank, world):
                                 "algorithmic_gflop": DENOISE_GFLOP_PER_STEP * STEPS_DMD, "ms": stage["denoise_ms"]},
             "cpu_baseline": cpu,
         }
+        if other is not None:
+            out["other_precision"] = other
         if in_flight is not None:
             out["in_flight"] = in_flight
         if config4 is not None:
@@ -415,6 +442,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fast", choices=["fast", "tight"],
+                    help="fast: bf16 tensor-core operands (headline); tight: the fp16-operand parity build")
+    ap.add_argument("--no-other-precision", action="store_true", help="skip the short run of the other precision mode")
     ap.add_argument("--no-config4", action="store_true", help="skip the configs[3] (64 mixed prompts, sharded) figure")
     ap.add_argument("--in-flight", type=int, default=2,
                     help="also report throughput with up to this many batches in flight on one GPU (N=1 only; 0 = skip)")

@@ -82,30 +82,37 @@ SIGNATURES = {
     "stts_test_convnext_fused": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
 }
 
-_lib = None
+# "tight": the parity build of the same sources with fp16 (11-bit significand, TF32's precision) instead of bf16 GEMM /
+# attention operands (csrc/op16.cuh).  Same C ABI, same kernels; an engine picks its library when it is created.
+LIB_PATH_TIGHT = os.environ.get("STTS_LIB_PATH_TIGHT") or os.path.join(HERE, "libsmalltts_b200_tight.so")
+PRECISIONS = {"fast": "bf16 operands, fp32 accumulation", "tight": "fp16 operands (11-bit significand), fp32 accumulation"}
+
+_libs = {}
 
 
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def lib(precision: str = "fast") -> C.CDLL:
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+    if precision not in _libs:
+        path = LIB_PATH_TIGHT if precision == "tight" else LIB_PATH
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m smalltts_b200.build`. "
+                f"{path} is missing: build it with `python -m smalltts_b200.build`. "
                 "smalltts_b200 has no CPU or PyTorch fallback for the synthesize path."
             )
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = l
-    return _lib
+        _libs[precision] = l
+    return _libs[precision]
 
 
-def check(rc: int, handle=None) -> None:
+def check(rc: int, handle=None, precision: str = "fast") -> None:
     if rc == OK:
         return
-    msg = lib().stts_last_error(handle)
+    msg = lib(precision).stts_last_error(handle)
     msg = msg.decode() if msg else "unknown error"
     if rc == -1:
         raise ValueError(f"smalltts_b200: {msg}")

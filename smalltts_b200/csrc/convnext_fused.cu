@@ -98,8 +98,7 @@ __device__ __forceinline__ uint32_t gelu2_half2(float a, float b, __half2 bias) 
   return *reinterpret_cast<const uint32_t*>(&g);
 }
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&p);
+  return op16_pack2(a, b);
 }
 // byte offset of element (row r, column k) in a [rows][64] bf16 K-major tile with 128-byte swizzle
 __device__ __forceinline__ uint32_t sw128_off(int r, int k) {

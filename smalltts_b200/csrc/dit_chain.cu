@@ -140,8 +140,7 @@ __device__ __forceinline__ void trace_ev(unsigned long long* trace, int seq, int
 }
 
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&p);
+  return op16_pack2(a, b);
 }
 __device__ __forceinline__ float fast_sigmoid(float x) {
   return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x));
@@ -786,9 +785,9 @@ __global__ void __launch_bounds__(256) chain_fold_kernel(const ChainWeights w, c
     ob = fold + kFoldBv + r;
   }
   float a = 0.f, b = 0.f;
-  const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(wr);
+  const uint32_t* w2 = reinterpret_cast<const uint32_t*>(wr);
   for (int i = lane; i < kChainD / 2; i += 32) {
-    const float2 wv = __bfloat1622float2(w2[i]);
+    const float2 wv = op16_unpack2(w2[i]);
     const float2 sc = *reinterpret_cast<const float2*>(scale + 2 * i);
     const float2 sh = *reinterpret_cast<const float2*>(shift + 2 * i);
     a = fmaf(wv.x, 1.0f + sc.x, fmaf(wv.y, 1.0f + sc.y, a));
@@ -851,7 +850,7 @@ __global__ void pack_rows_headpad_kernel(const float* __restrict__ src, int rows
   if (i >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(i / cols), cc = static_cast<int>(i % cols);
   const int dr = (r / kChainHD) * kChainHDP + r % kChainHD + row_off;
-  dst[static_cast<long long>(dr) * ld_dst + cc] = __float2bfloat16_rn(src[i]);
+  dst[static_cast<long long>(dr) * ld_dst + cc] = op16_from_float(src[i]);
 }
 __global__ void pack_vec_headpad_kernel(const float* __restrict__ src, int n, int off, float* __restrict__ dst) {
   ptx::pdl_wait();

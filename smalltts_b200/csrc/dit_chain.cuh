@@ -12,13 +12,12 @@
 //     (q, k, v weights are head-padded 120 -> 128 so that one 128-column tile is one head),
 //   * SwiGLU (dit.py:186), tanh-gated residuals and the padded-row mask (dit.py:115-118,198,201).
 #pragma once
-#include <cuda_bf16.h>
+#include "op16.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace stts {
 
-typedef __nv_bfloat16 bf16;
 
 enum ChainKind : int { CHAIN_QKVG = 0, CHAIN_OUT = 1, CHAIN_W13 = 2, CHAIN_W2 = 3, CHAIN_VEL = 4 };
 

@@ -1452,7 +1452,7 @@ int stts_cond_read_kv(stts_engine* e, const stts_cond* c, int layer, int which, 
         for (int n = 0; n < N; ++n)
           for (int d = 0; d < HD; ++d)
             dst[((static_cast<size_t>(b) * H + hh) * N + n) * HD + d] =
-                __bfloat162float(h[((static_cast<size_t>(b) * N + n) * H + hh) * HDP + d]);
+                op16_to_float(h[((static_cast<size_t>(b) * N + n) * H + hh) * HDP + d]);
   });
 }
 

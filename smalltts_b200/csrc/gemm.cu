@@ -96,8 +96,7 @@ __device__ __forceinline__ void mul4(float* v, const float* __restrict__ p) {
   v[0] *= x.x; v[1] *= x.y; v[2] *= x.z; v[3] *= x.w;
 }
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&p);
+  return op16_pack2(a, b);
 }
 
 // Persistent CTA: walks output tiles (tile = blockIdx.x + i * gridDim.x; n fastest, so concurrently running CTAs share

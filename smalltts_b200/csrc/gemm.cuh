@@ -13,7 +13,7 @@
 // W is bf16 [rows, taps*Kp] K-major (nn.Linear's own [out,in] layout), Kp = K rounded up to 64.
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include "op16.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -53,17 +53,17 @@ struct GemmEpi {
   const float* residual = nullptr;  // [B*T, ld_res] fp32 (may alias out_f32)
   int ld_res = 0;
   float* out_f32 = nullptr;
-  __nv_bfloat16* out_bf16 = nullptr;
+  bf16* out_bf16 = nullptr;
   int ld_out = 0;
 };
 
 struct GemmA {
-  const __nv_bfloat16* ptr;
+  const bf16* ptr;
   int cols;  // valid columns (tensor-map extent; reads beyond are zero)
   int ld;    // row pitch in elements (multiple of 8)
 };
 struct GemmW {
-  const __nv_bfloat16* ptr;
+  const bf16* ptr;
   int rows;  // tensor-map extent (rows beyond read as zero)
   int ld;    // row pitch in elements = taps*Kp (multiple of 8)
 };

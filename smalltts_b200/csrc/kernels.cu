@@ -28,11 +28,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b);
-  __nv_bfloat162 p1 = __floats2bfloat162_rn(c, d);
   uint2 r;
-  r.x = *reinterpret_cast<uint32_t*>(&p0);
-  r.y = *reinterpret_cast<uint32_t*>(&p1);
+  r.x = op16_pack2(a, b);
+  r.y = op16_pack2(c, d);
   return r;
 }
 
@@ -177,7 +175,7 @@ __device__ __forceinline__ void head_split_body(const float* __restrict__ in, in
   bf16* o = out + (static_cast<long long>(row) * heads + h) * (EPL * 32) + d0;
 #pragma unroll
   for (int e = 0; e < EPL; e += 2) {
-    *reinterpret_cast<__nv_bfloat162*>(o + e) = __floats2bfloat162_rn(v[e], v[e + 1]);
+    *reinterpret_cast<uint32_t*>(o + e) = op16_pack2(v[e], v[e + 1]);
   }
 }
 
@@ -368,10 +366,8 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const AttnLens lens, int
         const float p3 = exp2f((sc[j][3] - m_run[1]) * scale_log2);
         l_run[0] += p0 + p1;
         l_run[1] += p2 + p3;
-        __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(p2, p3);
-        pf[j >> 1][(j & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&lo);
-        pf[j >> 1][(j & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        pf[j >> 1][(j & 1) * 2 + 0] = op16_pack2(p0, p1);
+        pf[j >> 1][(j & 1) * 2 + 1] = op16_pack2(p2, p3);
       }
       if (it > 0) {
 #pragma unroll
@@ -538,7 +534,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, long long n, bf16
     const float4 v = *reinterpret_cast<const float4*>(in + i);
     *reinterpret_cast<uint2*>(out + i) = pack_bf16x4(v.x, v.y, v.z, v.w);
   } else {
-    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+    for (long long j = i; j < n; ++j) out[j] = op16_from_float(in[j]);
   }
 }
 
@@ -548,7 +544,7 @@ __global__ void repeat_cast_bf16_kernel(const float* __restrict__ in, long long 
   ptx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const bf16 v = __float2bfloat16(in[i]);
+  const bf16 v = op16_from_float(in[i]);
   for (int r = 0; r < reps; ++r) out[r * n + i] = v;
 }
 
@@ -573,7 +569,7 @@ __global__ void noise_mix_kernel(const float* __restrict__ xp, const float* __re
   if (i < n) {
     const float v = alpha * xp[i] + sigma * nz[i];
     xt[i] = v;
-    xtb[i] = __float2bfloat16_rn(v);
+    xtb[i] = op16_from_float(v);
   }
 }
 
@@ -976,7 +972,7 @@ __global__ void pack_conv_strided_kernel(const float* __restrict__ src, int O, i
   const int o = static_cast<int>(i / per_o);
   const int rem = static_cast<int>(i % per_o);
   const int tap = rem / (r * C), j = (rem % (r * C)) / C, c = rem % C;
-  dst[i] = __float2bfloat16_rn(src[(static_cast<long long>(o) * C + c) * (2 * r) + tap * r + j]);
+  dst[i] = op16_from_float(src[(static_cast<long long>(o) * C + c) * (2 * r) + tap * r + j]);
 }
 
 __device__ __forceinline__ int map_row(int r, int mode) {
@@ -995,7 +991,7 @@ __global__ void pack_matrix_kernel(const float* __restrict__ src, int rows, int 
   const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
   const int dr = map_row(r, row_mode) + row_off;
   const int dc = (col_mode == COL_HEADPAD_120_128 ? (c / 120) * 128 + c % 120 : c) + col_off;
-  dst[static_cast<long long>(dr) * ld_dst + dc] = __float2bfloat16_rn(scale * src[i]);
+  dst[static_cast<long long>(dr) * ld_dst + dc] = op16_from_float(scale * src[i]);
 }
 
 __global__ void pack_conv_taps_kernel(const float* __restrict__ src, int O, int cin, int taps, int kp, int opg,
@@ -1008,7 +1004,7 @@ __global__ void pack_conv_taps_kernel(const float* __restrict__ src, int O, int 
   const int c = static_cast<int>((i / taps) % cin);
   const int o = static_cast<int>(i / (static_cast<long long>(taps) * cin));
   const int dr = (o / opg) * group_pitch + o % opg;
-  dst[static_cast<long long>(dr) * ld_dst + tap * kp + c] = __float2bfloat16_rn(src[i]);
+  dst[static_cast<long long>(dr) * ld_dst + tap * kp + c] = op16_from_float(src[i]);
 }
 
 __global__ void pack_conv_dense_tiles_kernel(const float* __restrict__ src, int taps, bf16* __restrict__ dst) {
@@ -1020,7 +1016,7 @@ __global__ void pack_conv_dense_tiles_kernel(const float* __restrict__ src, int 
   const int c = static_cast<int>((i / taps) % 60);
   const int o = static_cast<int>(i / (static_cast<long long>(taps) * 60));
   const int kk = (o / 60 - o / 64) * 64 + c;
-  dst[static_cast<long long>(o) * (taps * 128) + tap * 128 + kk] = __float2bfloat16_rn(src[i]);
+  dst[static_cast<long long>(o) * (taps * 128) + tap * 128 + kk] = op16_from_float(src[i]);
 }
 
 __global__ void pack_convtr_kernel(const float* __restrict__ src, int cin, int cout, int r, bf16* __restrict__ dst) {
@@ -1033,7 +1029,7 @@ __global__ void pack_convtr_kernel(const float* __restrict__ src, int cin, int c
   const int o = static_cast<int>((i / kk) % cout);
   const int c = static_cast<int>(i / (static_cast<long long>(kk) * cout));
   const int tap = jj / r, j = jj % r;
-  dst[(static_cast<long long>(j) * cout + o) * (2 * cin) + tap * cin + c] = __float2bfloat16_rn(src[i]);
+  dst[(static_cast<long long>(j) * cout + o) * (2 * cin) + tap * cin + c] = op16_from_float(src[i]);
 }
 
 __global__ void pack_vector_kernel(const float* __restrict__ src, int n, float scale, int row_mode, int off,

@@ -1,13 +1,12 @@
 // Non-GEMM kernels of the engine (declarations).  All launch on the given stream and return the
 // CUDA launch status.  Layouts are channels-last: activations [B, T, C] row-major.
 #pragma once
-#include <cuda_bf16.h>
+#include "op16.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace stts {
 
-typedef __nv_bfloat16 bf16;
 
 // ---- normalisation producing the bf16 A operand of the next GEMM
 // LayerNorm(no affine, eps) * (1 + scale[b]) + shift[b]   (dit.py:24,199 / :38).  scale/shift: [B or 1, ld_mod].

@@ -3,7 +3,7 @@
 // fails with an error the C-ABI reports) instead of hanging the GPU.
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include "op16.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -171,8 +171,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor: D=f32, A=B=bf16, both K-major, M x N tile.
+// (operand format field: 1 = bf16, 0 = fp16 -- the STTS_OPERAND_F16 build feeds fp16 operands, see op16.cuh)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
+#ifdef STTS_OPERAND_F16
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+#else
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+#endif
 }
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2): two CTAs of a cluster on the
@@ -291,7 +296,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans_addr(uint32_t (&r)[4], uint32_
 }
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
+#ifdef STTS_OPERAND_F16
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#else
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#endif
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }

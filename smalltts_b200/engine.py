@@ -69,8 +69,12 @@ class Conditions:
 
 
 class Engine:
-    def __init__(self, device: int = 0):
-        self._lib = _cabi.lib()
+    def __init__(self, device: int = 0, precision: str = "fast"):
+        """precision: "fast" = bf16 GEMM / attention operands (the benchmarked build); "tight" = the parity build of the
+        same kernels with fp16 operands (11-bit significand like TF32; csrc/op16.cuh).  fp32 accumulation, norms,
+        softmax, RoPE and sampler in both."""
+        self._lib = _cabi.lib(precision)
+        self.precision = precision
         cfg = _cabi.Config(device=device)
         h = C.c_void_p()
         _cabi.check(self._lib.stts_create(C.byref(cfg), C.byref(h)), None)
@@ -85,6 +89,7 @@ class Engine:
         _cabi.check(self._lib.stts_engine_clone(self._h, C.byref(h)), self._h)
         c = Engine.__new__(Engine)
         c._lib, c._h, c.device, c._ready, c._parent = self._lib, h, self.device, True, self  # parent outlives the clone
+        c.precision = self.precision
         return c
 
     # ------------------------------------------------------------------ weights
@@ -277,7 +282,8 @@ class Engine:
 
     @staticmethod
     def launch_count() -> int:
-        return int(_cabi.lib().stts_launch_count())
+        """Kernels launched so far by every loaded build of the library in this process."""
+        return sum(int(l.stts_launch_count()) for l in _cabi._libs.values()) if _cabi._libs else int(_cabi.lib().stts_launch_count())
 
     def _out_like(self, like, shape, mem):
         if mem == _cabi.MEM_DEVICE:

@@ -69,6 +69,7 @@ class SmallTTS:
         seed: Optional[int] = None,
         shape_buckets: Optional[Sequence[int]] = None,  # (R, P, T) multiples the padded batch shape is rounded up to
         engine: Optional[Engine] = None,  # adopt an engine whose weights are already loaded (no second copy)
+        precision: str = "fast",  # "tight": the fp16-operand parity build of the same kernels (engine.Engine)
     ) -> None:
         self.num_steps = num_steps
         self.shape_buckets = tuple(int(x) for x in shape_buckets) if shape_buckets is not None else None
@@ -93,11 +94,11 @@ class SmallTTS:
                            load_model_weights([codec_decoder_path], synthetic.vocoder_specs(), "codec decoder"))
             if codec_encoder_path is not None:
                 state_dicts += (load_model_weights([codec_encoder_path], synthetic.encoder_specs(), "codec encoder"),)
-        self.engine = Engine(devs[0])
+        self.engine = Engine(devs[0], precision=precision)
         self.engine.load_state_dicts(*state_dicts)
         # one replica (own engine, own weights copy, own host thread per call) per extra GPU; utterances are independent
         self._replicas = [SmallTTS(state_dicts=state_dicts, device=d, num_steps=num_steps, seed=self._seed + 7919 * (k + 1),
-                                   shape_buckets=shape_buckets) for k, d in enumerate(devs[1:])]
+                                   shape_buckets=shape_buckets, precision=precision) for k, d in enumerate(devs[1:])]
 
     @classmethod
     def synthetic(cls, dit_seed: int = 0, vocoder_seed: int = 1, encoder_seed: Optional[int] = None, **kw) -> "SmallTTS":

@@ -41,10 +41,24 @@ def test_engine_fails_loudly_without_gpu(lib):
 def test_missing_library_is_an_error(monkeypatch, tmp_path):
     from smalltts_b200 import _cabi
 
-    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "_libs", {})
     monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _cabi.lib()
+    with pytest.raises(ValueError, match="precision"):
+        _cabi.lib("exact")
+
+
+def test_parity_build_exports_the_same_abi(lib):
+    """precision="tight": the same sources compiled with fp16 instead of bf16 operands (csrc/op16.cuh) -- a second
+    library with the identical C ABI."""
+    from smalltts_b200 import _cabi, build
+
+    build.build(tight=True)
+    tight = _cabi.lib("tight")
+    assert tight is not lib
+    for name in _cabi.SIGNATURES:
+        assert hasattr(tight, name), name
 
 
 def test_duration_and_frame_rules_match_reference():

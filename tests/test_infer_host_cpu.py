@@ -9,8 +9,8 @@ from smalltts_b200 import infer
 class FakeEngine:
     instances = []
 
-    def __init__(self, device=0):
-        self.device = device
+    def __init__(self, device=0, precision="fast"):
+        self.device, self.precision = device, precision
         self.calls = []
         FakeEngine.instances.append(self)
 
