@@ -52,13 +52,13 @@ class Conditions:
         idx = {"k_ref": 0, "v_ref": 1, "k_text": 2, "v_text": 3}[which]
         n = self.R if idx < 2 else self.P
         out = np.empty((self.B, 8, n, 120), dtype=np.float32)
-        _cabi.check(_cabi.lib().stts_cond_read_kv(self._engine._h, self._h, layer, idx, C.c_void_p(out.ctypes.data)),
+        _cabi.check(self._engine._lib.stts_cond_read_kv(self._engine._h, self._h, layer, idx, C.c_void_p(out.ctypes.data)),
                     self._engine._h)
         return out
 
     def free(self) -> None:
         if self._h is not None:
-            _cabi.lib().stts_cond_free(self._engine._h, self._h)
+            self._engine._lib.stts_cond_free(self._engine._h, self._h)
             self._h = None
 
     def __del__(self):
