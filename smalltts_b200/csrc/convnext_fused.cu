@@ -14,11 +14,8 @@
 //                       accumulators in TMEM (two 256-column buffers; O aliases the first C columns of H, which the
 //                       GELU warps have consumed by then); W1/W2 stay resident in shared memory (TMA-loaded once)
 //   warps 9-16  GELU  : tcgen05.ld H chunk -> +b1 -> GELU in packed fp16 -> swizzled shared-memory G chunk (fp16, double buffer)
-//   warps 17-..  out  : y rows -> registers (frees the x buffer early); tcgen05.ld O -> y + ffn_gamma*(O + b2) ->
-//                       fp32 (and optional bf16) store.  One warp per (TMEM lane quarter, 32-column slab): 4 warps for
-//                       C = 32, 8 for C = 64 -- with a full 64-column row per thread this role needed 96+ registers
-//                       against the CTA's cap of 80, spilled, and at 6.2k cycles per tile paced the whole pipeline
-//                       (role timeline, tools/trace_fused.py)
+//   warps 17-20 out   : y rows -> registers (frees the x buffer early); tcgen05.ld O -> y + ffn_gamma*(O + b2) ->
+//                       fp32 (and optional bf16) store, one full row per thread
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -35,8 +32,9 @@ namespace {
 constexpr int TM = 128;  // rows per tile
 constexpr int HALO = 6;  // causal context of the k=7 depthwise conv
 constexpr int XR = TM + HALO;
-// warp roles: [0,8) mixer | 8 MMA | [9,17) GELU | [17, 17 + C/8) out.  TMEM lane quarter of a warp = warp % 4.
+// warp roles: [0,8) mixer | 8 MMA | [9,17) GELU | [17,21) out.  TMEM lane quarter of a warp = warp % 4.
 constexpr int kMixWarps = 8, kMmaWarp = 8, kGeluWarp0 = 9, kOutWarp0 = 17;
+constexpr int kThreadsFused = 21 * 32;
 
 struct FusedParams {
   const float* x;
@@ -67,10 +65,8 @@ struct FC {
   static constexpr int OFF_VEC = OFF_X + 2 * X_BYTES;
   static constexpr int OFF_INV = OFF_VEC + VEC_FLOATS * 4;
   static constexpr int OFF_BAR = ((OFF_INV + XR * 4 + 15) / 16) * 16;
-  static constexpr int OUTW = C / 8;           // out warps: one per (lane quarter, 32-column slab)
-  static constexpr int THREADS = (kOutWarp0 + OUTW) * 32;
-  static constexpr int OFF_STG = ((OFF_BAR + 17 * 8 + 16 + 127) / 128) * 128;  // 2 KB per out warp: transposition staging
-  static constexpr int SMEM = OFF_STG + OUTW * 2048 + 1024;
+  static constexpr int OFF_STG = ((OFF_BAR + 17 * 8 + 16 + 127) / 128) * 128;  // 4 x 4 KB: out-warp transposition staging
+  static constexpr int SMEM = OFF_STG + 4 * 4096 + 1024;
   static_assert(SMEM <= 232448, "fused ConvNeXt tile does not fit in shared memory");
 };
 
@@ -127,11 +123,10 @@ __device__ long long g_fused_trace[64 * 16];
 #endif
 
 template <int C>
-__global__ void __launch_bounds__(FC<C>::THREADS, 1)
+__global__ void __launch_bounds__(kThreadsFused, 1)
 convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                       const FusedParams p) {
   using F = FC<C>;
-  constexpr int kThreadsFused = F::THREADS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -413,40 +408,38 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     }
   } else {
     // ================================================================== out: O (TMEM) + y -> global
-    // Thread <-> (tile row, 32-column slab).  y is pulled into registers as soon as the mixer has finished the tile,
-    // which frees the x buffer for the prefetch of tile it+2 long before the FFN of this tile completes.
+    // Thread <-> tile row.  y is pulled into registers as soon as the mixer has finished the tile, which frees the
+    // x buffer for the prefetch of tile it+2 long before the FFN of this tile completes.
     const int q = warp & 3;
-    const int ch = (warp - kOutWarp0) >> 2;  // column slab [32 ch, +32)
     const int r = q * 32 + lane;
     const int otid = threadIdx.x - kOutWarp0 * 32;
-    constexpr int kOutThreads = F::OUTW * 32;
-    const int l4r = lane >> 2, l4c = lane & 3;
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
       const int tile = first + it * stride;
       ptx::mbar_wait(&a_full[buf], (it >> 1) & 1);  // mixer done: y rows are final
-      float4 y[8];
+      float4 y[C / 4];
       {
-        const float* yrow = Xbuf(buf) + (r + HALO) * F::XP + 32 * ch;
+        const float* yrow = Xbuf(buf) + (r + HALO) * F::XP;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
+        for (int j = 0; j < C / 4; ++j) y[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
       }
-      ptx::named_bar_sync(3, kOutThreads);
+      ptx::named_bar_sync(3, 128);
       if (otid == 0) ptx::mbar_arrive(&x_empty[buf]);
       if (otid == 0) TRACE(it, 7);
       ptx::mbar_wait(&o_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (otid == 0) TRACE(it, 8);
-      {
+#pragma unroll
+      for (int cc = 0; cc < C / 32; ++cc) {
         uint32_t rr[32];
-        ptx::tmem_ld_32x32(tmem_base + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + ch * 32, rr);
+        ptx::tmem_ld_32x32(tmem_base + buf * 256 + (static_cast<uint32_t>(q * 32) << 16) + cc * 32, rr);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int col = ch * 32 + 4 * j;
+          const int col = cc * 32 + 4 * j;
           const float4 b2 = *reinterpret_cast<const float4*>(b2s + col);
           const float4 gf = *reinterpret_cast<const float4*>(gfs + col);
-          float4& yy = y[j];
+          float4& yy = y[cc * 8 + j];
           // O = (0.5 W2)(2 gelu) = W2 gelu (W2 is stored pre-scaled by 0.5): out = y + ffn_gamma*b2 + ffn_gamma * O
           yy.x = fmaf(gf.x, __uint_as_float(rr[4 * j + 0]), yy.x + b2.x);
           yy.y = fmaf(gf.y, __uint_as_float(rr[4 * j + 1]), yy.y + b2.y);
@@ -455,26 +448,28 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         }
       }
       ptx::tc_fence_before();
-      ptx::named_bar_sync(3, kOutThreads);
+      ptx::named_bar_sync(3, 128);
       if (otid == 0) ptx::mbar_arrive(&tm_empty[buf]);  // TMEM buffer may be overwritten by MMA1 of tile it+2
-      // Each thread holds 32 columns of one output row; storing them directly makes every store instruction touch 32
-      // different lines.  The slab is transposed 16 columns at a time through a warp-private, XOR-swizzled 2 KB staging
-      // buffer so that 4 consecutive lanes write one 64-byte row segment.
+      // Each thread holds one full output row; storing it directly makes every store instruction touch 32 different
+      // lines (2048 LSU wavefronts per tile on a pipe the mixer and GELU warps also need: measured 4.4k cycles per
+      // tile).  The row block is transposed 32 columns at a time through a warp-private, XOR-swizzled staging buffer
+      // so that 8 consecutive lanes write one 128-byte row segment.
       const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * TM;
       const int nlive = p.T - (t0 + q * 32);  // rows of this warp inside the sequence
-      float4* stg = reinterpret_cast<float4*>(smem + F::OFF_STG + (warp - kOutWarp0) * 2048);
-      const long long obase = (static_cast<long long>(b) * p.T + t0 + q * 32) * C + 32 * ch;
+      float4* stg = reinterpret_cast<float4*>(smem + F::OFF_STG + (warp - kOutWarp0) * 4096);
+      const int l8r = lane >> 3, l8c = lane & 7;
+      const long long obase = (static_cast<long long>(b) * p.T + t0 + q * 32) * C;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int cc = 0; cc < C / 32; ++cc) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = y[4 * h + j];
+        for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = y[cc * 8 + j];
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int rr = 8 * j + l4r;
-          const float4 v = stg[rr * 4 + (l4c ^ ((rr >> 1) & 3))];
+        for (int j = 0; j < 8; ++j) {
+          const int rr = 4 * j + l8r;
+          const float4 v = stg[rr * 8 + (l8c ^ (rr & 7))];
           if (rr < nlive) {
-            const long long o = obase + static_cast<long long>(rr) * C + 16 * h + 4 * l4c;
+            const long long o = obase + static_cast<long long>(rr) * C + cc * 32 + 4 * l8c;
             *reinterpret_cast<float4*>(p.out + o) = v;
             if (p.out_bf16 != nullptr) {
               uint2 pk;
@@ -539,7 +534,7 @@ cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, 
   if (!tmap_2d(&m2, w2, 4 * C, C, C)) return cudaErrorInvalidValue;      // W2 [C, 4C]: one box per 64-wide K chunk
   const int ntiles = p.B * ((p.T + TM - 1) / TM);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  const cudaError_t le = launch_k(convnext_fused_kernel<C>, dim3(grid), dim3(FC<C>::THREADS), FC<C>::SMEM, st, m1, m2, p);
+  const cudaError_t le = launch_k(convnext_fused_kernel<C>, dim3(grid), dim3(kThreadsFused), FC<C>::SMEM, st, m1, m2, p);
   count_launch();
   return le != cudaSuccess ? le : cudaGetLastError();
 }
