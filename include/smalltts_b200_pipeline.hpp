@@ -21,6 +21,7 @@
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
+#include <random>
 #include <string>
 #include <utility>
 #include <vector>
@@ -161,7 +162,7 @@ class Pipeline {
  public:
   Pipeline(const Pipeline&) = delete;
   Pipeline& operator=(const Pipeline&) = delete;
-  Pipeline(Pipeline&& o) noexcept : e_(o.e_) { o.e_ = nullptr; }
+  Pipeline(Pipeline&& o) noexcept : e_(o.e_), base_seed_(o.base_seed_), calls_(o.calls_) { o.e_ = nullptr; }
   ~Pipeline() {
     if (e_) stts_destroy(e_);
   }
@@ -207,7 +208,7 @@ class Pipeline {
   std::vector<std::vector<float>> synthesize_many(const std::vector<std::vector<float>>& ref_audio,
                                                   const std::vector<std::vector<int64_t>>& token_ids,
                                                   const std::vector<float>& duration_sec, Timing* timing = nullptr,
-                                                  uint64_t seed = 0) {
+                                                  uint64_t seed = kAutoSeed) {
     const int B = static_cast<int>(ref_audio.size());
     if (B == 0 || token_ids.size() != ref_audio.size() || duration_sec.size() != ref_audio.size()) {
       throw Error(STTS_ERR_INVALID, "ref_audio, token_ids and duration_sec must be equally long and non-empty");
@@ -238,7 +239,7 @@ class Pipeline {
 
   // The Python API's entry: reference LATENTS [R, 64] instead of audio (infer/onnx.py:68-83).
   std::vector<float> synthesize_latents(const std::vector<float>& ref_latents, const std::vector<int64_t>& token_ids,
-                                        float duration_sec, Timing* timing = nullptr, uint64_t seed = 0) {
+                                        float duration_sec, Timing* timing = nullptr, uint64_t seed = kAutoSeed) {
     const int R = static_cast<int>(ref_latents.size() / STTS_LATENT_DIM);
     if (R < 1 || ref_latents.size() % STTS_LATENT_DIM != 0) throw Error(STTS_ERR_INVALID, "ref_latents must be [R, 64]");
     const float fr = std::ceil(duration_sec * SR / HOP);
@@ -249,8 +250,17 @@ class Pipeline {
 
   stts_engine* handle() { return e_; }
 
+  // Noise: the reference draws fresh noise for every request (pipeline.rs:249-255).  Without an explicit seed every call
+  // gets base_seed + call counter; the base comes from std::random_device, so two pipelines (replicas, restarts) do
+  // not replay each other's streams.
+  static constexpr uint64_t kAutoSeed = ~static_cast<uint64_t>(0);
+  void set_base_seed(uint64_t s) { base_seed_ = s; calls_ = 0; }
+
  private:
-  explicit Pipeline(stts_engine* e) : e_(e) {}
+  explicit Pipeline(stts_engine* e) : e_(e) {
+    std::random_device rd;
+    base_seed_ = (static_cast<uint64_t>(rd()) << 32) ^ rd();
+  }
 
   void check(int rc, const char* what) const {
     if (rc != STTS_OK) throw Error(rc, std::string(what) + ": " + stts_last_error(e_));
@@ -266,6 +276,7 @@ class Pipeline {
     }
     const int hop = static_cast<int>(HOP);
     std::vector<float> audio(static_cast<size_t>(B) * T * hop);
+    if (seed == kAutoSeed) seed = base_seed_ + calls_++;
     check(stts_synthesize(e_, latents.data(), ref_len.data(), ids.data(), ph_len.data(), frames.data(), B, R, P, T, STEPS,
                           nullptr, nullptr, seed, STTS_MEM_HOST, audio.data()),
           "stts_synthesize");
@@ -287,6 +298,7 @@ class Pipeline {
   }
 
   stts_engine* e_ = nullptr;
+  uint64_t base_seed_ = 0, calls_ = 0;
 };
 
 }  // namespace stts

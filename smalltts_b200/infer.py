@@ -75,7 +75,9 @@ class SmallTTS:
         self.shape_buckets = tuple(int(x) for x in shape_buckets) if shape_buckets is not None else None
         if self.shape_buckets is not None and (len(self.shape_buckets) != 3 or min(self.shape_buckets) < 1):
             raise ValueError("shape_buckets must be three positive integers (R, P, T multiples)")
-        self._seed = 0 if seed is None else int(seed)
+        # the reference draws fresh, unseeded noise per request (infer/onnx.py:104): without an explicit seed the base of
+        # this instance's Philox streams is random, so replicas and restarts do not replay each other
+        self._seed = int.from_bytes(os.urandom(7), "little") if seed is None else int(seed)
         self._calls = 0
         devs = [int(d) for d in devices] if devices is not None else [int(device)]
         if not devs or len(set(devs)) != len(devs):
