@@ -228,7 +228,7 @@ def run_config4(eng, rank, world, local_rank, dist, reps: int = 3):
         stats = {}
         barrier()
         t0 = time.perf_counter()
-        out = parallel.synthesize_sharded(fn, frames, rank, world, stats=stats)
+        out = parallel.synthesize_sharded(fn, frames, rank, world, stats=stats, pinned_out=True)
         barrier()
         dt = time.perf_counter() - t0
         if rep > 0 and (best is None or dt < best):

@@ -844,44 +844,51 @@ __global__ void __launch_bounds__(256) convnext_mix_rows_kernel(const float* __r
   }
 }
 
-// 256 outputs per CTA; the 262 input rows are staged in shared memory with coalesced float4 loads (row pitch C+1
-// words so that the per-thread sliding reads below are bank-conflict free).
+// 256 outputs per CTA; the 262 input rows are staged in shared memory with cp.async (row pitch C+4 words: 16-byte
+// aligned rows whose float4 reads by consecutive threads are bank-conflict free).  One output per thread: 7 taps x C
+// channels as float4 FMAs against weights read as warp-uniform (broadcast) float4s -- a quarter of the shared-memory
+// instructions of the scalar version, which was LSU-bound at 124 us (HBM floor of the 246 MB read: 38 us).
 __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int T, int C,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         float* __restrict__ out) {
-  ptx::pdl_wait();
-  ptx::pdl_trigger();
-  extern __shared__ float sh[];
+  extern __shared__ __align__(16) float sh[];
   float* sw = sh;            // [7][C] tap-major
-  float* sx = sh + 7 * C;    // [262][C + 1]
-  const int P = C + 1;
-  for (int i = threadIdx.x; i < 7 * C; i += 256) {
+  float* sx = sh + 7 * C;    // [262][C + 4]
+  const int P = C + 4;
+  for (int i = threadIdx.x; i < 7 * C; i += 256) {  // weights: before the dependency wait
     const int j = i / C, c = i % C;
     sw[i] = w[c * 7 + j];
   }
+  const float b0 = bias[0];
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 256;
   const float* xb = x + static_cast<long long>(b) * T * C;
   const int cv = C >> 2;
+  const uint32_t dst0 = ptx::smem_u32(sx);
   for (int i = threadIdx.x; i < 262 * cv; i += 256) {
     const int r = i / cv, c4 = i % cv;
     const int t = t0 - 6 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t >= 0 && t < T) v = reinterpret_cast<const float4*>(xb + static_cast<long long>(t) * C)[c4];
-    float* d = sx + r * P + 4 * c4;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    const bool live = t >= 0 && t < T;
+    ptx::cp_async_16(dst0 + (r * P + 4 * c4) * 4, xb + static_cast<long long>(live ? t : 0) * C + 4 * c4, live ? 16u : 0u);
   }
+  ptx::cp_async_commit();
+  ptx::cp_async_wait<0>();
   __syncthreads();
   const int t = t0 + threadIdx.x;
   if (t >= T) return;
-  float acc = bias[0];
+  float a0 = b0, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   for (int j = 0; j < 7; ++j) {
-    const float* row = sx + (threadIdx.x + j) * P;
-    const float* wr = sw + j * C;
+    const float4* row = reinterpret_cast<const float4*>(sx + (threadIdx.x + j) * P);
+    const float4* wr = reinterpret_cast<const float4*>(sw + j * C);
 #pragma unroll 8
-    for (int c = 0; c < C; ++c) acc = fmaf(row[c], wr[c], acc);
+    for (int c = 0; c < cv; ++c) {
+      const float4 v = row[c], k = wr[c];
+      a0 = fmaf(v.x, k.x, a0); a1 = fmaf(v.y, k.y, a1); a2 = fmaf(v.z, k.z, a2); a3 = fmaf(v.w, k.w, a3);
+    }
   }
-  out[static_cast<long long>(b) * T + t] = acc;
+  out[static_cast<long long>(b) * T + t] = (a0 + a1) + (a2 + a3);
 }
 
 // Codec encoder stem (hf:300-312): causal Conv1d(1 -> C, k=7) on raw audio.  One thread per sample; the thread
@@ -1280,8 +1287,8 @@ cudaError_t head_conv(cudaStream_t st, const float* x, int B, int T, int C, cons
                       float* out) {
   if (C % 4 != 0) return cudaErrorInvalidValue;
   dim3 grid((T + 255) / 256, B);
-  if (C > 40) return cudaErrorInvalidValue;  // 262 x (C+1) fp32 tile must fit the default 48 KB
-  last_launch_status = launch_k(head_conv_kernel, dim3(grid), dim3(256), (7 * C + 262 * (C + 1)) * 4, st, x, T, C, w, bias, out);
+  if (C > 40) return cudaErrorInvalidValue;  // 262 x (C+4) fp32 tile must fit the default 48 KB
+  last_launch_status = launch_k(head_conv_kernel, dim3(grid), dim3(256), (7 * C + 262 * (C + 4)) * 4, st, x, T, C, w, bias, out);
   STTS_LAUNCH_OK();
 }
 

@@ -163,16 +163,32 @@ def synthesize_on_workers(workers: Sequence[Callable[[List[int]], List[np.ndarra
     return results
 
 
+_PINNED = {}
+
+
+def _pinned_buffer(n: int):
+    """Page-locked fp32 host buffer of at least n elements, cached per process (cudaHostAlloc costs milliseconds)."""
+    import torch
+
+    buf = _PINNED.get("buf")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1), dtype=torch.float32, pin_memory=True)
+        _PINNED["buf"] = buf
+    return buf
+
+
 def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], frames: Sequence[int], rank: int,
                        world: int, group=None, gather_to: int = 0, shards: Optional[List[List[int]]] = None,
-                       stats: Optional[dict] = None):
+                       stats: Optional[dict] = None, pinned_out: bool = False):
     """Run ``synthesize_fn`` on this rank's shard and gather every waveform to ``gather_to`` in input order.
 
     synthesize_fn(indices) -> list of (1, frames_i*3200) float32 arrays (numpy, or torch CUDA tensors when the engine
     leaves its output in HBM) for those utterances (on a GPU rank this is
     ``lambda idx: tts.synthesize_batch([refs[i] for i in idx], ..., device_out=True)``).  Returns the full list on ``gather_to``,
     None elsewhere.  world == 1 needs no process group.  ``shards`` overrides the split (default: :func:`partition_sorted`,
-    the same on every rank); ``stats`` receives ``compute_s`` and ``gather_s`` of this rank."""
+    the same on every rank); ``stats`` receives ``compute_s`` and ``gather_s`` of this rank.  ``pinned_out`` (NCCL only):
+    the gathered waveforms are views of ONE page-locked host buffer filled by a single device-to-host copy (about 2.5x
+    faster than pageable copies); the buffer is reused by the next call with ``pinned_out``, so copy what must outlive it."""
     import time
 
     t0 = time.perf_counter()
@@ -218,8 +234,19 @@ def synthesize_sharded(synthesize_fn: Callable[[List[int]], List[np.ndarray]], f
         for q in reqs:
             q.wait()
         out: List[np.ndarray] = [None] * len(frames)  # type: ignore[list-item]
+        if pinned_out and dev.type == "cuda":
+            total = sum(sizes)
+            host_all = _pinned_buffer(total)
+            host_all[:total].copy_(torch.cat([b.reshape(-1) for b in bufs]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            hosts, base = [], 0
+            for r in range(world):
+                hosts.append(host_all[base : base + sizes[r]].numpy())
+                base += sizes[r]
+        else:
+            hosts = [bufs[r].cpu().numpy() for r in range(world)]
         for r in range(world):
-            off, host = 0, bufs[r].cpu().numpy()
+            off, host = 0, hosts[r]
             for i in shards[r]:
                 n = frames[i] * HOP_SIZE
                 out[i] = host[off : off + n].reshape(1, n)
