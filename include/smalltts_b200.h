@@ -172,6 +172,11 @@ int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T
                    int groups, int a_group_koff, int w_group_rows, int out_group_cols, const float* bias, int act,
                    const int32_t* row_len, int rows_per_batch, int mask_bf16_only, const float* colscale, const float* rowgate, int ld_gate,
                    const float* residual, int ld_res, float* out_f32, void* out_bf16, int ld_out);
+/* Split-K linear (gemm.cuh GemmShape::splits): out = epi(A[M,K] W[N,K]^T) with `splits` parts per tile; runs the launch
+ * twice on one counter buffer (the kernel must leave its counters zero). */
+int stts_test_gemm_split(stts_engine* e, int block_n, int splits, const void* a_bf16, int M, int K, const void* w_bf16, int N,
+                         const float* bias, int gelu2_f16, const float* colscale, const float* residual, float* out_f32,
+                         void* out_bf16);
 int stts_test_attention(stts_engine* e, const void* q, int B, int tq, int H, int hd, int hd_pad, const void* k0,
                         const void* v0, const int32_t* len0, int n0, const void* k1, const void* v1,
                         const int32_t* len1, int n1, const float* gate, int ld_gate, void* out);

@@ -133,6 +133,11 @@ struct stts_engine {
   // chained DiT path (dit_chain.cu): the 12 blocks' GEMM weights stacked per type + folded LayerNorm vectors per timestep
   ChainWeights chain_w;
   std::map<uint32_t, float*> fold_cache;  // timestep bits -> device fold table [kFoldFloats]
+  // split-K scratch of the vocoder's wave-quantised GEMMs (gemm.cuh GemmShape::splits); engine stream only
+  float* split_scratch = nullptr;
+  int* split_cnt = nullptr;
+  long long split_scratch_floats = 0, split_cnt_ints = 0;
+  bool use_split = true;    // STTS_NO_SPLITK=1: every GEMM computes whole tiles (A/B timing)
   bool use_chain = true;    // STTS_NO_CHAIN=1: generic 8-launches-per-block path (also used for per-utterance timesteps)
   bool chain_split = false; // STTS_CHAIN_SPLIT=1: one GEMM per chain launch (debug / A-B timing of the in-kernel dependencies)
 
@@ -217,9 +222,38 @@ int pick_bn(long long m, int n, int iters) {
   return best;
 }
 
-// Plain linear over flattened rows: out = epi(A[rows, K] * W[N, K]^T)
+// Split-K factor for a GEMM of `tiles` output tiles x `iters` k-iterations on a persistent grid of 148 CTAs: whole
+// tiles come in rounds of 148, so 160 tiles take two rounds and 80 tiles of 128 iterations leave half of the chip
+// idle; S parts per tile turn that into ceil(tiles S / 148) rounds of iters / S.  Only when it pays by >= 10 %, the
+// parts keep >= 8 iterations and the fp32 partials fit the engine's scratch.
+int pick_splits(const stts_engine* e, long long tiles, int iters, int bn) {
+  if (!e->use_split || e->split_scratch == nullptr || (bn != 128 && bn != 256) || tiles >= 4 * 148) return 1;
+  auto cost = [&](int S) {  // k-iterations on the critical path (+ the fix-up of a split tile)
+    return static_cast<double>((tiles * S + 147) / 148) * ((iters + S - 1) / S) + (S > 1 ? 3.0 : 0.0);
+  };
+  int best = 1;
+  for (int S = 2; S <= 4; ++S) {
+    if (iters / S < 8) break;
+    if (tiles * S * 128 * bn > e->split_scratch_floats || tiles * 8 > e->split_cnt_ints) break;
+    if (cost(S) < cost(best)) best = S;
+  }
+  return cost(best) < 0.9 * cost(1) ? best : 1;
+}
+
+void set_splits(stts_engine* e, GemmShape& s, GemmEpi& epi, int bn) {
+  const long long tiles = static_cast<long long>(s.B) * ((s.T + 127) / 128) * ((s.N + bn - 1) / bn) * s.groups;
+  const bool epi_ok = epi.act == ACT_NONE || (epi.act == ACT_GELU && epi.gelu2_f16);
+  s.splits = epi_ok ? pick_splits(e, tiles, s.taps * ((s.K + 63) / 64), bn) : 1;
+  if (s.splits > 1) {
+    epi.split_scratch = e->split_scratch;
+    epi.split_counters = e->split_cnt;
+  }
+}
+
+// Plain linear over flattened rows: out = epi(A[rows, K] * W[N, K]^T).  split_ok: the call is on the engine's main
+// stream (the split-K scratch is per engine) and its epilogue has a split-K instantiation.
 void linear(stts_engine* e, const bf16* a, long long rows, int k, int lda, const bf16* w, int n, int ldw, GemmEpi epi,
-            int bn = 0, bool f16 = false) {
+            int bn = 0, bool f16 = false, bool split_ok = false) {
   GemmShape s;
   s.ab_f16 = f16 ? 1 : 0;
   s.B = 1;
@@ -229,6 +263,7 @@ void linear(stts_engine* e, const bf16* a, long long rows, int k, int lda, const
   GemmA ga{a, k, lda};
   GemmW gw{w, n, ldw};
   if (bn == 0) bn = pick_bn(rows, n, (k + 63) / 64);
+  if (split_ok) set_splits(e, s, epi, bn);
   CK(launch_gemm(e->st, bn, ga, gw, s, epi));
 }
 
@@ -510,6 +545,12 @@ void finalize_decoder(stts_engine* e) {
   }
   e->head_w = e->W(1, "head.conv.weight", {1, 32, 7}).d;
   e->head_b = e->W(1, "head.conv.bias", {1}).d;
+  if (e->split_scratch == nullptr) {  // fp32 partial tiles of the split-K GEMMs (largest user: 160 tiles x 3 parts x 128 x 256)
+    e->split_scratch_floats = 24ll << 20;  // 96 MB
+    e->split_cnt_ints = 64 << 10;
+    e->split_scratch = e->dalloc<float>(static_cast<size_t>(e->split_scratch_floats), false);
+    e->split_cnt = e->dalloc<int>(static_cast<size_t>(e->split_cnt_ints), true);
+  }
   e->has_decoder = true;
 }
 
@@ -951,11 +992,11 @@ void convnext_layers(stts_engine* e, const std::vector<VocLayerW>& layers, float
     }
     GemmEpi e1;
     e1.bias = w.b1; e1.act = ACT_GELU; e1.gelu2_f16 = 1; e1.out_bf16 = ws.hbuf; e1.ld_out = 4 * C;
-    linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1);
+    linear(e, ws.a, M, C, C, w.w1, 4 * C, C, e1, 0, false, /*split_ok=*/true);
     GemmEpi e2;  // x = y + ffn_gamma * (W2 h + b2)   (hf:296-297)
     e2.bias = w.b2; e2.colscale = w.ffn_gamma; e2.residual = oth; e2.ld_res = C; e2.out_f32 = cur; e2.ld_out = C;
     if (bf16_copy && l + 1 == nl) e2.out_bf16 = ws.xh;  // bf16 copy feeds the next (transposed / strided) conv GEMM
-    linear(e, ws.hbuf, M, 4 * C, 4 * C, static_cast<const bf16*>(w.w2h), C, 4 * C, e2, 0, /*f16=*/true);
+    linear(e, ws.hbuf, M, 4 * C, 4 * C, static_cast<const bf16*>(w.w2h), C, 4 * C, e2, 0, /*f16=*/true, /*split_ok=*/true);
   }
 }
 
@@ -995,7 +1036,9 @@ void decode(stts_engine* e, const float* lat_dev, int B, int T, float* audio_dev
         g.B = B; g.T = Ts; g.N = r * cout; g.K = C; g.taps = 2; g.tap_shift0 = 0; g.tap_step = -1;
         GemmEpi ep;
         ep.bias = e->up_b[s]; ep.out_f32 = oth; ep.ld_out = r * cout;
-        CK(launch_gemm(st, pick_bn(M, r * cout, 2 * ((C + 63) / 64)), GemmA{ws.xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
+        const int bn = pick_bn(M, r * cout, 2 * ((C + 63) / 64));
+        set_splits(e, g, ep, bn);
+        CK(launch_gemm(st, bn, GemmA{ws.xh, C, C}, GemmW{e->up_w[s], r * cout, 2 * C}, g, ep));
       }
       Ts *= VOC_R[s];
       std::swap(cur, oth);
@@ -1310,6 +1353,8 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     e->fused_tail = !(nf && nf[0] == '1');
     const char* nff = getenv("STTS_NO_FUSED_FFN");
     e->fused_ffn = !(nff && nff[0] == '1');
+    const char* ns = getenv("STTS_NO_SPLITK");
+    e->use_split = !(ns && ns[0] == '1');
     const char* nc = getenv("STTS_NO_CHAIN");
     e->use_chain = !(nc && nc[0] == '1');
     const char* cs = getenv("STTS_CHAIN_SPLIT");
@@ -1363,6 +1408,8 @@ int stts_engine_clone(stts_engine* src, stts_engine** out) {
     c->plans.clear();
     c->mod_cache.clear();
     c->fold_cache.clear();
+    c->split_scratch = nullptr;  // scratch is per handle (handles run concurrently): the clone gets its own below
+    c->split_cnt = nullptr;
     c->banks.clear();
     c->err.clear();
     c->use_counter = 0;
@@ -1375,6 +1422,10 @@ int stts_engine_clone(stts_engine* src, stts_engine** out) {
     c->seed_dev = nullptr;
     c->seed_host = nullptr;
     init_instance(c);
+    if (c->has_decoder) {
+      c->split_scratch = c->dalloc<float>(static_cast<size_t>(c->split_scratch_floats), false);
+      c->split_cnt = c->dalloc<int>(static_cast<size_t>(c->split_cnt_ints), true);
+    }
   });
   if (rc != STTS_OK) {
     if (c) stts_destroy(c);  // tolerates the handles init_instance did not get to
@@ -1790,6 +1841,28 @@ int stts_test_gemm(stts_engine* e, int block_n, const void* a_bf16, int B, int T
     CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), a_cols, a_ld},
                    GemmW{static_cast<const bf16*>(w_bf16), w_rows, w_ld}, s, ep));
     if (!e->test_async) CK(cudaStreamSynchronize(e->st));
+  });
+}
+
+int stts_test_gemm_split(stts_engine* e, int block_n, int splits, const void* a_bf16, int M, int K, const void* w_bf16, int N,
+                         const float* bias, int gelu2_f16, const float* colscale, const float* residual, float* out_f32,
+                         void* out_bf16) {
+  if (!e) return STTS_ERR_INVALID;
+  return guard_impl(e, [&] {
+    GemmShape s;
+    s.B = 1; s.T = M; s.N = N; s.K = K; s.splits = splits;
+    GemmEpi ep;
+    ep.bias = bias; ep.colscale = colscale; ep.residual = residual; ep.ld_res = N; ep.out_f32 = out_f32;
+    ep.out_bf16 = static_cast<bf16*>(out_bf16); ep.ld_out = N;
+    if (gelu2_f16) { ep.act = ACT_GELU; ep.gelu2_f16 = 1; }
+    Tmp<float> scratch(e->st, static_cast<size_t>(gemm_split_scratch_floats(s, block_n)));
+    Tmp<int> cnt(e->st, static_cast<size_t>(gemm_split_counters(s, block_n)));
+    CK(cudaMemsetAsync(cnt.p, 0, static_cast<size_t>(gemm_split_counters(s, block_n)) * sizeof(int), e->st));
+    ep.split_scratch = scratch; ep.split_counters = cnt;
+    CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), K, K}, GemmW{static_cast<const bf16*>(w_bf16), N, K}, s, ep));
+    // a second launch on the same counters: the kernel must have left them zero
+    CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), K, K}, GemmW{static_cast<const bf16*>(w_bf16), N, K}, s, ep));
+    CK(cudaStreamSynchronize(e->st));
   });
 }
 

@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t bf2(float a, float b) {
 // Persistent CTA: walks output tiles (tile = blockIdx.x + i * gridDim.x; n fastest, so concurrently running CTAs share
 // A rows in L2).  The smem ring runs ahead across tile boundaries and the accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
-template <int BN, int ACT, int CTAS = 1>
+template <int BN, int ACT, int CTAS = 1, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmShape s,
             const GemmEpi e, const int kStages, const int n_tiles, const int m_tiles, const int total_tiles) {
@@ -130,7 +130,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int kchunks = (s.K + BK - 1) / BK;
   const int iters = s.taps * kchunks;
   const int first = blockIdx.x / CTAS, stride = gridDim.x / CTAS;
-  const int n_my = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
+  // work item = (tile, part of the reduction); parts of one tile are adjacent items, i.e. run side by side
+  const int S = SPLIT ? s.splits : 1;  // compile-time 1 for the regular instantiations: their code is unchanged
+  const int total_items = total_tiles * S;
+  const int n_my = first < total_items ? (total_items - first + stride - 1) / stride : 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -160,13 +163,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   ptx::pdl_trigger();
   int w_pre = 0;  // stages of the first tile whose W box is already in flight (producer warp only)
   if (CTAS == 1 && warp == 0 && n_my > 0) {
-    w_pre = iters < kStages ? iters : kStages;
+    const int tile = first / S, part = first % S;
+    const int it0 = part * iters / S, it1 = (part + 1) * iters / S;
+    w_pre = it1 - it0 < kStages ? it1 - it0 : kStages;
     if (ptx::elect_one()) {
-      const int tile = first;
       const int nx = tile % n_tiles, g = tile / (n_tiles * m_tiles);
       for (int i = 0; i < w_pre; ++i) {
         ptx::mbar_expect_tx(&full[i], C::kABytes + C::kBBytes);
-        ptx::tma_load_2d(smB + i * C::kBBytes, &tmW, &full[i], i * BK, g * s.w_group_rows + nx * BN);
+        ptx::tma_load_2d(smB + i * C::kBBytes, &tmW, &full[i], (it0 + i) * BK, g * s.w_group_rows + nx * BN);
       }
     }
     __syncwarp();
@@ -181,14 +185,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // per-lane election loops); one elected lane issues.
     uint32_t st = 0, ph = 0;  // ring position and phase, continue across tiles
     for (int li = 0; li < n_my; ++li) {
-      const int tile = first + li * stride;
+      const int item = first + li * stride;
+      const int tile = item / S, part = item % S;
+      const int it0 = part * iters / S, it1 = (part + 1) * iters / S;
       const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
       const int b = my / tiles_t, t0 = (my % tiles_t) * BMS + static_cast<int>(rank) * BM, n0 = nx * BN;
       const int a_col0 = g * s.a_group_koff, w_row = g * s.w_group_rows + n0 + static_cast<int>(rank) * C::kBRows;
-      int kc = 0, a_row = t0 + s.tap_shift0;
-      for (int it = 0; it < iters; ++it) {
+      int kc = it0 % kchunks, a_row = t0 + s.tap_shift0 + (it0 / kchunks) * s.tap_step;
+      for (int it = it0; it < it1; ++it) {
         ptx::mbar_wait(&empty[st], ph ^ 1);
-        const bool w_done = li == 0 && it < w_pre;  // expect_tx + W box already issued ahead of the PDL wait
+        const bool w_done = li == 0 && it - it0 < w_pre;  // expect_tx + W box already issued ahead of the PDL wait
         if (ptx::elect_one()) {
           if constexpr (CTAS == 2) {
             // the leader's barrier counts the bytes of both CTAs; the peer's copies may complete before the leader
@@ -222,7 +228,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_wait(&acc_empty[ab], ((li >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + ab * BN;
-      for (int it = 0; it < iters; ++it) {
+      const int item = first + li * stride;
+      const int it0 = (item % S) * iters / S, it1 = (item % S + 1) * iters / S;
+      for (int it = it0; it < it1; ++it) {
         ptx::mbar_wait(&full[st], ph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -232,8 +240,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            if constexpr (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-            else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            if constexpr (CTAS == 2) ptx::umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it != it0 || k != 0) ? 1u : 0u);
+            else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it != it0 || k != 0) ? 1u : 0u);
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
           if constexpr (CTAS == 2) ptx::umma_commit_pair(&empty[st]);
@@ -263,7 +271,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int l8r = lane >> 3, l8c = lane & 7;  // 32-column chunks: rows 4j + l8r (j < 8), float4 column l8c
     const int l4r = lane >> 2, l4c = lane & 3;  // 64-byte row segments: rows 8j + l4r (j < 4), 16-byte column l4c
     for (int li = 0; li < n_my; ++li) {
-      const int tile = first + li * stride;
+      const int item = first + li * stride;
+      const int tile = item / S, part = item % S;
       const int nx = tile % n_tiles, my = (tile / n_tiles) % m_tiles, g = tile / (n_tiles * m_tiles);
       const int b = my / tiles_t, t0 = (my % tiles_t) * BMS + static_cast<int>(rank) * BM, n0 = nx * BN;
       const int ab = li & 1;
@@ -326,8 +335,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_wait(&acc_full[ab], (li >> 1) & 1);
       ptx::tc_fence_after();
 
+      // Split-K: park this part's accumulator chunks, count the arrival; only the last part of the tile goes on.
+      // Scratch: [(tile, part)][chunk][128 rows][32] fp32 -- a warp's chunk is one contiguous 4 KB block.
+      bool owner = true;
+      if (SPLIT) {
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += 2) {
+          if (n0 + c * 32 >= s.N) break;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+          ptx::tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(e.split_scratch + ((static_cast<long long>(tile) * S + part) * (BN / 32) + c) * (BM * 32) + row * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        }
+        __threadfence();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) {
+          int* cnt = e.split_counters + static_cast<long long>(tile) * kEpiWarps + (warp - 2);
+          old = atomicAdd(cnt, 1);
+          if (old == S - 1) *cnt = 0;  // every part has arrived: leave the counter clean for the next launch
+        }
+        owner = __shfl_sync(0xffffffffu, old, 0) == S - 1;
+        if (owner) __threadfence();
+      }
+
+#pragma unroll 1
+      for (int c = half; owner && c < BN / 32; c += 2) {
         const int nl0 = n0 + c * 32;  // column inside the group
         if (nl0 >= s.N) break;        // warp-uniform
         const int gc0 = gcol_base + nl0;
@@ -340,6 +375,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         ptx::tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
         ptx::tmem_ld_wait();
         if (okbits == 0u) continue;  // warp-uniform: no live row in this quarter
+        if (SPLIT) {  // the tile's accumulator = sum of its parts in part order (this part's share comes from TMEM)
+          const float4* src0 = reinterpret_cast<const float4*>(e.split_scratch + (static_cast<long long>(tile) * S * (BN / 32) + c) * (BM * 32) + row * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int pp = 0; pp < S; ++pp) {
+              float4 v;
+              if (pp == part) {
+                v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+              } else {
+                v = __ldcg(src0 + static_cast<long long>(pp) * (BN / 32) * (BM * 32 / 4) + i);
+              }
+              if (pp == 0) acc4 = v;
+              else { acc4.x += v.x; acc4.y += v.y; acc4.z += v.z; acc4.w += v.w; }
+            }
+            r[4 * i] = __float_as_uint(acc4.x); r[4 * i + 1] = __float_as_uint(acc4.y);
+            r[4 * i + 2] = __float_as_uint(acc4.z); r[4 * i + 3] = __float_as_uint(acc4.w);
+          }
+        }
         if (ACT == kActGelu2) {
           // FFN hidden activation of the vocoder: 2*gelu in packed fp16, stored as fp16 (no mask/scale/residual here)
           float v[32];
@@ -525,14 +579,14 @@ bool make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int ACT, int CTAS = 1>
+template <int BN, int ACT, int CTAS = 1, bool SPLIT = false>
 cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
                         const GemmEpi& e) {
   using C = Cfg<BN, CTAS>;
   static PerDeviceOnce attr_set;
   {
     const cudaError_t err = attr_set.run([] {
-      return cudaFuncSetAttribute(gemm_kernel<BN, ACT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      return cudaFuncSetAttribute(gemm_kernel<BN, ACT, CTAS, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::smem_bytes(C::kMaxStages));
     });
     if (err != cudaSuccess) return err;
@@ -548,10 +602,13 @@ cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUten
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int slots = num_sms / CTAS;  // persistent CTAs (CTA pairs)
-  const int grid = total < slots ? static_cast<int>(total) : slots;
+  const int splits = SPLIT ? s.splits : 1;
+  const long long items = total * splits;
+  if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const int grid = items < slots ? static_cast<int>(items) : slots;
   // deep ring (the producer runs ahead into the next tile); short reductions of small problems need fewer stages
-  const int iters = s.taps * ((s.K + BK - 1) / BK);
-  const long long ring = static_cast<long long>(iters) * ((total + grid - 1) / grid);
+  const int iters = s.taps * ((s.K + BK - 1) / BK) / splits;
+  const long long ring = static_cast<long long>(iters) * ((items + grid - 1) / grid);
   int stages = ring < 2 ? 2 : (ring > C::kMaxStages ? C::kMaxStages : static_cast<int>(ring));
   {
     static int forced = -1;  // STTS_GEMM_STAGES=n: pipeline-depth experiments (tools/bench_gemm.py)
@@ -562,9 +619,9 @@ cudaError_t launch_inst(cudaStream_t stream, const CUtensorMap& tmA, const CUten
     if (forced >= 2 && forced < stages) stages = forced;
   }
   const cudaError_t le =
-      CTAS == 2 ? launch_k_pair(gemm_kernel<BN, ACT, CTAS>, dim3(2 * grid), dim3(kThreads), C::smem_bytes(stages), stream, tmA,
+      CTAS == 2 ? launch_k_pair(gemm_kernel<BN, ACT, CTAS, SPLIT>, dim3(2 * grid), dim3(kThreads), C::smem_bytes(stages), stream, tmA,
                                 tmW, s, e, stages, n_tiles, m_tiles, static_cast<int>(total))
-                : launch_k(gemm_kernel<BN, ACT, CTAS>, dim3(grid), dim3(kThreads), C::smem_bytes(stages), stream, tmA, tmW,
+                : launch_k(gemm_kernel<BN, ACT, CTAS, SPLIT>, dim3(grid), dim3(kThreads), C::smem_bytes(stages), stream, tmA, tmW,
                            s, e, stages, n_tiles, m_tiles, static_cast<int>(total));
   count_launch();
   return le != cudaSuccess ? le : cudaGetLastError();
@@ -579,9 +636,22 @@ cudaError_t launch_pair(cudaStream_t stream, const CUtensorMap& tmA, const CUten
   return cudaErrorInvalidValue;
 }
 
+// Split-K instantiations exist for the epilogues of the vocoder's wave-quantised GEMMs (plain and fp16 2*gelu).
+template <int BN>
+cudaError_t launch_split(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
+                         const GemmEpi& e) {
+  if (e.act == ACT_NONE) return launch_inst<BN, ACT_NONE, 1, true>(stream, tmA, tmW, s, e);
+  if (e.act == ACT_GELU && e.gelu2_f16) return launch_inst<BN, kActGelu2, 1, true>(stream, tmA, tmW, s, e);
+  return cudaErrorInvalidValue;
+}
+
 template <int BN>
 cudaError_t launch_bn(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmShape& s,
                       const GemmEpi& e) {
+  if (s.splits > 1) {
+    if (BN == 128 || BN == 256) return launch_split<(BN == 128 || BN == 256) ? BN : 128>(stream, tmA, tmW, s, e);
+    return cudaErrorInvalidValue;
+  }
   switch (e.act) {
     case ACT_NONE:
       return launch_inst<BN, ACT_NONE>(stream, tmA, tmW, s, e);
@@ -602,6 +672,16 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+long long gemm_split_counters(const GemmShape& s, int block_n) {
+  block_n &= ~kGemmPairFlag;
+  const long long tiles = static_cast<long long>(s.B) * ((s.T + BM - 1) / BM) * ((s.N + block_n - 1) / block_n) * s.groups;
+  return tiles * kEpiWarps;
+}
+long long gemm_split_scratch_floats(const GemmShape& s, int block_n) {
+  block_n &= ~kGemmPairFlag;
+  return gemm_split_counters(s, block_n) / kEpiWarps * (s.splits > 1 ? s.splits : 1) * BM * block_n;
+}
+
 cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const GemmW& w, const GemmShape& s,
                         const GemmEpi& e) {
   if (s.T <= 0 || s.B <= 0 || s.N <= 0 || s.K <= 0) return cudaErrorInvalidValue;
@@ -621,6 +701,13 @@ cudaError_t launch_gemm(cudaStream_t stream, int block_n, const GemmA& a, const 
   // width as the single-CTA choice, enough tiles to occupy all 74 pairs.
   bool pair = (block_n & kGemmPairFlag) != 0;
   block_n &= ~kGemmPairFlag;
+  if (s.splits > 1) {
+    const int iters = s.taps * ((s.K + BK - 1) / BK);
+    if (pair || s.splits > 8 || iters < s.splits || e.split_scratch == nullptr || e.split_counters == nullptr ||
+        !aligned16(e.split_scratch)) {
+      return cudaErrorInvalidValue;
+    }
+  }
   if (!pair && (block_n == 128 || block_n == 256) && (e.act == ACT_NONE || (e.act == ACT_GELU && e.gelu2_f16))) {
     static int env = -1;
     if (env < 0) {

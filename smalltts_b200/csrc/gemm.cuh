@@ -37,6 +37,12 @@ struct GemmShape {
   // starts), W rows at g*w_group_rows, output columns at g*out_group_cols, residual columns at g*res_group_cols
   int groups = 1, a_group_koff = 0, w_group_rows = 0, out_group_cols = 0, res_group_cols = 0;
   int ab_f16 = 0;  // A and W hold fp16 (not bf16) values: selects the fp16 input format of tcgen05.mma kind::f16
+  // Split-K: every output tile is computed by `splits` work items, each over a contiguous part of the taps*K reduction
+  // (wave quantisation: 160 tiles on 148 SMs, or 80 tiles of 128 k-iterations, leave half of the chip idle).  Every part
+  // parks its fp32 accumulator in GemmEpi::split_scratch; the part that arrives LAST at the tile's counter adds the
+  // parts in part order (so the result does not depend on who was last) and runs the epilogue.  Nobody waits for
+  // anybody: no residency assumption.  Single-CTA kernel only.
+  int splits = 1;
 };
 
 struct GemmEpi {
@@ -55,7 +61,15 @@ struct GemmEpi {
   float* out_f32 = nullptr;
   bf16* out_bf16 = nullptr;
   int ld_out = 0;
+  // split-K only (GemmShape::splits > 1): fp32 scratch of gemm_split_scratch_floats() elements and zero-initialised
+  // counters (8 per output tile; the kernel leaves them zero)
+  float* split_scratch = nullptr;
+  int* split_counters = nullptr;
 };
+
+// Scratch elements / counters a split-K launch of this shape needs (block_n as passed to launch_gemm).
+long long gemm_split_scratch_floats(const GemmShape& s, int block_n);
+long long gemm_split_counters(const GemmShape& s, int block_n);
 
 struct GemmA {
   const bf16* ptr;

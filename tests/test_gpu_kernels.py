@@ -68,6 +68,42 @@ def test_linear(eng, bn, M, N, K):
     _assert_close(out, a.float() @ w.float().t() + bias)
 
 
+@pytest.mark.parametrize("M,N,K,bn,splits,gelu2", [(600, 2048, 8192, 128, 3, False), (600, 8192, 2048, 256, 3, True),
+                                                      (4800, 1024, 4096, 256, 3, False), (600, 8192, 4096, 256, 2, False),
+                                                      (130, 256, 1024, 128, 4, False)])
+def test_linear_split_k(eng, M, N, K, bn, splits, gelu2):
+    """Split-K (gemm.cuh GemmShape::splits): every tile is computed by `splits` work items over parts of the reduction;
+    the last part to arrive adds the parked fp32 partials in part order and runs the epilogue.  Same result as the
+    whole-tile GEMM up to fp32 summation order, bit-identical from run to run, counters left clean (the hook launches
+    twice on one counter buffer)."""
+    from smalltts_b200 import _cabi
+
+    torch.manual_seed(7)
+    a, w = _rand_bf16(M, K), _rand_bf16(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    if gelu2:  # the vocoder's FFN1 epilogue: 2 * gelu(x) written as fp16
+        outs = []
+        for _ in range(2):
+            o16 = torch.zeros(M, N, device="cuda", dtype=torch.float16)
+            rc = _cabi.lib().stts_test_gemm_split(eng._h, bn, splits, _p(a), M, K, _p(w), N, _p(bias), 1, None, None, None, _p(o16))
+            _cabi.check(rc, eng._h)
+            torch.cuda.synchronize()
+            outs.append(o16)
+        want = 2 * torch.nn.functional.gelu(a.float() @ w.float().t() + bias)
+        _assert_close(outs[0], want, tol=4e-3)
+    else:
+        cs, res = torch.rand(N, device="cuda") + 0.5, torch.randn(M, N, device="cuda")
+        outs = []
+        for _ in range(2):
+            o32 = torch.zeros(M, N, device="cuda")
+            rc = _cabi.lib().stts_test_gemm_split(eng._h, bn, splits, _p(a), M, K, _p(w), N, _p(bias), 0, _p(cs), _p(res), _p(o32), None)
+            _cabi.check(rc, eng._h)
+            torch.cuda.synchronize()
+            outs.append(o32)
+        _assert_close(outs[0], (a.float() @ w.float().t() + bias) * cs + res)
+    assert torch.equal(outs[0], outs[1])
+
+
 PAIR = 0x1000  # gemm.cuh kGemmPairFlag: clusters of two CTAs, 256 x bn tiles, cta_group::2 MMAs
 # The engine uses the pair variant only with STTS_GEMM_2CTA=1 (measured: wins on long reductions in isolation, no
 # end-to-end gain yet); its kernel tests run by default (STTS_TEST_PAIR=0 skips them).
