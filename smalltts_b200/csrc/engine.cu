@@ -137,7 +137,7 @@ struct stts_engine {
   float* split_scratch = nullptr;
   int* split_cnt = nullptr;
   long long split_scratch_floats = 0, split_cnt_ints = 0;
-  bool use_split = true;    // STTS_NO_SPLITK=1: every GEMM computes whole tiles (A/B timing)
+  bool use_split = false;   // STTS_SPLITK=1: split-K for the wave-quantised vocoder GEMMs.  Off: measured slower (below)
   bool use_chain = true;    // STTS_NO_CHAIN=1: generic 8-launches-per-block path (also used for per-utterance timesteps)
   bool chain_split = false; // STTS_CHAIN_SPLIT=1: one GEMM per chain launch (debug / A-B timing of the in-kernel dependencies)
 
@@ -226,6 +226,10 @@ int pick_bn(long long m, int n, int iters) {
 // tiles come in rounds of 148, so 160 tiles take two rounds and 80 tiles of 128 iterations leave half of the chip
 // idle; S parts per tile turn that into ceil(tiles S / 148) rounds of iters / S.  Only when it pays by >= 10 %, the
 // parts keep >= 8 iterations and the fp32 partials fit the engine's scratch.
+// MEASURED (tools/bench_splitk.py, profiles/r02_splitk_microbench.txt): it does not pay at these sizes -- the per-item
+// cost of parking / re-reading 128 x BN fp32 partials and of the longer two-pass epilogue exceeds the k-iterations a
+// part saves (600 x 8192 x 2048: 26.8 us whole tiles, 69.8 us with 2 parts; 600 x 2048 x 8192: 37.3 -> 44.6 / 48.0).
+// The kernel path is kept (tested, opt-in with STTS_SPLITK=1); the engine computes whole tiles.
 int pick_splits(const stts_engine* e, long long tiles, int iters, int bn) {
   if (!e->use_split || e->split_scratch == nullptr || (bn != 128 && bn != 256) || tiles >= 4 * 148) return 1;
   auto cost = [&](int S) {  // k-iterations on the critical path (+ the fix-up of a split tile)
@@ -1353,8 +1357,8 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     e->fused_tail = !(nf && nf[0] == '1');
     const char* nff = getenv("STTS_NO_FUSED_FFN");
     e->fused_ffn = !(nff && nff[0] == '1');
-    const char* ns = getenv("STTS_NO_SPLITK");
-    e->use_split = !(ns && ns[0] == '1');
+    const char* ns = getenv("STTS_SPLITK");
+    e->use_split = ns && ns[0] == '1';
     const char* nc = getenv("STTS_NO_CHAIN");
     e->use_chain = !(nc && nc[0] == '1');
     const char* cs = getenv("STTS_CHAIN_SPLIT");
@@ -1862,6 +1866,20 @@ int stts_test_gemm_split(stts_engine* e, int block_n, int splits, const void* a_
     CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), K, K}, GemmW{static_cast<const bf16*>(w_bf16), N, K}, s, ep));
     // a second launch on the same counters: the kernel must have left them zero
     CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), K, K}, GemmW{static_cast<const bf16*>(w_bf16), N, K}, s, ep));
+    if (e->test_async) {  // micro-benchmark mode: 20 more launches, timed on the stream
+      cudaEvent_t t0, t1;
+      CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+      CK(cudaEventRecord(t0, e->st));
+      for (int i = 0; i < 20; ++i) {
+        CK(launch_gemm(e->st, block_n, GemmA{static_cast<const bf16*>(a_bf16), K, K}, GemmW{static_cast<const bf16*>(w_bf16), N, K}, s, ep));
+      }
+      CK(cudaEventRecord(t1, e->st));
+      CK(cudaEventSynchronize(t1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, t0, t1));
+      e->voc_ms[0] = ms / 20;  // read back through stts_last_vocoder_ms(e, 0)
+      cudaEventDestroy(t0); cudaEventDestroy(t1);
+    }
     CK(cudaStreamSynchronize(e->st));
   });
 }

@@ -336,7 +336,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::tc_fence_after();
 
       // Split-K: park this part's accumulator chunks, count the arrival; only the last part of the tile goes on.
-      // Scratch: [(tile, part)][chunk][128 rows][32] fp32 -- a warp's chunk is one contiguous 4 KB block.
+      // Scratch: [(tile, part)][chunk][8 float4 columns][128 rows] -- every warp access is 512 contiguous bytes.
       bool owner = true;
       if (SPLIT) {
 #pragma unroll 1
@@ -345,9 +345,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t r[32];
           ptx::tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
           ptx::tmem_ld_wait();
-          uint4* dst = reinterpret_cast<uint4*>(e.split_scratch + ((static_cast<long long>(tile) * S + part) * (BN / 32) + c) * (BM * 32) + row * 32);
+          // [float4 column i][row]: the 32 lanes of a store instruction write 512 contiguous bytes
+          uint4* dst = reinterpret_cast<uint4*>(e.split_scratch + ((static_cast<long long>(tile) * S + part) * (BN / 32) + c) * (BM * 32)) + row;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) dst[i * BM] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
         }
         __threadfence();
         __syncwarp();
@@ -376,7 +377,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         ptx::tmem_ld_wait();
         if (okbits == 0u) continue;  // warp-uniform: no live row in this quarter
         if (SPLIT) {  // the tile's accumulator = sum of its parts in part order (this part's share comes from TMEM)
-          const float4* src0 = reinterpret_cast<const float4*>(e.split_scratch + (static_cast<long long>(tile) * S * (BN / 32) + c) * (BM * 32) + row * 32);
+          const float4* src0 = reinterpret_cast<const float4*>(e.split_scratch + (static_cast<long long>(tile) * S * (BN / 32) + c) * (BM * 32)) + row;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -385,7 +386,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (pp == part) {
                 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
               } else {
-                v = __ldcg(src0 + static_cast<long long>(pp) * (BN / 32) * (BM * 32 / 4) + i);
+                v = __ldcg(src0 + static_cast<long long>(pp) * (BN / 32) * (BM * 32 / 4) + i * BM);
               }
               if (pp == 0) acc4 = v;
               else { acc4.x += v.x; acc4.y += v.y; acc4.z += v.z; acc4.w += v.w; }
