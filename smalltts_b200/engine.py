@@ -181,7 +181,10 @@ class Engine:
 
     def encode_audio(self, audio):
         """Codec encoder (codec/onnx.py:56-75): audio (B, N) or (B, 1, N) fp32 @ 24 kHz -> latents (B, N // 3200, 64).
-        A tail shorter than one hop is dropped (the encoder is causal and floors, so no latent changes)."""
+        A tail shorter than one hop is dropped: the `transformers` port this engine is pinned on emits floor(N / 3200)
+        latents and is causal, so no latent changes.  (The published encoder.onnx is an export of Microsoft's VibeVoice,
+        whose non-streaming SConv1d may right-pad to ceil(N / 3200); unverified without the asset -- if it does, zero-pad
+        the clip to a whole hop before calling this.)"""
         if audio.ndim == 3:
             audio = audio[:, 0]
         B, N = audio.shape
