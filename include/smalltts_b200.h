@@ -193,18 +193,23 @@ int stts_test_convnext_fused(stts_engine* e, const float* x, int B, int T, int C
                              const float* ffn_gamma, float* out, void* out_bf16);
 
 
-/* Chained DiT GEMM kernel (csrc/dit_chain.cuh): weights of the 12 blocks stacked per GEMM type, activation buffers of
- * one denoiser evaluation and up to four dependent GEMM phases (kind: 0 q|k|v|gate, 1 to_out, 2 w1|w3, 3 w2, 4 velocity).
- * `ready` must hold zeroed counters (4 per 128-row block + 1, rounded up to 16 ints). */
+/* Chained DiT kernel (csrc/dit_chain.cuh): weights of the 12 blocks stacked per GEMM type, activation buffers of one
+ * denoiser evaluation and up to 64 dependent phases (kind: 0 q|k|v|gate, 1 to_out, 2 w1|w3, 3 w2, 4 velocity, 5 joint
+ * attention of block blk -- the attention fields below are only read when a phase of kind 5 is present).
+ * `ready` must hold zeroed counters: n_phases per 128-row block rounded up to 32 ints, + 64. */
 typedef struct stts_test_chain_args {
   const void *wqkvg, *wo, *w13, *w2, *wvel;                 /* bf16 */
   const float *bqkvg, *b13, *b2, *bvel, *qn, *kn, *cos_t, *sin_t;
-  float* x; void* xb; float* stats; void* qkv; float* gate; const void* ob; void* hb; float* vel; int32_t* ready;
+  float* x; void* xb; float* stats; void* qkv; float* gate; void* ob; void* hb; float* vel; int32_t* ready;
   const int32_t* frames; const float* mod; const float* fold;
   uint64_t* trace; /* optional role timeline [CTAs][64][16] (tools/trace_chain.py), else NULL */
+  const void *kv_ref, *kv_text;             /* cross K/V caches [12][2][B, R | P, 8, 128] bf16 */
+  const int32_t *ref_len, *ph_len;          /* [B] */
   int32_t M, T, n_phases;
-  int32_t kind[4];
-  int32_t blk[4];
+  int32_t B, R, P;
+  int32_t qkv_db;                           /* 1: qkv is [2][3][M][1024], block i uses half i & 1 (required with kind 5) */
+  int32_t kind[64];
+  int32_t blk[64];
 } stts_test_chain_args;
 int stts_test_chain(stts_engine* e, const stts_test_chain_args* a);
 /* fold table [stts_test_chain_fold_floats()] of the timestep whose adaLN table is a->mod, from the weights in `a` */

@@ -34,9 +34,9 @@ class ChainArgs(C.Structure):
 
     _fields_ = ([(n, vp) for n in ("wqkvg", "wo", "w13", "w2", "wvel", "bqkvg", "b13", "b2", "bvel", "qn", "kn", "cos_t",
                                    "sin_t", "x", "xb", "stats", "qkv", "gate", "ob", "hb", "vel", "ready", "frames", "mod",
-                                   "fold", "trace")]
-                + [("M", C.c_int32), ("T", C.c_int32), ("n_phases", C.c_int32), ("kind", C.c_int32 * 4),
-                   ("blk", C.c_int32 * 4)])
+                                   "fold", "trace", "kv_ref", "kv_text", "ref_len", "ph_len")]
+                + [(n, C.c_int32) for n in ("M", "T", "n_phases", "B", "R", "P", "qkv_db")]
+                + [("kind", C.c_int32 * 64), ("blk", C.c_int32 * 64)])
 
 
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header is exported

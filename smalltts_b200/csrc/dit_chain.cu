@@ -23,7 +23,9 @@
 #include "dit_chain.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 
+#include "chain_attn.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -47,12 +49,15 @@ constexpr int kAccCols = 256;           // TMEM columns per accumulator buffer
 constexpr int kTq = 4;                  // depth of the tile FIFO between the claiming warp and the other roles
 constexpr int kTqReaders = 2 + kEpiWarps;  // A producer, MMA issuer, epilogue warps
 constexpr int kColvecFloats = 192;         // per epilogue warp: 3 chunks x (cs | b') or 2 chunks x (cs | b') + norm weights
-constexpr int kSmem = kStages * kSlotBytes + 256 + kEpiWarps * kStgBytes + 2 * 2 * BM * 4 + kEpiWarps * kColvecFloats * 4 + 1024;
+constexpr int kCtrlBytes = 1024;            // mbarriers, tile FIFO, TMEM slot, phase table
+constexpr int kSmem = kStages * kSlotBytes + kCtrlBytes + kEpiWarps * kStgBytes + 2 * 2 * BM * 4 + kEpiWarps * kColvecFloats * 4 + 1024;
 static_assert(kSmem <= 232448, "chain kernel does not fit in shared memory");
+static_assert(chain_attn::kSmemBytes <= kStages * kSlotBytes, "an attention item borrows the operand ring");
 
 struct ChainMaps {
   CUtensorMap a[3];  // xb [M, 960], ob [M, 1024], hb [M, 2400]: box 64 x 128 rows
   CUtensorMap w[5];  // per ChainKind, all blocks stacked: box 64 x 64 rows
+  chain_attn::Maps at;
 };
 
 struct ChainDev {
@@ -60,6 +65,10 @@ struct ChainDev {
   ChainBuffers b;
   ChainCall c;
   int m_tiles;
+  // CHAIN_ATTN phases: items (utterance, 64-query tile, head), head fastest; to_out of row block m waits for
+  // attn_target[m] items (those whose query rows touch the block)
+  int q_tiles, attn_items;
+  int attn_target[kChainMaxRowBlocks];
 };
 
 // ---------------------------------------------------------------- static shape tables
@@ -89,25 +98,29 @@ __device__ __forceinline__ void tile_cols(int kind, int n, int& n0, int& bn) {
 __device__ __forceinline__ int slot_kblocks(int bn) { return bn == 64 ? STTS_CHAIN_KPB : 1; }
 
 struct Tile {
-  int p, kind, blk, m, n, g;
+  int p, kind, blk, m, n, g;  // attention items: m = utterance * q_tiles + query tile, n = head
 };
-// global tile number -> (phase, row block, column tile); phases are numbered back to back, n fastest inside a phase
-__device__ __forceinline__ Tile decode_tile(int g, const ChainCall& c, int m_tiles) {
+__device__ __forceinline__ int phase_items(const ChainDev& d, int p) {
+  return d.c.kind[p] == CHAIN_ATTN ? d.attn_items : kind_ntiles(d.c.kind[p]) * d.m_tiles;
+}
+// Global tile number -> (phase, row block, column tile); phases are numbered back to back (pstart: first tile of every
+// phase, in shared memory), n fastest inside a phase.  A role sees increasing tile numbers: `cur` is its phase cursor.
+__device__ __forceinline__ Tile decode_tile(int g, const ChainDev& d, const int* pstart, int& cur) {
+  while (g >= pstart[cur + 1]) ++cur;
   Tile t;
   t.g = g;
-  t.p = 0;
-  for (;;) {
-    const int total = kind_ntiles(c.kind[t.p]) * m_tiles;
-    if (g < total || t.p + 1 >= c.n_phases) break;
-    g -= total;
-    ++t.p;
-  }
-  t.kind = c.kind[t.p];
-  t.blk = c.blk[t.p];
-  const int nt = kind_ntiles(t.kind);
+  t.p = cur;
+  g -= pstart[cur];
+  t.kind = d.c.kind[cur];
+  t.blk = d.c.blk[cur];
+  const int nt = t.kind == CHAIN_ATTN ? kChainH : kind_ntiles(t.kind);
   t.m = g / nt;
   t.n = g % nt;
   return t;
+}
+// completed items of phase p a consumer of row block m waits for
+__device__ __forceinline__ int phase_target(const ChainDev& d, int p, int m) {
+  return d.c.kind[p] == CHAIN_ATTN ? d.attn_target[m] : kind_ntiles(d.c.kind[p]);
 }
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -141,6 +154,12 @@ __device__ __forceinline__ void trace_ev(unsigned long long* trace, int seq, int
 
 __device__ __forceinline__ uint32_t bf2(float a, float b) {
   return op16_pack2(a, b);
+}
+// 2^x on the special-function unit, no range fix-ups (no branches): inputs here are <= 0 or moderate, tiny results flush to 0
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ float fast_sigmoid(float x) {
   return __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x));
@@ -237,7 +256,188 @@ __device__ __forceinline__ void store_f32_chunk(const Epi& e, const float (&v)[3
   }
 }
 
+// ---------------------------------------------------------------- attention item, epilogue-warp side (chain_attn.cuh)
+// Softmax over the score accumulator and the gated output.  The two warps of a lane quarter split the 32-key chunks of S by
+// parity and exchange row max / row sum through `ssx` (named barrier 1 + quarter, like the head RMSNorm of the q|k|v tiles).
+// Not inlined: the GEMM epilogues around the call site must not pay for its registers.  Returns the updated exchange count.
+__device__ __noinline__ int attn_epilogue(const ChainDev& d, Epi e, uint32_t tmem_base, uint8_t* ring, uint64_t* s_full,
+                                          uint64_t* p_full, uint64_t* o_full, uint32_t par, int hcount, int b, int h, int q0,
+                                          unsigned long long* trow) {
+  const ChainCall& c = d.c;
+  const chain_attn::Keys ak = chain_attn::keys_of(c, b);
+  const int lane = e.lane;
+  const int row = e.q * 32 + lane;  // row of the item = TMEM lane
+  const bool row_ok = q0 + row < c.T;
+  e.m0 = b * c.T + q0 + e.q * 32;
+  e.okbits = __ballot_sync(0xffffffffu, row_ok);
+  const bool live = e.okbits != 0u;  // a quarter past the end of the utterance only keeps the barriers company
+  const uint32_t s_acc = tmem_base + chain_attn::kSCol + (static_cast<uint32_t>(e.q * 32) << 16);
+  const uint32_t o_acc = tmem_base + chain_attn::kOCol + (static_cast<uint32_t>(e.q * 32) << 16);
+  const float scale_log2 = 1.4426950408889634f * 0.09128709291752769f;  // log2(e) / sqrt(120)
+  const int nch = (ak.e2 + 31) >> 5;  // 32-key chunks of S that hold keys
+  auto stamp = [&](int ev) {
+    if (trow != nullptr && e.q == 0 && e.half == 0 && lane == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trow[ev] = t;
+    }
+  };
+
+  // ---- sigmoid(gate) of the item's rows -> shared memory (fp16, [128 rows][128 dims], 16-byte chunks XOR-swizzled by the
+  // row), fetched while Q / K are still in flight.  Coalesced: a warp reads one row (120 floats) per instruction -- the
+  // per-thread row-form read (32 rows x 16 bytes per instruction) is bound by the load/store unit, not by L2.
+  // fp16: values in (0, 1), 2^-12 absolute error, well below the rounding of the 16-bit output they multiply.
+  uint8_t* sgate = ring + chain_attn::kGateOff;
+  {
+    const int wid = e.half * 4 + e.q;  // 0..7: rows 16 wid .. + 16
+    const int rows_live = min(c.T - q0, chain_attn::kRows);
+    constexpr float kNegLog2e = -1.4426950408889634f;
+    float4 g4[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int rr = wid * 16 + i;
+      g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rr < rows_live && lane < kChainHD / 4) {  // written in this launch by other CTAs: L2, not L1
+        g4[i] = __ldcg(reinterpret_cast<const float4*>(d.b.gate + static_cast<long long>(b * c.T + q0 + rr) * kChainD + h * kChainHD) + lane);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int rr = wid * 16 + i;
+      const __half2 lo = __floats2half2_rn(__fdividef(1.0f, 1.0f + ex2_approx(kNegLog2e * g4[i].x)),
+                                           __fdividef(1.0f, 1.0f + ex2_approx(kNegLog2e * g4[i].y)));
+      const __half2 hi = __floats2half2_rn(__fdividef(1.0f, 1.0f + ex2_approx(kNegLog2e * g4[i].z)),
+                                           __fdividef(1.0f, 1.0f + ex2_approx(kNegLog2e * g4[i].w)));
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      // dims 4 lane .. + 4 = 8 bytes at byte 8 lane of the row: 16-byte chunk lane / 2, half lane & 1
+      *reinterpret_cast<uint2*>(sgate + rr * 256 + ((((lane >> 1) ^ (rr & 15)) << 4) | ((lane & 1) << 3))) = pk;
+    }
+  }
+  ptx::named_bar_sync(6, kEpiWarps * 32);  // (also orders the previous item's reads of the gate tile before these writes)
+  ptx::mbar_wait(s_full, par);
+  ptx::tc_fence_after();
+#ifndef STTS_ATTN_DEBUG_TRACE
+  stamp(8);
+#endif
+  // ---- pass 1: row max over this warp's chunks (padded keys masked)
+  float mx = -INFINITY;
+  if (live) {
+#pragma unroll 1
+    for (int cc = e.half; cc < nch; cc += 2) {
+      const uint32_t vm = __ballot_sync(0xffffffffu, chain_attn::key_valid(ak, cc * 32 + lane));
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(s_acc + cc * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if ((vm >> i) & 1u) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+    }
+  }
+  {
+    float* sx = e.ssx + (hcount & 1) * (2 * BM);
+    sx[e.half * BM + row] = mx;
+    ptx::named_bar_sync(1 + e.q, 64);
+    mx = fmaxf(sx[row], sx[BM + row]);
+    ++hcount;
+  }
+  // ---- pass 2: P = exp2((S - max) * scale) as bf16 into the A-operand layout (K-major, 128-byte swizzle, 64-key blocks)
+  float sum = 0.f;
+  if (live) {
+    const float mxs = mx == -INFINITY ? 0.f : mx * scale_log2;
+#pragma unroll 1
+    for (int cc = e.half; cc < nch; cc += 2) {
+      const uint32_t vm = __ballot_sync(0xffffffffu, chain_attn::key_valid(ak, cc * 32 + lane));
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(s_acc + cc * 32, r);
+      ptx::tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {  // masked keys: 2^-inf = 0 (selects, no branches around the special-function unit)
+        const float s0 = (vm >> (2 * i)) & 1u ? __uint_as_float(r[2 * i]) : -INFINITY;
+        const float s1 = (vm >> (2 * i + 1)) & 1u ? __uint_as_float(r[2 * i + 1]) : -INFINITY;
+        const float p0 = ex2_approx(fmaf(s0, scale_log2, -mxs));
+        const float p1 = ex2_approx(fmaf(s1, scale_log2, -mxs));
+        sum += p0 + p1;
+        pk[i] = op16_pack2(p0, p1);
+      }
+      uint8_t* prow = ring + chain_attn::kPOff + (cc >> 1) * (chain_attn::kRows * 128) + row * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int ch = (cc & 1) * 4 + q4;
+        *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+      }
+    }
+  }
+  fence_proxy_async_all();  // P (generic-proxy writes to shared memory) -> the MMA's async-proxy reads
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive(p_full);
+#ifdef STTS_ATTN_DEBUG_TRACE
+  if (trow != nullptr && lane == 0 && e.half * 4 + e.q < 6) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trow[8 + e.half * 4 + e.q] = t;
+  }
+#else
+  stamp(9);
+#endif
+  {
+    float* sx = e.ssx + (hcount & 1) * (2 * BM);
+    sx[e.half * BM + row] = sum;
+    ptx::named_bar_sync(1 + e.q, 64);
+    sum = sx[row] + sx[BM + row];
+    ++hcount;
+  }
+  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+  ptx::mbar_wait(o_full, par);
+  ptx::tc_fence_after();
+#ifndef STTS_ATTN_DEBUG_TRACE
+  stamp(10);
+#else
+  stamp(14);
+#endif
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int cc = e.half + 2 * j;
+      uint32_t r[32];
+      float v[32];
+      ptx::tmem_ld_32x32(o_acc + cc * 32, r);
+      uint2 sg[8];  // this row's gates of dims 32 cc .. + 32: four 16-byte chunks
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint4 x = *reinterpret_cast<const uint4*>(sgate + row * 256 + (((cc * 4 + q4) ^ (row & 15)) << 4));
+        sg[2 * q4] = make_uint2(x.x, x.y);
+        sg[2 * q4 + 1] = make_uint2(x.z, x.w);
+      }
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&sg[i].x));
+        const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&sg[i].y));
+        // the pad dims (120..127) hold exact zeros: V's pad columns are zero
+        v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) * inv * g01.x;
+        v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) * inv * g01.y;
+        v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) * inv * g23.x;
+        v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) * inv * g23.y;
+      }
+      store_bf16_chunk(e, v, d.b.ob + h * kChainHDP, kChainH * kChainHDP, cc * 32);
+    }
+  }
+  ptx::tc_fence_before();
+#ifndef STTS_ATTN_DEBUG_TRACE
+  stamp(11);
+#endif
+  return hcount;
+}
+
 // ---------------------------------------------------------------- the kernel
+// kAttn: instantiation that can run CHAIN_ATTN phases (the attention item costs registers around its call site; launches
+// without such a phase use the lean instantiation)
+template <bool kAttn>
 __global__ void __launch_bounds__(kThreads, 1)
 dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainDev d) {
   extern __shared__ uint8_t smem_raw[];
@@ -251,9 +451,16 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   uint64_t* tq_full = acc_empty + 2;     // [kTq]
   uint64_t* tq_empty = tq_full + kTq;    // [kTq]
   uint64_t* dep_full = tq_empty + kTq;   // [kTq] the A producer has seen the row block's flag for the tile in this FIFO slot
-  int* tileq = reinterpret_cast<int*>(dep_full + kTq);  // [kTq]
+  uint64_t* attn_bars = dep_full + kTq;  // [chain_attn::kBarriers] attention item: qk_full, v_full, s_full, p_full, o_full
+  uint64_t* const at_qk_full = attn_bars, * const at_v_full = attn_bars + 1, * const at_s_full = attn_bars + 2,
+                * const at_p_full = attn_bars + 3, * const at_o_full = attn_bars + 4;
+  uint64_t* attn_done = attn_bars + chain_attn::kBarriers;  // an attention item has released the ring
+  int* tileq = reinterpret_cast<int*>(attn_done + 1);   // [kTq]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tileq + kTq);
-  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full) + 256;
+  int* pstart = reinterpret_cast<int*>(tmem_slot + 1);  // [n_phases + 1]
+  static_assert((3 * kStages + 4 + 3 * kTq + chain_attn::kBarriers + 1) * 8 + kTq * 4 + 4 + (kChainMaxPhases + 1) * 4 <= kCtrlBytes,
+                "control block overflows");
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full) + kCtrlBytes;
   float* ssx = reinterpret_cast<float*>(stage_base + kEpiWarps * kStgBytes);
   float* colvec = ssx + 2 * 2 * BM;
 
@@ -265,6 +472,21 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) ptx::prefetch_tmap(&maps.a[i]);
     for (int i = 0; i < 5; ++i) ptx::prefetch_tmap(&maps.w[i]);
+    ptx::mbar_init(at_qk_full, 2);  // A producer (Q) + W producer (K), each with its own byte count
+    ptx::mbar_init(at_v_full, 1);
+    ptx::mbar_init(at_s_full, 1);
+    ptx::mbar_init(at_p_full, kEpiWarps);
+    ptx::mbar_init(at_o_full, 1);
+    ptx::mbar_init(attn_done, 1);
+    if (kAttn) {
+      ptx::prefetch_tmap(&maps.at.q);
+      ptx::prefetch_tmap(&maps.at.kv_self[0]);
+      ptx::prefetch_tmap(&maps.at.kv_self[1]);
+      ptx::prefetch_tmap(&maps.at.ref);
+      ptx::prefetch_tmap(&maps.at.text);
+    }
+    pstart[0] = 0;
+    for (int p = 0; p < c.n_phases; ++p) pstart[p + 1] = pstart[p] + phase_items(d, p);
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full[i], 2);  // W producer + A producer (each arrives with its own byte count)
       ptx::mbar_init(&empty[i], 1);
@@ -287,23 +509,22 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   ptx::pdl_trigger();
 
-  int total_tiles = 0;
-  for (int p = 0; p < c.n_phases; ++p) total_tiles += kind_ntiles(c.kind[p]) * m_tiles;
-  // counters of this launch (dit_chain.cuh chain_ready_ints): tile-completion counts per (phase, row block), the
-  // "row block complete" flags the consumers poll (kept on other cache lines than the atomics), the claim counter
-  const int cstride = (4 * m_tiles + 31) & ~31;
+  const int total_tiles = pstart[c.n_phases];
+  // counters of this launch (dit_chain.cuh chain_ready_ints): completed items per (phase, row block), then the claim
+  // counter on a line of its own
   int* const done_cnt = d.b.ready;
-  int* const next_tile = d.b.ready + 2 * cstride;
+  int* const next_tile = d.b.ready + ((c.n_phases * m_tiles + 31) & ~31) + 32;
 
   // Consumer side of the tile FIFO: calls fn(tile, slot, parity) for every tile this CTA claimed, in claim order.  The
   // slot is handed back only after the tile has been processed, so per-slot state (dep_full) cannot be recycled early.
   auto walk = [&](auto&& fn) {
     uint32_t slot = 0, tph = 0;
+    int cur = 0;
     for (;;) {
       ptx::mbar_wait(&tq_full[slot], tph);
       const int g = tileq[slot];
       __syncwarp();
-      if (g >= 0) fn(decode_tile(g, c, m_tiles), slot, tph);
+      if (g >= 0) fn(decode_tile(g, d, pstart, cur), slot, tph);
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tq_empty[slot]);
       if (g < 0) break;
@@ -321,9 +542,11 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       if (lane == 0) g = atomicAdd(next_tile, 1);
       return __shfl_sync(0xffffffffu, g, 0);
     };
-    int g = claim(), g_raw = 0, wseq = 0;
+    int g = claim(), g_raw = 0, wseq = 0, cur = 0;
+    uint32_t attn_seen = 0, last_st = 0, last_ph = 0;  // last ring slot filled (and the round it was filled in)
     for (;;) {
       const bool live = g < total_tiles;
+      const uint32_t my_slot = slot, my_tph = tph;
       ptx::mbar_wait(&tq_empty[slot], tph ^ 1);
       if (lane == 0) {
         tileq[slot] = live ? g : -1;
@@ -332,9 +555,39 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       __syncwarp();
       if (++slot == kTq) { slot = 0; tph ^= 1; }
       if (!live) break;
-      const Tile t = decode_tile(g, c, m_tiles);
+      const Tile t = decode_tile(g, d, pstart, cur);
       if (lane == 0) { trace_ev(d.b.trace, wseq, 0); trace_ev(d.b.trace, wseq, 15, g + 1); }
       ++wseq;
+      if (kAttn && t.kind == CHAIN_ATTN) {
+        // ---- attention item: this warp loads K and V (one lane per 16-key group and dim half) into the ring, which the
+        // item borrows: first every operand of the previous tile must have been consumed
+        if (!waited) {
+          ptx::pdl_wait();
+          waited = true;
+        }
+        if (lane == 0) g_raw = atomicAdd(next_tile, 1);
+        const int b = t.m / d.q_tiles, h = t.n;
+        const chain_attn::Keys ak = chain_attn::keys_of(c, b);
+        if (issued > 0) ptx::mbar_wait(&empty[last_st], last_ph);
+        if (lane == 0) {
+          ptx::mbar_expect_tx(at_qk_full, static_cast<uint32_t>(ak.ng * 4096));
+          ptx::mbar_expect_tx(at_v_full, static_cast<uint32_t>(ak.ng * 4096));
+        }
+        __syncwarp();
+        const int kg = lane >> 1, hf = lane & 1, par = c.qkv_db ? (t.blk & 1) : 0;
+        const bool mine = kg < ak.ng, self = kg * 16 < ak.e0;
+        // the cross-attention caches do not depend on this launch: requested while the q|k|v phase may still be running
+        if (mine && !self) chain_attn::load_group(maps.at, c, ak, t.blk, par, b, h, kg, hf, ring, at_qk_full, at_v_full);
+        ptx::mbar_wait(&dep_full[my_slot], my_tph);  // raised by the A producer: q|k|v of the utterance are complete
+        if (t.p > 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        fence_proxy_async_all();
+        if (mine && self) chain_attn::load_group(maps.at, c, ak, t.blk, par, b, h, kg, hf, ring, at_qk_full, at_v_full);
+        __syncwarp();
+        ptx::mbar_wait(attn_done, attn_seen & 1);  // nothing may be loaded into the ring until the item is done with it
+        ++attn_seen;
+        g = __shfl_sync(0xffffffffu, g_raw, 0);
+        continue;
+      }
       int n0, bn;
       tile_cols(t.kind, t.n, n0, bn);
       const int wrow = t.blk * kind_wrows(t.kind) + n0;
@@ -364,6 +617,8 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
         }
         __syncwarp();
         ++issued;
+        last_st = st;
+        last_ph = ph;
         if (++st == kStages) { st = 0; ph ^= 1; }
       }
       g = __shfl_sync(0xffffffffu, g_raw, 0);  // the atomic's result is first needed here
@@ -372,14 +627,41 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
   } else if (warp == 1) {
     // ================================================================== A producer
     ptx::pdl_wait();
-    uint32_t st = 0, ph = 0;
+    uint32_t st = 0, ph = 0, attn_seen = 0, last_st = 0, last_ph = 0;
+    bool filled = false;
     int aseq = 0;
     walk([&](const Tile& t, uint32_t slot, uint32_t) {
       const int p = t.p, kind = t.kind, m = t.m;
       if (lane == 0) trace_ev(d.b.trace, aseq, 1);
+      if (kAttn && kind == CHAIN_ATTN) {
+        // q of the item's rows and k, v of the whole utterance: every row block the utterance touches
+        if (p > 0 && lane == 0) {
+          const int b = m / d.q_tiles;
+          const int m_lo = (b * c.T) / BM, m_hi = (b * c.T + c.T - 1) / BM;
+          for (int mm = m_lo; mm <= m_hi; ++mm) wait_flag(done_cnt + (p - 1) * m_tiles + mm, phase_target(d, p - 1, mm));
+        }
+        __syncwarp();
+        fence_proxy_async_all();  // q was written through the generic proxy by other CTAs; read below by TMA
+        if (lane == 0) ptx::mbar_arrive(&dep_full[slot]);
+        if (lane == 0) trace_ev(d.b.trace, aseq, 2);
+        ++aseq;
+        if (filled) ptx::mbar_wait(&empty[last_st], last_ph);  // the previous tile's operands have been consumed
+        if (ptx::elect_one()) {
+          const int b = m / d.q_tiles, q0 = (m % d.q_tiles) * chain_attn::kRows, par = c.qkv_db ? (t.blk & 1) : 0;
+          ptx::mbar_expect_tx(at_qk_full, chain_attn::kQBytes);
+          for (int hf = 0; hf < 2; ++hf) {
+            ptx::tma_load_3d(ring + chain_attn::kQOff + hf * (chain_attn::kRows * 128), &maps.at.q, at_qk_full, hf * 64, t.n,
+                             par * 3 * c.M + b * c.T + q0);
+          }
+        }
+        __syncwarp();
+        ptx::mbar_wait(attn_done, attn_seen & 1);  // the ring belongs to the item until then
+        ++attn_seen;
+        return;
+      }
       if (p > 0) {
         // all tiles of the previous phase that write rows [128 m, +128) must be done
-        if (lane == 0) wait_flag(done_cnt + (p - 1) * m_tiles + m, kind_ntiles(c.kind[p - 1]));
+        if (lane == 0) wait_flag(done_cnt + (p - 1) * m_tiles + m, phase_target(d, p - 1, m));
         __syncwarp();
         fence_proxy_async_all();  // generic-proxy writes of other CTAs -> this thread's async-proxy (TMA) reads
       }
@@ -402,6 +684,9 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
           }
         }
         __syncwarp();
+        last_st = st;
+        last_ph = ph;
+        filled = true;
         if (++st == kStages) { st = 0; ph ^= 1; }
       }
     });
@@ -410,9 +695,59 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
     ptx::pdl_wait();
     const uint64_t d0 = ptx::umma_desc_sw128(ptx::smem_u32(ring));
     uint32_t st = 0, ph = 0;
-    int li = 0;
+    int li = 0, tseq = 0;
+    uint32_t attn_seen = 0;
     walk([&](const Tile& t, uint32_t, uint32_t) {
       const int kind = t.kind;
+      if (kAttn && kind == CHAIN_ATTN) {
+        // ---- attention item: S = Q K^T into TMEM columns [0, 256), then O = P V into [256, 384).  Both accumulator
+        // buffers of the GEMM tiles are idle here (their epilogues ran before this item's) and li does not advance.
+        const chain_attn::Keys ak = chain_attn::keys_of(c, t.m / d.q_tiles);
+        const uint32_t par = attn_seen & 1;
+        ++attn_seen;
+        ptx::mbar_wait(at_qk_full, par);
+        ptx::tc_fence_after();
+        if (lane == 0) trace_ev(d.b.trace, tseq, 3);
+        if (ptx::elect_one()) {
+          if (ak.ng > 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BM, static_cast<uint32_t>(ak.ng * 16));
+            const uint64_t dq = d0 + (chain_attn::kQOff >> 4), dk = d0 + (chain_attn::kKOff >> 4);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                ptx::umma_bf16(tmem_base + chain_attn::kSCol, dq + kb * ((chain_attn::kRows * 128) >> 4) + 2 * k,
+                               dk + kb * ((chain_attn::kMaxKeys * 128) >> 4) + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          ptx::umma_commit(at_s_full);
+        }
+        __syncwarp();
+        ptx::mbar_wait(at_v_full, par);
+#ifdef STTS_ATTN_DEBUG_TRACE
+        if (lane == 0) trace_ev(d.b.trace, tseq, 3);
+#endif
+        ptx::mbar_wait(at_p_full, par);  // the epilogue warps have written P (and are done reading S)
+        ptx::tc_fence_after();
+#ifdef STTS_ATTN_DEBUG_TRACE
+        if (lane == 0) trace_ev(d.b.trace, tseq, 1);
+#endif
+        if (ptx::elect_one()) {
+          const uint32_t idesc = ptx::umma_idesc_bf16(BM, chain_attn::kHD) | chain_attn::kIdescBMajorMN;
+          const uint64_t dp = d0 + (chain_attn::kPOff >> 4);
+          const uint32_t v_addr = ptx::smem_u32(ring) + chain_attn::kVOff;
+          for (int kg = 0; kg < ak.ng; ++kg) {  // K step = one 16-key group
+            ptx::umma_bf16(tmem_base + chain_attn::kOCol, dp + (kg >> 2) * ((chain_attn::kRows * 128) >> 4) + 2 * (kg & 3),
+                           chain_attn::umma_desc_mn_sw128(v_addr + kg * 2048, chain_attn::kMaxKeys * 128), idesc, kg != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(at_o_full);
+        }
+        __syncwarp();
+        if (lane == 0) trace_ev(d.b.trace, tseq, 4);
+        ++tseq;
+        return;
+      }
       int n0, bn;
       tile_cols(kind, t.n, n0, bn);
       const uint32_t idesc = ptx::umma_idesc_bf16(BM, static_cast<uint32_t>(bn));
@@ -425,7 +760,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       for (int it = 0; it < iters; ++it) {
         ptx::mbar_wait(&full[st], ph);
         ptx::tc_fence_after();
-        if (it == 0 && lane == 0) trace_ev(d.b.trace, li, 3);
+        if (it == 0 && lane == 0) trace_ev(d.b.trace, tseq, 3);
         if (ptx::elect_one()) {
           const int nkb = kblocks - it * kpb < kpb ? kblocks - it * kpb : kpb;
           // descriptor start-address field is (addr >> 4)
@@ -446,8 +781,9 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       }
       if (ptx::elect_one()) ptx::umma_commit(&acc_full[ab]);
       __syncwarp();
-      if (lane == 0) trace_ev(d.b.trace, li, 4);
+      if (lane == 0) trace_ev(d.b.trace, tseq, 4);
       ++li;
+      ++tseq;
     });
   } else if (warp >= kEpiWarp0) {
     // ================================================================== epilogue (8 warps)
@@ -460,9 +796,32 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
     e.ssx = ssx;
     // warp-private column vectors of the current tile (fold vectors, head norm weights): fetched BEFORE the waits
     float* cv = colvec + (warp - kEpiWarp0) * kColvecFloats;
-    int li = 0, hcount = 0;
+    int li = 0, hcount = 0, tseq = 0;
+    uint32_t attn_seen = 0;
     walk([&](const Tile& t, uint32_t slot, uint32_t tph) {
       const int p = t.p, kind = t.kind, blk = t.blk, m = t.m, n = t.n;
+      if constexpr (kAttn) if (kind == CHAIN_ATTN) {
+        // ---- attention item (utterance b, 128 queries from q0, head n): softmax + output on these eight warps
+        const int b = m / d.q_tiles, q0 = (m % d.q_tiles) * chain_attn::kRows;
+        ptx::mbar_wait(&dep_full[slot], tph);
+        if (p > 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");  // the gate rows come from the q|k|v|gate phase
+        if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, tseq, 5);
+        hcount = attn_epilogue(d, e, tmem_base, ring, at_s_full, at_p_full, at_o_full, attn_seen & 1, hcount, b, n, q0,
+                               d.b.trace != nullptr && tseq < 64 ? d.b.trace + (static_cast<size_t>(blockIdx.x) * 64 + tseq) * 16 : nullptr);
+        ++attn_seen;
+        if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, tseq, 6);
+        fence_proxy_async_all();  // ob is read by TMA (to_out); the ring is next written by TMA
+        ptx::named_bar_sync(5, kEpiWarps * 32);
+        if (warp == kEpiWarp0 && lane == 0) {
+          ptx::mbar_arrive(attn_done);
+          __threadfence();
+          const int r0 = b * c.T + q0, r1 = b * c.T + min(q0 + chain_attn::kRows, c.T) - 1;
+          for (int mm = r0 / BM; mm <= r1 / BM; ++mm) atomicAdd(done_cnt + p * m_tiles + mm, 1);
+          trace_ev(d.b.trace, tseq, 7);
+        }
+        ++tseq;
+        return;
+      }
       int n0, bn;
       tile_cols(kind, n, n0, bn);
       const int ab = li & 1;
@@ -552,7 +911,7 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       // ---- (3) the accumulator
       ptx::mbar_wait(&acc_full[ab], (li >> 1) & 1);
       ptx::tc_fence_after();
-      if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, li, 5);
+      if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, tseq, 5);
 
       if (e.okbits != 0u) {
         if (head_tile) {
@@ -577,7 +936,8 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
             rn = rsqrtf(tot * (1.0f / kChainHD) + 1e-6f);
             ++hcount;
           }
-          bf16* out = d.b.qkv + static_cast<long long>(kind3) * c.M * (kChainH * kChainHDP) + head * kChainHDP;
+          bf16* out = d.b.qkv + static_cast<long long>(kind3 + (c.qkv_db ? 3 * (blk & 1) : 0)) * c.M * (kChainH * kChainHDP) +
+                      head * kChainHDP;
 #pragma unroll 1
           for (int j = 0; j < 2; ++j) {
             const int cc = e.half + 2 * j;
@@ -724,15 +1084,16 @@ dit_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__
       // ... and with its share of the tile.  Publish the tile once all eight warps are done: each thread makes its
       // global writes visible to the async proxy (the consumer reads them with TMA), the barrier orders them before
       // thread 0, whose gpu-scope fence + atomic is the (cumulative) release.
-      if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, li, 6);
+      if (warp == kEpiWarp0 && lane == 0) trace_ev(d.b.trace, tseq, 6);
       fence_proxy_async_all();
       ptx::named_bar_sync(5, kEpiWarps * 32);
       if (warp == kEpiWarp0 && lane == 0) {
         __threadfence();
         atomicAdd(done_cnt + p * m_tiles + m, 1);  // the consumers' (one per CTA) pollers watch this count
-        trace_ev(d.b.trace, li, 7);
+        trace_ev(d.b.trace, tseq, 7);
       }
       ++li;
+      ++tseq;
     });
   } else {
     ptx::pdl_wait();  // warp 3: idle
@@ -869,14 +1230,28 @@ bool make_map(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, u
 }  // namespace
 
 cudaError_t launch_dit_chain(cudaStream_t st, const ChainWeights& w, const ChainBuffers& b, const ChainCall& c) {
-  if (c.M < 1 || c.T < 1 || c.n_phases < 1 || c.n_phases > 4 || !c.mod || !c.fold || !b.ready) return cudaErrorInvalidValue;
+  if (c.M < 1 || c.T < 1 || c.n_phases < 1 || c.n_phases > kChainMaxPhases || !c.mod || !c.fold || !b.ready) {
+    return cudaErrorInvalidValue;
+  }
+  bool has_attn = false;
   for (int p = 0; p < c.n_phases; ++p) {
-    if (c.kind[p] < CHAIN_QKVG || c.kind[p] > CHAIN_VEL || c.blk[p] < 0 || c.blk[p] >= kChainBlocks) return cudaErrorInvalidValue;
+    if (c.kind[p] < CHAIN_QKVG || c.kind[p] > CHAIN_ATTN || c.blk[p] < 0 || c.blk[p] >= kChainBlocks) return cudaErrorInvalidValue;
+    has_attn = has_attn || c.kind[p] == CHAIN_ATTN;
+  }
+  const int m_tiles = (c.M + BM - 1) / BM;
+  if (has_attn) {
+    const ChainAttn& a = c.attn;
+    if (a.B < 1 || a.B * c.T != c.M || a.R < 1 || a.P < 1 || !a.ref_len || !a.ph_len || !a.kv_ref || !a.kv_text || !c.frames ||
+        m_tiles > kChainMaxRowBlocks || !chain_attn_fits(c.T, a.R, a.P)) {
+      return cudaErrorInvalidValue;
+    }
   }
   static PerDeviceOnce attr_set;
   {
-    const cudaError_t err = attr_set.run(
-        [] { return cudaFuncSetAttribute(dit_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); });
+    const cudaError_t err = attr_set.run([] {
+      const cudaError_t e0 = cudaFuncSetAttribute(dit_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      return e0 != cudaSuccess ? e0 : cudaFuncSetAttribute(dit_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    });
     if (err != cudaSuccess) return err;
   }
   static int num_sms = 0;
@@ -899,15 +1274,45 @@ cudaError_t launch_dit_chain(cudaStream_t st, const ChainWeights& w, const Chain
   d.w = w;
   d.b = b;
   d.c = c;
-  d.m_tiles = (c.M + BM - 1) / BM;
+  d.m_tiles = m_tiles;
+  d.q_tiles = (c.T + chain_attn::kRows - 1) / chain_attn::kRows;
+  d.attn_items = 0;
+  for (int m = 0; m < kChainMaxRowBlocks; ++m) d.attn_target[m] = 0;
+  if (has_attn) {
+    const ChainAttn& a = c.attn;
+    auto make3 = [&](CUtensorMap* mp, const bf16* ptr, uint64_t rows, uint32_t box_rows) {
+      const uint64_t dims[3] = {kChainHDP, kChainH, rows};
+      const uint64_t str[2] = {kChainHDP * 2, kChainH * kChainHDP * 2};
+      const uint32_t box[3] = {64, 1, box_rows};
+      return tmap_tiled(mp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ptr, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    const size_t half = static_cast<size_t>(3) * M * kChainH * kChainHDP;  // elements of one q|k|v buffer
+    ok = make3(&maps.at.q, b.qkv, (c.qkv_db ? 6 : 3) * M, chain_attn::kRows) && make3(&maps.at.kv_self[0], b.qkv, 3 * M, 16) &&
+         make3(&maps.at.kv_self[1], b.qkv + (c.qkv_db ? half : 0), 3 * M, 16) &&
+         make3(&maps.at.ref, a.kv_ref, static_cast<uint64_t>(kChainBlocks) * 2 * a.B * a.R, 16) &&
+         make3(&maps.at.text, a.kv_text, static_cast<uint64_t>(kChainBlocks) * 2 * a.B * a.P, 16);
+    if (!ok) return cudaErrorInvalidValue;
+    d.attn_items = a.B * d.q_tiles * kChainH;
+    for (int u = 0; u < a.B; ++u) {
+      for (int qt = 0; qt < d.q_tiles; ++qt) {
+        const int r0 = u * c.T + qt * chain_attn::kRows;
+        const int r1 = u * c.T + (qt * chain_attn::kRows + chain_attn::kRows < c.T ? qt * chain_attn::kRows + chain_attn::kRows : c.T) - 1;
+        for (int m = r0 / BM; m <= r1 / BM; ++m) d.attn_target[m] += kChainH;
+      }
+    }
+  } else {
+    maps.at = chain_attn::Maps{};
+  }
   // every CTA must be resident at the same time (the phases wait on each other): one CTA per SM, never more
   int most = 0;
   for (int p = 0; p < c.n_phases; ++p) {
     const int nt = c.kind[p] == CHAIN_QKVG ? 29 : (c.kind[p] == CHAIN_W13 ? 25 : (c.kind[p] == CHAIN_VEL ? 1 : 15));
-    most = nt * d.m_tiles > most ? nt * d.m_tiles : most;
+    const int items = c.kind[p] == CHAIN_ATTN ? d.attn_items : nt * d.m_tiles;
+    most = items > most ? items : most;
   }
   const int grid = most < num_sms ? most : num_sms;
-  const cudaError_t le = launch_k(dit_chain_kernel, dim3(grid), dim3(kThreads), kSmem, st, maps, d);
+  const cudaError_t le = has_attn ? launch_k(dit_chain_kernel<true>, dim3(grid), dim3(kThreads), kSmem, st, maps, d)
+                                  : launch_k(dit_chain_kernel<false>, dim3(grid), dim3(kThreads), kSmem, st, maps, d);
   count_launch();
   return le != cudaSuccess ? le : cudaGetLastError();
 }

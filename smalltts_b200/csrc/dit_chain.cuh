@@ -19,7 +19,11 @@
 namespace stts {
 
 
-enum ChainKind : int { CHAIN_QKVG = 0, CHAIN_OUT = 1, CHAIN_W13 = 2, CHAIN_W2 = 3, CHAIN_VEL = 4 };
+// CHAIN_ATTN: the joint self | ref | text attention of a block (chain_attn.cuh) as a phase between q|k|v|gate and to_out,
+// so that a whole denoiser evaluation (1 + 12 x 5 phases) is ONE launch.
+enum ChainKind : int { CHAIN_QKVG = 0, CHAIN_OUT = 1, CHAIN_W13 = 2, CHAIN_W2 = 3, CHAIN_VEL = 4, CHAIN_ATTN = 5 };
+constexpr int kChainMaxPhases = 64;
+constexpr int kChainMaxRowBlocks = 64;  // launches with a CHAIN_ATTN phase: M <= 64 * 128 rows
 
 constexpr int kChainD = 960, kChainH = 8, kChainHD = 120, kChainHDP = 128, kChainFF = 2400, kChainBlocks = 12;
 constexpr int kChainQKVG = 3 * kChainH * kChainHDP + kChainD;  // 4032 rows: q | k | v head-padded, then the gate
@@ -56,13 +60,20 @@ struct ChainBuffers {  // activations of one denoiser evaluation, M = B*T rows
   float* x = nullptr;      // [M][960]  fp32 residual stream
   bf16* xb = nullptr;      // [M][960]  bf16(x * (1 + scale of the consuming LayerNorm))
   float* stats = nullptr;  // [M][30][2] partial (sum, sumsq) of x per 32-column chunk
-  bf16* qkv = nullptr;     // [3][M][1024]  q | k | v, [row][head][128]
+  bf16* qkv = nullptr;     // [3][M][1024]  q | k | v, [row][head][128]; [2][3][M][1024] (by block parity, zero-initialised
+                           // once) when ChainCall::qkv_db
   float* gate = nullptr;   // [M][960]  pre-sigmoid attention gate
-  const bf16* ob = nullptr;  // [M][1024] gated attention output (written by the attention kernel)
+  bf16* ob = nullptr;      // [M][1024] gated attention output (attention kernel between launches, or a CHAIN_ATTN phase)
   bf16* hb = nullptr;      // [M][2400] SwiGLU hidden
   float* vel = nullptr;    // [M][64]
   int* ready = nullptr;    // zero-initialised counters of THIS launch (chain_ready_ints of them)
   unsigned long long* trace = nullptr;  // optional role timeline [grid][64 tiles][16] (tools/trace_chain.py)
+};
+
+struct ChainAttn {  // cross-attention caches of the conditions (engine.cu stts_cond); needed by CHAIN_ATTN phases only
+  int B = 0, R = 0, P = 0;                                 // utterances, max reference frames, max phonemes
+  const int *ref_len = nullptr, *ph_len = nullptr;         // [B] (device)
+  const bf16 *kv_ref = nullptr, *kv_text = nullptr;        // [12][2][B, R | P, 8, 128]
 };
 
 struct ChainCall {
@@ -71,13 +82,20 @@ struct ChainCall {
   const float* mod = nullptr;   // adaLN table of the timestep [kChainModLd] (gates already tanh'ed)
   const float* fold = nullptr;  // folded vectors of the timestep [kFoldFloats]
   int n_phases = 0;
-  int kind[4] = {0, 0, 0, 0};
-  int blk[4] = {0, 0, 0, 0};
+  int kind[kChainMaxPhases] = {};
+  int blk[kChainMaxPhases] = {};
+  // q|k|v of block i go to half (i & 1) of a double buffer: with attention inside the launch, block i + 1's q|k|v GEMM of
+  // one row block may run while attention items of block i still read K / V rows of that row block for other queries.
+  bool qkv_db = false;
+  ChainAttn attn;
 };
 
-// Number of int counters one launch needs: completed tiles per (phase, row block) | "row block complete" flags | the
-// tile-claim counter, each group on its own 128-byte lines.
-inline int chain_ready_ints(int M) { return 2 * ((4 * ((M + 127) / 128) + 31) / 32 * 32) + 32; }
+// Number of int counters one launch needs: completed work items per (phase, row block), then (on its own 128-byte line)
+// the tile-claim counter.
+inline int chain_ready_ints(int M, int n_phases = 4) { return (n_phases * ((M + 127) / 128) + 31) / 32 * 32 + 64; }
+
+// CHAIN_ATTN phases keep all keys of an utterance (self | ref | text, each padded to 16) in one 256-column accumulator.
+inline bool chain_attn_fits(int T, int R, int P) { return ((T + 15) & ~15) + ((R + 15) & ~15) + ((P + 15) & ~15) <= 256; }
 
 cudaError_t launch_dit_chain(cudaStream_t st, const ChainWeights& w, const ChainBuffers& b, const ChainCall& c);
 

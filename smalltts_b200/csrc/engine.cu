@@ -140,6 +140,12 @@ struct stts_engine {
   bool use_split = false;   // STTS_SPLITK=1: split-K for the wave-quantised vocoder GEMMs.  Off: measured slower (below)
   bool use_chain = true;    // STTS_NO_CHAIN=1: generic 8-launches-per-block path (also used for per-utterance timesteps)
   bool chain_split = false; // STTS_CHAIN_SPLIT=1: one GEMM per chain launch (debug / A-B timing of the in-kernel dependencies)
+  // attention inside the chained kernel (csrc/chain_attn.cuh): 1 = a whole denoiser evaluation is ONE launch (61
+  // phases), 2 = one launch per block (attention, to_out, w1|w3, w2, next q|k|v|gate), 0 = stand-alone attention kernel
+  // between chain launches.  Default 0: measured on B200 at the headline shape the one-launch schedule is correct but
+  // slower (3.72 vs 2.93 ms per 4-step loop): the item's serial chain (loads -> scores -> softmax ->
+  // P V -> store -> publish) is longer than what the stand-alone kernel costs between two launches.
+  int chain_attn = 0;       // STTS_CHAIN_ATTN=0|1|2
 
   // packed vocoder weights
   bf16* stem_w;
@@ -746,6 +752,8 @@ const float* cached_fold(stts_engine* e, float t) {
 
 // ------------------------------------------------------------------ denoiser (dit.py:316-327, model.py:97-100)
 constexpr int kChainLaunches = NBLK + 1;  // q|k|v|gate of block 0, then one launch per block (the last ends in the velocity head)
+constexpr int kEvalPhases = 1 + 5 * NBLK;  // one-launch evaluation: q|k|v|gate, then (attention, to_out, w1|w3, w2, next) x 12
+static_assert(kEvalPhases <= kChainMaxPhases, "phase table of the chained kernel too small");
 struct DenoiseWs {
   Tmp<float> h, x, qkvg, v, stats;
   Tmp<bf16> hm, c1, a, qkv, ob, hb;
@@ -754,11 +762,20 @@ struct DenoiseWs {
   void alloc(cudaStream_t st, long long M) {
     h.alloc(st, M * D); x.alloc(st, M * D); qkvg.alloc(st, M * 4 * D);
     hm.alloc(st, M * DP); c1.alloc(st, M * DP); a.alloc(st, M * D);
-    qkv.alloc(st, 3 * M * H * HDP); ob.alloc(st, M * H * HDP);
+    // two q|k|v buffers (by block parity) for the launches that run attention inside the chain.  Zeroed once: attention
+    // fetches whole 16-key boxes, and a masked key's V row must never hold a NaN pattern left behind by an earlier owner
+    // of the memory (0 x NaN), even before its row block has been written for the first time.
+    qkv.alloc(st, 2 * 3 * M * H * HDP); ob.alloc(st, M * H * HDP);
+    CK(cudaMemsetAsync(qkv.p, 0, static_cast<size_t>(2) * 3 * M * H * HDP * sizeof(bf16), st));
     qb = qkv.p; kb = qb + M * H * HDP; vb = kb + M * H * HDP;
     hb.alloc(st, M * FF);
     stats.alloc(st, M * 2 * kChainParts);
-    ready.alloc(st, static_cast<size_t>(kChainLaunches) * chain_ready_ints(static_cast<int>(M)));
+    ready.alloc(st, ready_ints(M));
+  }
+  static size_t ready_ints(long long M) {  // the largest of the three launch schedules of denoise()
+    const size_t a = static_cast<size_t>(kChainLaunches) * chain_ready_ints(static_cast<int>(M), 5);
+    const size_t b = chain_ready_ints(static_cast<int>(M), kEvalPhases);
+    return a > b ? a : b;
   }
 };
 
@@ -792,14 +809,33 @@ void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_b
   }
   if (fold != nullptr && ld_mod == 0 && e->use_chain) {
     const int Mi = static_cast<int>(M);
-    const int ready_ints = chain_ready_ints(Mi);
+    // attention inside the chain: all keys of an utterance in one 256-column accumulator, and the per-row-block target
+    // table must fit (M <= 64 x 128 rows); other shapes run the stand-alone attention kernel between chain launches
+    const int attn_mode =
+        (Mi + 127) / 128 <= kChainMaxRowBlocks && chain_attn_fits(T, c->R, c->P) && !e->chain_split ? e->chain_attn : 0;
+    const int ready_ints = chain_ready_ints(Mi, 5);
     ChainBuffers cb;
     cb.x = ws.x; cb.xb = ws.a; cb.stats = ws.stats; cb.qkv = ws.qkv; cb.gate = ws.qkvg; cb.ob = ws.ob; cb.hb = ws.hb;
     cb.vel = v_out;
     ChainCall cc;
     cc.M = Mi; cc.T = T; cc.frames = frames_dev; cc.mod = mod; cc.fold = fold;
-    CK(cudaMemsetAsync(ws.ready, 0, static_cast<size_t>(kChainLaunches) * ready_ints * sizeof(int), st));
+    cc.attn.B = B; cc.attn.R = c->R; cc.attn.P = c->P; cc.attn.ref_len = c->ref_len; cc.attn.ph_len = c->ph_len;
+    cc.attn.kv_ref = c->kv_ref; cc.attn.kv_text = c->kv_text;
+    cc.qkv_db = attn_mode != 0;
+    CK(cudaMemsetAsync(ws.ready, 0, DenoiseWs::ready_ints(M) * sizeof(int), st));
     CK(chain_stats_cast(st, ws.x, Mi, mod + D /*scale_msa of block 0*/, ws.a, ws.stats));
+    if (attn_mode == 1) {  // the whole evaluation in one launch
+      cb.ready = ws.ready;
+      cc.n_phases = 0;
+      auto add = [&](int kind, int blk) { cc.kind[cc.n_phases] = kind; cc.blk[cc.n_phases] = blk; ++cc.n_phases; };
+      add(CHAIN_QKVG, 0);
+      for (int i = 0; i < NBLK; ++i) {
+        add(CHAIN_ATTN, i); add(CHAIN_OUT, i); add(CHAIN_W13, i); add(CHAIN_W2, i);
+        if (i + 1 < NBLK) add(CHAIN_QKVG, i + 1); else add(CHAIN_VEL, 0);
+      }
+      CK(launch_dit_chain(st, e->chain_w, cb, cc));
+      return;
+    }
     int launch = 0;
     auto run = [&](std::initializer_list<std::pair<int, int>> phases) {
       cb.ready = ws.ready + launch * ready_ints;
@@ -817,6 +853,12 @@ void denoise(stts_engine* e, const stts_cond* c, DenoiseWs& ws, const bf16* xt_b
       ++launch;
     };
     run({{CHAIN_QKVG, 0}});
+    if (attn_mode == 2) {  // one launch per block
+      for (int i = 0; i < NBLK; ++i) {
+        run({{CHAIN_ATTN, i}, {CHAIN_OUT, i}, {CHAIN_W13, i}, {CHAIN_W2, i}, {i + 1 < NBLK ? CHAIN_QKVG : CHAIN_VEL, i + 1 < NBLK ? i + 1 : 0}});
+      }
+      return;
+    }
     for (int i = 0; i < NBLK; ++i) {
       AttnSeg segs[3];
       segs[0].k = ws.kb; segs[0].v = ws.vb; segs[0].len = frames_dev; segs[0].n_max = T;
@@ -1363,6 +1405,8 @@ int stts_create(const stts_config* cfg, stts_engine** out) {
     e->use_chain = !(nc && nc[0] == '1');
     const char* cs = getenv("STTS_CHAIN_SPLIT");
     e->chain_split = cs && cs[0] == '1';
+    const char* ca = getenv("STTS_CHAIN_ATTN");
+    if (ca && ca[0] >= '0' && ca[0] <= '2') e->chain_attn = ca[0] - '0';
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, e->device));
     uint64_t thr = UINT64_MAX;
@@ -1948,11 +1992,15 @@ int stts_test_chain(stts_engine* e, const stts_test_chain_args* a) {
   return guard_impl(e, [&] {
     ChainBuffers b;
     b.x = a->x; b.xb = static_cast<bf16*>(a->xb); b.stats = a->stats; b.qkv = static_cast<bf16*>(a->qkv); b.gate = a->gate;
-    b.ob = static_cast<const bf16*>(a->ob); b.hb = static_cast<bf16*>(a->hb); b.vel = a->vel; b.ready = a->ready;
+    b.ob = static_cast<bf16*>(a->ob); b.hb = static_cast<bf16*>(a->hb); b.vel = a->vel; b.ready = a->ready;
     b.trace = reinterpret_cast<unsigned long long*>(a->trace);
     ChainCall c;
     c.M = a->M; c.T = a->T; c.frames = a->frames; c.mod = a->mod; c.fold = a->fold; c.n_phases = a->n_phases;
-    for (int i = 0; i < 4; ++i) { c.kind[i] = a->kind[i]; c.blk[i] = a->blk[i]; }
+    if (a->n_phases < 0 || a->n_phases > kChainMaxPhases) throw Err(STTS_ERR_INVALID, "n_phases out of range");
+    for (int i = 0; i < a->n_phases; ++i) { c.kind[i] = a->kind[i]; c.blk[i] = a->blk[i]; }
+    c.qkv_db = a->qkv_db != 0;
+    c.attn.B = a->B; c.attn.R = a->R; c.attn.P = a->P; c.attn.ref_len = a->ref_len; c.attn.ph_len = a->ph_len;
+    c.attn.kv_ref = static_cast<const bf16*>(a->kv_ref); c.attn.kv_text = static_cast<const bf16*>(a->kv_text);
     CK(launch_dit_chain(e->st, chain_weights_of(a), b, c));
     if (!e->test_async) CK(cudaStreamSynchronize(e->st));
   });

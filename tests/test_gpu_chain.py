@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 D, H, HD, HDP, FF, NBLK = 960, 8, 120, 128, 2400, 12
 NQ, N13, PARTS = 3 * H * HDP + D, 2 * FF, 30
 MOD_LD = NBLK * 6 * D + 2 * D
-QKVG, OUT, W13, W2, VEL = range(5)
+QKVG, OUT, W13, W2, VEL, ATTN = range(6)
 
 
 @pytest.fixture(scope="module")
@@ -41,7 +41,7 @@ class Case:
     """Random weights of TWO blocks (blk 1 and 2; the rest of the stacked arrays stays zero), one timestep's adaLN
     table and activations for M rows of utterances of T rows."""
 
-    def __init__(self, M, T, frames, seed=0):
+    def __init__(self, M, T, frames, seed=0, R=0, P=0, ref_len=None, ph_len=None):
         g = torch.Generator(device="cuda").manual_seed(seed)
         r = lambda *s, scale=1.0: torch.randn(*s, device="cuda", generator=g) * scale  # noqa: E731
         self.M, self.T = M, T
@@ -97,7 +97,18 @@ class Case:
         self.ob.view(M, H, HDP)[:, :, :HD] = _bf(r(M, H, HD))
         self.xb = torch.zeros(M, D, device="cuda", dtype=torch.bfloat16)
         self.stats = torch.zeros(M, PARTS, 2, device="cuda")
-        self.qkv = torch.zeros(3, M, H * HDP, device="cuda", dtype=torch.bfloat16)
+        self.qkv = torch.zeros(2, 3, M, H * HDP, device="cuda", dtype=torch.bfloat16)  # [block parity] when qkv_db
+        self.qkv_db = 0
+        # cross-attention caches of the conditions (only read by ATTN phases)
+        self.B, self.R, self.P = M // T, R, P
+        self.kv_ref = self.kv_text = self.ref_len = self.ph_len = None
+        if R:
+            self.kv_ref = torch.zeros(NBLK, 2, self.B, R, H, HDP, device="cuda", dtype=torch.bfloat16)
+            self.kv_text = torch.zeros(NBLK, 2, self.B, P, H, HDP, device="cuda", dtype=torch.bfloat16)
+            self.kv_ref[..., :HD] = _bf(r(NBLK, 2, self.B, R, H, HD))
+            self.kv_text[..., :HD] = _bf(r(NBLK, 2, self.B, P, H, HD))
+            self.ref_len = torch.tensor(ref_len, dtype=torch.int32, device="cuda")
+            self.ph_len = torch.tensor(ph_len, dtype=torch.int32, device="cuda")
         self.gate = torch.zeros(M, D, device="cuda")
         self.hb = torch.zeros(M, FF, device="cuda", dtype=torch.bfloat16)
         self.vel = torch.zeros(M, 64, device="cuda")
@@ -115,13 +126,14 @@ class Case:
 
         a = _cabi.ChainArgs()
         for n in ("wqkvg", "wo", "w13", "w2", "wvel", "bqkvg", "b13", "b2", "bvel", "qn", "kn", "cos_t", "sin_t", "x", "xb",
-                  "stats", "qkv", "gate", "ob", "hb", "vel", "frames", "mod", "fold"):
+                  "stats", "qkv", "gate", "ob", "hb", "vel", "frames", "mod", "fold", "kv_ref", "kv_text", "ref_len", "ph_len"):
             t = getattr(self, n)
             setattr(a, n, None if t is None else _ptr(t))
-        n_ready = 2 * ((4 * ((self.M + 127) // 128) + 31) // 32 * 32) + 32  # dit_chain.cuh chain_ready_ints
+        n_ready = (len(phases) * ((self.M + 127) // 128) + 31) // 32 * 32 + 64  # dit_chain.cuh chain_ready_ints
         self.ready = torch.zeros(n_ready, dtype=torch.int32, device="cuda")
         a.ready = _ptr(self.ready)
         a.M, a.T, a.n_phases = self.M, self.T, len(phases)
+        a.B, a.R, a.P, a.qkv_db = self.B, self.R, self.P, self.qkv_db
         for i, (k, b) in enumerate(phases):
             a.kind[i], a.blk[i] = k, b
         return a
@@ -229,7 +241,7 @@ def test_fold_table_stats_cast_and_qkvg_phase(eng, M, T, frames):
 
     c.run(eng, [(QKVG, 1)])
     q, k, v, g = ref_qkvg(c, 1, c.x)
-    got = c.qkv.float().view(3, M, H, HDP)
+    got = c.qkv[0].float().view(3, M, H, HDP)
     assert float(got[..., HD:].abs().max()) == 0.0  # head padding stays zero
     for i, (name, want) in enumerate((("q", q), ("k", k), ("v", v))):
         err = rel(got[i, :, :, :HD], want)
@@ -296,7 +308,7 @@ def test_four_phase_chain_equals_single_launches_and_the_textbook_block(eng, M, 
     x2, _ = ref_mlp(c, 1, x1)
     assert rel(c.x, x2) < 1e-2
     q, k, v, g = ref_qkvg(c, 2, x2)
-    got = c.qkv.float().view(3, M, H, HDP)
+    got = c.qkv[0].float().view(3, M, H, HDP)
     for i, want in enumerate((q, k, v)):
         assert rel(got[i, :, :, :HD], want) < 2e-2, i
     assert rel(c.gate, g) < 2e-2
@@ -320,3 +332,106 @@ def test_last_chain_ends_in_the_velocity_head(eng):
     err = rel(c.vel, vel)
     print("chain velocity", err)
     assert err < 2e-2
+
+
+# ---------------------------------------------------------------- attention as a phase of the chain (chain_attn.cuh)
+def ref_attention(c, blk, qkv, gate):
+    """Joint self | ref | text attention of block blk (dit.py:110-119,131-135) from bf16 q|k|v [3, M, H*HDP] and the
+    pre-sigmoid gate [M, D]: -> [M, H*HDP] fp32 (head padding zero).  Keys beyond the valid lengths are masked; query rows
+    beyond frames[b] are computed like any other (to_out masks them)."""
+    M, T, B = c.M, c.T, c.B
+    q, k, v = (qkv[i].float().view(B, T, H, HDP) for i in range(3))
+    out = torch.zeros(B, T, H, HDP, device="cuda")
+    for b in range(B):
+        n0, n1, n2 = int(c.frames[b]), int(c.ref_len[b]), int(c.ph_len[b])
+        ks = torch.cat([k[b, :n0], c.kv_ref[blk, 0, b, :n1].float(), c.kv_text[blk, 0, b, :n2].float()])  # [N, H, HDP]
+        vs = torch.cat([v[b, :n0], c.kv_ref[blk, 1, b, :n1].float(), c.kv_text[blk, 1, b, :n2].float()])
+        sc = torch.einsum("qhd,khd->hqk", q[b], ks) * HD ** -0.5
+        out[b] = torch.einsum("hqk,khd->qhd", sc.softmax(-1), vs)
+    out = out.view(M, H, HDP)
+    out[:, :, :HD] *= torch.sigmoid(gate.view(M, H, HD))
+    return out.view(M, H * HDP)
+
+
+ATTN_CASES = [
+    # M, T, frames, R, P, ref_len, ph_len
+    (640, 80, [80] * 8, 75, 60, [75, 60, 75, 30, 75, 75, 1, 75], [60, 55, 41, 60, 13, 60, 60, 60]),
+    (210, 70, [70, 33, 1], 20, 17, [20, 1, 7], [17, 16, 1]),
+    (450, 150, [150, 97, 131], 40, 30, [40, 17, 33], [30, 3, 16]),  # two query tiles per utterance; 160 + 48 + 32 keys
+]
+
+
+@pytest.mark.parametrize("M,T,frames,R,P,ref_len,ph_len", ATTN_CASES)
+@pytest.mark.parametrize("blk", [1, 2])
+def test_attention_phase_alone(eng, M, T, frames, R, P, ref_len, ph_len, blk):
+    c = Case(M, T, frames, seed=5, R=R, P=P, ref_len=ref_len, ph_len=ph_len)
+    c.make_fold(eng)
+    c.qkv_db = 1
+    g = torch.Generator(device="cuda").manual_seed(50 + blk)
+    par = blk & 1
+    c.qkv[par].view(3, M, H, HDP)[..., :HD] = _bf(torch.randn(3, M, H, HD, device="cuda", generator=g))
+    # the OTHER half holds NaNs: an item must never touch it
+    c.qkv[1 - par].fill_(float("nan"))
+    c.gate.copy_(torch.randn(M, D, device="cuda", generator=g))
+    c.ob.fill_(float("nan"))
+    c.run(eng, [(ATTN, blk)])
+    want = ref_attention(c, blk, c.qkv[par], c.gate)
+    assert torch.isfinite(c.ob.float()).all()
+    assert float(c.ob.float().view(M, H, HDP)[..., HD:].abs().max()) == 0.0
+    err = rel(c.ob, want)
+    print("attention phase", err)
+    assert err < 1e-2
+    counts = c.ready[: (M + 127) // 128].tolist()  # items per row block: 8 heads x query tiles touching the block
+    want_counts = [0] * ((M + 127) // 128)
+    for b in range(M // T):
+        for q0 in range(0, T, 128):
+            r0, r1 = b * T + q0, b * T + min(q0 + 128, T) - 1
+            for m in range(r0 // 128, r1 // 128 + 1):
+                want_counts[m] += H
+    assert counts == want_counts
+
+
+@pytest.mark.parametrize("M,T,frames,R,P,ref_len,ph_len", ATTN_CASES)
+def test_whole_block_in_one_launch_equals_phase_by_phase(eng, M, T, frames, R, P, ref_len, ph_len):
+    """q|k|v|gate(1) -> attention(1) -> to_out(1) -> w1|w3(1) -> w2(1) -> q|k|v|gate(2) -> attention(2) in ONE launch is
+    bit-identical to the same phases launched one at a time, and matches the textbook block."""
+    c = Case(M, T, frames, seed=6, R=R, P=P, ref_len=ref_len, ph_len=ph_len)
+    c.make_fold(eng)
+    c.qkv_db = 1
+    c.stats_cast(eng, c.m(1, 1))
+    x0 = c.x.clone()
+    xb0, stats0 = c.xb.clone(), c.stats.clone()
+    phases = [(QKVG, 1), (ATTN, 1), (OUT, 1), (W13, 1), (W2, 1), (QKVG, 2), (ATTN, 2)]
+    bufs = ("x", "xb", "stats", "hb", "qkv", "gate", "ob")
+
+    def reset():
+        c.x.copy_(x0), c.xb.copy_(xb0), c.stats.copy_(stats0)
+        for n in ("hb", "qkv", "gate", "ob"):
+            getattr(c, n).zero_()
+
+    reset()
+    for i, ph in enumerate(phases):
+        c.run(eng, [ph])
+        if i == 1:
+            ob1 = c.ob.clone()  # attention of block 1, consumed by to_out
+    single = [getattr(c, n).clone() for n in bufs]
+    for rep in range(3):
+        reset()
+        c.run(eng, phases)
+        for n, want in zip(bufs, single):
+            got = getattr(c, n)
+            assert torch.equal(got, want), (rep, n, float((got.float() - want.float()).abs().max()))
+    # textbook: block 1 from x0, then q|k|v|gate and attention of block 2
+    q, k, v, g = ref_qkvg(c, 1, x0)
+    assert rel(c.qkv[1].float().view(3, M, H, HDP)[0, :, :, :HD], q) < 1e-2
+    a1 = ref_attention(c, 1, c.qkv[1], g)
+    assert rel(ob1, a1) < 2e-2
+    x1 = ref_out(c, 1, x0, ob1)
+    x2, _ = ref_mlp(c, 1, x1)
+    assert rel(c.x, x2) < 1e-2
+    q, k, v, g = ref_qkvg(c, 2, x2)
+    assert rel(c.gate, g) < 2e-2
+    a2 = ref_attention(c, 2, c.qkv[0], c.gate)
+    err = rel(c.ob, a2)
+    print("block in one launch: attention of the next block", err)
+    assert err < 1e-2

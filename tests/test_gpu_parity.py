@@ -204,6 +204,39 @@ def test_config2_headline_batch_vs_oracle(tts, config2_oracle):
     assert rel_l2(dev[5][0].cpu().numpy(), want_audio[5]) <= TOL_FP32
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_attention_inside_the_chained_kernel_vs_oracle(mode, dit_sd, voc_sd, config2_oracle, monkeypatch):
+    """STTS_CHAIN_ATTN=1: a whole denoiser evaluation is ONE launch of the chained kernel (attention runs on tcgen05 as a
+    phase between q|k|v|gate and to_out, csrc/chain_attn.cuh); =2: one launch per block.  Same bar as the default
+    schedule on the headline batch, and far fewer kernels per step."""
+    from smalltts_b200.engine import pad_batch
+    from smalltts_b200.infer import SmallTTS
+
+    refs, ids, frames, noise, want_lat, want_audio = config2_oracle
+    monkeypatch.setenv("STTS_CHAIN_ATTN", mode)
+    t = SmallTTS(state_dicts=(dit_sd, voc_sd))  # the schedule is read when the engine is created
+    try:
+        ref, ref_len, idt, ph_len = pad_batch(refs, ids, frames)
+        cond = t.engine.encode_conditions(ref, ref_len, idt, ph_len)
+        t.engine.sample(cond, frames, 75, noise=noise.numpy())  # the first call also builds the per-timestep adaLN tables
+        n0 = t.engine.launch_count()
+        lat = t.engine.sample(cond, frames, 75, noise=noise.numpy())
+        launches = t.engine.launch_count() - n0
+        cond.free()
+        for b in range(8):
+            err = rel_l2(lat[b], want_lat[b])
+            print("chain attention mode", mode, "latents row", b, "rel_l2", err)
+            assert err <= TOL_FP32, (b, err)
+        # per evaluation: 4 input-embedding GEMMs + stats/cast + 1 (or 13) chained launches, against 25 by default
+        print("kernels in the 4-step DMD loop:", launches)
+        assert launches <= (4 * 8 + 10 if mode == "1" else 4 * 20 + 10)
+        got = t.synthesize_batch(refs, ids, [10.0] * 8, noise=noise.numpy())
+        for b, w in want_audio.items():
+            assert rel_l2(got[b][0], w) <= TOL_FP32
+    finally:
+        t.engine.close()
+
+
 def test_tight_precision_mode_vs_reference_fixtures_and_oracle(tts_tight, tts, config2_oracle):
     """precision="tight" (fp16 operands, 11-bit significand like TF32): the reference's fp32 results within TOL_TIGHT on
     the reference-made fixtures (K/V caches, velocity, vocoder, config 1 end to end) and on the headline batch (B=8 x
