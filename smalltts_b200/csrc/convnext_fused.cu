@@ -211,9 +211,19 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       }
       ptx::cp_async_commit();
     };
+    // The x buffers give a prefetch distance of ONE tile (~3 k cycles of mixing): the rows of tile it+2 are requested into
+    // L2 two tiles ahead (one bulk prefetch: a tile's rows are one contiguous range), so that the cp.async of the next
+    // iteration is an L2 hit.  Measured: tail 2.777 -> 2.753 ms.
+    auto l2_prefetch = [&](int tile) {
+      const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * TM;
+      const int r0 = t0 - HALO > 0 ? t0 - HALO : 0, r1 = t0 + TM < p.T ? t0 + TM : p.T;
+      ptx::l2_prefetch_bulk(p.x + (static_cast<long long>(b) * p.T + r0) * C, static_cast<uint32_t>((r1 - r0) * C * 4));
+    };
+    if (tid == 0 && n_my > 1) l2_prefetch(first + stride);
     if (n_my > 0) issue_load(first, 0);
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
+      if (tid == 0 && it + 2 < n_my) l2_prefetch(first + (it + 2) * stride);
       // Prefetch of tile it+1 into the other x buffer, which last held tile it-1 and is released by the out warps once
       // they hold y(it-1) in registers.  The out warps are the slowest role (role timeline, tools/trace_fused.py), so
       // the mixer never BLOCKS on them before computing a tile whose data is already here: if the buffer is not free

@@ -79,7 +79,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 // Bounded wait: ~seconds of spinning means a protocol bug; trap so the host sees an error.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+#ifdef STTS_MBAR_SPIN  // compile-time experiment: pure polling with the non-blocking probe instead of try_wait
+  while (!mbar_test(bar, parity)) {
+#else
   while (!mbar_try_wait(bar, parity)) {
+#endif
     if (++spins > (1u << 24)) {
       __trap();
     }
