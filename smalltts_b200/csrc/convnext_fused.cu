@@ -49,12 +49,16 @@ template <int C>
 struct FC {
   static constexpr int HID = 4 * C;
   static constexpr int NCH = HID / 64;  // 64-wide hidden chunks
-  static constexpr int XP = C + 4;      // fp32 tile pitch: 16-byte aligned rows, conflict-free float4 row access
+  // fp32 x tile as TMA writes it: C / 32 column halves of [XRP rows][32 floats = 128 bytes], 128-byte swizzle (16-byte
+  // chunk index XOR row & 7): conflict-free both for "one thread = one row" float4 reads and "one lane = one channel".
+  static constexpr int XH = C / 32;
+  static constexpr int XRP = (XR + 7) / 8 * 8;  // rows per half rounded up so that every half starts 1024-byte aligned
   static constexpr int W1_BYTES = HID * 128;      // [HID rows][64 k] bf16, K zero-padded to 64
   static constexpr int W2_BYTES = NCH * C * 128;  // NCH chunks of [C rows][64 k]
   static constexpr int A_BYTES = TM * 128;
   static constexpr int G_BYTES = TM * 128;
-  static constexpr int X_BYTES = ((XR * XP * 4 + 127) / 128) * 128;
+  static constexpr int X_BYTES = XH * XRP * 128;
+  static constexpr int X_TX_BYTES = XR * C * 4;  // bytes one tile load delivers (out-of-range rows arrive as zeros)
   // vectors: b1[HID] b2[C] ffn_gamma[C] norm_w[C] ffn_norm_w[C] gamma[C] conv_b[C] conv_w[7][C]
   static constexpr int VEC_FLOATS = HID + 6 * C + 7 * C;
   static constexpr int OFF_W1 = 0;
@@ -65,9 +69,15 @@ struct FC {
   static constexpr int OFF_VEC = OFF_X + 2 * X_BYTES;
   static constexpr int OFF_INV = OFF_VEC + VEC_FLOATS * 4;
   static constexpr int OFF_BAR = ((OFF_INV + XR * 4 + 15) / 16) * 16;
-  static constexpr int OFF_STG = ((OFF_BAR + 17 * 8 + 16 + 127) / 128) * 128;  // 4 x 4 KB: out-warp transposition staging
+  static constexpr int OFF_STG = ((OFF_BAR + 19 * 8 + 16 + 127) / 128) * 128;  // 4 x 4 KB: out-warp transposition staging
   static constexpr int SMEM = OFF_STG + 4 * 4096 + 1024;
   static_assert(SMEM <= 232448, "fused ConvNeXt tile does not fit in shared memory");
+  static_assert(OFF_X % 1024 == 0 && X_BYTES % 1024 == 0, "x tiles must sit on swizzle-atom boundaries");
+  // float index of 16-byte chunk j (4 channels) of row r / of channel c of row r inside an x tile
+  __device__ static __forceinline__ int chunk(int r, int j) {
+    return (j >> 3) * (XRP * 32) + r * 32 + (((j & 7) ^ (r & 7)) << 2);
+  }
+  __device__ static __forceinline__ int elem(int r, int c) { return chunk(r, c >> 2) + (c & 3); }
 };
 
 // (fp32 reference form, kept for documentation) TWICE the erf-GELU: x (1 + tanh(u)), u = x (a + b x^2 + c x^4) fitted to the erf form (max abs err 2.6e-5 before
@@ -125,7 +135,7 @@ __device__ long long g_fused_trace[64 * 16];
 template <int C>
 __global__ void __launch_bounds__(kThreadsFused, 1)
 convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                      const FusedParams p) {
+                      const __grid_constant__ CUtensorMap tmX, const FusedParams p) {
   using F = FC<C>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -152,7 +162,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   uint64_t* o_full = bars + 11;
   uint64_t* tm_empty = bars + 13;
   uint64_t* x_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* x_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   auto Abuf = [&](int i) { return smem + F::OFF_A + i * F::A_BYTES; };
   auto Gbuf = [&](int i) { return smem + F::OFF_G + i * F::G_BYTES; };
   auto Xbuf = [&](int i) { return reinterpret_cast<float*>(smem + F::OFF_X + i * F::X_BYTES); };
@@ -177,7 +188,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     reinterpret_cast<uint4*>(smem + F::OFF_A)[i] = make_uint4(0, 0, 0, 0);  // K padding (C = 32) stays zero
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 17; ++i) ptx::mbar_init(&bars[i], (i == 7 || i == 8) ? 8u : 1u);  // g_full: one arrive per GELU warp
+    for (int i = 0; i < 19; ++i) ptx::mbar_init(&bars[i], (i == 7 || i == 8) ? 8u : 1u);  // g_full: one arrive per GELU warp
     ptx::fence_barrier_init();
   }
   if (warp == kMmaWarp) ptx::tmem_alloc<512>(tmem_slot);
@@ -198,118 +209,120 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     constexpr int CV = C / 4;       // float4 per row
     constexpr int NSEG = NT / C;    // time segments per channel
     constexpr int SEGLEN = TM / NSEG;
+    // x tiles arrive by TMA (one 3-D box per 128-byte column half: rows before the start of the utterance and past its
+    // end are filled with zeros), issued by thread 0.  The same load as 1 k cp.async of 16 bytes cost the 256 mixer
+    // threads ~1.1 k cycles of issue time and ~0.5 k of a block-wide vote per tile (role timeline, tools/trace_fused.py).
     auto issue_load = [&](int tile, int buf) {
       const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * TM;
-      const float* src_b = p.x + static_cast<long long>(b) * p.T * C;
-      const uint32_t dst0 = ptx::smem_u32(Xbuf(buf));
-      for (int i = tid; i < XR * CV; i += NT) {
-        const int r = i / CV, c4 = i % CV;
-        const int t = t0 - HALO + r;
-        const bool ok = (t >= 0) && (t < p.T);
-        const float* src = src_b + static_cast<long long>(ok ? t : 0) * C + c4 * 4;
-        ptx::cp_async_16(dst0 + (r * F::XP + c4 * 4) * 4, src, ok ? 16u : 0u);
+      ptx::mbar_expect_tx(&x_full[buf], F::X_TX_BYTES);
+#pragma unroll
+      for (int h = 0; h < F::XH; ++h) {
+        ptx::tma_load_3d(Xbuf(buf) + h * (F::XRP * 32), &tmX, &x_full[buf], h * 32, t0 - HALO, b);
       }
-      ptx::cp_async_commit();
     };
-    // The x buffers give a prefetch distance of ONE tile (~3 k cycles of mixing): the rows of tile it+2 are requested into
-    // L2 two tiles ahead (one bulk prefetch: a tile's rows are one contiguous range), so that the cp.async of the next
-    // iteration is an L2 hit.  Measured: tail 2.777 -> 2.753 ms.
-    auto l2_prefetch = [&](int tile) {
-      const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * TM;
-      const int r0 = t0 - HALO > 0 ? t0 - HALO : 0, r1 = t0 + TM < p.T ? t0 + TM : p.T;
-      ptx::l2_prefetch_bulk(p.x + (static_cast<long long>(b) * p.T + r0) * C, static_cast<uint32_t>((r1 - r0) * C * 4));
-    };
-    if (tid == 0 && n_my > 1) l2_prefetch(first + stride);
-    if (n_my > 0) issue_load(first, 0);
+    if (tid == 0 && n_my > 0) issue_load(first, 0);
     for (int it = 0; it < n_my; ++it) {
       const int buf = it & 1;
-      if (tid == 0 && it + 2 < n_my) l2_prefetch(first + (it + 2) * stride);
       // Prefetch of tile it+1 into the other x buffer, which last held tile it-1 and is released by the out warps once
-      // they hold y(it-1) in registers.  The out warps are the slowest role (role timeline, tools/trace_fused.py), so
-      // the mixer never BLOCKS on them before computing a tile whose data is already here: if the buffer is not free
-      // yet the prefetch is issued after this tile's token mixing instead.
-      bool issued_now = false;
-      if (it + 1 < n_my) {
-        const bool free_now = it == 0 || ptx::mbar_test(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
-        if (ptx::named_bar_and(1, NT, free_now)) {  // uniform decision for the 256 mixer threads
-          issue_load(first + (it + 1) * stride, buf ^ 1);
-          issued_now = true;
+      // they hold y(it-1) in registers.  Thread 0 asks at every step of the iteration and only blocks at its end.
+      bool pending = it + 1 < n_my;
+      auto try_prefetch = [&](bool block) {
+        if (tid != 0 || !pending) return;
+        bool free_now = it == 0;
+        if (!free_now) {
+          if (block) {
+            ptx::mbar_wait(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
+            free_now = true;
+          } else {
+            free_now = ptx::mbar_test(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
+          }
         }
-      }
-      if (issued_now) {
-        ptx::cp_async_wait<1>();
-      } else {
-        ptx::cp_async_wait<0>();
-      }
-      ptx::named_bar_sync(1, NT);
+        if (free_now) {
+          issue_load(first + (it + 1) * stride, buf ^ 1);
+          pending = false;
+        }
+      };
+      try_prefetch(false);
+      ptx::mbar_wait(&x_full[buf], (it >> 1) & 1);
       if (tid == 0) TRACE(it, 0);
       float* xs = Xbuf(buf);
       // (1) 1/rms of every staged row: thread t owns row t
       if (tid < XR) {
-        const float4* row = reinterpret_cast<const float4*>(xs + tid * F::XP);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < CV; ++j) {
-          const float4 v = row[j];
-          s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+          const float4 v = *reinterpret_cast<const float4*>(xs + F::chunk(tid, j));
+          s01 = ptx::f2_fma(make_float2(v.x, v.y), make_float2(v.x, v.y), s01);
+          s23 = ptx::f2_fma(make_float2(v.z, v.w), make_float2(v.z, v.w), s23);
         }
-        inv1[tid] = rsqrtf((s0 + s1 + s2 + s3) * (1.0f / C) + p.eps);
+        inv1[tid] = rsqrtf((s01.x + s01.y + s23.x + s23.y) * (1.0f / C) + p.eps);
       }
       ptx::named_bar_sync(1, NT);
-      // (2) depthwise causal conv along time, one (channel, segment) per thread, y written in place
+      try_prefetch(false);
+      // (2) depthwise causal conv along time, y written in place: one (channel PAIR, time segment) per thread, all
+      // arithmetic as packed fp32 pairs (FFMA2: bit-identical to the scalar form, half the instructions)
       {
-        const int c = tid % C, seg = tid / C;
-        const int rs = HALO + seg * SEGLEN;
-        float w[7];
+        constexpr int NP = C / 2, NSEG2 = NT / NP, SEGLEN2 = TM / NSEG2;
+        const int c = 2 * (tid % NP), seg = tid / NP;
+        const int rs = HALO + seg * SEGLEN2;
+        float2 w[7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) w[j] = cws[j * C + c];
-        const float cb = cbs[c], gm = gms[c];
-        float win[7];
-        win[0] = 0.f;
+        for (int j = 0; j < 7; ++j) w[j] = *reinterpret_cast<const float2*>(cws + j * C + c);
+        const float2 cb = *reinterpret_cast<const float2*>(cbs + c), gm = *reinterpret_cast<const float2*>(gms + c);
+        float2 win[7];
+        win[0] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 1; j < 7; ++j) {
           const int r = rs - 7 + j;
-          win[j] = xs[r * F::XP + c] * inv1[r];
+          win[j] = ptx::f2_scale(*reinterpret_cast<const float2*>(xs + F::elem(r, c)), inv1[r]);
         }
         ptx::named_bar_sync(1, NT);  // every warm-up read precedes the in-place writes of the previous segment
 #pragma unroll 8
-        for (int r = rs; r < rs + SEGLEN; ++r) {
-          const float xv = xs[r * F::XP + c];
+        for (int r = rs; r < rs + SEGLEN2; ++r) {
+          float2* xp = reinterpret_cast<float2*>(xs + F::elem(r, c));
+          const float2 xv = *xp;
 #pragma unroll
           for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-          win[6] = xv * inv1[r];
+          win[6] = ptx::f2_scale(xv, inv1[r]);
           // two independent partial sums shorten the dependent FMA chain
-          float a0 = fmaf(w[0], win[0], cb), a1 = w[1] * win[1];
-          a0 = fmaf(w[2], win[2], a0); a1 = fmaf(w[3], win[3], a1);
-          a0 = fmaf(w[4], win[4], a0); a1 = fmaf(w[5], win[5], a1);
-          a0 = fmaf(w[6], win[6], a0);
-          xs[r * F::XP + c] = fmaf(gm, a0 + a1, xv);
+          float2 a0 = ptx::f2_fma(w[0], win[0], cb), a1 = ptx::f2_mul(w[1], win[1]);
+          a0 = ptx::f2_fma(w[2], win[2], a0); a1 = ptx::f2_fma(w[3], win[3], a1);
+          a0 = ptx::f2_fma(w[4], win[4], a0); a1 = ptx::f2_fma(w[5], win[5], a1);
+          a0 = ptx::f2_fma(w[6], win[6], a0);
+          *xp = ptx::f2_fma(gm, ptx::f2_add(a0, a1), xv);
         }
       }
       ptx::named_bar_sync(1, NT);
+      try_prefetch(false);
       if (tid == 0) TRACE(it, 1);
       // (3) second RMSNorm -> bf16 A operand (UMMA K-major, 128B swizzle); A buffer must be free (MMA1 of it-2 done)
       if (it >= 2) ptx::mbar_wait(&a_empty[buf], ((it - 2) >> 1) & 1);
       if (tid < TM) {
-        const float4* row = reinterpret_cast<const float4*>(xs + (tid + HALO) * F::XP);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const int yr = tid + HALO;
+        float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < CV; ++j) {
-          const float4 v = row[j];
-          s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+          const float4 v = *reinterpret_cast<const float4*>(xs + F::chunk(yr, j));
+          s01 = ptx::f2_fma(make_float2(v.x, v.y), make_float2(v.x, v.y), s01);
+          s23 = ptx::f2_fma(make_float2(v.z, v.w), make_float2(v.z, v.w), s23);
         }
-        const float inv = rsqrtf((s0 + s1 + s2 + s3) * (1.0f / C) + p.eps);
+        const float inv = rsqrtf((s01.x + s01.y + s23.x + s23.y) * (1.0f / C) + p.eps);
         uint8_t* As = Abuf(buf);
 #pragma unroll
         for (int j = 0; j < CV / 2; ++j) {  // 8 columns = one 16-byte swizzle chunk
-          const float4 v0 = row[2 * j], v1 = row[2 * j + 1];
+          const float4 v0 = *reinterpret_cast<const float4*>(xs + F::chunk(yr, 2 * j));
+          const float4 v1 = *reinterpret_cast<const float4*>(xs + F::chunk(yr, 2 * j + 1));
           const float4 f0 = *reinterpret_cast<const float4*>(fws + 8 * j);
           const float4 f1 = *reinterpret_cast<const float4*>(fws + 8 * j + 4);
+          const float2 q0 = ptx::f2_mul(ptx::f2_scale(make_float2(v0.x, v0.y), inv), make_float2(f0.x, f0.y));
+          const float2 q1 = ptx::f2_mul(ptx::f2_scale(make_float2(v0.z, v0.w), inv), make_float2(f0.z, f0.w));
+          const float2 q2 = ptx::f2_mul(ptx::f2_scale(make_float2(v1.x, v1.y), inv), make_float2(f1.x, f1.y));
+          const float2 q3 = ptx::f2_mul(ptx::f2_scale(make_float2(v1.z, v1.w), inv), make_float2(f1.z, f1.w));
           uint4 pk;
-          pk.x = bf2(v0.x * inv * f0.x, v0.y * inv * f0.y);
-          pk.y = bf2(v0.z * inv * f0.z, v0.w * inv * f0.w);
-          pk.z = bf2(v1.x * inv * f1.x, v1.y * inv * f1.y);
-          pk.w = bf2(v1.z * inv * f1.z, v1.w * inv * f1.w);
+          pk.x = bf2(q0.x, q0.y);
+          pk.y = bf2(q1.x, q1.y);
+          pk.z = bf2(q2.x, q2.y);
+          pk.w = bf2(q3.x, q3.y);
           *reinterpret_cast<uint4*>(As + sw128_off(tid, 8 * j)) = pk;
         }
       }
@@ -317,10 +330,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       ptx::named_bar_sync(1, NT);
       if (tid == 0) ptx::mbar_arrive(&a_full[buf]);
       if (tid == 0) TRACE(it, 2);
-      if (it + 1 < n_my && !issued_now) {  // deferred prefetch: now the mixer has nothing better to do than wait
-        if (it >= 1) ptx::mbar_wait(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
-        issue_load(first + (it + 1) * stride, buf ^ 1);
-      }
+      try_prefetch(true);  // still pending: now thread 0 has nothing better to do than wait for the buffer
     }
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer
@@ -429,9 +439,9 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       ptx::mbar_wait(&a_full[buf], (it >> 1) & 1);  // mixer done: y rows are final
       float4 y[C / 4];
       {
-        const float* yrow = Xbuf(buf) + (r + HALO) * F::XP;
+        const float* ys = Xbuf(buf);
 #pragma unroll
-        for (int j = 0; j < C / 4; ++j) y[j] = *reinterpret_cast<const float4*>(yrow + 4 * j);
+        for (int j = 0; j < C / 4; ++j) y[j] = *reinterpret_cast<const float4*>(ys + F::chunk(r + HALO, j));
       }
       ptx::named_bar_sync(3, 128);
       if (otid == 0) ptx::mbar_arrive(&x_empty[buf]);
@@ -451,10 +461,11 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           const float4 gf = *reinterpret_cast<const float4*>(gfs + col);
           float4& yy = y[cc * 8 + j];
           // O = (0.5 W2)(2 gelu) = W2 gelu (W2 is stored pre-scaled by 0.5): out = y + ffn_gamma*b2 + ffn_gamma * O
-          yy.x = fmaf(gf.x, __uint_as_float(rr[4 * j + 0]), yy.x + b2.x);
-          yy.y = fmaf(gf.y, __uint_as_float(rr[4 * j + 1]), yy.y + b2.y);
-          yy.z = fmaf(gf.z, __uint_as_float(rr[4 * j + 2]), yy.z + b2.z);
-          yy.w = fmaf(gf.w, __uint_as_float(rr[4 * j + 3]), yy.w + b2.w);
+          const float2 o01 = ptx::f2_fma(make_float2(gf.x, gf.y), make_float2(__uint_as_float(rr[4 * j + 0]), __uint_as_float(rr[4 * j + 1])),
+                                         ptx::f2_add(make_float2(yy.x, yy.y), make_float2(b2.x, b2.y)));
+          const float2 o23 = ptx::f2_fma(make_float2(gf.z, gf.w), make_float2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])),
+                                         ptx::f2_add(make_float2(yy.z, yy.w), make_float2(b2.z, b2.w)));
+          yy = make_float4(o01.x, o01.y, o23.x, o23.y);
         }
       }
       ptx::tc_fence_before();
@@ -542,9 +553,22 @@ cudaError_t launch_fused(cudaStream_t st, const FusedParams& p, const bf16* w1, 
   CUtensorMap m1, m2;
   if (!tmap_2d(&m1, w1, C, 4 * C, 4 * C)) return cudaErrorInvalidValue;  // W1 [4C, C]: one box of all rows, K padded to 64
   if (!tmap_2d(&m2, w2, 4 * C, C, C)) return cudaErrorInvalidValue;      // W2 [C, 4C]: one box per 64-wide K chunk
+  CUtensorMap mx;  // x [B][T][C] fp32: box = 32 channels x XR rows of one utterance
+  {
+    EncodeFn fn = encode_fn();
+    if (!fn) return cudaErrorInvalidValue;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(p.T), static_cast<cuuint64_t>(p.B)};
+    cuuint64_t str[2] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(p.T) * C * 4};
+    cuuint32_t box[3] = {32, XR, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (fn(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.x), dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      return cudaErrorInvalidValue;
+    }
+  }
   const int ntiles = p.B * ((p.T + TM - 1) / TM);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  const cudaError_t le = launch_k(convnext_fused_kernel<C>, dim3(grid), dim3(kThreadsFused), FC<C>::SMEM, st, m1, m2, p);
+  const cudaError_t le = launch_k(convnext_fused_kernel<C>, dim3(grid), dim3(kThreadsFused), FC<C>::SMEM, st, m1, m2, mx, p);
   count_launch();
   return le != cudaSuccess ? le : cudaGetLastError();
 }
