@@ -696,6 +696,35 @@ __global__ void __launch_bounds__(256) convnext_mix_kernel(const float* __restri
   const int seg = C >= 256 ? 0 : threadIdx.x / C;
   const int rs = 6 + seg * seg_len;                       // first output row (tile coordinates)
   const int re = min(6 + nrows, rs + seg_len);
+  if (C >= 512) {
+    // wide stages: one channel PAIR per thread and iteration, packed fp32 arithmetic (FFMA2; the scalar form below
+    // contracts to the same fused multiply-adds, so the results are identical)
+    for (int c = 2 * threadIdx.x; c < C; c += 512) {
+      float2 w[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) w[j] = make_float2(cw[c * 7 + j], cw[(c + 1) * 7 + j]);
+      const float2 cb = make_float2(cbs[c], cbs[c + 1]), gm = make_float2(gms[c], gms[c + 1]), nw = make_float2(nws[c], nws[c + 1]);
+      float2 win[7];
+      win[0] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 1; j < 7; ++j) {
+        const int r = rs - 7 + j;  // rows rs-6 .. rs-1
+        win[j] = (r >= 0 && rs < re) ? ptx::f2_mul(ptx::f2_scale(*reinterpret_cast<const float2*>(tile + r * C + c), inv1[r]), nw)
+                                     : make_float2(0.f, 0.f);
+      }
+      for (int r = rs; r < re; ++r) {
+        float2* xp = reinterpret_cast<float2*>(tile + r * C + c);
+        const float2 xv = *xp;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+        win[6] = ptx::f2_mul(ptx::f2_scale(xv, inv1[r]), nw);
+        float2 acc = cb;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc = ptx::f2_fma(w[j], win[j], acc);
+        *xp = ptx::f2_fma(gm, acc, xv);
+      }
+    }
+  } else
   for (int c = (C >= 256 ? threadIdx.x : threadIdx.x % C); c < C; c += 256) {
     float w[7];
 #pragma unroll
@@ -787,49 +816,58 @@ __global__ void __launch_bounds__(256) convnext_mix_rows_kernel(const float* __r
   __syncthreads();
   if (tid < R) {
     const float4* row = reinterpret_cast<const float4*>(tile + tid * P);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);  // packed fp32 (FFMA2): same sums, half the issue slots
 #pragma unroll 8
     for (int j = 0; j < CV; ++j) {
       const float4 v = row[j];
-      s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+      s01 = ptx::f2_fma(make_float2(v.x, v.y), make_float2(v.x, v.y), s01);
+      s23 = ptx::f2_fma(make_float2(v.z, v.w), make_float2(v.z, v.w), s23);
     }
+    const float s0 = s01.x, s1 = s01.y, s2 = s23.x, s3 = s23.y;
     inv1[tid] = rsqrtf((s0 + s1 + s2 + s3) * (1.0f / C) + eps);
   }
   __syncthreads();
   {
-    const int c = tid % C, seg = tid / C;
-    const int rs = 6 + seg * SEGLEN;
-    float w[7];
+    // one (channel PAIR, time segment) per thread; packed fp32 arithmetic, bit-identical to the scalar form
+    constexpr int NP = C / 2, NSEG2 = 256 / NP, SEGLEN2 = TT / NSEG2;
+    const int c = 2 * (tid % NP), seg = tid / NP;
+    const int rs = 6 + seg * SEGLEN2;
+    float2 w[7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) w[j] = conv_w[c * 7 + j] * norm_w[c];
-    const float cb = conv_b[c], gm = gamma[c];
-    float win[7];
-    win[0] = 0.f;
+    for (int j = 0; j < 7; ++j) w[j] = make_float2(conv_w[c * 7 + j] * norm_w[c], conv_w[(c + 1) * 7 + j] * norm_w[c + 1]);
+    const float2 cb = make_float2(conv_b[c], conv_b[c + 1]), gm = make_float2(gamma[c], gamma[c + 1]);
+    float2 win[7];
+    win[0] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 1; j < 7; ++j) win[j] = tile[(rs - 7 + j) * P + c] * inv1[rs - 7 + j];
-    if (NSEG > 1) __syncthreads();
+    for (int j = 1; j < 7; ++j) {
+      win[j] = ptx::f2_scale(*reinterpret_cast<const float2*>(tile + (rs - 7 + j) * P + c), inv1[rs - 7 + j]);
+    }
+    __syncthreads();  // every warm-up read precedes the in-place writes of the previous segment
 #pragma unroll 8
-    for (int r = rs; r < rs + SEGLEN; ++r) {
-      const float xv = tile[r * P + c];
+    for (int r = rs; r < rs + SEGLEN2; ++r) {
+      float2* xp = reinterpret_cast<float2*>(tile + r * P + c);
+      const float2 xv = *xp;
 #pragma unroll
       for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-      win[6] = xv * inv1[r];
-      float a0 = fmaf(w[0], win[0], cb), a1 = w[1] * win[1];
-      a0 = fmaf(w[2], win[2], a0); a1 = fmaf(w[3], win[3], a1);
-      a0 = fmaf(w[4], win[4], a0); a1 = fmaf(w[5], win[5], a1);
-      a0 = fmaf(w[6], win[6], a0);
-      tile[r * P + c] = fmaf(gm, a0 + a1, xv);
+      win[6] = ptx::f2_scale(xv, inv1[r]);
+      float2 a0 = ptx::f2_fma(w[0], win[0], cb), a1 = ptx::f2_mul(w[1], win[1]);
+      a0 = ptx::f2_fma(w[2], win[2], a0); a1 = ptx::f2_fma(w[3], win[3], a1);
+      a0 = ptx::f2_fma(w[4], win[4], a0); a1 = ptx::f2_fma(w[5], win[5], a1);
+      a0 = ptx::f2_fma(w[6], win[6], a0);
+      *xp = ptx::f2_fma(gm, ptx::f2_add(a0, a1), xv);
     }
   }
   __syncthreads();
   if (tid < TT) {
     const float4* row = reinterpret_cast<const float4*>(tile + (tid + 6) * P);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);  // packed fp32 (FFMA2): same sums, half the issue slots
 #pragma unroll 8
     for (int j = 0; j < CV; ++j) {
       const float4 v = row[j];
-      s0 = fmaf(v.x, v.x, s0); s1 = fmaf(v.y, v.y, s1); s2 = fmaf(v.z, v.z, s2); s3 = fmaf(v.w, v.w, s3);
+      s01 = ptx::f2_fma(make_float2(v.x, v.y), make_float2(v.x, v.y), s01);
+      s23 = ptx::f2_fma(make_float2(v.z, v.w), make_float2(v.z, v.w), s23);
     }
+    const float s0 = s01.x, s1 = s01.y, s2 = s23.x, s3 = s23.y;
     inv2[tid] = rsqrtf((s0 + s1 + s2 + s3) * (1.0f / C) + eps);
   }
   __syncthreads();
@@ -840,7 +878,9 @@ __global__ void __launch_bounds__(256) convnext_mix_rows_kernel(const float* __r
     reinterpret_cast<float4*>(y + obase)[i] = v;
     const float4 fw = reinterpret_cast<const float4*>(ffn_norm_w)[c4];
     const float s = inv2[r];
-    reinterpret_cast<uint2*>(a + obase)[i] = pack_bf16x4(v.x * s * fw.x, v.y * s * fw.y, v.z * s * fw.z, v.w * s * fw.w);
+    const float2 q0 = ptx::f2_mul(ptx::f2_scale(make_float2(v.x, v.y), s), make_float2(fw.x, fw.y));
+    const float2 q1 = ptx::f2_mul(ptx::f2_scale(make_float2(v.z, v.w), s), make_float2(fw.z, fw.w));
+    reinterpret_cast<uint2*>(a + obase)[i] = pack_bf16x4(q0.x, q0.y, q1.x, q1.y);
   }
 }
 
@@ -878,17 +918,18 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
   __syncthreads();
   const int t = t0 + threadIdx.x;
   if (t >= T) return;
-  float a0 = b0, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float2 a01 = make_float2(b0, 0.f), a23 = make_float2(0.f, 0.f);  // packed fp32: same four partial sums as before
   for (int j = 0; j < 7; ++j) {
     const float4* row = reinterpret_cast<const float4*>(sx + (threadIdx.x + j) * P);
     const float4* wr = reinterpret_cast<const float4*>(sw + j * C);
 #pragma unroll 8
     for (int c = 0; c < cv; ++c) {
       const float4 v = row[c], k = wr[c];
-      a0 = fmaf(v.x, k.x, a0); a1 = fmaf(v.y, k.y, a1); a2 = fmaf(v.z, k.z, a2); a3 = fmaf(v.w, k.w, a3);
+      a01 = ptx::f2_fma(make_float2(v.x, v.y), make_float2(k.x, k.y), a01);
+      a23 = ptx::f2_fma(make_float2(v.z, v.w), make_float2(k.z, k.w), a23);
     }
   }
-  out[static_cast<long long>(b) * T + t] = (a0 + a1) + (a2 + a3);
+  out[static_cast<long long>(b) * T + t] = (a01.x + a01.y) + (a23.x + a23.y);
 }
 
 // Codec encoder stem (hf:300-312): causal Conv1d(1 -> C, k=7) on raw audio.  One thread per sample; the thread

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "=== vocoder tests"; timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parity.py -x -q -k "convnext or vocoder or fused or config2_headline or ragged or edge" 2>&1 | tail -3
+echo "=== vocoder tests"; timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parity.py -x -q -k "mix or convnext or vocoder or fused or head or config2_headline or ragged or edge or tight or encoder" 2>&1 | tail -3
 B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --in-flight 0 --no-config4 --no-other-precision"
 for v in base; do
   timeout 600 $B 2>&1 | tail -1 > gpurun_out/bench_$v.json
