@@ -59,6 +59,15 @@ struct FC {
   static constexpr int G_BYTES = TM * 128;
   static constexpr int X_BYTES = XH * XRP * 128;
   static constexpr int X_TX_BYTES = XR * C * 4;  // bytes one tile load delivers (out-of-range rows arrive as zeros)
+  // x tile buffers: the out warps release one only when they pick up y of its tile, which is late in the tile's life (they
+  // are still storing the previous tile), so with two buffers the prefetch of tile it+1 is gated by them.  C = 32 has room
+  // for a third buffer (prefetch distance 2: the buffer it needs was released a whole tile ago).
+#ifdef STTS_FUSED_NXB
+  static constexpr int NXB = STTS_FUSED_NXB;
+#else
+  static constexpr int NXB = C == 32 ? 3 : 2;
+#endif
+  static constexpr int PD = NXB - 1;
   // vectors: b1[HID] b2[C] ffn_gamma[C] norm_w[C] ffn_norm_w[C] gamma[C] conv_b[C] conv_w[7][C]
   static constexpr int VEC_FLOATS = HID + 6 * C + 7 * C;
   static constexpr int OFF_W1 = 0;
@@ -66,10 +75,10 @@ struct FC {
   static constexpr int OFF_A = OFF_W2 + W2_BYTES;
   static constexpr int OFF_G = OFF_A + 2 * A_BYTES;
   static constexpr int OFF_X = OFF_G + 2 * G_BYTES;
-  static constexpr int OFF_VEC = OFF_X + 2 * X_BYTES;
+  static constexpr int OFF_VEC = OFF_X + NXB * X_BYTES;
   static constexpr int OFF_INV = OFF_VEC + VEC_FLOATS * 4;
   static constexpr int OFF_BAR = ((OFF_INV + XR * 4 + 15) / 16) * 16;
-  static constexpr int OFF_STG = ((OFF_BAR + 19 * 8 + 16 + 127) / 128) * 128;  // 4 x 4 KB: out-warp transposition staging
+  static constexpr int OFF_STG = ((OFF_BAR + 21 * 8 + 16 + 127) / 128) * 128;  // 4 x 4 KB: out-warp transposition staging
   static constexpr int SMEM = OFF_STG + 4 * 4096 + 1024;
   static_assert(SMEM <= 232448, "fused ConvNeXt tile does not fit in shared memory");
   static_assert(OFF_X % 1024 == 0 && X_BYTES % 1024 == 0, "x tiles must sit on swizzle-atom boundaries");
@@ -161,9 +170,9 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   uint64_t* g_empty = bars + 9;
   uint64_t* o_full = bars + 11;
   uint64_t* tm_empty = bars + 13;
-  uint64_t* x_empty = bars + 15;
-  uint64_t* x_full = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* x_empty = bars + 15;  // [NXB <= 3]
+  uint64_t* x_full = bars + 18;   // [NXB <= 3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   auto Abuf = [&](int i) { return smem + F::OFF_A + i * F::A_BYTES; };
   auto Gbuf = [&](int i) { return smem + F::OFF_G + i * F::G_BYTES; };
   auto Xbuf = [&](int i) { return reinterpret_cast<float*>(smem + F::OFF_X + i * F::X_BYTES); };
@@ -188,7 +197,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     reinterpret_cast<uint4*>(smem + F::OFF_A)[i] = make_uint4(0, 0, 0, 0);  // K padding (C = 32) stays zero
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 19; ++i) ptx::mbar_init(&bars[i], (i == 7 || i == 8) ? 8u : 1u);  // g_full: one arrive per GELU warp
+    for (int i = 0; i < 21; ++i) ptx::mbar_init(&bars[i], (i == 7 || i == 8) ? 8u : 1u);  // g_full: one arrive per GELU warp
     ptx::fence_barrier_init();
   }
   if (warp == kMmaWarp) ptx::tmem_alloc<512>(tmem_slot);
@@ -220,32 +229,39 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         ptx::tma_load_3d(Xbuf(buf) + h * (F::XRP * 32), &tmX, &x_full[buf], h * 32, t0 - HALO, b);
       }
     };
-    if (tid == 0 && n_my > 0) issue_load(first, 0);
+    constexpr int NXB = F::NXB, PD = F::PD;
+    if (tid == 0) {
+      for (int j = 0; j < PD && j < n_my; ++j) issue_load(first + j * stride, j);
+    }
     for (int it = 0; it < n_my; ++it) {
-      const int buf = it & 1;
-      // Prefetch of tile it+1 into the other x buffer, which last held tile it-1 and is released by the out warps once
-      // they hold y(it-1) in registers.  Thread 0 asks at every step of the iteration and only blocks at its end.
-      bool pending = it + 1 < n_my;
+      const int buf = it & 1;    // A operand / TMEM buffer
+      const int xb = it % NXB;   // x tile buffer
+      // Prefetch of tile it+PD into the x buffer that last held tile it-1 and is released by the out warps once they hold
+      // y(it-1) in registers.  Thread 0 asks at every step of the iteration and only blocks at its end.
+      const int pf_buf = (it + PD) % NXB;
+      bool pending = it + PD < n_my;
       auto try_prefetch = [&](bool block) {
         if (tid != 0 || !pending) return;
         bool free_now = it == 0;
         if (!free_now) {
           if (block) {
-            ptx::mbar_wait(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
+            ptx::mbar_wait(&x_empty[pf_buf], ((it - 1) / NXB) & 1);
             free_now = true;
           } else {
-            free_now = ptx::mbar_test(&x_empty[buf ^ 1], ((it - 1) >> 1) & 1);
+            free_now = ptx::mbar_test(&x_empty[pf_buf], ((it - 1) / NXB) & 1);
           }
         }
         if (free_now) {
-          issue_load(first + (it + 1) * stride, buf ^ 1);
+          issue_load(first + (it + PD) * stride, pf_buf);
           pending = false;
         }
       };
+      if (tid == 0) TRACE(it, 10);
       try_prefetch(false);
-      ptx::mbar_wait(&x_full[buf], (it >> 1) & 1);
+      if (tid == 0) TRACE(it, 11);
+      ptx::mbar_wait(&x_full[xb], (it / NXB) & 1);
       if (tid == 0) TRACE(it, 0);
-      float* xs = Xbuf(buf);
+      float* xs = Xbuf(xb);
       // (1) 1/rms of every staged row: thread t owns row t
       if (tid < XR) {
         float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
@@ -277,19 +293,29 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           win[j] = ptx::f2_scale(*reinterpret_cast<const float2*>(xs + F::elem(r, c)), inv1[r]);
         }
         ptx::named_bar_sync(1, NT);  // every warm-up read precedes the in-place writes of the previous segment
-#pragma unroll 8
-        for (int r = rs; r < rs + SEGLEN2; ++r) {
-          float2* xp = reinterpret_cast<float2*>(xs + F::elem(r, c));
-          const float2 xv = *xp;
+        // rows are processed 8 at a time: all loads of a group first (the in-place stores below would otherwise
+        // serialise them -- the compiler cannot see that a thread only re-reads rows of its own segment)
+#pragma unroll 1
+        for (int r0 = rs; r0 < rs + SEGLEN2; r0 += 8) {
+          float2 xv[8];
+          float iv[8];
 #pragma unroll
-          for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-          win[6] = ptx::f2_scale(xv, inv1[r]);
-          // two independent partial sums shorten the dependent FMA chain
-          float2 a0 = ptx::f2_fma(w[0], win[0], cb), a1 = ptx::f2_mul(w[1], win[1]);
-          a0 = ptx::f2_fma(w[2], win[2], a0); a1 = ptx::f2_fma(w[3], win[3], a1);
-          a0 = ptx::f2_fma(w[4], win[4], a0); a1 = ptx::f2_fma(w[5], win[5], a1);
-          a0 = ptx::f2_fma(w[6], win[6], a0);
-          *xp = ptx::f2_fma(gm, ptx::f2_add(a0, a1), xv);
+          for (int k = 0; k < 8; ++k) {
+            xv[k] = *reinterpret_cast<const float2*>(xs + F::elem(r0 + k, c));
+            iv[k] = inv1[r0 + k];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+            win[6] = ptx::f2_scale(xv[k], iv[k]);
+            // two independent partial sums shorten the dependent FMA chain
+            float2 a0 = ptx::f2_fma(w[0], win[0], cb), a1 = ptx::f2_mul(w[1], win[1]);
+            a0 = ptx::f2_fma(w[2], win[2], a0); a1 = ptx::f2_fma(w[3], win[3], a1);
+            a0 = ptx::f2_fma(w[4], win[4], a0); a1 = ptx::f2_fma(w[5], win[5], a1);
+            a0 = ptx::f2_fma(w[6], win[6], a0);
+            *reinterpret_cast<float2*>(xs + F::elem(r0 + k, c)) = ptx::f2_fma(gm, ptx::f2_add(a0, a1), xv[k]);
+          }
         }
       }
       ptx::named_bar_sync(1, NT);
@@ -330,7 +356,9 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       ptx::named_bar_sync(1, NT);
       if (tid == 0) ptx::mbar_arrive(&a_full[buf]);
       if (tid == 0) TRACE(it, 2);
+      if (tid == 0) TRACE(it, 12);
       try_prefetch(true);  // still pending: now thread 0 has nothing better to do than wait for the buffer
+      if (tid == 0) TRACE(it, 13);
     }
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer
@@ -439,12 +467,12 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       ptx::mbar_wait(&a_full[buf], (it >> 1) & 1);  // mixer done: y rows are final
       float4 y[C / 4];
       {
-        const float* ys = Xbuf(buf);
+        const float* ys = Xbuf(it % F::NXB);
 #pragma unroll
         for (int j = 0; j < C / 4; ++j) y[j] = *reinterpret_cast<const float4*>(ys + F::chunk(r + HALO, j));
       }
       ptx::named_bar_sync(3, 128);
-      if (otid == 0) ptx::mbar_arrive(&x_empty[buf]);
+      if (otid == 0) ptx::mbar_arrive(&x_empty[it % F::NXB]);
       if (otid == 0) TRACE(it, 7);
       ptx::mbar_wait(&o_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();

@@ -1,6 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-for v in ftrace; do
-L=$PWD/smalltts_b200/variants/libsmalltts_b200_$v.so
-echo "=== $v C=32"; STTS_LIB_PATH=$L timeout 300 python tools/trace_fused.py 32 2>&1 | tail -26 | tee gpurun_out/trace_${v}_32.txt
-done
+L=$PWD/smalltts_b200/variants/libsmalltts_b200_ftrace.so
+for c in 32; do echo "=== C=$c"; STTS_LIB_PATH=$L timeout 300 python tools/trace_fused.py $c 2>&1 | tail -9; done

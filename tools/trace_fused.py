@@ -41,4 +41,7 @@ t0 = tr[8, 0]
 print("tile " + " ".join(f"{n:>13s}" for n in names))
 for it in range(8, 20):
     print(f"{it:4d} " + " ".join(f"{tr[it, e] - t0:13d}" for e in range(10)))
+print("mixer thread 0: tile | loop top | after try_prefetch | data seen | a_full | before blocking try | after")
+for it in range(8, 14):
+    print(f"   {it:3d} " + " ".join(f"{tr[it, e] - t0:10d}" for e in (10, 11, 0, 2, 12, 13)))
 print("cycles per tile (data-landed deltas):", np.diff(tr[8:24, 0]).tolist())
