@@ -68,6 +68,12 @@ struct FC {
   static constexpr int NXB = C == 32 ? 3 : 2;
 #endif
   static constexpr int PD = NXB - 1;
+#ifdef STTS_FUSED_MG
+  static constexpr int MG = STTS_FUSED_MG;
+#else
+  static constexpr int MG = 2;  // mixer groups (each works on every MG-th tile)
+#endif
+  static_assert(MG == 1 || MG == 2, "the A operand buffers are indexed by tile parity");
   // vectors: b1[HID] b2[C] ffn_gamma[C] norm_w[C] ffn_norm_w[C] gamma[C] conv_b[C] conv_w[7][C]
   static constexpr int VEC_FLOATS = HID + 6 * C + 7 * C;
   static constexpr int OFF_W1 = 0;
@@ -77,7 +83,7 @@ struct FC {
   static constexpr int OFF_X = OFF_G + 2 * G_BYTES;
   static constexpr int OFF_VEC = OFF_X + NXB * X_BYTES;
   static constexpr int OFF_INV = OFF_VEC + VEC_FLOATS * 4;
-  static constexpr int OFF_BAR = ((OFF_INV + XR * 4 + 15) / 16) * 16;
+  static constexpr int OFF_BAR = ((OFF_INV + 2 * XR * 4 + 15) / 16) * 16;  // inv1: one copy per mixer group
   static constexpr int OFF_STG = ((OFF_BAR + 21 * 8 + 16 + 127) / 128) * 128;  // 4 x 4 KB: out-warp transposition staging
   static constexpr int SMEM = OFF_STG + 4 * 4096 + 1024;
   static_assert(SMEM <= 232448, "fused ConvNeXt tile does not fit in shared memory");
@@ -210,17 +216,20 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   ptx::pdl_trigger();
 
   if (warp < kMixWarps) {
-    // ================================================================== mixer (8 warps)
-    // Row statistics are computed one row per thread (float4 row reads are bank-conflict free with the C+4 pitch),
-    // so there are no shuffle chains; the conv runs one (channel, time segment) per thread.
-    const int tid = threadIdx.x;
-    constexpr int NT = kMixWarps * 32;
+    // ================================================================== mixer (8 warps = MG groups on alternate tiles)
+    // Row statistics are computed one row per thread (float4 row reads of the swizzled tile are bank-conflict free), so
+    // there are no shuffle chains; the conv runs one (channel pair, time segment) per thread.  A tile's mixing is a chain
+    // of short, barrier-separated steps (statistics -> conv -> second norm): with MG = 2 the two halves of the role work
+    // on consecutive tiles at the same time instead of waiting on each other's latencies.
+    constexpr int MG = F::MG;
+    constexpr int NT = kMixWarps * 32 / MG;   // threads per group
+    const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+    const uint32_t gbar = 1 + grp;            // named barrier of the group (the out warps use 3)
+    float* inv1g = inv1 + grp * XR;
     constexpr int CV = C / 4;       // float4 per row
-    constexpr int NSEG = NT / C;    // time segments per channel
-    constexpr int SEGLEN = TM / NSEG;
     // x tiles arrive by TMA (one 3-D box per 128-byte column half: rows before the start of the utterance and past its
-    // end are filled with zeros), issued by thread 0.  The same load as 1 k cp.async of 16 bytes cost the 256 mixer
-    // threads ~1.1 k cycles of issue time and ~0.5 k of a block-wide vote per tile (role timeline, tools/trace_fused.py).
+    // end are filled with zeros), issued by the group's thread 0.  The same load as 1 k cp.async of 16 bytes cost the 256
+    // mixer threads ~1.1 k cycles of issue time and ~0.5 k of a block-wide vote per tile (tools/trace_fused.py).
     auto issue_load = [&](int tile, int buf) {
       const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * TM;
       ptx::mbar_expect_tx(&x_full[buf], F::X_TX_BYTES);
@@ -229,30 +238,31 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         ptx::tma_load_3d(Xbuf(buf) + h * (F::XRP * 32), &tmX, &x_full[buf], h * 32, t0 - HALO, b);
       }
     };
-    constexpr int NXB = F::NXB, PD = F::PD;
+    constexpr int NXB = F::NXB;
+    // Tiles are loaded in order; tile j goes to x buffer j % NXB, which last held tile j - NXB and is released by the out
+    // warps once they hold y(j - NXB) in registers.  The group working on tile `it` requests tile it + PF.
+    constexpr int PF = MG == 1 ? NXB - 1 : MG;
     if (tid == 0) {
-      for (int j = 0; j < PD && j < n_my; ++j) issue_load(first + j * stride, j);
+      for (int j = grp; j < PF && j < n_my; j += MG) issue_load(first + j * stride, j % NXB);  // nothing to wait for yet
     }
-    for (int it = 0; it < n_my; ++it) {
+    for (int it = grp; it < n_my; it += MG) {
       const int buf = it & 1;    // A operand / TMEM buffer
       const int xb = it % NXB;   // x tile buffer
-      // Prefetch of tile it+PD into the x buffer that last held tile it-1 and is released by the out warps once they hold
-      // y(it-1) in registers.  Thread 0 asks at every step of the iteration and only blocks at its end.
-      const int pf_buf = (it + PD) % NXB;
-      bool pending = it + PD < n_my;
+      const int pf_tile = it + PF, pf_buf = pf_tile % NXB, pf_prev = pf_tile - NXB;  // pf_prev: the buffer's last tenant
+      bool pending = pf_tile < n_my;  // every tile >= PF is requested exactly once, by the iteration PF tiles before it
       auto try_prefetch = [&](bool block) {
         if (tid != 0 || !pending) return;
-        bool free_now = it == 0;
+        bool free_now = pf_prev < 0;
         if (!free_now) {
           if (block) {
-            ptx::mbar_wait(&x_empty[pf_buf], ((it - 1) / NXB) & 1);
+            ptx::mbar_wait(&x_empty[pf_buf], (pf_prev / NXB) & 1);
             free_now = true;
-          } else {
-            free_now = ptx::mbar_test(&x_empty[pf_buf], ((it - 1) / NXB) & 1);
+          } else if (pf_prev != it) {  // (the current tile's own buffer cannot be free before this tile is mixed)
+            free_now = ptx::mbar_test(&x_empty[pf_buf], (pf_prev / NXB) & 1);
           }
         }
         if (free_now) {
-          issue_load(first + (it + PD) * stride, pf_buf);
+          issue_load(first + pf_tile * stride, pf_buf);
           pending = false;
         }
       };
@@ -262,23 +272,24 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       ptx::mbar_wait(&x_full[xb], (it / NXB) & 1);
       if (tid == 0) TRACE(it, 0);
       float* xs = Xbuf(xb);
-      // (1) 1/rms of every staged row: thread t owns row t
-      if (tid < XR) {
+      // (1) 1/rms of every staged row: one row per thread
+      for (int r = tid; r < XR; r += NT) {
         float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < CV; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(xs + F::chunk(tid, j));
+          const float4 v = *reinterpret_cast<const float4*>(xs + F::chunk(r, j));
           s01 = ptx::f2_fma(make_float2(v.x, v.y), make_float2(v.x, v.y), s01);
           s23 = ptx::f2_fma(make_float2(v.z, v.w), make_float2(v.z, v.w), s23);
         }
-        inv1[tid] = rsqrtf((s01.x + s01.y + s23.x + s23.y) * (1.0f / C) + p.eps);
+        inv1g[r] = rsqrtf((s01.x + s01.y + s23.x + s23.y) * (1.0f / C) + p.eps);
       }
-      ptx::named_bar_sync(1, NT);
+      ptx::named_bar_sync(gbar, NT);
       try_prefetch(false);
       // (2) depthwise causal conv along time, y written in place: one (channel PAIR, time segment) per thread, all
       // arithmetic as packed fp32 pairs (FFMA2: bit-identical to the scalar form, half the instructions)
       {
         constexpr int NP = C / 2, NSEG2 = NT / NP, SEGLEN2 = TM / NSEG2;
+        static_assert(SEGLEN2 % 8 == 0, "segments are processed 8 rows at a time");
         const int c = 2 * (tid % NP), seg = tid / NP;
         const int rs = HALO + seg * SEGLEN2;
         float2 w[7];
@@ -290,9 +301,9 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
 #pragma unroll
         for (int j = 1; j < 7; ++j) {
           const int r = rs - 7 + j;
-          win[j] = ptx::f2_scale(*reinterpret_cast<const float2*>(xs + F::elem(r, c)), inv1[r]);
+          win[j] = ptx::f2_scale(*reinterpret_cast<const float2*>(xs + F::elem(r, c)), inv1g[r]);
         }
-        ptx::named_bar_sync(1, NT);  // every warm-up read precedes the in-place writes of the previous segment
+        ptx::named_bar_sync(gbar, NT);  // every warm-up read precedes the in-place writes of the previous segment
         // rows are processed 8 at a time: all loads of a group first (the in-place stores below would otherwise
         // serialise them -- the compiler cannot see that a thread only re-reads rows of its own segment)
 #pragma unroll 1
@@ -302,7 +313,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             xv[k] = *reinterpret_cast<const float2*>(xs + F::elem(r0 + k, c));
-            iv[k] = inv1[r0 + k];
+            iv[k] = inv1g[r0 + k];
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -318,13 +329,13 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           }
         }
       }
-      ptx::named_bar_sync(1, NT);
+      ptx::named_bar_sync(gbar, NT);
       try_prefetch(false);
       if (tid == 0) TRACE(it, 1);
       // (3) second RMSNorm -> bf16 A operand (UMMA K-major, 128B swizzle); A buffer must be free (MMA1 of it-2 done)
       if (it >= 2) ptx::mbar_wait(&a_empty[buf], ((it - 2) >> 1) & 1);
-      if (tid < TM) {
-        const int yr = tid + HALO;
+      for (int row = tid; row < TM; row += NT) {
+        const int yr = row + HALO;
         float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < CV; ++j) {
@@ -349,15 +360,19 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           pk.y = bf2(q1.x, q1.y);
           pk.z = bf2(q2.x, q2.y);
           pk.w = bf2(q3.x, q3.y);
-          *reinterpret_cast<uint4*>(As + sw128_off(tid, 8 * j)) = pk;
+          *reinterpret_cast<uint4*>(As + sw128_off(row, 8 * j)) = pk;
         }
       }
       ptx::fence_proxy_async();
-      ptx::named_bar_sync(1, NT);
+      ptx::named_bar_sync(gbar, NT);
+      // a_full[buf] is a two-phase (parity) barrier with two consumers, the MMA warp and the out warps.  The MMA warp's
+      // pace is bounded by a_empty above; the out warps must have seen the phase of tile it-2 before this one may complete,
+      // or their parity wait would alias (with two x buffers the buffer hand-over implies it, with three it does not).
+      if (NXB > 2 && it >= 2 && tid == 0) ptx::mbar_wait(&x_empty[(it - 2) % NXB], ((it - 2) / NXB) & 1);
       if (tid == 0) ptx::mbar_arrive(&a_full[buf]);
       if (tid == 0) TRACE(it, 2);
       if (tid == 0) TRACE(it, 12);
-      try_prefetch(true);  // still pending: now thread 0 has nothing better to do than wait for the buffer
+      try_prefetch(true);  // still pending: now the group's thread 0 has nothing better to do than wait for the buffer
       if (tid == 0) TRACE(it, 13);
     }
   } else if (warp == kMmaWarp) {

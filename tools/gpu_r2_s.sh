@@ -1,3 +1,3 @@
 #!/bin/bash
-L=$PWD/smalltts_b200/variants/libsmalltts_b200_ftrace.so
-for c in 32; do echo "=== C=$c"; STTS_LIB_PATH=$L timeout 300 python tools/trace_fused.py $c 2>&1 | tail -9; done
+echo "== default (MG=2, NXB=3 for C=32)"; timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "convnext_fused" 2>&1 | tail -3
+for i in 1 2 3; do timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "convnext_fused" 2>&1 | tail -1; done
