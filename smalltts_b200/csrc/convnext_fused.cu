@@ -33,7 +33,11 @@ constexpr int TM = 128;  // rows per tile
 constexpr int HALO = 6;  // causal context of the k=7 depthwise conv
 constexpr int XR = TM + HALO;
 // warp roles: [0,8) mixer | 8 MMA | [9,17) GELU | [17,21) out.  TMEM lane quarter of a warp = warp % 4.
-constexpr int kMixWarps = 8, kMmaWarp = 8, kGeluWarp0 = 9, kOutWarp0 = 17;
+// Roles sit on warp-group (4-warp) boundaries so that the out warps can raise their register limit with setmaxnreg: one
+// thread of that role keeps a whole fp32 row of y (C / 4 float4) next to a 32-column accumulator chunk; at the kernel-wide
+// 80 registers the C = 64 instantiation spilled the row to local memory.
+constexpr int kOutWarp0 = 0, kMixWarp0 = 4, kMixWarps = 8, kGeluWarp0 = 12, kMmaWarp = 20;
+constexpr int kOutRegs = 112, kGeluRegs = 64;  // measured: tail 2.54 -> 2.46 ms
 constexpr int kThreadsFused = 21 * 32;
 
 struct FusedParams {
@@ -147,8 +151,13 @@ __device__ long long g_fused_trace[64 * 16];
   } while (0)
 #endif
 
+// setmaxnreg moves registers between the warps of ONE CTA: what a role gives up with .dec is what another can take with
+// .inc (the SM's unallocated registers are not available to it).  The launch-time allocation stays at 80 per thread
+// (registers are handed out per 4 warps: 24 x 32 x 96 would not fit), the GELU warps go down to 64 (8 x 32 x 16 = 4 096
+// registers) and the out warps up to 112 (4 x 32 x 32 = 4 096).
+#define STTS_FUSED_BOUNDS __launch_bounds__(kThreadsFused, 1)
 template <int C>
-__global__ void __launch_bounds__(kThreadsFused, 1)
+__global__ void STTS_FUSED_BOUNDS
 convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                       const __grid_constant__ CUtensorMap tmX, const FusedParams p) {
   using F = FC<C>;
@@ -215,7 +224,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   ptx::pdl_wait();  // PDL: the setup above only read weights; x (written by the predecessor) is read from here on
   ptx::pdl_trigger();
 
-  if (warp < kMixWarps) {
+  if (warp >= kMixWarp0 && warp < kMixWarp0 + kMixWarps) {
     // ================================================================== mixer (8 warps = MG groups on alternate tiles)
     // Row statistics are computed one row per thread (float4 row reads of the swizzled tile are bank-conflict free), so
     // there are no shuffle chains; the conv runs one (channel pair, time segment) per thread.  A tile's mixing is a chain
@@ -223,7 +232,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     // on consecutive tiles at the same time instead of waiting on each other's latencies.
     constexpr int MG = F::MG;
     constexpr int NT = kMixWarps * 32 / MG;   // threads per group
-    const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+    const int mtid = threadIdx.x - kMixWarp0 * 32;
+    const int grp = mtid / NT, tid = mtid % NT;
     const uint32_t gbar = 1 + grp;            // named barrier of the group (the out warps use 3)
     float* inv1g = inv1 + grp * XR;
     constexpr int CV = C / 4;       // float4 per row
@@ -430,8 +440,11 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         if (!next_issued) mma1(it + 1);
       }
     }
-  } else if (warp < kOutWarp0) {
+  } else if (warp >= kGeluWarp0 && warp < kGeluWarp0 + 8) {
     // ================================================================== GELU: H (TMEM) -> G (smem, bf16)
+#ifndef STTS_FUSED_NO_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGeluRegs));  // two whole warp groups (warps 12-19)
+#endif
     const int gw = warp - kGeluWarp0;
     const int q = warp & 3;      // TMEM lane quarter this warp may access
     const int half = gw >> 2;    // which 32 of the chunk's 64 columns
@@ -473,6 +486,9 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     // ================================================================== out: O (TMEM) + y -> global
     // Thread <-> tile row.  y is pulled into registers as soon as the mixer has finished the tile, which frees the
     // x buffer for the prefetch of tile it+2 long before the FFN of this tile completes.
+#ifndef STTS_FUSED_NO_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kOutRegs));  // the whole warp group (warps 0-3) is here
+#endif
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int otid = threadIdx.x - kOutWarp0 * 32;

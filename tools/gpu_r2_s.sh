@@ -1,3 +1,2 @@
 #!/bin/bash
-echo "== default (MG=2, NXB=3 for C=32)"; timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "convnext_fused" 2>&1 | tail -3
-for i in 1 2 3; do timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "convnext_fused" 2>&1 | tail -1; done
+echo "== setmaxnreg: launch 80, GELU 64, out 112"; STTS_LIB_PATH=$PWD/smalltts_b200/variants/libsmalltts_b200_smr64.so timeout 60 python -m pytest tests/test_gpu_kernels.py -x -q -k "convnext_fused" 2>&1 | tail -2
