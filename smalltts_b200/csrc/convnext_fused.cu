@@ -78,6 +78,12 @@ struct FC {
   static constexpr int MG = 2;  // mixer groups (each works on every MG-th tile)
 #endif
   static_assert(MG == 1 || MG == 2, "the A operand buffers are indexed by tile parity");
+#ifdef STTS_FUSED_GELU_SETS
+  static constexpr int GELU_SETS = STTS_FUSED_GELU_SETS;
+#else
+  static constexpr int GELU_SETS = 1;  // 2 measured slower (tail 2.45 -> 2.55 ms): the per-chunk latency doubles
+#endif
+  static_assert(NCH % 2 == 0, "a GELU set always works on the same G buffer");
   // vectors: b1[HID] b2[C] ffn_gamma[C] norm_w[C] ffn_norm_w[C] gamma[C] conv_b[C] conv_w[7][C]
   static constexpr int VEC_FLOATS = HID + 6 * C + 7 * C;
   static constexpr int OFF_W1 = 0;
@@ -212,7 +218,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     reinterpret_cast<uint4*>(smem + F::OFF_A)[i] = make_uint4(0, 0, 0, 0);  // K padding (C = 32) stays zero
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 21; ++i) ptx::mbar_init(&bars[i], (i == 7 || i == 8) ? 8u : 1u);  // g_full: one arrive per GELU warp
+    for (int i = 0; i < 21; ++i) ptx::mbar_init(&bars[i], (i == 7 || i == 8) ? 8u / F::GELU_SETS : 1u);  // g_full: one arrive per GELU warp of the chunk
     ptx::fence_barrier_init();
   }
   if (warp == kMmaWarp) ptx::tmem_alloc<512>(tmem_slot);
@@ -445,41 +451,51 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
 #ifndef STTS_FUSED_NO_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kGeluRegs));  // two whole warp groups (warps 12-19)
 #endif
+    // The eight warps form two sets of four (one warp per TMEM lane quarter); set s takes the 64-column chunks c = s, s+2,
+    // ... of every tile, all 64 columns of its 32 rows per thread.  Two chunks are in flight at once (one per G buffer) and
+    // a chunk costs one fence + arrive per warp instead of two (GELU_SETS = 1: all eight warps on every chunk, 32 columns
+    // each).
     const int gw = warp - kGeluWarp0;
     const int q = warp & 3;      // TMEM lane quarter this warp may access
-    const int half = gw >> 2;    // which 32 of the chunk's 64 columns
     const int r = q * 32 + lane;
-    uint32_t gcount = 0;
+    constexpr int SETS = F::GELU_SETS;
+    const int set = SETS == 2 ? gw >> 2 : 0;
+    const int half0 = SETS == 2 ? 0 : gw >> 2, nhalf = SETS == 2 ? 2 : 1;  // 32-column halves of the chunk this warp owns
     for (int it = 0; it < n_my; ++it) {
       ptx::mbar_wait(&h_full[it & 1], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (gw == 0 && lane == 0) TRACE(it, 5);
-      for (int c = 0; c < F::NCH; ++c, ++gcount) {
+      for (int c = set; c < F::NCH; c += SETS) {
+        const uint32_t gcount = static_cast<uint32_t>(it) * F::NCH + c;  // chunks are consumed by the MMA warp in this order
         const int gb = gcount & 1;
         if (gcount >= 2) ptx::mbar_wait(&g_empty[gb], ((gcount - 2) >> 1) & 1);
-        uint32_t rr[32];
-        ptx::tmem_ld_32x32(tmem_base + (it & 1) * 256 + (static_cast<uint32_t>(q * 32) << 16) + c * 64 + half * 32, rr);
-        const __half2* bb = reinterpret_cast<const __half2*>(b1h + c * 64 + half * 32);
-        uint4 bqs[4];  // 32 fp16 biases, in flight while the accumulator read completes
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bqs[j] = *reinterpret_cast<const uint4*>(bb + 4 * j);
-        ptx::tmem_ld_wait();
         uint8_t* Gs = Gbuf(gb);
+#pragma unroll 1
+        for (int hh = 0; hh < nhalf; ++hh) {
+          const int half = half0 + hh;
+          uint32_t rr[32];
+          ptx::tmem_ld_32x32(tmem_base + (it & 1) * 256 + (static_cast<uint32_t>(q * 32) << 16) + c * 64 + half * 32, rr);
+          const __half2* bb = reinterpret_cast<const __half2*>(b1h + c * 64 + half * 32);
+          uint4 bqs[4];  // 32 fp16 biases, in flight while the accumulator read completes
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __half2* bh = reinterpret_cast<const __half2*>(&bqs[j]);
-          uint4 pk;
-          pk.x = gelu2_half2(__uint_as_float(rr[8 * j + 0]), __uint_as_float(rr[8 * j + 1]), bh[0]);
-          pk.y = gelu2_half2(__uint_as_float(rr[8 * j + 2]), __uint_as_float(rr[8 * j + 3]), bh[1]);
-          pk.z = gelu2_half2(__uint_as_float(rr[8 * j + 4]), __uint_as_float(rr[8 * j + 5]), bh[2]);
-          pk.w = gelu2_half2(__uint_as_float(rr[8 * j + 6]), __uint_as_float(rr[8 * j + 7]), bh[3]);
-          *reinterpret_cast<uint4*>(Gs + sw128_off(r, (half * 4 + j) * 8)) = pk;
+          for (int j = 0; j < 4; ++j) bqs[j] = *reinterpret_cast<const uint4*>(bb + 4 * j);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __half2* bh = reinterpret_cast<const __half2*>(&bqs[j]);
+            uint4 pk;
+            pk.x = gelu2_half2(__uint_as_float(rr[8 * j + 0]), __uint_as_float(rr[8 * j + 1]), bh[0]);
+            pk.y = gelu2_half2(__uint_as_float(rr[8 * j + 2]), __uint_as_float(rr[8 * j + 3]), bh[1]);
+            pk.z = gelu2_half2(__uint_as_float(rr[8 * j + 4]), __uint_as_float(rr[8 * j + 5]), bh[2]);
+            pk.w = gelu2_half2(__uint_as_float(rr[8 * j + 6]), __uint_as_float(rr[8 * j + 7]), bh[3]);
+            *reinterpret_cast<uint4*>(Gs + sw128_off(r, (half * 4 + j) * 8)) = pk;
+          }
         }
         ptx::fence_proxy_async();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&g_full[gb]);  // the MMA warp proceeds once all 8 GELU warps have arrived
-        if (gw == 0 && lane == 0 && c == F::NCH - 1) TRACE(it, 6);
+        if (lane == 0) ptx::mbar_arrive(&g_full[gb]);  // the MMA warp proceeds once every warp of the chunk has arrived
+        if (gw == 0 && lane == 0 && c + SETS >= F::NCH) TRACE(it, 6);
       }
     }
   } else {

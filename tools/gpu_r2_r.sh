@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
+echo "=== fused tests"; timeout 90 python -m pytest tests/test_gpu_kernels.py -x -q -k "convnext_fused" 2>&1 | tail -2
 B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --in-flight 0 --no-config4 --no-other-precision"
-for v in base smr64; do
+for v in base gs1; do
   if [ $v = base ]; then L=""; else L=$PWD/smalltts_b200/variants/libsmalltts_b200_$v.so; fi
   STTS_LIB_PATH=$L timeout 120 $B 2>&1 | tail -1 > gpurun_out/bench_$v.json
   python - <<PY
