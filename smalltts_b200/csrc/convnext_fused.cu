@@ -75,7 +75,10 @@ struct FC {
 #ifdef STTS_FUSED_MG
   static constexpr int MG = STTS_FUSED_MG;
 #else
-  static constexpr int MG = 2;  // mixer groups (each works on every MG-th tile)
+  // Mixer groups (each works on every MG-th tile).  MG = 2 is 2 % faster on the tail (2.60 -> 2.54 ms) and passes the
+  // kernel tests, but the end-to-end run-to-run determinism test (tests/test_gpu_parity.py::test_full_size_config2_properties)
+  // fails with it on long tile sequences: an unresolved race between the two groups.  Kept for the experiment only.
+  static constexpr int MG = 1;
 #endif
   static_assert(MG == 1 || MG == 2, "the A operand buffers are indexed by tile parity");
 #ifdef STTS_FUSED_GELU_SETS
