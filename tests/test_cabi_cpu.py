@@ -61,6 +61,33 @@ def test_parity_build_exports_the_same_abi(lib):
         assert hasattr(tight, name), name
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in _cabi.py must have the size and field offsets the C compiler gives the structs of
+    include/smalltts_b200.h (a drifted test-hook struct would corrupt arguments silently)."""
+    import subprocess
+
+    from smalltts_b200 import _cabi
+
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "smalltts_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("config %zu %zu\\n", sizeof(stts_config), offsetof(stts_config, reserved));\n'
+        '  printf("timing %zu %zu\\n", sizeof(stts_timing), offsetof(stts_timing, total_ms));\n'
+        '  printf("chain %zu %zu %zu %zu %zu %zu\\n", sizeof(stts_test_chain_args), offsetof(stts_test_chain_args, ready),\n'
+        "         offsetof(stts_test_chain_args, kv_ref), offsetof(stts_test_chain_args, M), offsetof(stts_test_chain_args, qkv_db),\n"
+        "         offsetof(stts_test_chain_args, blk));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict((l.split()[0], [int(x) for x in l.split()[1:]]) for l in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                                                      text=True).stdout.splitlines())
+    assert out["config"] == [ctypes.sizeof(_cabi.Config), _cabi.Config.reserved.offset]
+    assert out["timing"] == [ctypes.sizeof(_cabi.Timing), _cabi.Timing.total_ms.offset]
+    ca = _cabi.ChainArgs
+    assert out["chain"] == [ctypes.sizeof(ca), ca.ready.offset, ca.kv_ref.offset, ca.M.offset, ca.qkv_db.offset, ca.blk.offset]
+
+
 def test_duration_and_frame_rules_match_reference():
     from smalltts_b200 import infer
 
