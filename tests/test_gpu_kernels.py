@@ -344,6 +344,41 @@ def test_convnext_fused(eng, C_, T):
     _assert_close(out16, want, tol=1e-2)
 
 
+@pytest.mark.parametrize("C_", [32, 64])
+def test_convnext_fused_long_tile_sequences_are_deterministic(eng, C_):
+    """Every CTA of the persistent fused layer walks 13 tiles here (the pipeline's buffer rotations and barrier parities go
+    through several full cycles, which the short cases above do not reach): result vs torch, and bit-identical run to
+    run -- the warp roles hand tiles over through shared memory, so a protocol slip shows up as run-to-run noise."""
+    from smalltts_b200 import _cabi
+
+    torch.manual_seed(11)
+    B, T = 2, 148 * 13 * 64 - 37  # 2 x 962 tiles of 128 rows on 148 CTAs, ragged last tile
+    x = torch.randn(B, T, C_, device="cuda")
+    nw, fw = 1 + 0.1 * torch.randn(C_, device="cuda"), 1 + 0.1 * torch.randn(C_, device="cuda")
+    cw, cb = torch.randn(C_, 7, device="cuda") * 0.4, torch.randn(C_, device="cuda")
+    gamma, fgamma = 0.1 + 0.1 * torch.rand(C_, device="cuda"), 0.1 + 0.1 * torch.rand(C_, device="cuda")
+    w1 = _rand_bf16(4 * C_, C_, scale=C_ ** -0.5)
+    w2 = (torch.randn(C_, 4 * C_, device="cuda") * (4 * C_) ** -0.5).to(torch.float16)
+    b1, b2 = torch.randn(4 * C_, device="cuda") * 0.3, torch.randn(C_, device="cuda") * 0.3
+    w2h = (w2 * 0.5).contiguous()
+    outs = []
+    for _ in range(3):
+        out = torch.zeros_like(x)
+        rc = _cabi.lib().stts_test_convnext_fused(eng._h, _p(x), B, T, C_, _p(nw), _p(cw), _p(cb), _p(gamma), _p(fw),
+                                                  _p(w1), _p(b1), _p(w2h), _p(b2), _p(fgamma), _p(out), None)
+        _cabi.check(rc, eng._h)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * nw
+    conv = torch.nn.functional.conv1d(torch.nn.functional.pad(xn.transpose(1, 2), (6, 0)), cw[:, None, :], cb, groups=C_)
+    y = x + gamma * conv.transpose(1, 2)
+    a = (y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + 1e-5) * fw).to(torch.bfloat16).float()
+    h = torch.nn.functional.gelu(a @ w1.float().t() + b1).to(torch.float16).float()
+    want = y + fgamma * (h @ w2.float().t() + b2)
+    _assert_close(outs[0], want, tol=2e-3)
+
+
 @pytest.mark.parametrize("M", [128, 1000, 37, 40000])
 def test_ffn_fused(eng, M):
     """ConvNeXt feed-forward for C = 128 in one kernel (hidden activation in TMEM / shared memory only) vs torch fp32
