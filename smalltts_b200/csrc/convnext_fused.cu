@@ -71,7 +71,6 @@ struct FC {
 #else
   static constexpr int NXB = C == 32 ? 3 : 2;
 #endif
-  static constexpr int PD = NXB - 1;
 #ifdef STTS_FUSED_MG
   static constexpr int MG = STTS_FUSED_MG;
 #else
