@@ -351,7 +351,7 @@ def main_ours(args, rank, local_rank, world):
             rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
             if rows:
                 in_flight = {"by_batches_in_flight": {str(x["batches_in_flight"]): round(x["value"], 1) for x in rows},
-                             "unit": UNIT, "timing": "wall clock around all replica threads, device-resident inputs",
+                             "unit": UNIT, "timing": "wall clock around all replica threads (best of two passes), device-resident inputs",
                              "note": "N engine replicas on one GPU; the headline value above is 1 batch at a time"}
         except Exception:  # noqa: BLE001 - strictly optional
             in_flight = None

@@ -41,11 +41,13 @@ for n in range(1, max_replicas + 1):
         for i in range(steps):
             e.synthesize(dev[0], ref_len, dev[1], ph_len, frames, 75, seed=10 + i, out=out)
 
-    ths = [threading.Thread(target=work, args=(k,)) for k in range(n)]
-    t0 = time.perf_counter()
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    dt = time.perf_counter() - t0
+    dt = float("inf")
+    for _ in range(2):  # wall clock around host threads: best of two passes (a host hiccup costs a whole pass otherwise)
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(n)]
+        t0 = time.perf_counter()
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        dt = min(dt, time.perf_counter() - t0)
     print(f"replicas={n}: {n * steps} batches of 8 x 10 s in {dt * 1e3:.1f} ms -> {n * steps * 80 / dt:.0f} audio-s/s "
           f"({dt * 1e3 / (n * steps):.2f} ms per batch)", flush=True)
     print(json.dumps({"batches_in_flight": n, "value": n * steps * 80 / dt, "unit": "audio-s/s",
